@@ -1,0 +1,145 @@
+/* reslic_b200.h — C ABI of the B200-native entropy-model hot path for ResLIC_TCM.
+ *
+ * The reference (AlbertoPresta/ResLIC_TCM) has no FFI layer of its own: the operator
+ * API for this path is the CompressAI `EntropyModel` nn.Module family that
+ * `TCM.forward/compress/decompress` call per slice.  This header is the
+ * C boundary a drop-in module binds instead (ctypes stub: reslic_tcm_b200/_cabi.py;
+ * reference-side binding shown in INTEGRATION.md).  Each entry cites the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative RESLIC_ERR_* on a bad argument, or
+ *    a positive cudaError_t; `reslic_last_error()` gives a thread-local message.
+ *    No exception crosses the ABI.
+ *  - all data pointers are DEVICE pointers owned by the caller; the library never
+ *    allocates, frees or retains them.  Work is enqueued on the caller's stream
+ *    (`stream` = a cudaStream_t cast to void*; NULL = legacy default stream) and is
+ *    asynchronous; the caller synchronises.
+ *  - tensors are fp32 (integer outputs int32), "image-major": image b of a tensor starts
+ *    at base + b*batch_stride (in ELEMENTS) and is one contiguous run of `n` elements.
+ *    This lets a channel slice of y[B,320,h,w] (tcm.py:438 `y.chunk`) be passed without a
+ *    copy.  16-byte aligned bases and strides%4==0 and n%4==0 take the 128-bit path; any
+ *    other layout takes a scalar CUDA path (never a CPU fallback).
+ *  - `workspace`: device scratch of at least reslic_workspace_bytes() bytes, zero-filled
+ *    ONCE by the caller before first use (kernels leave it zeroed); one workspace per
+ *    stream in flight.
+ */
+#ifndef RESLIC_B200_H
+#define RESLIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RESLIC_ABI_VERSION 1
+
+enum {
+  RESLIC_OK = 0,
+  RESLIC_ERR_ARG = -1,       /* null/negative/inconsistent argument */
+  RESLIC_ERR_WORKSPACE = -2, /* workspace missing or too small      */
+  RESLIC_ERR_UNSUPPORTED = -3
+};
+
+/* CompressAI EntropyModel.quantize modes. */
+enum {
+  RESLIC_Q_DEQUANTIZE = 0, /* "dequantize": round(x - mu) + mu  (eval)            */
+  RESLIC_Q_NOISE = 1       /* "noise":      x + U(-1/2, 1/2)    (training)        */
+};
+
+int reslic_abi_version(void);
+const char* reslic_last_error(void);
+/* Number of SMs of the current device (grid sizing is done inside the library). */
+int reslic_device_sm_count(void);
+/* Scratch bytes needed by any *_fwd call with a `bits` output for B images. */
+int64_t reslic_workspace_bytes(int64_t B);
+
+/* ----------------------------------------------------------------------------------
+ * Gaussian conditional, fused forward.
+ * Replaces, in ONE pass over a slice (any subset of outputs):
+ *   compressai GaussianConditional.forward            (call site tcm.py:455)
+ *     = EntropyModel.quantize "noise"/"dequantize"     (copy: adaptive_gaussian_conditional.py:95-141)
+ *     + _likelihood + both LowerBounds                 (twin: tcm.py:570-588)
+ *   ste_round(y - mu) + mu                             (tcm.py:36-37, 457)
+ *   quantize(y, "symbols", mu)                         (tcm.py:548)
+ *   build_indexes(sigma)                               (adaptive_gaussian_conditional.py:606-617; tcm.py:544,619)
+ *   sum log(L) / -ln2  per image                       (training/loss.py:24-27; eval.py:27-31)
+ * -------------------------------------------------------------------------------- */
+typedef struct reslic_gc_desc {
+  /* inputs */
+  const float* y;       int64_t y_bs;      /* latent slice                                */
+  const float* mu;      int64_t mu_bs;     /* means; NULL = no means (values = inputs)    */
+  const float* sigma;   int64_t sigma_bs;  /* scales (pre-LowerBound)                     */
+  const float* noise;   int64_t noise_bs;  /* NOISE mode: explicit U(-.5,.5) draw; NULL = */
+                                           /* in-kernel Philox4x32-10 (seed, offset)      */
+  int64_t B;                               /* images                                      */
+  int64_t n;                               /* elements per image (C*h*w of the slice)     */
+  int32_t mode;                            /* RESLIC_Q_*                                  */
+  float scale_bound;                       /* LowerBound on sigma (0.11)                  */
+  float likelihood_bound;                  /* LowerBound on L (1e-9); <= 0 disables       */
+  const float* scale_table;                /* [table_len] ascending; needed iff idx != 0  */
+  int32_t table_len;                       /* <= 256                                      */
+  /* outputs, each nullable */
+  float* yhat;   int64_t yhat_bs;          /* quantize() output: y+u or round(y-mu)+mu    */
+  float* ste;    int64_t ste_bs;           /* round(y-mu)+mu regardless of mode           */
+  float* lik;    int64_t lik_bs;           /* bounded likelihood                          */
+  int32_t* sym;  int64_t sym_bs;           /* int32(round(y-mu))                          */
+  int32_t* idx;  int64_t idx_bs;           /* scale-table / CDF index, 0..table_len-1     */
+  double* bits;                            /* [B] -sum_i log2 L  (OVERWRITTEN, not +=)    */
+  void* workspace; int64_t workspace_bytes;/* required iff bits != NULL                   */
+  uint64_t philox_seed, philox_offset;
+} reslic_gc_desc;
+
+int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream);
+
+/* build_indexes alone (adaptive_gaussian_conditional.py:606-617): flat, n elements. */
+int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound,
+                             const float* scale_table, int32_t table_len,
+                             int32_t* idx, void* stream);
+
+/* EntropyModel.dequantize (App. A.1; tcm.py:623): out = float(sym) + mu (mu nullable). */
+int reslic_dequantize_f32(const int32_t* sym, const float* mu, int64_t n, float* out,
+                          void* stream);
+
+/* ----------------------------------------------------------------------------------
+ * Factorized entropy bottleneck on z, fused forward.
+ * Replaces compressai EntropyBottleneck.forward (call site tcm.py:429) incl. the
+ * permute/reshape wrapper (adaptive_entropy_bottleneck.py:679-708), quantize about the
+ * medians, 2x _logits_cumulative (:525-543), sign-trick likelihood (:658-666), the
+ * LowerBound, ste_round(z - med) + med (tcm.py:431-433), the compress-path symbols
+ * (tcm.py:507) and the per-image rate sum.  filters must be (3,3,3,3).
+ * z is [B, C, hw] with batch stride z_bs; parameters are the module's raw tensors.
+ * -------------------------------------------------------------------------------- */
+typedef struct reslic_eb_desc {
+  const float* z;      int64_t z_bs;
+  const float* noise;  int64_t noise_bs;   /* as in reslic_gc_desc                        */
+  int64_t B, C, hw;
+  int32_t mode;                            /* RESLIC_Q_*                                  */
+  float likelihood_bound;
+  const float* matrix[5];                  /* _matrix{i} [C,f_{i+1},f_i] raw (softplus in-kernel) */
+  const float* bias[5];                    /* _bias{i}   [C,f_{i+1},1]                    */
+  const float* factor[4];                  /* _factor{i} [C,f_{i+1},1] raw (tanh in-kernel) */
+  const float* medians;                    /* [C] = quantiles[:,0,1]                      */
+  float* zhat;  int64_t zhat_bs;           /* quantize() output                           */
+  float* ste;   int64_t ste_bs;            /* round(z-med)+med regardless of mode         */
+  float* lik;   int64_t lik_bs;
+  int32_t* sym; int64_t sym_bs;            /* int32(round(z-med))                         */
+  double* bits;                            /* [B]                                         */
+  void* workspace; int64_t workspace_bytes;
+  uint64_t philox_seed, philox_offset;
+} reslic_eb_desc;
+
+int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream);
+
+/* ----------------------------------------------------------------------------------
+ * Host-side setup helper (no GPU work): pmf[n] -> cdf[n+1] with 2^precision total mass
+ * and every symbol's frequency >= 1.  Replaces compressai._CXX.pmf_to_quantized_cdf
+ * (src/entropy_models/coder.py:53-56; adaptive_gaussian_conditional.py:197-205).
+ * HOST pointers. */
+int reslic_pmf_to_quantized_cdf(const float* pmf, int32_t n, int32_t precision, uint32_t* cdf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESLIC_B200_H */

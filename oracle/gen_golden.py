@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz from the reference's OWN code.
+
+Run in the build container (needs /root/reference):  python -m oracle.gen_golden
+
+The reference ships no tests or golden vectors, so the oracle is pinned
+against outputs of the reference itself:
+
+* ``gc_golden.npz``  — TCM._likelihood / _standardized_cumulative, get_scale_table and
+  ste_round EXECUTED FROM tcm.py's source (reference_shim.load_tcm_functions), plus the
+  reference's unmodified ``GaussianConditionalStanh`` (default STanH parameters, for which
+  its eval forward coincides with the CompressAI path away from ties/saturation) for
+  forward() and build_indexes().
+* ``eb_golden.npz``  — the reference's unmodified ``EntropyBottleneckStanh`` eval forward
+  (default STanH parameters, medians 0): pins _logits_cumulative, the sign trick and the
+  permute wrapper.
+
+Third-party pieces that are NOT in the reference tree (compressai's quantize-about-medians,
+GaussianConditional.update, pmf_to_quantized_cdf) have no runnable reference here; those
+parts of the oracle are restated from the published algorithm and remain "unpinned".
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import reference_shim as shim
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _edge_vectors(table: torch.Tensor):
+    """Edge cases of SURVEY.md §8c: ties, -0.0, sigma at/around every table value, below the
+    bound, above the table, huge |y - mu| / sigma."""
+    nxt = lambda t, d: torch.nextafter(t, torch.full_like(t, d))
+    sig = torch.cat([table, nxt(table, math.inf), nxt(table, -math.inf),
+                     torch.tensor([0.0, 0.01, 0.05, 0.10999, 0.11, 0.11001, 255.9, 256.0, 256.1, 300.0, 1e4])])
+    d = torch.tensor([-0.0, 0.0, 0.5, -0.5, 1.5, -1.5, 2.5, -2.5, 0.49999997, 0.50000006, 3.0, -7.0, 40.0,
+                      -40.0, 79.5, -80.5, 200.0, 1000.0, 1e-8, -1e-8])
+    S, D = torch.meshgrid(sig, d, indexing="ij")
+    mu = torch.zeros_like(S)
+    mu[::2] = 0.375  # exactly representable offsets keep the ties exact
+    mu[1::4] = -1.25
+    y = D + mu
+    return y.reshape(1, 1, -1, d.numel()).contiguous(), mu.reshape(1, 1, -1, d.numel()).contiguous(), \
+        S.reshape(1, 1, -1, d.numel()).contiguous()
+
+
+def gen_gc():
+    t = shim.load_tcm_functions()
+    em, _ = shim.load_stanh_modules()
+    table = t.get_scale_table()
+    g = torch.Generator().manual_seed(20261018)
+    shape = (2, 64, 8, 8)
+    mu = torch.randn(shape, generator=g)
+    sigma = torch.exp(torch.empty(shape).uniform_(math.log(0.05), math.log(300.0), generator=g))
+    y = mu + sigma * torch.randn(shape, generator=g)
+    noise = torch.empty(shape).uniform_(-0.5, 0.5, generator=g)
+    ey, emu, esig = _edge_vectors(table)
+
+    cfg = dict(beta=10, num_sigmoids=0, extrema=80, trainable=True, removing_mean=True, symmetry=False)
+    gcs = em.GaussianConditionalStanh(None, channels=64, gaussian_configuration=cfg)
+    gcs.stanh.update_state(torch.device("cpu"))
+    gcs.scale_table = table.clone()
+
+    out = {"scale_table": table, "y": y, "mu": mu, "sigma": sigma, "noise": noise,
+           "edge_y": ey, "edge_mu": emu, "edge_sigma": esig}
+    with torch.no_grad():
+        for tag, (yy, mm, ss) in {"": (y, mu, sigma), "edge_": (ey, emu, esig)}.items():
+            ste = t.ste_round(yy - mm) + mm                                    # tcm.py:457
+            out[tag + "ste"] = ste
+            out[tag + "lik_unbounded"] = t.tcm._likelihood(ste, ss, mm)       # tcm.py:570-582
+            out[tag + "indexes"] = gcs.build_indexes(ss)                       # adaptive_gaussian_conditional.py:606-617
+        # noise-mode likelihood of y + u through the TCM twin
+        out["lik_noise_unbounded"] = t.tcm._likelihood(y + noise, sigma, mu)
+        # the reference's own STanH module, default parameters, eval mode; restricted to the
+        # region where the hard STanH equals round(): |y - mu| < 79 and no ties
+        yh, lik = gcs(y, sigma, training=False, means=mu)
+        inside = ((y - mu).abs() < 79.0)
+        out["stanh_yhat"], out["stanh_lik"], out["stanh_valid"] = yh, lik, inside
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gc_golden.npz"),
+                        **{k: v.numpy() for k, v in out.items()})
+    return out
+
+
+def gen_eb():
+    em, _ = shim.load_stanh_modules()
+    torch.manual_seed(77)
+    cfg = dict(beta=10, num_sigmoids=0, extrema=30, trainable=True, symmetry=False)
+    C = 8
+    eb = em.EntropyBottleneckStanh(C, factorized_configuration=cfg)
+    eb.stanh.update_state(torch.device("cpu"))
+    g = torch.Generator().manual_seed(78)
+    with torch.no_grad():
+        for i in range(5):
+            m = getattr(eb, f"_matrix{i}")
+            m.add_(0.3 * torch.randn(m.shape, generator=g))
+            if i < 4:
+                f = getattr(eb, f"_factor{i}")
+                f.copy_(0.5 * torch.randn(f.shape, generator=g))
+    z = 3.0 * torch.randn((3, C, 4, 6), generator=g)
+    # keep clear of ties (hard STanH yields half levels there) and inside +-extrema
+    frac = z - torch.floor(z)
+    z = torch.where((frac - 0.5).abs() < 1e-3, z + 0.01, z).clamp(-29.0, 29.0)
+    with torch.no_grad():
+        zhat, lik = eb(z, training=False)
+    out = {"z": z, "zhat": zhat, "lik": lik}
+    for i in range(5):
+        out[f"_matrix{i}"] = getattr(eb, f"_matrix{i}").detach()
+        out[f"_bias{i}"] = getattr(eb, f"_bias{i}").detach()
+        if i < 4:
+            out[f"_factor{i}"] = getattr(eb, f"_factor{i}").detach()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "eb_golden.npz"), **{k: v.numpy() for k, v in out.items()})
+    return out
+
+
+if __name__ == "__main__":
+    if not shim.available():
+        raise SystemExit("reference not available: golden vectors can only be generated in the build container")
+    a = gen_gc()
+    b = gen_eb()
+    print("wrote", GOLDEN_DIR, {k: tuple(v.shape) for k, v in a.items()}, {k: tuple(v.shape) for k, v in b.items()})

@@ -1,0 +1,147 @@
+"""ctypes binding of the C ABI in ``include/reslic_b200.h``.
+
+There is deliberately NO fallback: if the shared library is missing or a kernel call
+fails, the call raises.  Tensors cross the boundary as raw device pointers
+(``tensor.data_ptr()``) plus sizes/strides; the current torch CUDA stream is passed
+explicitly, so the kernels are ordered with the surrounding torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import torch
+
+from . import _build
+
+ABI_VERSION = 1
+Q_DEQUANTIZE, Q_NOISE = 0, 1
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+
+
+class GcDesc(C.Structure):
+    """struct reslic_gc_desc (field order must match the header)."""
+
+    _fields_ = [
+        ("y", C.c_void_p), ("y_bs", C.c_int64),
+        ("mu", C.c_void_p), ("mu_bs", C.c_int64),
+        ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
+        ("noise", C.c_void_p), ("noise_bs", C.c_int64),
+        ("B", C.c_int64), ("n", C.c_int64),
+        ("mode", C.c_int32), ("scale_bound", C.c_float), ("likelihood_bound", C.c_float),
+        ("scale_table", C.c_void_p), ("table_len", C.c_int32),
+        ("yhat", C.c_void_p), ("yhat_bs", C.c_int64),
+        ("ste", C.c_void_p), ("ste_bs", C.c_int64),
+        ("lik", C.c_void_p), ("lik_bs", C.c_int64),
+        ("sym", C.c_void_p), ("sym_bs", C.c_int64),
+        ("idx", C.c_void_p), ("idx_bs", C.c_int64),
+        ("bits", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+    ]
+
+
+class EbDesc(C.Structure):
+    """struct reslic_eb_desc."""
+
+    _fields_ = [
+        ("z", C.c_void_p), ("z_bs", C.c_int64),
+        ("noise", C.c_void_p), ("noise_bs", C.c_int64),
+        ("B", C.c_int64), ("C", C.c_int64), ("hw", C.c_int64),
+        ("mode", C.c_int32), ("likelihood_bound", C.c_float),
+        ("matrix", C.c_void_p * 5), ("bias", C.c_void_p * 5), ("factor", C.c_void_p * 4),
+        ("medians", C.c_void_p),
+        ("zhat", C.c_void_p), ("zhat_bs", C.c_int64),
+        ("ste", C.c_void_p), ("ste_bs", C.c_int64),
+        ("lik", C.c_void_p), ("lik_bs", C.c_int64),
+        ("sym", C.c_void_p), ("sym_bs", C.c_int64),
+        ("bits", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+    ]
+
+
+# every symbol include/reslic_b200.h declares: name -> (restype, argtypes)
+EXPORTS = {
+    "reslic_abi_version": (C.c_int, []),
+    "reslic_last_error": (C.c_char_p, []),
+    "reslic_device_sm_count": (C.c_int, []),
+    "reslic_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "reslic_gc_fwd_f32": (C.c_int, [C.POINTER(GcDesc), C.c_void_p]),
+    "reslic_build_indexes_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_void_p]),
+    "reslic_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
+    "reslic_pmf_to_quantized_cdf": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class ReslicError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.environ.get("RESLIC_B200_LIB", _build.LIB_PATH)
+
+
+def load():
+    """Load (once) and type the shared library.  Raises if it is absent — there is no
+    CPU or PyTorch fallback for this path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ReslicError(
+                f"CUDA extension not built: {path} is missing. Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (needs nvcc). There is no fallback path."
+            )
+        lib = C.CDLL(path)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if lib.reslic_abi_version() != ABI_VERSION:
+            raise ReslicError(f"ABI mismatch: library {lib.reslic_abi_version()} != binding {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().reslic_last_error()
+        raise ReslicError(f"{what} failed with code {code}: {msg.decode() if msg else ''}")
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------ workspace cache
+_ws = {}
+
+
+def workspace(device: torch.device, B: int) -> torch.Tensor:
+    """Zero-initialised scratch for the per-image rate reduction, one per (device, stream).
+    Kernels leave it zeroed, so it is allocated/zeroed once and reused."""
+    stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
+    need = int(load().reslic_workspace_bytes(B))
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf

@@ -1,0 +1,89 @@
+// cabi.cu — the extern "C" boundary declared in include/reslic_b200.h.
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+#include "reslic_internal.h"
+
+namespace reslic {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* msg) {
+  std::snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int set_cuda_error(cudaError_t err, const char* where) {
+  std::snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(err), cudaGetErrorString(err));
+  return static_cast<int>(err);
+}
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+__global__ void __launch_bounds__(kThreads) dequantize_kernel(const int32_t* __restrict__ sym,
+                                                             const float* __restrict__ mu, int64_t n,
+                                                             float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const float v = static_cast<float>(sym[i]);
+    out[i] = mu ? v + mu[i] : v;
+  }
+}
+
+int dequantize_launch(const int32_t* sym, const float* mu, int64_t n, float* out, cudaStream_t st) {
+  if (n < 0) return set_error(RESLIC_ERR_ARG, "dequantize: negative size");
+  if (n == 0) return RESLIC_OK;
+  if (!sym || !out) return set_error(RESLIC_ERR_ARG, "dequantize: null pointer");
+  int64_t blocks = (n + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  dequantize_kernel<<<static_cast<int>(blocks), kThreads, 0, st>>>(sym, mu, n, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "dequantize launch");
+  return RESLIC_OK;
+}
+
+}  // namespace reslic
+
+extern "C" {
+
+int reslic_abi_version(void) { return RESLIC_ABI_VERSION; }
+const char* reslic_last_error(void) { return reslic::g_err; }
+int reslic_device_sm_count(void) { return reslic::sm_count(); }
+int64_t reslic_workspace_bytes(int64_t B) {
+  if (B < 0) return 0;
+  return reslic::counters_bytes(B) + B * reslic::kMaxBpi * static_cast<int64_t>(sizeof(double));
+}
+
+int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream) {
+  return reslic::gc_fwd_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound, const float* scale_table,
+                             int32_t table_len, int32_t* idx, void* stream) {
+  reslic_gc_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.sigma = sigma; d.sigma_bs = n; d.B = 1; d.n = n; d.mode = RESLIC_Q_DEQUANTIZE;
+  d.scale_bound = scale_bound; d.scale_table = scale_table; d.table_len = table_len;
+  d.idx = idx; d.idx_bs = n;
+  if (n > 0 && !idx) return reslic::set_error(RESLIC_ERR_ARG, "build_indexes: idx is null");
+  return reslic::gc_fwd_launch(&d, static_cast<cudaStream_t>(stream));
+}
+
+int reslic_dequantize_f32(const int32_t* sym, const float* mu, int64_t n, float* out, void* stream) {
+  return reslic::dequantize_launch(sym, mu, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
+  return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,19 @@
+// reslic_internal.h — host-side glue shared by the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/reslic_b200.h"
+
+namespace reslic {
+
+int set_error(int code, const char* msg);                 // returns code
+int set_cuda_error(cudaError_t err, const char* where);   // returns (int)err
+int sm_count();                                           // SMs of the current device (cached per device)
+
+inline int64_t counters_bytes(int64_t B) { return ((B * 4 + 15) / 16) * 16; }
+
+int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);
+int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st);
+int dequantize_launch(const int32_t* sym, const float* mu, int64_t n, float* out, cudaStream_t st);
+
+}  // namespace reslic

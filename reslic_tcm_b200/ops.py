@@ -1,0 +1,311 @@
+"""Functional entry points: torch tensors in, one fused CUDA launch, torch tensors out.
+
+These are thin marshalling layers over the C ABI (``include/reslic_b200.h``); all
+arithmetic happens in the sm_100a kernels.  CPU tensors are rejected — there is no
+fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+
+
+@dataclass
+class GcOutputs:
+    yhat: Optional[Tensor] = None     # quantize() output (noisy / rounded)
+    ste: Optional[Tensor] = None      # round(y - mu) + mu
+    lik: Optional[Tensor] = None      # bounded likelihood
+    sym: Optional[Tensor] = None      # int32 symbols
+    idx: Optional[Tensor] = None      # int32 scale-table indexes
+    bits: Optional[Tensor] = None     # [B] float64, -sum log2 L per image
+
+
+@dataclass
+class EbOutputs:
+    zhat: Optional[Tensor] = None
+    ste: Optional[Tensor] = None
+    lik: Optional[Tensor] = None
+    sym: Optional[Tensor] = None
+    bits: Optional[Tensor] = None
+
+
+def _require_cuda(name: str, t: Tensor, dtype=torch.float32):
+    if not isinstance(t, Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise _cabi.ReslicError(
+            f"{name} is on {t.device}: the entropy-model path runs only on CUDA (sm_100a); there is no CPU fallback"
+        )
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def image_major(t: Tensor) -> Tuple[Tensor, int, int]:
+    """Return (tensor, batch_stride, elems_per_image) such that image b is the contiguous
+    run [b*batch_stride, b*batch_stride + n).  A channel slice of a contiguous NCHW tensor
+    (``y.chunk(5, 1)[k]``, tcm.py:438) qualifies without a copy."""
+    if t.dim() < 1:
+        t = t.reshape(1)
+    B = t.shape[0]
+    n = 1
+    for s in t.shape[1:]:
+        n *= s
+    ok = True
+    expect = 1
+    for size, stride in zip(reversed(t.shape[1:]), reversed(t.stride()[1:])):
+        if size != 1 and stride != expect:
+            ok = False
+            break
+        expect *= size
+    if not ok:
+        t = t.contiguous()
+    bs = t.stride(0) if (B > 1 and t.dim() > 0) else n
+    return t, int(bs), int(n)
+
+
+def _out_like(x: Tensor, dtype) -> Tensor:
+    return torch.empty(x.shape, dtype=dtype, device=x.device)
+
+
+def gc_forward(
+    y: Tensor,
+    scales: Optional[Tensor] = None,
+    means: Optional[Tensor] = None,
+    *,
+    training: bool = False,
+    noise: Optional[Tensor] = None,
+    scale_table: Optional[Tensor] = None,
+    scale_bound: float = 0.11,
+    likelihood_bound: float = 1e-9,
+    want: Sequence[str] = ("yhat", "lik"),
+    out: Optional[dict] = None,
+    seed: int = 0,
+    offset: int = 0,
+) -> GcOutputs:
+    """One fused pass over a Gaussian-conditional slice.
+
+    ``want`` ⊆ {"yhat","ste","lik","sym","idx","bits"}; ``out`` may map any of those names
+    to a preallocated tensor (e.g. a channel slice of a full ``y_hat``) to write into.
+    Mirrors GaussianConditional.forward + ste_round + build_indexes + quantize("symbols")
+    + the log2-rate sum (tcm.py:455,457,544,548; loss.py:24-27).
+    """
+    lib = _cabi.load()
+    _require_cuda("inputs", y)
+    want = set(want)
+    bad = want - {"yhat", "ste", "lik", "sym", "idx", "bits"}
+    if bad:
+        raise ValueError(f"unknown outputs requested: {sorted(bad)}")
+    if not want:
+        raise ValueError("no output requested")
+    if want & {"lik", "bits", "idx"}:
+        if scales is None:
+            raise ValueError("scales are required for likelihood / indexes")
+        _require_cuda("scales", scales)
+        if scales.shape != y.shape:
+            raise ValueError(f"scales shape {tuple(scales.shape)} != inputs shape {tuple(y.shape)}")
+    else:
+        scales = None
+    if means is not None:
+        _require_cuda("means", means)
+        if means.shape != y.shape:
+            means = means.expand_as(y)
+    if noise is not None:
+        _require_cuda("noise", noise)
+        if noise.shape != y.shape:
+            raise ValueError("noise shape must match inputs")
+    if "idx" in want:
+        if scale_table is None or scale_table.numel() == 0:
+            raise ValueError("build_indexes needs a scale_table (call update_scale_table first)")
+        _require_cuda("scale_table", scale_table)
+        scale_table = scale_table.contiguous()
+    out = dict(out or {})
+    shape = y.shape
+    B = shape[0] if y.dim() > 0 else 1
+    d = _cabi.GcDesc()
+    keep = []  # keep temporaries alive until the launch is enqueued
+
+    def bind_in(name, t):
+        t, bs, n = image_major(t)
+        keep.append(t)
+        setattr(d, name, t.data_ptr())
+        setattr(d, name + "_bs", bs)
+        return n
+
+    n = bind_in("y", y)
+    if scales is not None:
+        bind_in("sigma", scales)
+    if means is not None:
+        bind_in("mu", means)
+    if noise is not None:
+        bind_in("noise", noise)
+    d.B, d.n = B, n
+    d.mode = _cabi.Q_NOISE if training else _cabi.Q_DEQUANTIZE
+    d.scale_bound = float(scale_bound)
+    d.likelihood_bound = float(likelihood_bound)
+    if "idx" in want:
+        d.scale_table = scale_table.data_ptr()
+        d.table_len = scale_table.numel()
+        keep.append(scale_table)
+    res = GcOutputs()
+    copies = []
+    for name, dtype in (("yhat", torch.float32), ("ste", torch.float32), ("lik", torch.float32),
+                        ("sym", torch.int32), ("idx", torch.int32)):
+        if name not in want:
+            continue
+        t = out.get(name)
+        if t is None:
+            t = _out_like(y, dtype)
+        else:
+            if t.shape != shape or t.dtype != dtype or not t.is_cuda:
+                raise ValueError(f"out[{name!r}] has wrong shape/dtype/device")
+        tm, bs, _ = image_major(t)
+        if tm is not t:  # caller's buffer is not image-major: compute into a temp, copy after
+            copies.append((t, tm))
+        keep.append(tm)
+        setattr(d, name, tm.data_ptr())
+        setattr(d, name + "_bs", bs)
+        setattr(res, name, t)
+    if "bits" in want:
+        bits = out.get("bits")
+        if bits is None:
+            bits = torch.empty(B, dtype=torch.float64, device=y.device)
+        elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
+            raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
+        ws = _cabi.workspace(y.device, B)
+        d.bits = bits.data_ptr()
+        d.workspace = ws.data_ptr()
+        d.workspace_bytes = ws.numel()
+        keep.append(ws)
+        res.bits = bits
+    d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    with torch.cuda.device(y.device):
+        code = lib.reslic_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(y.device))
+    _cabi.check(code, "reslic_gc_fwd_f32")
+    for dst, src in copies:
+        dst.copy_(src)
+    return res
+
+
+def build_indexes(scales: Tensor, scale_table: Tensor, scale_bound: float = 0.11) -> Tensor:
+    """adaptive_gaussian_conditional.py:606-617 as one launch (int32, same shape)."""
+    lib = _cabi.load()
+    _require_cuda("scales", scales)
+    _require_cuda("scale_table", scale_table)
+    s = scales.contiguous()
+    tab = scale_table.contiguous()
+    idx = torch.empty(s.shape, dtype=torch.int32, device=s.device)
+    with torch.cuda.device(s.device):
+        code = lib.reslic_build_indexes_f32(s.data_ptr(), s.numel(), float(scale_bound), tab.data_ptr(),
+                                            tab.numel(), idx.data_ptr(), _cabi.current_stream_ptr(s.device))
+    _cabi.check(code, "reslic_build_indexes_f32")
+    return idx
+
+
+def dequantize(symbols: Tensor, means: Optional[Tensor] = None) -> Tensor:
+    """EntropyModel.dequantize: float(sym) + means (tcm.py:623)."""
+    lib = _cabi.load()
+    _require_cuda("symbols", symbols, torch.int32)
+    s = symbols.contiguous()
+    m = None
+    if means is not None:
+        _require_cuda("means", means)
+        m = means.expand_as(s).contiguous()
+    out = torch.empty(s.shape, dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        code = lib.reslic_dequantize_f32(s.data_ptr(), _cabi.ptr(m), s.numel(), out.data_ptr(),
+                                         _cabi.current_stream_ptr(s.device))
+    _cabi.check(code, "reslic_dequantize_f32")
+    return out
+
+
+def eb_forward(
+    z: Tensor,
+    matrices: Sequence[Tensor],
+    biases: Sequence[Tensor],
+    factors: Sequence[Tensor],
+    medians: Tensor,
+    *,
+    training: bool = False,
+    noise: Optional[Tensor] = None,
+    likelihood_bound: float = 1e-9,
+    want: Sequence[str] = ("zhat", "lik"),
+    seed: int = 0,
+    offset: int = 0,
+) -> EbOutputs:
+    """One fused pass of the factorized bottleneck over z [B, C, *spatial] (tcm.py:429-433)."""
+    lib = _cabi.load()
+    _require_cuda("z", z)
+    if z.dim() < 2:
+        raise ValueError("z must be at least [B, C]")
+    if len(matrices) != 5 or len(biases) != 5 or len(factors) != 4:
+        raise _cabi.ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
+    B, Cc = z.shape[0], z.shape[1]
+    expect_m = [(Cc, 3, 1), (Cc, 3, 3), (Cc, 3, 3), (Cc, 3, 3), (Cc, 1, 3)]
+    for i, m in enumerate(matrices):
+        if tuple(m.shape) != expect_m[i]:
+            raise _cabi.ReslicError(f"_matrix{i} has shape {tuple(m.shape)}; filters must be (3,3,3,3)")
+    want = set(want)
+    bad = want - {"zhat", "ste", "lik", "sym", "bits"}
+    if bad:
+        raise ValueError(f"unknown outputs requested: {sorted(bad)}")
+    zc = z.contiguous()
+    hw = 1
+    for s in z.shape[2:]:
+        hw *= s
+    d = _cabi.EbDesc()
+    keep = [zc]
+    d.z, d.z_bs = zc.data_ptr(), Cc * hw
+    if noise is not None:
+        _require_cuda("noise", noise)
+        nc = noise.contiguous()
+        keep.append(nc)
+        d.noise, d.noise_bs = nc.data_ptr(), Cc * hw
+    d.B, d.C, d.hw = B, Cc, hw
+    d.mode = _cabi.Q_NOISE if training else _cabi.Q_DEQUANTIZE
+    d.likelihood_bound = float(likelihood_bound)
+    for i in range(5):
+        m = matrices[i].detach().contiguous()
+        b = biases[i].detach().contiguous()
+        _require_cuda(f"_matrix{i}", m)
+        _require_cuda(f"_bias{i}", b)
+        keep += [m, b]
+        d.matrix[i] = m.data_ptr()
+        d.bias[i] = b.data_ptr()
+    for i in range(4):
+        f = factors[i].detach().contiguous()
+        _require_cuda(f"_factor{i}", f)
+        keep.append(f)
+        d.factor[i] = f.data_ptr()
+    med = medians.detach().reshape(-1).contiguous()
+    _require_cuda("medians", med)
+    if med.numel() != Cc:
+        raise ValueError("medians must have one entry per channel")
+    keep.append(med)
+    d.medians = med.data_ptr()
+    res = EbOutputs()
+    for name, dtype in (("zhat", torch.float32), ("ste", torch.float32), ("lik", torch.float32),
+                        ("sym", torch.int32)):
+        if name in want:
+            t = torch.empty(zc.shape, dtype=dtype, device=z.device)
+            setattr(d, name, t.data_ptr())
+            setattr(d, name + "_bs", Cc * hw)
+            setattr(res, name, t)
+    if "bits" in want:
+        bits = torch.empty(B, dtype=torch.float64, device=z.device)
+        ws = _cabi.workspace(z.device, B)
+        d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
+        keep.append(ws)
+        res.bits = bits
+    d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    with torch.cuda.device(z.device):
+        code = lib.reslic_eb_fwd_f32(C.byref(d), _cabi.current_stream_ptr(z.device))
+    _cabi.check(code, "reslic_eb_fwd_f32")
+    return res

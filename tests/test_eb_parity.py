@@ -1,0 +1,121 @@
+"""GPU parity: fused EntropyBottleneck kernel (through the C ABI) vs the CPU oracle and the
+golden vectors produced by the reference's own EntropyBottleneckStanh."""
+import pytest
+import torch
+
+from oracle import compressai_ref as cr
+from reslic_tcm_b200 import EntropyBottleneck, synthetic
+from tests.util import assert_equal_exact, assert_lik_close, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pair(C, trained_like, seed=1234):
+    params = synthetic.eb_parameters(C, trained_like=trained_like, seed=seed)
+    mod = EntropyBottleneck(C).to(DEV).eval()
+    synthetic.load_eb_parameters(mod, params)
+    ref = cr.EntropyBottleneckRef(C)
+    ref.matrices = [params[f"_matrix{i}"] for i in range(5)]
+    ref.biases = [params[f"_bias{i}"] for i in range(5)]
+    ref.factors = [params[f"_factor{i}"] for i in range(4)]
+    ref.quantiles = params["quantiles"]
+    return mod, ref
+
+
+def _check(mod, ref, z, training=False, noise=None, what=""):
+    with torch.no_grad():
+        r = mod.forward_fused(z.to(DEV), training=training, want=("zhat", "ste", "lik", "sym", "bits"),
+                              noise=None if noise is None else noise.to(DEV))
+    zhat_ref, lik_ref = ref.forward(z, training=training, noise=noise)
+    med = ref._get_medians().reshape(1, -1, *([1] * (z.dim() - 2)))
+    assert_equal_exact(r.zhat, zhat_ref, what + " z_hat")
+    assert_equal_exact(r.ste, cr.ste_round(z - med) + med, what + " ste_round(z - med) + med (tcm.py:431-433)")
+    assert_equal_exact(r.sym, ref.symbols(z), what + " symbols")
+    # fp64 evaluation of the same parameters: the CUDA kernel must be as close to it as the
+    # fp32 reference is (both are fp32 evaluations of a 5-layer MLP; they differ in fma use)
+    _, lik64 = ref.to(torch.float64).forward(z.double(), training=training,
+                                             noise=None if noise is None else noise.double())
+    assert_lik_close(r.lik, lik_ref, what=what + " likelihood vs fp32 oracle")
+    assert_lik_close(r.lik, lik64.float(), what=what + " likelihood vs fp64 oracle")
+    bits_ref = cr.per_image_bits(lik_ref)
+    assert torch.allclose(r.bits.cpu(), bits_ref, rtol=1e-5), (r.bits.cpu(), bits_ref)
+    own = -(torch.log2(r.lik.double()).reshape(z.shape[0], -1).sum(1)).cpu()
+    assert torch.allclose(r.bits.cpu(), own, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("trained_like", [False, True])
+@pytest.mark.parametrize("shape", [(1, 192, 4, 4), (3, 192, 12, 8), (2, 7, 3, 5), (2, 192, 1, 1), (1, 3, 33, 9),
+                                   (5, 1, 2, 2)])
+def test_eval_forward(shape, trained_like):
+    mod, ref = _pair(shape[1], trained_like)
+    g = torch.Generator().manual_seed(sum(shape))
+    z = 2.0 * torch.randn(shape, generator=g)
+    _check(mod, ref, z, what=f"eval {shape} trained={trained_like}")
+
+
+@pytest.mark.parametrize("shape", [(1, 192, 4, 4), (2, 64, 6, 10)])
+def test_noise_forward_explicit_noise(shape):
+    mod, ref = _pair(shape[1], True)
+    g = torch.Generator().manual_seed(5 + sum(shape))
+    z = 2.0 * torch.randn(shape, generator=g)
+    noise = torch.empty(shape).uniform_(-0.5, 0.5, generator=g)
+    _check(mod, ref, z, training=True, noise=noise, what=f"noise {shape}")
+
+
+def test_far_tails_and_ties():
+    mod, ref = _pair(4, True)
+    z = torch.tensor([-0.0, 0.0, 0.5, -0.5, 1.5, 2.5, 30.0, -30.0, 80.0, -80.0, 1e3, -1e3, 0.49999997, 7.25]
+                     ).repeat(1, 4, 1).reshape(1, 4, 14, 1)
+    _check(mod, ref, z, what="tails/ties")
+
+
+def test_golden_vectors_from_reference_module():
+    g = load_golden("eb_golden.npz")
+    C = g["z"].shape[1]
+    mod = EntropyBottleneck(C).to(DEV).eval()
+    with torch.no_grad():
+        for i in range(5):
+            getattr(mod, f"_matrix{i}").copy_(g[f"_matrix{i}"])
+            getattr(mod, f"_bias{i}").copy_(g[f"_bias{i}"])
+            if i < 4:
+                getattr(mod, f"_factor{i}").copy_(g[f"_factor{i}"])
+        zhat, lik = mod(g["z"].to(DEV), training=False)
+    assert_equal_exact(zhat, g["zhat"], "z_hat vs reference EntropyBottleneckStanh")
+    assert_lik_close(lik, g["lik"], what="z likelihood vs reference EntropyBottleneckStanh")
+
+
+def test_philox_noise_mode_consistency():
+    mod, ref = _pair(192, True)
+    g = torch.Generator().manual_seed(9)
+    z = 2.0 * torch.randn((4, 192, 8, 8), generator=g)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        r = mod.forward_fused(z.to(DEV), training=True, want=("zhat", "lik"))
+    u = (r.zhat.cpu() - z)
+    assert float(u.abs().max()) <= 0.5 + 1e-6 and abs(float(u.mean())) < 5e-3
+    lik_ref = cr.lower_bound(ref._likelihood(r.zhat.cpu().permute(1, 0, 2, 3).reshape(192, 1, -1)), 1e-9)
+    lik_ref = lik_ref.reshape(192, 4, 8, 8).permute(1, 0, 2, 3)
+    assert_lik_close(r.lik, lik_ref, what="philox-mode z likelihood")
+
+
+def test_full_size_config2_properties():
+    c = synthetic.CONFIGS[2]
+    batch = synthetic.make_batch(2, range(c.batch))
+    mod, ref = _pair(192, True)
+    z = batch["z"]
+    with torch.no_grad():
+        r = mod.forward_fused(z.to(DEV), want=("ste", "lik", "sym", "bits"))
+    med = mod.quantiles[:, 0, 1].reshape(1, -1, 1, 1)
+    assert torch.equal(r.sym.float() + med, r.ste)
+    own = -(torch.log2(r.lik.double()).reshape(c.batch, -1).sum(1))
+    assert torch.allclose(r.bits, own, rtol=2e-6)
+    _, lik_ref = ref.forward(z[:2])
+    assert_lik_close(r.lik[:2], lik_ref)
+
+
+def test_unsupported_filters_fail_loudly():
+    mod = EntropyBottleneck(4, filters=(3, 3)).to(DEV)
+    with pytest.raises(RuntimeError, match="filters"):
+        with torch.no_grad():
+            mod(torch.zeros(1, 4, 2, 2, device=DEV))

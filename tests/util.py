@@ -1,0 +1,53 @@
+"""Shared comparison helpers for the parity tests."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Likelihood tolerance (north star: 1e-5 relative).  The absolute term covers the
+# cancellation regime of the reference formula itself (upper - lower with both ~O(1) for
+# large sigma): there the reference's OWN fp32 result deviates from fp64 by up to ~1.1e-7
+# absolute (7.2e-5 relative at sigma=256, L~1.5e-3), so two correct fp32
+# implementations can differ by twice that.  SURVEY.md §7.4 H2.
+LIK_RTOL = 1e-5
+LIK_ATOL = 2e-7
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+def lik_close(actual: torch.Tensor, ref: torch.Tensor, rtol=LIK_RTOL, atol=LIK_ATOL):
+    """|a - r| <= rtol*|r| + atol elementwise, NaN == NaN; returns (ok, worst-violation message)."""
+    a, r = actual.double().cpu(), ref.double().cpu()
+    nan_ok = torch.isnan(a) == torch.isnan(r)
+    a0, r0 = torch.nan_to_num(a), torch.nan_to_num(r)
+    err = (a0 - r0).abs()
+    tol = rtol * r0.abs() + atol
+    bad = (err > tol) | ~nan_ok
+    if bad.any():
+        i = int(torch.argmax((err - tol) * bad))
+        return False, f"{int(bad.sum())} bad; worst at flat {i}: got {a.reshape(-1)[i].item():.9g} ref {r.reshape(-1)[i].item():.9g}"
+    return True, f"max abs err {err.max().item():.3g}, max rel err {(err / r0.abs().clamp_min(1e-30)).max().item():.3g}"
+
+
+def assert_lik_close(actual, ref, rtol=LIK_RTOL, atol=LIK_ATOL, what="likelihood"):
+    ok, msg = lik_close(actual, ref, rtol, atol)
+    assert ok, f"{what}: {msg}"
+
+
+def assert_equal_exact(actual: torch.Tensor, ref: torch.Tensor, what="tensor"):
+    a, r = actual.cpu(), ref.cpu()
+    assert a.shape == r.shape, f"{what}: shape {tuple(a.shape)} != {tuple(r.shape)}"
+    assert a.dtype == r.dtype, f"{what}: dtype {a.dtype} != {r.dtype}"
+    if a.is_floating_point():
+        same = (a == r) | (torch.isnan(a) & torch.isnan(r))
+    else:
+        same = a == r
+    n = int((~same).sum())
+    if n:
+        i = int(torch.nonzero(~same.reshape(-1))[0])
+        raise AssertionError(f"{what}: {n} mismatches; first at flat {i}: got {a.reshape(-1)[i].item()} ref {r.reshape(-1)[i].item()}")
