@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py — entropy-model hot path throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic latents of the named
+config (default: BASELINE.json configs[1] = TCM N=64, Kodak-shaped 768x512, batch 24,
+eval-mode round quantization + build_indexes): 1 EntropyBottleneck launch on z + 5
+Gaussian-conditional launches (one per channel slice, as TCM drives them) + the per-image
+rate sum.  Prints ONE JSON line (rank 0).
+
+* value      — latent elements (y + z) of ALL ranks / second, inputs resident in HBM,
+               steps replayed as CUDA graphs, CUDA-event timed, max over ranks.
+* e2e        — same metric through the public API with HOST (pinned) buffers: H2D of
+               y/mu/sigma/z and D2H of symbols/indexes/bits inside the timed region.
+* roofline   — the Gaussian-conditional kernel alone: algorithmic bytes / its average
+               launch duration (graph of the 5 slice launches replayed back to back).
+* cpu_baseline / --impl reference — the oracle restatement of the reference's own CPU op
+               chain (oracle/compressai_ref.py) on the host cores, bounded sample.
+Multi-GPU: weak scaling — every rank processes its own config-shaped batch of distinct
+images; the only collective is one packed-scalar all-reduce per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from reslic_tcm_b200 import synthetic  # noqa: E402
+
+METRIC = "entropy_model_latent_melem_per_s"
+UNIT = "Melem/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nbuf", type=int, default=3, help="rotating buffer sets (L2-cold inputs)")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def bytes_per_y_elem(c: synthetic.Config) -> int:
+    """Algorithmic HBM bytes per y element of one GC launch: read y, mu,
+    sigma (12) + write y_hat, L (8) [+ symbols, indexes (8)] [+ noisy y (4) in training]."""
+    return 12 + 8 + (8 if c.with_indexes else 0) + (4 if c.training else 0)
+
+
+def ref_eb(params):
+    from oracle import compressai_ref as cr
+
+    eb = cr.EntropyBottleneckRef(synthetic.Z_CHANNELS)
+    eb.matrices = [params[f"_matrix{i}"] for i in range(5)]
+    eb.biases = [params[f"_bias{i}"] for i in range(5)]
+    eb.factors = [params[f"_factor{i}"] for i in range(4)]
+    eb.quantiles = params["quantiles"]
+    return eb
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_reference_throughput(c: synthetic.Config, n_images: int, repeats: int, budget_s: float = 25.0):
+    """Time the oracle (reference op order, unfused torch CPU ops, all host threads) on
+    `n_images` images of the config.  Returns (Melem/s best, seconds per pass list, cores)."""
+    from oracle import compressai_ref as cr
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = synthetic.make_batch(c.cfg, range(n_images), with_noise=c.training)
+    eb = ref_eb(synthetic.eb_parameters())
+    table = synthetic.scale_table()
+    elems = n_images * (c.y_elems_per_image + c.z_elems_per_image)
+    times = []
+    t_all = time.perf_counter()
+    for i in range(repeats + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            cr.tcm_entropy_step(batch["y"], batch["mu"], batch["sigma"], batch["z"], eb, table,
+                                training=c.training, with_indexes=c.with_indexes,
+                                num_pixels=n_images * c.num_pixels_per_image,
+                                noise_y=batch.get("noise_y"), noise_z=batch.get("noise_z"))
+        dt = time.perf_counter() - t0
+        if i > 0:  # first pass is the warm-up
+            times.append(dt)
+        if time.perf_counter() - t_all > budget_s and times:
+            break
+    best = min(times)
+    return elems / best / 1e6, times, cores, elems
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port;
+    compressai itself is not installable here), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = synthetic.CONFIGS[args.config]
+    n_img = args.cpu_images or min(c.batch, 4)
+    from oracle import compressai_ref as cr
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = synthetic.make_batch(c.cfg, range(n_img), with_noise=c.training)
+    eb = ref_eb(synthetic.eb_parameters())
+    table = synthetic.scale_table()
+    elems = n_img * (c.y_elems_per_image + c.z_elems_per_image)
+
+    def step():
+        with torch.no_grad():
+            cr.tcm_entropy_step(batch["y"], batch["mu"], batch["sigma"], batch["z"], eb, table,
+                                training=c.training, with_indexes=c.with_indexes,
+                                num_pixels=n_img * c.num_pixels_per_image,
+                                noise_y=batch.get("noise_y"), noise_z=batch.get("noise_z"))
+
+    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = elems * steps / dt / 1e6
+    sample = f"{n_img} of {c.batch} images of config {c.cfg} per step ({elems} latent elements), {steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": c.name, "cfg": c.cfg, "images_per_step": n_img, "cpu": cpu_model()},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed loops run."""
+
+    def __init__(self, index: int, uuid: str = None, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.uuid, self.period = index, uuid, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.active = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(self.uuid)
+                except Exception:
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(self.uuid.encode())
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                if self.active.is_set():
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    mask = get_reasons(h)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                time.sleep(self.period)
+        except Exception as exc:  # NVML missing: report, do not fake
+            self.error = repr(exc)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from reslic_tcm_b200 import _cabi, dist as rdist, ops
+    from reslic_tcm_b200.pipeline import TcmEntropyPath
+
+    _cabi.load()  # no extension -> loud failure, never a fallback
+    rank, local, world = rdist.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    c = synthetic.CONFIGS[args.config]
+    B = c.batch                                   # weak scaling: every rank gets a full batch
+    images = range(rank * B, (rank + 1) * B)      # of distinct images
+    host = synthetic.make_batch(c.cfg, images, with_noise=False, pin=True)
+    params = synthetic.eb_parameters()
+    kw = dict(training=c.training, with_indexes=c.with_indexes, num_pixels=c.num_pixels_per_image, seed=1234)
+
+    sets = []
+    for i in range(max(1, args.nbuf)):
+        path = TcmEntropyPath().to(dev).eval()
+        synthetic.load_eb_parameters(path.entropy_bottleneck, params)
+        path.gaussian_conditional.scale_table = synthetic.scale_table(dev)
+        inp = {k: host[k].to(dev, non_blocking=True) for k in ("y", "mu", "sigma", "z")}
+        torch.cuda.synchronize()
+        graph, res = path.capture(inp["y"], inp["mu"], inp["sigma"], inp["z"], **kw)
+        sets.append({"path": path, "inp": inp, "graph": graph, "res": res})
+    reducer = rdist.RateReducer(dev)
+    y_elems, z_elems = B * c.y_elems_per_image, B * c.z_elems_per_image
+    elems_rank = y_elems + z_elems
+    launches_per_step = 1 + synthetic.NUM_SLICES
+
+    def step(i):
+        s = sets[i % len(sets)]
+        s["graph"].replay()
+        if world > 1:  # the path's only exchange: one packed-scalar all-reduce per step
+            reducer.pack(s["res"]["bits"], None, B * c.num_pixels_per_image)
+            reducer.all_reduce()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
+    sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # the timed region may be shorter than an NVML sample: keep the identical loop running
+    # (untimed) until the sampler has seen >= 1 s of it
+    t_end = time.perf_counter() + max(0.0, 1.0 - ms / 1e3)
+    i = args.steps
+    while time.perf_counter() < t_end:
+        step(i)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    sampler.active.clear()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = elems_rank * world / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline leg: the GC kernel alone, 5 slice launches per graph, replayed back to back
+    roof = None
+    bpe = bytes_per_y_elem(c)
+    gsets = []
+    cs = synthetic.M_LATENT // synthetic.NUM_SLICES
+    for s in sets:
+        path, inp, b = s["path"], s["inp"], s["path"]._bufs
+        gc = path.gaussian_conditional
+        want = ["ste", "lik", "bits"] + (["sym", "idx"] if c.with_indexes else []) + (["yhat"] if c.training else [])
+
+        def gc_only(inp=inp, b=b, gc=gc, want=want):
+            for k in range(synthetic.NUM_SLICES):
+                sl = slice(cs * k, cs * (k + 1))
+                out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits": b["bits_slices"][k + 1],
+                       "workspace": b["workspace"]}
+                if c.with_indexes:
+                    out["sym"], out["idx"] = b["symbols"][:, sl], b["indexes"][:, sl]
+                if c.training:
+                    out["yhat"] = b["y_noisy"][:, sl]
+                ops.gc_forward(inp["y"][:, sl], inp["sigma"][:, sl], inp["mu"][:, sl], training=c.training,
+                               scale_table=gc.scale_table if c.with_indexes else None, want=want, out=out,
+                               seed=1234, offset=1 + k)
+
+        gc_only()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gc_only()
+        gsets.append(g)
+    reps = max(args.steps, 50)
+    for i in range(5):
+        gsets[i % len(gsets)].replay()
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for i in range(reps):
+        gsets[i % len(gsets)].replay()
+    r1.record()
+    torch.cuda.synchronize()
+    gc_ms = r0.elapsed_time(r1) / (reps * synthetic.NUM_SLICES)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    launch_bytes = bpe * (y_elems // synthetic.NUM_SLICES)
+    achieved = launch_bytes / (gc_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "gc_fwd_kernel", "bytes_per_elem": bpe,
+            "elems_per_launch": y_elems // synthetic.NUM_SLICES, "us_per_launch": gc_ms * 1e3,
+            "peak_source": peak_src,
+            "gc_melem_per_s": (y_elems // synthetic.NUM_SLICES) / (gc_ms * 1e-3) / 1e6}
+
+    # ---- e2e leg: public API with host buffers (H2D inputs, D2H symbols/indexes/bits)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, c, sets[0], host, dev, world, B, elems_rank, kw)
+
+    sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- CPU baseline (rank 0, single-GPU runs only): oracle on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_img = args.cpu_images or min(c.batch, 8)
+        v, times, cores, el = cpu_reference_throughput(c, n_img, repeats=8, budget_s=20.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_img} of {c.batch} images of config {c.cfg} ({el} latent elements), best of {len(times)} passes "
+                         f"after 1 warm-up, oracle/compressai_ref.py tcm_entropy_step, torch {torch.__version__} CPU",
+               "cpu": cpu_model()}
+
+    if rank == 0:
+        bits = sets[0]["res"]["bits"].double().cpu()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c.name, "cfg": c.cfg, "images_per_gpu": B, "y_shape": [B, 320, *c.y_hw],
+                       "z_shape": [B, 192, *c.z_hw], "launches_per_step": launches_per_step,
+                       "mode": "per-slice launches (5 GC + 1 EB) replayed as a CUDA graph",
+                       "l2": f"{len(sets)} rotating buffer sets of {(bpe * y_elems + 12 * z_elems) / 1e6:.0f} MB each (> 126 MB L2)",
+                       "bpp_mean_image0_set": float(bits.mean()) / c.num_pixels_per_image},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw):
+    """Same step through the public API with host buffers: every step copies y, mu, sigma, z
+    from pinned host memory, runs the pass, and reads symbols/indexes (the rANS coder's
+    input, tcm.py:551-552) — or the likelihood-free rate for forward configs — back."""
+    import torch.distributed as dist
+
+    path, inp = s["path"], s["inp"]
+    res = s["res"]
+    outs = ["bits"] + (["symbols", "indexes"] if c.with_indexes else [])
+    host_out = {k: torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory() for k in outs}
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("y", "mu", "sigma", "z"))
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    def step():
+        for k in ("y", "mu", "sigma", "z"):
+            inp[k].copy_(host[k], non_blocking=True)
+        s["graph"].replay()
+        for k in outs:
+            host_out[k].copy_(res[k], non_blocking=True)
+
+    steps = max(3, min(args.steps, 30))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": elems_rank * world / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms / steps, "steps": steps,
+            "what": "pinned host y/mu/sigma/z -> H2D -> graph -> D2H " + "/".join(outs)}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -48,6 +48,16 @@ enum {
   RESLIC_Q_NOISE = 1       /* "noise":      x + U(-1/2, 1/2)    (training)        */
 };
 
+/* Likelihood arithmetic of the Gaussian-conditional kernel (process-wide switch).
+ *  FAST   (default): custom erfc (1 RCP + 1 EX2 + 21 FP32 ops) and MUFU log2 for the rate;
+ *                    same operand path (true fp32 divides, same constants) as the reference.
+ *  MIRROR          : CUDA erfcf / log2f, i.e. the instruction-for-instruction arithmetic the
+ *                    reference's torch CUDA kernels execute; slower, kept for cross-checks.
+ * Integers (symbols, indexes) and y_hat are identical in both modes. */
+enum { RESLIC_MATH_FAST = 0, RESLIC_MATH_MIRROR = 1 };
+int reslic_set_math_mode(int mode);
+int reslic_get_math_mode(void);
+
 int reslic_abi_version(void);
 const char* reslic_last_error(void);
 /* Number of SMs of the current device (grid sizing is done inside the library). */

@@ -18,6 +18,7 @@ from . import _build
 
 ABI_VERSION = 1
 Q_DEQUANTIZE, Q_NOISE = 0, 1
+MATH_FAST, MATH_MIRROR = 0, 1
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p
@@ -70,6 +71,8 @@ EXPORTS = {
     "reslic_abi_version": (C.c_int, []),
     "reslic_last_error": (C.c_char_p, []),
     "reslic_device_sm_count": (C.c_int, []),
+    "reslic_set_math_mode": (C.c_int, [C.c_int]),
+    "reslic_get_math_mode": (C.c_int, []),
     "reslic_workspace_bytes": (C.c_int64, [C.c_int64]),
     "reslic_gc_fwd_f32": (C.c_int, [C.POINTER(GcDesc), C.c_void_p]),
     "reslic_build_indexes_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int32,
@@ -112,8 +115,17 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.reslic_abi_version() != ABI_VERSION:
             raise ReslicError(f"ABI mismatch: library {lib.reslic_abi_version()} != binding {ABI_VERSION}")
+        mode = os.environ.get("RESLIC_MATH_MODE")
+        if mode:
+            check_code = lib.reslic_set_math_mode({"fast": MATH_FAST, "mirror": MATH_MIRROR}[mode.lower()])
+            if check_code != 0:
+                raise ReslicError("bad RESLIC_MATH_MODE")
         _lib = lib
     return _lib
+
+
+def set_math_mode(mode: int) -> None:
+    check(load().reslic_set_math_mode(int(mode)), "reslic_set_math_mode")
 
 
 def check(code: int, what: str):

@@ -1,5 +1,6 @@
 // cabi.cu — the extern "C" boundary declared in include/reslic_b200.h.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "reslic_internal.h"
@@ -7,6 +8,17 @@
 namespace reslic {
 
 static thread_local char g_err[512] = "";
+static int g_math_mode = RESLIC_MATH_FAST;
+int math_mode() { return g_math_mode; }
+int gc_iters_target() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = std::getenv("RESLIC_GC_ITERS");
+    v = e ? std::atoi(e) : 4;
+    if (v < 1 || v > 64) v = 4;
+  }
+  return v;
+}
 
 int set_error(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -58,9 +70,16 @@ extern "C" {
 int reslic_abi_version(void) { return RESLIC_ABI_VERSION; }
 const char* reslic_last_error(void) { return reslic::g_err; }
 int reslic_device_sm_count(void) { return reslic::sm_count(); }
+int reslic_set_math_mode(int mode) {
+  if (mode != RESLIC_MATH_FAST && mode != RESLIC_MATH_MIRROR)
+    return reslic::set_error(RESLIC_ERR_ARG, "set_math_mode: unknown mode");
+  reslic::g_math_mode = mode;
+  return RESLIC_OK;
+}
+int reslic_get_math_mode(void) { return reslic::g_math_mode; }
 int64_t reslic_workspace_bytes(int64_t B) {
   if (B < 0) return 0;
-  return reslic::counters_bytes(B) + B * reslic::kMaxBpi * static_cast<int64_t>(sizeof(double));
+  return B * reslic::kWsRow * static_cast<int64_t>(sizeof(double));
 }
 
 int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream) {

@@ -80,10 +80,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Workspace layout: one row of (kMaxBpi partials + 1 arrival counter) doubles per image.  A
+// row's layout does not depend on B, so a counter slot is never reused as a partial by a
+// later launch with a different batch size — the "zero once" contract stays valid.
+constexpr int kWsRow = kMaxBpi + 1;
+
 // Returns through bits_out[image] = -(sum of all CTAs' acc).  Must be called by all threads.
 __device__ __forceinline__ void image_sum_finish(float acc, int image, int chunk, int bpi,
-                                                 unsigned int* counters, double* partials,
-                                                 double* bits_out) {
+                                                 double* workspace, double* bits_out) {
+  double* partials = workspace + static_cast<int64_t>(image) * kWsRow;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials + kMaxBpi);
   __shared__ double s_warp[kThreads / 32];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,9 +104,9 @@ __device__ __forceinline__ void image_sum_finish(float acc, int image, int chunk
         bits_out[image] = -v;
         s_last = false;
       } else {
-        partials[static_cast<int64_t>(image) * kMaxBpi + chunk] = v;
+        partials[chunk] = v;
         __threadfence();
-        const unsigned int prev = atomicAdd(&counters[image], 1u);
+        const unsigned int prev = atomicAdd(counter, 1u);
         s_last = (prev == static_cast<unsigned int>(bpi - 1));
       }
     }
@@ -108,13 +114,13 @@ __device__ __forceinline__ void image_sum_finish(float acc, int image, int chunk
   __syncthreads();
   if (s_last && warp == 0) {
     __threadfence();
-    const volatile double* pp = partials + static_cast<int64_t>(image) * kMaxBpi;
+    const volatile double* pp = partials;
     double t = 0.0;
     for (int i = lane; i < bpi; i += 32) t += pp[i];
     t = warp_sum(t);
     if (lane == 0) {
       bits_out[image] = -t;
-      counters[image] = 0u;
+      *counter = 0u;
     }
   }
 }

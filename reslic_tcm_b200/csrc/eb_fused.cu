@@ -26,7 +26,7 @@ struct EbParams {
   const float* matrix[5]; const float* bias[5]; const float* factor[4]; const float* medians;
   float* zhat; float* ste; float* lik; int32_t* sym;
   int64_t zhat_bs, ste_bs, lik_bs, sym_bs;
-  double* bits; unsigned int* counters; double* partials;
+  double* bits; double* workspace;
   int64_t ne;       // elements per image = C*hw
   int hw, C, tile, bpi, noise_mode;
   float lik_bound;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
       }
     }
   }
-  if (p.bits) image_sum_finish(acc, image, chunk, p.bpi, p.counters, p.partials, p.bits);
+  if (p.bits) image_sum_finish(acc, image, chunk, p.bpi, p.workspace, p.bits);
 }
 
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
@@ -187,8 +187,7 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
       return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace missing or too small for `bits`");
     p.bits = d->bits;
-    p.counters = static_cast<unsigned int*>(d->workspace);
-    p.partials = reinterpret_cast<double*>(static_cast<char*>(d->workspace) + counters_bytes(d->B));
+    p.workspace = static_cast<double*>(d->workspace);
   }
   const int64_t grid64 = bpi * d->B;
   if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");

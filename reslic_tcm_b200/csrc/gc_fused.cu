@@ -24,7 +24,7 @@ struct GcParams {
   int64_t y_bs, mu_bs, sigma_bs, noise_bs;
   float* yhat; float* ste; float* lik; int32_t* sym; int32_t* idx;
   int64_t yhat_bs, ste_bs, lik_bs, sym_bs, idx_bs;
-  double* bits; unsigned int* counters; double* partials;
+  double* bits; double* workspace;
   const float* table; int table_len;
   int64_t n;          // elements per image
   int bpi;            // CTAs per image
@@ -51,6 +51,40 @@ __device__ __forceinline__ void div2_rn(float n1, float n2, float s, float& q1, 
   q2 = fmaf(rem, r, q);
 }
 
+// erfc(x) for 0 <= x <= 12 as exp(-x^2) * (1-u) * Q(u), u = x/(x+2.5): one MUFU.RCP, one
+// MUFU.EX2, 21 FP32 ops (CUDA's erfcf: 3 MUFU + FRND + ~44).  Q is a degree-9 near-minimax
+// fit (|rel err| < 1.4e-8 in exact arithmetic); u = x*r keeps small x free of cancellation
+// and (1-u) carries the 1/x decay so Horner stays well conditioned.  exp(-x^2) gets the
+// rounding errors of x*x and of the log2(e) product back as a first-order correction, so
+// the relative error stays ~3e-7 out to the likelihood floor (x^2 ~ 20).
+__device__ __forceinline__ float erfc_pos_fast(float x) {
+  const float r = rcp_approx(x + 2.5f);
+  const float u = x * r;
+  const float w = fmaf(-x, r, 1.0f);
+  float q = 2.651532926e-02f;
+  q = fmaf(q, u, -5.741734803e-02f);
+  q = fmaf(q, u, -3.597635776e-02f);
+  q = fmaf(q, u, 1.268966794e-01f);
+  q = fmaf(q, u, 1.091585010e-01f);
+  q = fmaf(q, u, -2.630832791e-01f);
+  q = fmaf(q, u, -4.676126838e-01f);
+  q = fmaf(q, u, 1.608165503e+00f);
+  q = fmaf(q, u, -1.820949554e+00f);
+  q = fmaf(q, u, 1.0f);
+  const float L2E = 1.44269502162933349609375f;       // fp32(log2 e)
+  const float L2E_LO = 1.925963033500011e-08f;        // log2 e - fp32(log2 e)
+  const float s2 = x * x;
+  const float e = fmaf(x, x, -s2);                    // exact low part of x*x
+  const float t = s2 * L2E;
+  float tl = fmaf(s2, L2E, -t);                       // exact low part of s2*L2E
+  tl = fmaf(e, L2E, tl);
+  tl = fmaf(s2, L2E_LO, tl);
+  const float E0 = ex2_approx(-t);
+  const float E = fmaf(E0 * tl, -0.693147182464599609375f, E0);   // 2^-(t+tl) ~ E0*(1 - ln2*tl)
+  return E * (w * q);
+}
+
+template <bool FAST>
 __device__ __forceinline__ float gc_likelihood(float v, float s) {
   // clamps keep every intermediate finite (inf/inf, 0*inf); they change no result for
   // |y-mu|, sigma <= 1e30 and give the reference's limit values (L -> 0 -> bound) beyond.
@@ -59,29 +93,52 @@ __device__ __forceinline__ float gc_likelihood(float v, float s) {
   float a, b;
   div2_rn(0.5f - vc, -0.5f - vc, sc, a, b);
   const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5)) cast to fp32
-  const float upper = 0.5f * erfcf(c * a);
-  const float lower = 0.5f * erfcf(c * b);
+  const float xa = c * a, xb = c * b;        // xb > 0 always; xa < 0 iff v < 0.5
+  if (FAST) {
+    float ea = erfc_pos_fast(min_nan(fabsf(xa), 12.0f));
+    const float eb = erfc_pos_fast(min_nan(xb, 12.0f));
+    ea = (xa < 0.0f) ? 2.0f - ea : ea;
+    return fmaf(0.5f, ea, -0.5f * eb);
+  }
+  const float upper = 0.5f * erfcf(xa);
+  const float lower = 0.5f * erfcf(xb);
   return upper - lower;
 }
 
-// #{ j < len-1 : !(s <= table[j]) }  ==  (len-1) - sum_j [s <= table[j]]   (NaN -> len-1).
-// `tab` is the shared-memory copy padded with +inf up to 2^k - 1 entries.
+// build_indexes: idx = #{ j < len-1 : !(s <= table[j]) } = (len-1) - sum_j [s <= table[j]].
+// Shared-memory layout `pad`: pad[0] = -inf, pad[1+j] = table[j] (j < len-1), +inf beyond, so
+// idx = g  <=>  pad[g] < s <= pad[g+1].  The scale table is log-spaced
+// (exp(linspace(ln .11, ln 256, 64)), tcm.py:26-34), so g is GUESSED from one MUFU.LG2 and
+// a fused multiply-add, then PROVEN with the two exact comparisons the reference makes; a
+// failed proof (s within rounding of a table value, a table that is not log-spaced, NaN)
+// falls back to the branch-free binary search.  The result is bit-exact for any table.
+constexpr int kPadLen = 260;
+
 template <int STEPS>
-__device__ __forceinline__ int scale_index(float s, const float* tab) {
+__device__ __forceinline__ int scale_index_search(float s, const float* pad) {
   int lo = 0;
 #pragma unroll
   for (int step = 1 << (STEPS - 1); step > 0; step >>= 1) {
-    const float t = tab[lo + step - 1];
+    const float t = pad[lo + step];            // == table[lo + step - 1]
     lo += (!(s <= t)) ? step : 0;
   }
   return lo;  // NaN walks to 2^STEPS - 1; the caller clamps to table_len - 1
 }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, int STEPS>
+template <int STEPS>
+__device__ __forceinline__ int scale_index(float s, const float* pad, float g_scale, float g_off, int last) {
+  int g = __float2int_ru(fmaf(lg2_approx(s), g_scale, g_off));
+  g = max(0, min(g, last));
+  const float lo = pad[g], hi = pad[g + 1];
+  if (!((lo < s) && (s <= hi))) g = min(scale_index_search<STEPS>(s, pad), last);
+  return g;
+}
+
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, int STEPS, bool FAST>
 struct GcElem {
-  __device__ __forceinline__ static void run(const GcParams& p, const float* tab, float y, float mu,
-                                             float sg, float u, float& yhat, float& ste,
-                                             float& lik, int& sym, int& idx, float& acc) {
+  __device__ __forceinline__ static void run(const GcParams& p, const float* pad, float g_scale, float g_off,
+                                             float y, float mu, float sg, float u, float& yhat,
+                                             float& ste, float& lik, int& sym, int& idx, float& acc) {
     const float d = y - mu;
     const float q = rintf(d);            // torch.round: half to even
     sym = __float2int_rn(q);
@@ -90,23 +147,38 @@ struct GcElem {
     const float s = max_nan(sg, p.scale_bound);
     if (NEED_LIK) {
       const float v = fabsf(yhat - mu);  // reference re-subtracts mu from the quantized value
-      float L = gc_likelihood(v, s);
+      float L = gc_likelihood<FAST>(v, s);
       if (p.lik_bound > 0.0f) L = max_nan(L, p.lik_bound);
       lik = L;
-      acc += log2f(L);
+      // FAST: MUFU.LG2 (abs err <= 2^-22 for L in (0.5,2), rel err 2^-22 elsewhere)
+      acc += FAST ? lg2_approx(L) : log2f(L);
     }
-    if (NEED_IDX) idx = min(scale_index<STEPS>(s, tab), p.table_len - 1);
+    if (NEED_IDX) idx = scale_index<STEPS>(s, pad, g_scale, g_off, p.table_len - 1);
   }
 };
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS>
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST>
 __global__ void __launch_bounds__(kThreads)
 gc_fwd_kernel(const GcParams p) {
-  __shared__ float tab[(1 << STEPS)];
+  __shared__ float pad[NEED_IDX ? kPadLen : 1];
+  __shared__ float s_guess[2];
+  float g_scale = 0.0f, g_off = 0.0f;
   if (NEED_IDX) {
-    for (int i = threadIdx.x; i < (1 << STEPS); i += kThreads)
-      tab[i] = (i < p.table_len - 1) ? p.table[i] : __int_as_float(0x7f800000);
+    const float inf = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < kPadLen; i += kThreads)
+      pad[i] = (i == 0) ? -inf : ((i <= p.table_len - 1) ? p.table[i - 1] : inf);
+    if (threadIdx.x == 0) {
+      // guess(s) = ceil((log2 s - log2 t_0) * (len-2) / (log2 t_{len-2} - log2 t_0))
+      float sc = 0.0f, off = 0.0f;
+      if (p.table_len >= 3) {
+        const float l0 = log2f(p.table[0]), l1 = log2f(p.table[p.table_len - 2]);
+        // the small downward bias makes sigma == table[j] (notably the 0.11 bound itself) guess j
+        if (l1 > l0) { sc = static_cast<float>(p.table_len - 2) / (l1 - l0); off = -l0 * sc - 2.44140625e-4f; }
+      }
+      s_guess[0] = sc; s_guess[1] = off;
+    }
     __syncthreads();
+    g_scale = s_guess[0]; g_off = s_guess[1];
   }
   const int image = blockIdx.x / p.bpi;
   const int chunk = blockIdx.x - image * p.bpi;
@@ -155,7 +227,7 @@ gc_fwd_kernel(const GcParams p) {
     float oy[4], os[4], ol[4]; int osym[4], oidx[4];
 #pragma unroll
     for (int k = 0; k < W; ++k)
-      GcElem<NEED_LIK, NEED_IDX, NOISE, STEPS>::run(p, tab, yv[k], mv[k], sv[k], uv[k], oy[k], os[k],
+      GcElem<NEED_LIK, NEED_IDX, NOISE, STEPS, FAST>::run(p, pad, g_scale, g_off, yv[k], mv[k], sv[k], uv[k], oy[k], os[k],
                                                     ol[k], osym[k], oidx[k], acc);
     if (VEC) {
       if (yhat) st_stream4(yhat + e, make_float4(oy[0], oy[1], oy[2], oy[3]));
@@ -172,27 +244,34 @@ gc_fwd_kernel(const GcParams p) {
     }
   }
   if (NEED_LIK && p.bits)
-    image_sum_finish(acc, image, chunk, p.bpi, p.counters, p.partials, p.bits);
+    image_sum_finish(acc, image, chunk, p.bpi, p.workspace, p.bits);
 }
 
 // ------------------------------------------------------------------ host-side launch
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
-static cudaError_t launch_steps(const GcParams& p, int grid, int steps, cudaStream_t st) {
-  if (steps <= 6) gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 6><<<grid, kThreads, 0, st>>>(p);
-  else gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 8><<<grid, kThreads, 0, st>>>(p);
+static cudaError_t launch_steps(const GcParams& p, int grid, int steps, bool fast, cudaStream_t st) {
+  // the math policy only matters when a likelihood is computed
+  if (NEED_LIK && !fast) {
+    if (steps <= 6) gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 6, false><<<grid, kThreads, 0, st>>>(p);
+    else gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 8, false><<<grid, kThreads, 0, st>>>(p);
+  } else {
+    if (steps <= 6) gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 6, true><<<grid, kThreads, 0, st>>>(p);
+    else gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 8, true><<<grid, kThreads, 0, st>>>(p);
+  }
   return cudaGetLastError();
 }
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE>
-static cudaError_t launch_vec(const GcParams& p, int grid, int steps, bool vec, cudaStream_t st) {
-  return vec ? launch_steps<NEED_LIK, NEED_IDX, NOISE, true>(p, grid, steps, st)
-             : launch_steps<NEED_LIK, NEED_IDX, NOISE, false>(p, grid, steps, st);
+static cudaError_t launch_vec(const GcParams& p, int grid, int steps, bool vec, bool fast, cudaStream_t st) {
+  return vec ? launch_steps<NEED_LIK, NEED_IDX, NOISE, true>(p, grid, steps, fast, st)
+             : launch_steps<NEED_LIK, NEED_IDX, NOISE, false>(p, grid, steps, fast, st);
 }
 template <bool NEED_LIK, bool NEED_IDX>
-static cudaError_t launch_noise(const GcParams& p, int grid, int steps, bool vec, bool noise, cudaStream_t st) {
-  return noise ? launch_vec<NEED_LIK, NEED_IDX, true>(p, grid, steps, vec, st)
-               : launch_vec<NEED_LIK, NEED_IDX, false>(p, grid, steps, vec, st);
+static cudaError_t launch_noise(const GcParams& p, int grid, int steps, bool vec, bool noise, bool fast,
+                                cudaStream_t st) {
+  return noise ? launch_vec<NEED_LIK, NEED_IDX, true>(p, grid, steps, vec, fast, st)
+               : launch_vec<NEED_LIK, NEED_IDX, false>(p, grid, steps, vec, fast, st);
 }
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
@@ -231,11 +310,15 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   chk(d->yhat, d->yhat_bs); chk(d->ste, d->ste_bs); chk(d->lik, d->lik_bs); chk(d->sym, d->sym_bs);
   chk(d->idx, d->idx_bs);
 
+  // CTAs per image: each CTA walks `iters` grid-stride steps of kThreads groups so that the
+  // prologue (table staging) and the fp64 reduction epilogue are amortised, while the grid
+  // still fills every SM a few times over.
   const int64_t groups = vec ? d->n / 4 : d->n;
-  int64_t bpi = (groups + kThreads - 1) / kThreads;
-  // keep the grid within a few waves of the machine; CTAs then loop (grid-stride per image)
-  const int64_t max_ctas = static_cast<int64_t>(sm_count()) * 64;
-  if (bpi * d->B > max_ctas) bpi = (max_ctas + d->B - 1) / d->B;
+  const int64_t tiles = (groups + kThreads - 1) / kThreads;       // per image
+  int64_t iters = gc_iters_target();
+  const int64_t min_ctas = static_cast<int64_t>(sm_count()) * 4;
+  while (iters > 1 && ((tiles + iters - 1) / iters) * d->B < min_ctas) --iters;
+  int64_t bpi = (tiles + iters - 1) / iters;
   if (bpi > kMaxBpi) bpi = kMaxBpi;
   if (bpi < 1) bpi = 1;
   p.bpi = static_cast<int>(bpi);
@@ -243,8 +326,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
     if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
       return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace missing or too small for `bits`");
     p.bits = d->bits;
-    p.counters = static_cast<unsigned int*>(d->workspace);
-    p.partials = reinterpret_cast<double*>(static_cast<char*>(d->workspace) + counters_bytes(d->B));
+    p.workspace = static_cast<double*>(d->workspace);
   }
   const int64_t grid64 = bpi * d->B;
   if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "gc_fwd: grid too large");
@@ -253,10 +335,11 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   const bool noise = d->mode == RESLIC_Q_NOISE;
   const int grid = static_cast<int>(grid64);
   cudaError_t err;
-  if (need_lik) err = need_idx ? launch_noise<true, true>(p, grid, steps, vec, noise, st)
-                               : launch_noise<true, false>(p, grid, steps, vec, noise, st);
-  else err = need_idx ? launch_noise<false, true>(p, grid, steps, vec, noise, st)
-                      : launch_noise<false, false>(p, grid, steps, vec, noise, st);
+  const bool fast = math_mode() != RESLIC_MATH_MIRROR;
+  if (need_lik) err = need_idx ? launch_noise<true, true>(p, grid, steps, vec, noise, fast, st)
+                               : launch_noise<true, false>(p, grid, steps, vec, noise, fast, st);
+  else err = need_idx ? launch_noise<false, true>(p, grid, steps, vec, noise, fast, st)
+                      : launch_noise<false, false>(p, grid, steps, vec, noise, fast, st);
   if (err != cudaSuccess) return set_cuda_error(err, "gc_fwd launch");
   return RESLIC_OK;
 }

@@ -8,9 +8,9 @@ namespace reslic {
 
 int set_error(int code, const char* msg);                 // returns code
 int set_cuda_error(cudaError_t err, const char* where);   // returns (int)err
-int sm_count();                                           // SMs of the current device (cached per device)
-
-inline int64_t counters_bytes(int64_t B) { return ((B * 4 + 15) / 16) * 16; }
+int sm_count();
+int gc_iters_target();                                    // grid-stride steps per CTA (tuning)
+int math_mode();                                          // RESLIC_MATH_*                                           // SMs of the current device (cached per device)
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st);

@@ -177,7 +177,9 @@ def gc_forward(
             bits = torch.empty(B, dtype=torch.float64, device=y.device)
         elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
             raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
-        ws = _cabi.workspace(y.device, B)
+        ws = out.get("workspace")
+        if ws is None:
+            ws = _cabi.workspace(y.device, B)
         d.bits = bits.data_ptr()
         d.workspace = ws.data_ptr()
         d.workspace_bytes = ws.numel()
@@ -236,6 +238,7 @@ def eb_forward(
     noise: Optional[Tensor] = None,
     likelihood_bound: float = 1e-9,
     want: Sequence[str] = ("zhat", "lik"),
+    out: Optional[dict] = None,
     seed: int = 0,
     offset: int = 0,
 ) -> EbOutputs:
@@ -290,16 +293,27 @@ def eb_forward(
     keep.append(med)
     d.medians = med.data_ptr()
     res = EbOutputs()
+    out = dict(out or {})
     for name, dtype in (("zhat", torch.float32), ("ste", torch.float32), ("lik", torch.float32),
                         ("sym", torch.int32)):
         if name in want:
-            t = torch.empty(zc.shape, dtype=dtype, device=z.device)
+            t = out.get(name)
+            if t is None:
+                t = torch.empty(zc.shape, dtype=dtype, device=z.device)
+            elif t.shape != zc.shape or t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"out[{name!r}] must be a contiguous {dtype} CUDA tensor shaped like z")
             setattr(d, name, t.data_ptr())
             setattr(d, name + "_bs", Cc * hw)
             setattr(res, name, t)
     if "bits" in want:
-        bits = torch.empty(B, dtype=torch.float64, device=z.device)
-        ws = _cabi.workspace(z.device, B)
+        bits = out.get("bits")
+        if bits is None:
+            bits = torch.empty(B, dtype=torch.float64, device=z.device)
+        elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
+            raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
+        ws = out.get("workspace")
+        if ws is None:
+            ws = _cabi.workspace(z.device, B)
         d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
         keep.append(ws)
         res.bits = bits

@@ -1,0 +1,121 @@
+"""The per-batch entropy pass as TCM drives it, minus the dense networks.
+
+``TcmEntropyPath`` owns the two drop-in entropy models exactly as ``TCM.__init__`` does
+(src/models/reference/tcm.py:416-417) and runs, for one batch of latents, what
+``TCM.forward`` / ``TCM.compress`` run between the dense transforms (tcm.py:429-466,
+527-552) and what ``RateDistortionLoss`` / ``compute_bpp`` reduce afterwards
+(training/loss.py:24-27, eval.py:27-31):
+
+    z  -> EntropyBottleneck:  z_hat (ste_round about the medians), L_z, bits_z[B]
+    for each of the 5 channel slices of y (sequential in the real model: mu, sigma of
+    slice k depend on y_hat of slices < k):
+        GaussianConditional fused pass -> y_hat slice, L_y slice, [symbols, indexes], bits_y[B]
+    bpp[B] = (bits_y + bits_z) / num_pixels
+
+= 1 + 5 kernel launches per batch.  Static output buffers make the pass CUDA-graph
+capturable (``capture()``), which removes the Python/launch overhead from steady state.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _cabi, ops, synthetic
+from .entropy_models import EntropyBottleneck, GaussianConditional
+
+
+class TcmEntropyPath(nn.Module):
+    def __init__(self, z_channels: int = synthetic.Z_CHANNELS, num_slices: int = synthetic.NUM_SLICES):
+        super().__init__()
+        self.num_slices = int(num_slices)
+        self.entropy_bottleneck = EntropyBottleneck(z_channels)      # tcm.py:416
+        self.gaussian_conditional = GaussianConditional(None)        # tcm.py:417
+        self._bufs: Optional[Dict[str, Tensor]] = None
+        self._key = None
+
+    # ------------------------------------------------------------------ static buffers
+    def buffers(self, y: Tensor, z: Tensor, with_indexes: bool, training: bool) -> Dict[str, Tensor]:
+        key = (tuple(y.shape), tuple(z.shape), bool(with_indexes), bool(training), y.device)
+        if self._key != key:
+            dev, B = y.device, y.shape[0]
+            b = {
+                "y_hat": torch.empty_like(y),
+                "y_lik": torch.empty_like(y),
+                "z_hat": torch.empty_like(z),
+                "z_lik": torch.empty_like(z),
+                "bits_slices": torch.zeros(self.num_slices + 1, B, dtype=torch.float64, device=dev),
+                "bits": torch.zeros(B, dtype=torch.float64, device=dev),
+                "workspace": torch.zeros(max(int(_cabi.load().reslic_workspace_bytes(B)), 16),
+                                         dtype=torch.uint8, device=dev),
+            }
+            if with_indexes:
+                b["symbols"] = torch.empty(y.shape, dtype=torch.int32, device=dev)
+                b["indexes"] = torch.empty(y.shape, dtype=torch.int32, device=dev)
+            if training:
+                b["y_noisy"] = torch.empty_like(y)
+            self._bufs, self._key = b, key
+        return self._bufs
+
+    # ------------------------------------------------------------------ one pass
+    @torch.no_grad()
+    def forward(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, *, training: bool = False,
+                with_indexes: bool = False, num_pixels: Optional[int] = None, seed: int = 0,
+                offset: int = 0, noise_y: Optional[Tensor] = None, noise_z: Optional[Tensor] = None
+                ) -> Dict[str, Tensor]:
+        """All tensors on the GPU, NCHW fp32: y/mu/sigma [B, 320, h, w], z [B, 192, h/4, w/4].
+        Returns views of static buffers (valid until the next call)."""
+        gc, eb = self.gaussian_conditional, self.entropy_bottleneck
+        b = self.buffers(y, z, with_indexes, training)
+        C = y.shape[1]
+        if C % self.num_slices:
+            raise ValueError(f"{C} channels do not split into {self.num_slices} slices")
+        cs = C // self.num_slices
+        m, bi, f = eb._params()
+        ez = ops.eb_forward(z, m, bi, f, eb.quantiles[:, 0, 1], training=training, noise=noise_z,
+                            likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"),
+                            out={"ste": b["z_hat"], "lik": b["z_lik"], "bits": b["bits_slices"][0],
+                                 "workspace": b["workspace"]}, seed=seed, offset=offset)
+        del ez
+        want = ["ste", "lik", "bits"] + (["sym", "idx"] if with_indexes else []) + (["yhat"] if training else [])
+        for k in range(self.num_slices):
+            sl = slice(cs * k, cs * (k + 1))
+            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits": b["bits_slices"][k + 1],
+                   "workspace": b["workspace"]}
+            if with_indexes:
+                out["sym"], out["idx"] = b["symbols"][:, sl], b["indexes"][:, sl]
+            if training:
+                out["yhat"] = b["y_noisy"][:, sl]
+            ops.gc_forward(y[:, sl], sigma[:, sl], mu[:, sl], training=training,
+                           noise=None if noise_y is None else noise_y[:, sl],
+                           scale_table=gc.scale_table if with_indexes else None, scale_bound=gc._scale_bound,
+                           likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
+                           offset=offset + 1 + k)
+        torch.sum(b["bits_slices"], dim=0, out=b["bits"])
+        res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
+               "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
+        if with_indexes:
+            res["symbols"], res["indexes"] = b["symbols"], b["indexes"]
+        if training:
+            res["y_noisy"] = b["y_noisy"]
+        if num_pixels is not None:
+            res["bpp"] = b["bits"] / float(num_pixels)
+        return res
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, **kw):
+        """Capture one pass over the given (static) input tensors into a CUDA graph.
+        Returns (graph, result dict); refill the inputs in place and ``graph.replay()``."""
+        self.buffers(y, z, kw.get("with_indexes", False), kw.get("training", False))
+        side = torch.cuda.Stream(device=y.device)
+        side.wait_stream(torch.cuda.current_stream(y.device))
+        with torch.cuda.stream(side):      # warm-up outside capture (lazy module init, allocator)
+            self.forward(y, mu, sigma, z, **kw)
+        torch.cuda.current_stream(y.device).wait_stream(side)
+        torch.cuda.synchronize(y.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = self.forward(y, mu, sigma, z, **kw)
+        return graph, res

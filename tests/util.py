@@ -7,12 +7,15 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # Likelihood tolerance (north star: 1e-5 relative).  The absolute term covers the
-# cancellation regime of the reference formula itself (upper - lower with both ~O(1) for
-# large sigma): there the reference's OWN fp32 result deviates from fp64 by up to ~1.1e-7
-# absolute (7.2e-5 relative at sigma=256, L~1.5e-3), so two correct fp32
-# implementations can differ by twice that.  SURVEY.md §7.4 H2.
+# cancellation regime of the reference formula itself (L = upper - lower with both terms
+# O(1) for large sigma; erfc values in [1,2) have a 1.2e-7 ulp): there the reference's OWN
+# fp32 result deviates from the exact value by up to ~1.1e-7 absolute (BASELINE.md §4:
+# 7.2e-5 relative at sigma=256, L~1.5e-3), so two correct fp32 implementations can differ
+# by the sum of their errors.  SURVEY.md §7.4 H2 proposes 2e-7; against the exact (fp64)
+# value we hold that (LIK_ATOL_EXACT), against the fp32 oracle we allow 3e-7.
 LIK_RTOL = 1e-5
-LIK_ATOL = 2e-7
+LIK_ATOL = 3e-7
+LIK_ATOL_EXACT = 2e-7
 
 
 def load_golden(name):
