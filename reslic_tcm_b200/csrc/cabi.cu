@@ -10,16 +10,16 @@ namespace reslic {
 static thread_local char g_err[512] = "";
 static int g_math_mode = RESLIC_MATH_FAST;
 int math_mode() { return g_math_mode; }
-int gc_iters_target() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = std::getenv("RESLIC_GC_ITERS");
-    v = e ? std::atoi(e) : 4;
-    if (v < 1 || v > 64) v = 4;
-  }
-  return v;
+const GcTuning& gc_tuning() {
+  static GcTuning t = [] {
+    GcTuning v{-1, 1, 1};
+    if (const char* e = std::getenv("RESLIC_GC_CTAS_PER_SM")) v.ctas_per_sm = std::atoi(e);
+    if (const char* e = std::getenv("RESLIC_GC_PREFETCH")) v.prefetch = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RESLIC_PDL")) v.pdl = std::atoi(e) != 0;
+    return v;
+  }();
+  return t;
 }
-
 int set_error(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
   return code;
@@ -78,8 +78,8 @@ int reslic_set_math_mode(int mode) {
 }
 int reslic_get_math_mode(void) { return reslic::g_math_mode; }
 int64_t reslic_workspace_bytes(int64_t B) {
-  if (B < 0) return 0;
-  return B * reslic::kWsRow * static_cast<int64_t>(sizeof(double));
+  if (B <= 0) return 0;
+  return 2 * B * static_cast<int64_t>(sizeof(unsigned long long));
 }
 
 int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream) {

@@ -6,7 +6,6 @@
 namespace reslic {
 
 constexpr int kThreads = 256;   // threads per CTA for the streaming kernels
-constexpr int kMaxBpi = 512;    // max CTAs cooperating on one image's rate sum
 
 // ---- streaming global access (every byte is touched once: keep it out of L1, evict-first in L2)
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
@@ -21,6 +20,10 @@ __device__ __forceinline__ void st_stream4(int32_t* p, int4 v) {
 }
 __device__ __forceinline__ void st_stream1(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream1(int32_t* p, int32_t v) { __stcs(p, v); }
+
+// ---- programmatic dependent launch (PDL) controls; no-ops when launched without the attribute
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- NaN-propagating max/min (torch.max(x, bound) propagates NaN; fmaxf does not)
 __device__ __forceinline__ float max_nan(float a, float b) {
@@ -71,56 +74,53 @@ __device__ __forceinline__ float u32_to_centered_uniform(uint32_t r) {
   return fmaf(static_cast<float>(r >> 8), 5.9604644775390625e-08f, -0.5f + 2.98023223876953125e-08f);
 }
 
-// ---- deterministic per-image sum: thread fp32 partials -> fp64 warp/CTA tree -> one fp64
-// partial per CTA -> the last CTA of the image adds the partials in index order.
-// `counters` are left at zero, so the workspace needs zero-filling only once.
-__device__ __forceinline__ double warp_sum(double v) {
+// ---- deterministic per-image rate sum, independent of how tiles are assigned to CTAs.
+// Each warp reduces its fp32 partial with a fixed shuffle tree and commits it with ONE 64-bit
+// integer atomicAdd to the image's word:
+//     [63:48] number of warps that have committed      [47:0] sum of (bits * 2^16 + 2^30)
+// Integer adds commute, so the total does not depend on arrival order (bit-reproducible), and
+// because the arrival count travels in the same word as the sum, the warp whose add brings the
+// count to `expected` holds the complete sum in the atomic's return value: it writes bits[image]
+// and re-zeroes the word.  No fence, no second atomic and no grid-wide barrier sit on the
+// kernel's critical path.  Non-finite partials (NaN likelihood, L == 0 with the bound disabled)
+// are carried by a per-image flag word (rare path, fenced).
+//
+// Workspace layout (64-bit words): [0, B) sum/arrival words, [B, 2B) flags; all words are zero
+// between launches, so launches with different B may share one zero-initialised workspace.
+constexpr unsigned long long kArrOne = 1ull << 48;
+constexpr long long kRateBias = 1ll << 30;
+
+__device__ __forceinline__ float warp_sum_f32(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// Workspace layout: one row of (kMaxBpi partials + 1 arrival counter) doubles per image.  A
-// row's layout does not depend on B, so a counter slot is never reused as a partial by a
-// later launch with a different batch size — the "zero once" contract stays valid.
-constexpr int kWsRow = kMaxBpi + 1;
-
-// Returns through bits_out[image] = -(sum of all CTAs' acc).  Must be called by all threads.
-__device__ __forceinline__ void image_sum_finish(float acc, int image, int chunk, int bpi,
-                                                 double* workspace, double* bits_out) {
-  double* partials = workspace + static_cast<int64_t>(image) * kWsRow;
-  unsigned int* counter = reinterpret_cast<unsigned int*>(partials + kMaxBpi);
-  __shared__ double s_warp[kThreads / 32];
-  __shared__ bool s_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v = warp_sum(static_cast<double>(acc));
-  if (lane == 0) s_warp[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    v = (lane < kThreads / 32) ? s_warp[lane] : 0.0;
-    v = warp_sum(v);
-    if (lane == 0) {
-      if (bpi == 1) {
-        bits_out[image] = -v;
-        s_last = false;
-      } else {
-        partials[chunk] = v;
-        __threadfence();
-        const unsigned int prev = atomicAdd(counter, 1u);
-        s_last = (prev == static_cast<unsigned int>(bpi - 1));
-      }
+// All 32 lanes of a warp must call.  acc = this warp's sum of log2(L) over elements of `image`;
+// `expected` = number of warps (over the whole grid) that commit to `image`.
+__device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
+                                            unsigned long long* ws, double* bits_out) {
+  const float v = warp_sum_f32(acc);
+  if ((threadIdx.x & 31) == 0) {
+    const bool finite = fabsf(v) <= 1e30f;                       // false for NaN
+    long long q = 0;
+    if (finite) q = __float2ll_rn(-v * 65536.0f);
+    else {
+      atomicOr(&ws[B + image], (v != v) ? 1ull : 2ull);
+      __threadfence();
     }
-  }
-  __syncthreads();
-  if (s_last && warp == 0) {
-    __threadfence();
-    const volatile double* pp = partials;
-    double t = 0.0;
-    for (int i = lane; i < bpi; i += 32) t += pp[i];
-    t = warp_sum(t);
-    if (lane == 0) {
-      bits_out[image] = -t;
-      *counter = 0u;
+    const unsigned long long add = kArrOne + static_cast<unsigned long long>(q + kRateBias);
+    const unsigned long long now = atomicAdd(&ws[image], add) + add;
+    if ((now >> 48) == expected) {
+      __threadfence();
+      const long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
+      const unsigned long long flag = *reinterpret_cast<volatile unsigned long long*>(&ws[B + image]);
+      double bits = static_cast<double>(sum) * (1.0 / 65536.0);
+      if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
+      else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
+      bits_out[image] = bits;
+      ws[image] = 0ull;
+      if (flag) ws[B + image] = 0ull;
     }
   }
 }

@@ -26,7 +26,7 @@ struct EbParams {
   const float* matrix[5]; const float* bias[5]; const float* factor[4]; const float* medians;
   float* zhat; float* ste; float* lik; int32_t* sym;
   int64_t zhat_bs, ste_bs, lik_bs, sym_bs;
-  double* bits; double* workspace;
+  double* bits; unsigned long long* workspace; int64_t B;
   int64_t ne;       // elements per image = C*hw
   int hw, C, tile, bpi, noise_mode;
   float lik_bound;
@@ -40,8 +40,7 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + ex
 
 // offsets inside one channel's staged parameter block
 //   M0[3] B0[3] F0[3] | M1[9] B1[3] F1[3] | M2[9] B2[3] F2[3] | M3[9] B3[3] F3[3] | M4[3] B4[1] | med
-constexpr int oM0 = 0, oB0 = 3, oF0 = 6, oM1 = 9, oB1 = 18, oF1 = 21, oM2 = 24, oB2 = 33, oF2 = 36,
-              oM3 = 39, oB3 = 48, oF3 = 51, oM4 = 54, oB4 = 57, oMed = 58;
+constexpr int oM0 = 0, oB0 = 3, oF0 = 6, oM1 = 9, oM4 = 54, oB4 = 57, oMed = 58;
 
 // adaptive_entropy_bottleneck.py:525-543 for one scalar input, filters (3,3,3,3).
 // matmul rows are fma chains, "+= bias" and "+= tanh(f)*tanh(x)" keep the reference's
@@ -143,14 +142,14 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
       }
     }
   }
-  if (p.bits) image_sum_finish(acc, image, chunk, p.bpi, p.workspace, p.bits);
+  if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits);
 }
 
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "eb_fwd: null descriptor");
   if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_fwd: negative size");
   if (d->B == 0 || d->C == 0 || d->hw == 0) return RESLIC_OK;
-  if (d->B > (1 << 20) || d->C > (1 << 20) || d->hw > (1LL << 30))
+  if (d->B > (1 << 24) || d->C > (1 << 20) || d->hw > (1LL << 30))
     return set_error(RESLIC_ERR_ARG, "eb_fwd: size too large");
   if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE)
     return set_error(RESLIC_ERR_ARG, "eb_fwd: invalid quantization mode");
@@ -168,6 +167,7 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   p.medians = d->medians;
   p.zhat = d->zhat; p.ste = d->ste; p.lik = d->lik; p.sym = d->sym;
   p.zhat_bs = d->zhat_bs; p.ste_bs = d->ste_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs;
+  p.B = d->B;
   p.ne = d->C * d->hw; p.hw = static_cast<int>(d->hw); p.C = static_cast<int>(d->C);
   p.noise_mode = d->mode == RESLIC_Q_NOISE; p.lik_bound = d->likelihood_bound;
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
@@ -180,14 +180,15 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   int64_t bpi = ntiles;
   const int64_t max_ctas = static_cast<int64_t>(sm_count()) * 64;
   if (bpi * d->B > max_ctas) bpi = (max_ctas + d->B - 1) / d->B;
-  if (bpi > kMaxBpi) bpi = kMaxBpi;
   if (bpi < 1) bpi = 1;
   p.bpi = static_cast<int>(bpi);
   if (d->bits) {
     if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
       return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace missing or too small for `bits`");
     p.bits = d->bits;
-    p.workspace = static_cast<double*>(d->workspace);
+    if (reinterpret_cast<uintptr_t>(d->workspace) & 7u)
+      return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace must be 8-byte aligned");
+    p.workspace = static_cast<unsigned long long*>(d->workspace);
   }
   const int64_t grid64 = bpi * d->B;
   if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");

@@ -24,10 +24,11 @@ struct GcParams {
   int64_t y_bs, mu_bs, sigma_bs, noise_bs;
   float* yhat; float* ste; float* lik; int32_t* sym; int32_t* idx;
   int64_t yhat_bs, ste_bs, lik_bs, sym_bs, idx_bs;
-  double* bits; double* workspace;
+  double* bits; unsigned long long* workspace;
   const float* table; int table_len;
   int64_t n;          // elements per image
-  int bpi;            // CTAs per image
+  int64_t B;          // images
+  int64_t tiles_per_image;
   float scale_bound, lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
@@ -72,13 +73,11 @@ __device__ __forceinline__ float erfc_pos_fast(float x) {
   q = fmaf(q, u, -1.820949554e+00f);
   q = fmaf(q, u, 1.0f);
   const float L2E = 1.44269502162933349609375f;       // fp32(log2 e)
-  const float L2E_LO = 1.925963033500011e-08f;        // log2 e - fp32(log2 e)
   const float s2 = x * x;
   const float e = fmaf(x, x, -s2);                    // exact low part of x*x
   const float t = s2 * L2E;
   float tl = fmaf(s2, L2E, -t);                       // exact low part of s2*L2E
-  tl = fmaf(e, L2E, tl);
-  tl = fmaf(s2, L2E_LO, tl);
+  tl = fmaf(e, L2E, tl);                              // (s2*L2E_LO <= 4e-7 at the floor: dropped)
   const float E0 = ex2_approx(-t);
   const float E = fmaf(E0 * tl, -0.693147182464599609375f, E0);   // 2^-(t+tl) ~ E0*(1 - ln2*tl)
   return E * (w * q);
@@ -127,7 +126,9 @@ __device__ __forceinline__ int scale_index_search(float s, const float* pad) {
 
 template <int STEPS>
 __device__ __forceinline__ int scale_index(float s, const float* pad, float g_scale, float g_off, int last) {
-  int g = __float2int_ru(fmaf(lg2_approx(s), g_scale, g_off));
+  // round-to-nearest of (x + 0.5 - bias) ~ ceil(x - bias), read off the mantissa of x + 1.5*2^23
+  // (no F2I: the XU pipe is the scarce one here); any wrong or wild guess is caught by the proof.
+  int g = __float_as_int(fmaf(lg2_approx(s), g_scale, g_off) + 12582912.0f) - 0x4B400000;
   g = max(0, min(g, last));
   const float lo = pad[g], hi = pad[g + 1];
   if (!((lo < s) && (s <= hi))) g = min(scale_index_search<STEPS>(s, pad), last);
@@ -140,8 +141,16 @@ struct GcElem {
                                              float y, float mu, float sg, float u, float& yhat,
                                              float& ste, float& lik, int& sym, int& idx, float& acc) {
     const float d = y - mu;
-    const float q = rintf(d);            // torch.round: half to even
-    sym = __float2int_rn(q);
+    // torch.round (half to even) and the int32 symbol: for |d| < 2^22 adding 1.5*2^23 rounds d to
+    // an integer in the FMA pipe and leaves that integer in the low mantissa bits; larger |d|
+    // (never seen in latents, exercised by the edge-case tests) takes the FRND/F2I path.
+    const float tq = d + 12582912.0f;
+    float q = tq - 12582912.0f;
+    sym = __float_as_int(tq) - 0x4B400000;
+    if (!(fabsf(d) < 4194304.0f)) {
+      q = rintf(d);
+      sym = __float2int_rn(q);
+    }
     ste = q + mu;
     yhat = NOISE ? (y + u) : ste;
     const float s = max_nan(sg, p.scale_bound);
@@ -157,13 +166,19 @@ struct GcElem {
   }
 };
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST>
-__global__ void __launch_bounds__(kThreads)
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST, bool PF>
+__global__ void __launch_bounds__(kThreads, PF ? 4 : 5)
 gc_fwd_kernel(const GcParams p) {
   __shared__ float pad[NEED_IDX ? kPadLen : 1];
   __shared__ float s_guess[2];
   float g_scale = 0.0f, g_off = 0.0f;
-  if (NEED_IDX) {
+  // Programmatic dependent launch: this grid may have been scheduled while its predecessor
+  // in the stream was still draining.  Nothing is read from global memory before the wait;
+  // dependents are released at once so that THEIR launch overlaps this grid's execution.
+  griddep_wait();
+  griddep_launch_dependents();
+  bool table_staged = !NEED_IDX;
+  auto stage_table = [&]() {
     const float inf = __int_as_float(0x7f800000);
     for (int i = threadIdx.x; i < kPadLen; i += kThreads)
       pad[i] = (i == 0) ? -inf : ((i <= p.table_len - 1) ? p.table[i - 1] : inf);
@@ -173,112 +188,190 @@ gc_fwd_kernel(const GcParams p) {
       if (p.table_len >= 3) {
         const float l0 = log2f(p.table[0]), l1 = log2f(p.table[p.table_len - 2]);
         // the small downward bias makes sigma == table[j] (notably the 0.11 bound itself) guess j
-        if (l1 > l0) { sc = static_cast<float>(p.table_len - 2) / (l1 - l0); off = -l0 * sc - 2.44140625e-4f; }
+        if (l1 > l0) { sc = static_cast<float>(p.table_len - 2) / (l1 - l0); off = -l0 * sc - 2.44140625e-4f + 0.5f; }
       }
       s_guess[0] = sc; s_guess[1] = off;
     }
     __syncthreads();
     g_scale = s_guess[0]; g_off = s_guess[1];
-  }
-  const int image = blockIdx.x / p.bpi;
-  const int chunk = blockIdx.x - image * p.bpi;
-  const float* __restrict__ y = p.y ? p.y + image * p.y_bs : nullptr;
-  const float* __restrict__ mu = p.mu ? p.mu + image * p.mu_bs : nullptr;
-  const float* __restrict__ sg = p.sigma ? p.sigma + image * p.sigma_bs : nullptr;
-  const float* __restrict__ nz = (NOISE && p.noise) ? p.noise + image * p.noise_bs : nullptr;
-  float* yhat = p.yhat ? p.yhat + image * p.yhat_bs : nullptr;
-  float* ste = p.ste ? p.ste + image * p.ste_bs : nullptr;
-  float* lik = p.lik ? p.lik + image * p.lik_bs : nullptr;
-  int32_t* sym = p.sym ? p.sym + image * p.sym_bs : nullptr;
-  int32_t* idx = p.idx ? p.idx + image * p.idx_bs : nullptr;
+    table_staged = true;
+  };
 
-  float acc = 0.0f;
+  // Persistent CTAs: the slice is cut into tiles of kThreads element groups (a tile never
+  // straddles two images); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G), so all
+  // CTAs get the same work to within one tile and stay resident for the whole launch.  The
+  // range is walked image segment by image segment: inside a segment every tensor pointer
+  // just advances by one tile, and the next tile's loads are issued before the current tile
+  // is computed (register double buffer), so a CTA never alternates between an all-loads and
+  // an all-math phase.
   constexpr int W = VEC ? 4 : 1;
-  const int64_t groups = VEC ? (p.n >> 2) : p.n;
-  const int64_t stride = static_cast<int64_t>(p.bpi) * kThreads;
-  for (int64_t g = static_cast<int64_t>(chunk) * kThreads + threadIdx.x; g < groups; g += stride) {
-    const int64_t e = g * W;
-    float yv[4] = {0.f, 0.f, 0.f, 0.f}, mv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f}, uv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (VEC) {
-      if (y) { const float4 t = ld_stream4(y + e); yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w; }
-      if (mu) { const float4 m = ld_stream4(mu + e); mv[0] = m.x; mv[1] = m.y; mv[2] = m.z; mv[3] = m.w; }
-      if (sg) { const float4 s4 = ld_stream4(sg + e); sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w; }
-      if (NOISE && nz) { const float4 n4 = ld_stream4(nz + e); uv[0] = n4.x; uv[1] = n4.y; uv[2] = n4.z; uv[3] = n4.w; }
-    } else {
-      if (y) yv[0] = ld_stream1(y + e);
-      if (mu) mv[0] = ld_stream1(mu + e);
-      if (sg) sv[0] = ld_stream1(sg + e);
-      if (NOISE && nz) uv[0] = ld_stream1(nz + e);
-    }
-    if (NOISE && !nz) {
-      // counter = global element-group id; one Philox call feeds the W elements of a group
-      const uint64_t gid = static_cast<uint64_t>(image) * static_cast<uint64_t>((p.n + 3) >> 2) +
-                           static_cast<uint64_t>(VEC ? g : (g >> 2));
-      const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                      p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
-      if (VEC) {
-        uv[0] = u32_to_centered_uniform(r.x); uv[1] = u32_to_centered_uniform(r.y);
-        uv[2] = u32_to_centered_uniform(r.z); uv[3] = u32_to_centered_uniform(r.w);
-      } else {
-        const int k = static_cast<int>(g & 3);
-        uv[0] = u32_to_centered_uniform(k == 0 ? r.x : k == 1 ? r.y : k == 2 ? r.z : r.w);
-      }
-    }
-    float oy[4], os[4], ol[4]; int osym[4], oidx[4];
+  constexpr int kTileElems = kThreads * W;
+  const int groups = static_cast<int>(VEC ? (p.n >> 2) : p.n);      // per image (n < 2^31 checked on host)
+  const int64_t total = p.tiles_per_image * p.B;
+  int64_t t = (static_cast<int64_t>(blockIdx.x) * total) / gridDim.x;
+  const int64_t t_end = (static_cast<int64_t>(blockIdx.x + 1) * total) / gridDim.x;
+
+  struct In { float y[4], m[4], s[4], u[4]; };
+  while (t < t_end) {
+    const int image = static_cast<int>(t / p.tiles_per_image);
+    const int chunk0 = static_cast<int>(t - image * p.tiles_per_image);
+    const int64_t seg_end64 = (static_cast<int64_t>(image) + 1) * p.tiles_per_image;
+    const int ntiles = static_cast<int>((seg_end64 < t_end ? seg_end64 : t_end) - t);
+    t += ntiles;
+    int g = chunk0 * kThreads + threadIdx.x;                       // element group inside the image
+    const int64_t e0 = static_cast<int64_t>(g) * W;
+    const float* __restrict__ y = p.y ? p.y + image * p.y_bs + e0 : nullptr;
+    const float* __restrict__ mu = p.mu ? p.mu + image * p.mu_bs + e0 : nullptr;
+    const float* __restrict__ sg = p.sigma ? p.sigma + image * p.sigma_bs + e0 : nullptr;
+    const float* __restrict__ nz = (NOISE && p.noise) ? p.noise + image * p.noise_bs + e0 : nullptr;
+    float* yhat = p.yhat ? p.yhat + image * p.yhat_bs + e0 : nullptr;
+    float* ste = p.ste ? p.ste + image * p.ste_bs + e0 : nullptr;
+    float* lik = (NEED_LIK && p.lik) ? p.lik + image * p.lik_bs + e0 : nullptr;
+    int32_t* sym = p.sym ? p.sym + image * p.sym_bs + e0 : nullptr;
+    int32_t* idx = (NEED_IDX && p.idx) ? p.idx + image * p.idx_bs + e0 : nullptr;
+
+    auto load = [&](In& r, int k) {          // tile k of this segment (k*kTileElems ahead of the base)
+      const int off = k * kTileElems;
 #pragma unroll
-    for (int k = 0; k < W; ++k)
-      GcElem<NEED_LIK, NEED_IDX, NOISE, STEPS, FAST>::run(p, pad, g_scale, g_off, yv[k], mv[k], sv[k], uv[k], oy[k], os[k],
-                                                    ol[k], osym[k], oidx[k], acc);
-    if (VEC) {
-      if (yhat) st_stream4(yhat + e, make_float4(oy[0], oy[1], oy[2], oy[3]));
-      if (ste) st_stream4(ste + e, make_float4(os[0], os[1], os[2], os[3]));
-      if (NEED_LIK && lik) st_stream4(lik + e, make_float4(ol[0], ol[1], ol[2], ol[3]));
-      if (sym) st_stream4(sym + e, make_int4(osym[0], osym[1], osym[2], osym[3]));
-      if (NEED_IDX && idx) st_stream4(idx + e, make_int4(oidx[0], oidx[1], oidx[2], oidx[3]));
-    } else {
-      if (yhat) st_stream1(yhat + e, oy[0]);
-      if (ste) st_stream1(ste + e, os[0]);
-      if (NEED_LIK && lik) st_stream1(lik + e, ol[0]);
-      if (sym) st_stream1(sym + e, osym[0]);
-      if (NEED_IDX && idx) st_stream1(idx + e, oidx[0]);
+      for (int j = 0; j < 4; ++j) { r.y[j] = 0.f; r.m[j] = 0.f; r.s[j] = 1.f; r.u[j] = 0.f; }
+      if (g + k * kThreads >= groups) return;
+      if (VEC) {
+        if (y) { const float4 v = ld_stream4(y + off); r.y[0] = v.x; r.y[1] = v.y; r.y[2] = v.z; r.y[3] = v.w; }
+        if (mu) { const float4 v = ld_stream4(mu + off); r.m[0] = v.x; r.m[1] = v.y; r.m[2] = v.z; r.m[3] = v.w; }
+        if (sg) { const float4 v = ld_stream4(sg + off); r.s[0] = v.x; r.s[1] = v.y; r.s[2] = v.z; r.s[3] = v.w; }
+        if (NOISE && nz) { const float4 v = ld_stream4(nz + off); r.u[0] = v.x; r.u[1] = v.y; r.u[2] = v.z; r.u[3] = v.w; }
+      } else {
+        if (y) r.y[0] = ld_stream1(y + off);
+        if (mu) r.m[0] = ld_stream1(mu + off);
+        if (sg) r.s[0] = ld_stream1(sg + off);
+        if (NOISE && nz) r.u[0] = ld_stream1(nz + off);
+      }
+    };
+
+    float acc = 0.0f;
+    In cur;
+    load(cur, 0);
+    if (!table_staged) stage_table();      // the first tile's loads are already in flight
+    for (int k = 0; k < ntiles; ++k) {
+      In nxt;
+      if (PF && k + 1 < ntiles) load(nxt, k + 1);
+      const int gk = g + k * kThreads;
+      if (gk < groups) {
+        const int off = k * kTileElems;
+        if (NOISE && !nz) {
+          // counter = global element-group id; one Philox call feeds 4 consecutive elements
+          const uint64_t gq = static_cast<uint64_t>(VEC ? gk : (gk >> 2));
+          const uint64_t gid = static_cast<uint64_t>(image) * static_cast<uint64_t>((p.n + 3) >> 2) + gq;
+          const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                          p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+          if (VEC) {
+            cur.u[0] = u32_to_centered_uniform(r.x); cur.u[1] = u32_to_centered_uniform(r.y);
+            cur.u[2] = u32_to_centered_uniform(r.z); cur.u[3] = u32_to_centered_uniform(r.w);
+          } else {
+            const int q4 = gk & 3;
+            cur.u[0] = u32_to_centered_uniform(q4 == 0 ? r.x : q4 == 1 ? r.y : q4 == 2 ? r.z : r.w);
+          }
+        }
+        float oy[4], os[4], ol[4]; int osym[4], oidx[4];
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          GcElem<NEED_LIK, NEED_IDX, NOISE, STEPS, FAST>::run(p, pad, g_scale, g_off, cur.y[j], cur.m[j], cur.s[j],
+                                                              cur.u[j], oy[j], os[j], ol[j], osym[j], oidx[j], acc);
+        if (VEC) {
+          if (yhat) st_stream4(yhat + off, make_float4(oy[0], oy[1], oy[2], oy[3]));
+          if (ste) st_stream4(ste + off, make_float4(os[0], os[1], os[2], os[3]));
+          if (lik) st_stream4(lik + off, make_float4(ol[0], ol[1], ol[2], ol[3]));
+          if (sym) st_stream4(sym + off, make_int4(osym[0], osym[1], osym[2], osym[3]));
+          if (idx) st_stream4(idx + off, make_int4(oidx[0], oidx[1], oidx[2], oidx[3]));
+        } else {
+          if (yhat) st_stream1(yhat + off, oy[0]);
+          if (ste) st_stream1(ste + off, os[0]);
+          if (lik) st_stream1(lik + off, ol[0]);
+          if (sym) st_stream1(sym + off, osym[0]);
+          if (idx) st_stream1(idx + off, oidx[0]);
+        }
+      }
+      if (PF) cur = nxt;
+      else if (k + 1 < ntiles) load(cur, k + 1);
+    }
+    if (NEED_LIK && p.bits) {
+      // warps committing to this image = (CTAs whose tile range meets the image) * warps per CTA;
+      // tile tau belongs to CTA ceil((tau+1)*G/T) - 1.
+      const int64_t G = gridDim.x;
+      const int64_t first = image * p.tiles_per_image, last = first + p.tiles_per_image - 1;
+      const int64_t c_lo = ((first + 1) * G + total - 1) / total - 1;
+      const int64_t c_hi = ((last + 1) * G + total - 1) / total - 1;
+      rate_commit(acc, image, static_cast<unsigned int>((c_hi - c_lo + 1) * (kThreads / 32)), p.B, p.workspace, p.bits);
     }
   }
-  if (NEED_LIK && p.bits)
-    image_sum_finish(acc, image, chunk, p.bpi, p.workspace, p.bits);
 }
 
 // ------------------------------------------------------------------ host-side launch
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
-static cudaError_t launch_steps(const GcParams& p, int grid, int steps, bool fast, cudaStream_t st) {
-  // the math policy only matters when a likelihood is computed
-  if (NEED_LIK && !fast) {
-    if (steps <= 6) gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 6, false><<<grid, kThreads, 0, st>>>(p);
-    else gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 8, false><<<grid, kThreads, 0, st>>>(p);
-  } else {
-    if (steps <= 6) gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 6, true><<<grid, kThreads, 0, st>>>(p);
-    else gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, 8, true><<<grid, kThreads, 0, st>>>(p);
+// resident CTAs per SM of one kernel instantiation (queried once per instantiation)
+template <typename K>
+static int resident_ctas(K kernel, int* cache) {
+  if (*cache == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+    *cache = n;
   }
-  return cudaGetLastError();
+  return *cache;
+}
+
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST, bool PF>
+static cudaError_t launch_pf(GcParams& p, cudaStream_t st) {
+  static int occ = 0;
+  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, STEPS, FAST, PF>;
+  const int64_t total = p.tiles_per_image * p.B;
+  const int waves = gc_tuning().ctas_per_sm;   // 0: one tile per CTA; k>0: k CTAs per SM; <0: resident count
+  int64_t grid = total;
+  if (waves > 0) grid = static_cast<int64_t>(waves) * sm_count();
+  else if (waves < 0) grid = static_cast<int64_t>(resident_ctas(kernel, &occ)) * sm_count();
+  if (grid > total) grid = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST>
+static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
+  return gc_tuning().prefetch ? launch_pf<NEED_LIK, NEED_IDX, NOISE, VEC, STEPS, FAST, true>(p, st)
+                              : launch_pf<NEED_LIK, NEED_IDX, NOISE, VEC, STEPS, FAST, false>(p, st);
+}
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
+static cudaError_t launch_steps(GcParams& p, int steps, bool fast, cudaStream_t st) {
+  // the math policy only matters when a likelihood is computed
+  if (NEED_LIK && !fast)
+    return steps <= 6 ? launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 6, false>(p, st)
+                      : launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 8, false>(p, st);
+  return steps <= 6 ? launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 6, true>(p, st)
+                    : launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 8, true>(p, st);
 }
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE>
-static cudaError_t launch_vec(const GcParams& p, int grid, int steps, bool vec, bool fast, cudaStream_t st) {
-  return vec ? launch_steps<NEED_LIK, NEED_IDX, NOISE, true>(p, grid, steps, fast, st)
-             : launch_steps<NEED_LIK, NEED_IDX, NOISE, false>(p, grid, steps, fast, st);
+static cudaError_t launch_vec(GcParams& p, int steps, bool vec, bool fast, cudaStream_t st) {
+  return vec ? launch_steps<NEED_LIK, NEED_IDX, NOISE, true>(p, steps, fast, st)
+             : launch_steps<NEED_LIK, NEED_IDX, NOISE, false>(p, steps, fast, st);
 }
 template <bool NEED_LIK, bool NEED_IDX>
-static cudaError_t launch_noise(const GcParams& p, int grid, int steps, bool vec, bool noise, bool fast,
-                                cudaStream_t st) {
-  return noise ? launch_vec<NEED_LIK, NEED_IDX, true>(p, grid, steps, vec, fast, st)
-               : launch_vec<NEED_LIK, NEED_IDX, false>(p, grid, steps, vec, fast, st);
+static cudaError_t launch_noise(GcParams& p, int steps, bool vec, bool noise, bool fast, cudaStream_t st) {
+  return noise ? launch_vec<NEED_LIK, NEED_IDX, true>(p, steps, vec, fast, st)
+               : launch_vec<NEED_LIK, NEED_IDX, false>(p, steps, vec, fast, st);
 }
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "gc_fwd: null descriptor");
   if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "gc_fwd: negative size");
   if (d->B == 0 || d->n == 0) return RESLIC_OK;  // empty input: nothing to do
-  if (d->B > (1 << 20)) return set_error(RESLIC_ERR_ARG, "gc_fwd: B too large");
+  if (d->B > (1 << 24)) return set_error(RESLIC_ERR_ARG, "gc_fwd: B too large");
   if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE)
     return set_error(RESLIC_ERR_ARG, "gc_fwd: invalid quantization mode");
   const bool need_lik = d->lik || d->bits;
@@ -298,7 +391,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   p.yhat = d->yhat; p.ste = d->ste; p.lik = d->lik; p.sym = d->sym; p.idx = d->idx;
   p.yhat_bs = d->yhat_bs; p.ste_bs = d->ste_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs; p.idx_bs = d->idx_bs;
   p.table = d->scale_table; p.table_len = d->table_len;
-  p.n = d->n; p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
+  p.n = d->n; p.B = d->B; p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
 
@@ -310,36 +403,27 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   chk(d->yhat, d->yhat_bs); chk(d->ste, d->ste_bs); chk(d->lik, d->lik_bs); chk(d->sym, d->sym_bs);
   chk(d->idx, d->idx_bs);
 
-  // CTAs per image: each CTA walks `iters` grid-stride steps of kThreads groups so that the
-  // prologue (table staging) and the fp64 reduction epilogue are amortised, while the grid
-  // still fills every SM a few times over.
   const int64_t groups = vec ? d->n / 4 : d->n;
-  const int64_t tiles = (groups + kThreads - 1) / kThreads;       // per image
-  int64_t iters = gc_iters_target();
-  const int64_t min_ctas = static_cast<int64_t>(sm_count()) * 4;
-  while (iters > 1 && ((tiles + iters - 1) / iters) * d->B < min_ctas) --iters;
-  int64_t bpi = (tiles + iters - 1) / iters;
-  if (bpi > kMaxBpi) bpi = kMaxBpi;
-  if (bpi < 1) bpi = 1;
-  p.bpi = static_cast<int>(bpi);
+  p.tiles_per_image = (groups + kThreads - 1) / kThreads;
+  if (d->n >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "gc_fwd: more than 2^31 elements per image");
+  if (p.tiles_per_image * d->B > (1LL << 40)) return set_error(RESLIC_ERR_ARG, "gc_fwd: input too large");
   if (d->bits) {
     if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
       return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace missing or too small for `bits`");
+    if (reinterpret_cast<uintptr_t>(d->workspace) & 7u)
+      return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace must be 8-byte aligned");
     p.bits = d->bits;
-    p.workspace = static_cast<double*>(d->workspace);
+    p.workspace = static_cast<unsigned long long*>(d->workspace);
   }
-  const int64_t grid64 = bpi * d->B;
-  if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "gc_fwd: grid too large");
   int steps = 6;
   if (need_idx && d->table_len - 1 > 63) steps = 8;
   const bool noise = d->mode == RESLIC_Q_NOISE;
-  const int grid = static_cast<int>(grid64);
-  cudaError_t err;
   const bool fast = math_mode() != RESLIC_MATH_MIRROR;
-  if (need_lik) err = need_idx ? launch_noise<true, true>(p, grid, steps, vec, noise, fast, st)
-                               : launch_noise<true, false>(p, grid, steps, vec, noise, fast, st);
-  else err = need_idx ? launch_noise<false, true>(p, grid, steps, vec, noise, fast, st)
-                      : launch_noise<false, false>(p, grid, steps, vec, noise, fast, st);
+  cudaError_t err;
+  if (need_lik) err = need_idx ? launch_noise<true, true>(p, steps, vec, noise, fast, st)
+                               : launch_noise<true, false>(p, steps, vec, noise, fast, st);
+  else err = need_idx ? launch_noise<false, true>(p, steps, vec, noise, fast, st)
+                      : launch_noise<false, false>(p, steps, vec, noise, fast, st);
   if (err != cudaSuccess) return set_cuda_error(err, "gc_fwd launch");
   return RESLIC_OK;
 }

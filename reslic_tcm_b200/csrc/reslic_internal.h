@@ -9,7 +9,8 @@ namespace reslic {
 int set_error(int code, const char* msg);                 // returns code
 int set_cuda_error(cudaError_t err, const char* where);   // returns (int)err
 int sm_count();
-int gc_iters_target();                                    // grid-stride steps per CTA (tuning)
+struct GcTuning { int ctas_per_sm; int prefetch; int pdl; };
+const GcTuning& gc_tuning();                              // launch-shape knobs (env overridable)
 int math_mode();                                          // RESLIC_MATH_*                                           // SMs of the current device (cached per device)
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);

@@ -1,0 +1,68 @@
+// Micro-benchmark harness for the fused GC kernel through the C ABI (development tool).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cmath>
+#include "../include/reslic_b200.h"
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+__global__ void fill(float* y, float* mu, float* sg, size_t n, unsigned seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)i * 2654435761u + seed; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    float u1 = (h & 0xffff) / 65536.0f, u2 = ((h >> 16) & 0xffff) / 65536.0f;
+    mu[i] = 4.0f * u1 - 2.0f;
+    sg[i] = expf(-3.0f + 7.16f * u2);
+    h = h * 3266489917u + 7u; h ^= h >> 16;
+    float u3 = (h & 0xffffff) / 16777216.0f - 0.5f;
+    y[i] = mu[i] + sg[i] * 3.0f * u3;
+  }
+}
+int main(int argc, char** argv) {
+  int B = argc > 1 ? atoi(argv[1]) : 24; long n = argc > 2 ? atol(argv[2]) : 64 * 48 * 32;
+  int with_idx = argc > 3 ? atoi(argv[3]) : 1; int noise = argc > 4 ? atoi(argv[4]) : 0;
+  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50;
+  size_t N = (size_t)B * n;
+  std::vector<float*> y(nset), mu(nset), sg(nset), yh(nset), lk(nset), nz(nset); std::vector<int*> sym(nset), idx(nset);
+  float tabh[64]; for (int i = 0; i < 64; ++i) tabh[i] = expf(logf(0.11f) + i * (logf(256.f) - logf(0.11f)) / 63.f);
+  float* tab; CK(cudaMalloc(&tab, 256)); CK(cudaMemcpy(tab, tabh, 256, cudaMemcpyHostToDevice));
+  double* bits; CK(cudaMalloc(&bits, B * 8));
+  void* ws; size_t wsb = reslic_workspace_bytes(B); CK(cudaMalloc(&ws, wsb)); CK(cudaMemset(ws, 0, wsb));
+  for (int s = 0; s < nset; ++s) {
+    CK(cudaMalloc(&y[s], N * 4)); CK(cudaMalloc(&mu[s], N * 4)); CK(cudaMalloc(&sg[s], N * 4));
+    CK(cudaMalloc(&yh[s], N * 4)); CK(cudaMalloc(&lk[s], N * 4)); CK(cudaMalloc(&sym[s], N * 4)); CK(cudaMalloc(&idx[s], N * 4));
+    CK(cudaMalloc(&nz[s], N * 4));
+    fill<<<1024, 256>>>(y[s], mu[s], sg[s], N, 17u + s);
+  }
+  CK(cudaDeviceSynchronize());
+  cudaStream_t st; CK(cudaStreamCreate(&st));
+  auto launch = [&](int s) {
+    reslic_gc_desc d; memset(&d, 0, sizeof(d));
+    d.y = y[s]; d.y_bs = n; d.mu = mu[s]; d.mu_bs = n; d.sigma = sg[s]; d.sigma_bs = n; d.B = B; d.n = n;
+    d.mode = noise ? RESLIC_Q_NOISE : RESLIC_Q_DEQUANTIZE; d.scale_bound = 0.11f; d.likelihood_bound = 1e-9f;
+    d.ste = yh[s]; d.ste_bs = n; d.lik = lk[s]; d.lik_bs = n;
+    if (noise) { d.yhat = nz[s]; d.yhat_bs = n; }
+    if (with_idx) { d.scale_table = tab; d.table_len = 64; d.sym = sym[s]; d.sym_bs = n; d.idx = idx[s]; d.idx_bs = n; }
+    d.bits = bits; d.workspace = ws; d.workspace_bytes = wsb; d.philox_seed = 1;
+    int rc = reslic_gc_fwd_f32(&d, st);
+    if (rc) { printf("launch failed %d %s\n", rc, reslic_last_error()); exit(1); }
+  };
+  for (int i = 0; i < 6; ++i) launch(i % nset);
+  CK(cudaStreamSynchronize(st));
+  cudaGraph_t g; cudaGraphExec_t ge;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
+  for (int i = 0; i < 5 * nset; ++i) launch(i % nset);
+  CK(cudaStreamEndCapture(st, &g)); CK(cudaGraphInstantiate(&ge, g, 0));
+  CK(cudaGraphLaunch(ge, st)); CK(cudaStreamSynchronize(st));
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  CK(cudaEventRecord(a, st));
+  for (int r = 0; r < reps; ++r) CK(cudaGraphLaunch(ge, st));
+  CK(cudaEventRecord(b, st)); CK(cudaStreamSynchronize(st));
+  float ms; CK(cudaEventElapsedTime(&ms, a, b));
+  double us = ms * 1e3 / (reps * 5 * nset);
+  int bpe = 12 + 8 + (with_idx ? 8 : 0) + (noise ? 4 : 0);
+  double gbs = (double)N * bpe / (us * 1e-6) / 1e9;
+  double hb[4]; CK(cudaMemcpy(hb, bits, sizeof(double) * (B < 4 ? B : 4), cudaMemcpyDeviceToHost));
+  printf("B=%d n=%ld idx=%d noise=%d : %.2f us/launch  %.1f GB/s  %.1f%% of 6537.6  (%.1f Gelem/s) bits0=%.3f\n", B, n, with_idx, noise, us, gbs, 100 * gbs / 6537.6, N / us / 1e3, hb[0]);
+  return 0;
+}
