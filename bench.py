@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-whole-y", action="store_true")
     return ap.parse_args()
 
 
@@ -222,7 +223,7 @@ class ClockSampler(threading.Thread):
 def run_ours(args):
     import torch.distributed as dist
 
-    from reslic_tcm_b200 import _cabi, dist as rdist, ops
+    from reslic_tcm_b200 import _cabi, dist as rdist
     from reslic_tcm_b200.pipeline import TcmEntropyPath
 
     _cabi.load()  # no extension -> loud failure, never a fallback
@@ -301,45 +302,7 @@ def run_ours(args):
     value = elems_rank * world / (ms_per_step * 1e-3) / 1e6
 
     # ---- roofline leg: the GC kernel alone, 5 slice launches per graph, replayed back to back
-    roof = None
     bpe = bytes_per_y_elem(c)
-    gsets = []
-    cs = synthetic.M_LATENT // synthetic.NUM_SLICES
-    for s in sets:
-        path, inp, b = s["path"], s["inp"], s["path"]._bufs
-        gc = path.gaussian_conditional
-        want = ["ste", "lik", "bits"] + (["sym", "idx"] if c.with_indexes else []) + (["yhat"] if c.training else [])
-
-        def gc_only(inp=inp, b=b, gc=gc, want=want):
-            for k in range(synthetic.NUM_SLICES):
-                sl = slice(cs * k, cs * (k + 1))
-                out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits": b["bits_slices"][k + 1],
-                       "workspace": b["workspace"]}
-                if c.with_indexes:
-                    out["sym"], out["idx"] = b["symbols"][:, sl], b["indexes"][:, sl]
-                if c.training:
-                    out["yhat"] = b["y_noisy"][:, sl]
-                ops.gc_forward(inp["y"][:, sl], inp["sigma"][:, sl], inp["mu"][:, sl], training=c.training,
-                               scale_table=gc.scale_table if c.with_indexes else None, want=want, out=out,
-                               seed=1234, offset=1 + k)
-
-        gc_only()
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            gc_only()
-        gsets.append(g)
-    reps = max(args.steps, 50)
-    for i in range(5):
-        gsets[i % len(gsets)].replay()
-    torch.cuda.synchronize()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    for i in range(reps):
-        gsets[i % len(gsets)].replay()
-    r1.record()
-    torch.cuda.synchronize()
-    gc_ms = r0.elapsed_time(r1) / (reps * synthetic.NUM_SLICES)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -347,13 +310,73 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    launch_bytes = bpe * (y_elems // synthetic.NUM_SLICES)
-    achieved = launch_bytes / (gc_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "gc_fwd_kernel", "bytes_per_elem": bpe,
-            "elems_per_launch": y_elems // synthetic.NUM_SLICES, "us_per_launch": gc_ms * 1e3,
-            "peak_source": peak_src,
-            "gc_melem_per_s": (y_elems // synthetic.NUM_SLICES) / (gc_ms * 1e-3) / 1e6}
+
+    def gc_only_leg(fuse):
+        """Graph of only the GC launches of a step (5 per-slice, or 1 over the whole y),
+        replayed back to back over the rotating buffer sets; returns us per launch."""
+        graphs = []
+        for s in sets:
+            kk = dict(kw, skip_z=True, fuse_slices=fuse)
+            s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
+            graphs.append(g)
+        n_launch = 1 if fuse else synthetic.NUM_SLICES
+        reps = max(args.steps, 50)
+        for i in range(5):
+            graphs[i % len(graphs)].replay()
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for i in range(reps):
+            graphs[i % len(graphs)].replay()
+        r1.record()
+        torch.cuda.synchronize()
+        return r0.elapsed_time(r1) * 1e3 / (reps * n_launch), n_launch
+
+    def roof_obj(us, n_launch):
+        elems = y_elems // n_launch
+        achieved = bpe * elems / (us * 1e-6) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "gc_fwd_kernel", "bytes_per_elem": bpe, "elems_per_launch": elems,
+                "us_per_launch": us, "peak_source": peak_src, "gc_melem_per_s": elems / us}
+
+    us_slice, n5 = gc_only_leg(False)
+    roof = roof_obj(us_slice, n5)
+    roof["launch"] = "one 64-channel slice of y per launch (TCM's call pattern, tcm.py:443-457)"
+
+    # ---- whole-y mode: all 320 channels in ONE GC launch (models whose mu/sigma exist for all
+    # channels at once, e.g. the reference's ScaleHyperprior); reported beside the per-slice mode
+    whole = None
+    if not args.no_whole_y:
+        wgraphs = []
+        for s in sets:
+            kk = dict(kw, fuse_slices=True)
+            s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
+            wgraphs.append(g)
+        for i in range(5):
+            wgraphs[i % len(wgraphs)].replay()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for i in range(args.steps):
+            wgraphs[i % len(wgraphs)].replay()
+        w1.record()
+        barrier()
+        wms = w0.elapsed_time(w1)
+        if world > 1:
+            tt = torch.tensor([wms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            wms = float(tt.item())
+        us_whole, n1 = gc_only_leg(True)
+        whole = {"value": elems_rank * world / (wms / args.steps * 1e-3) / 1e6, "unit": UNIT,
+                 "ms_per_step": wms / args.steps, "launches_per_step": 2, "roofline": roof_obj(us_whole, n1)}
 
     # ---- e2e leg: public API with host buffers (H2D inputs, D2H symbols/indexes/bits)
     e2e = None
@@ -384,7 +407,7 @@ def run_ours(args):
                        "mode": "per-slice launches (5 GC + 1 EB) replayed as a CUDA graph",
                        "l2": f"{len(sets)} rotating buffer sets of {(bpe * y_elems + 12 * z_elems) / 1e6:.0f} MB each (> 126 MB L2)",
                        "bpp_mean_image0_set": float(bits.mean()) / c.num_pixels_per_image},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "whole_y": whole, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 1
+#define RESLIC_ABI_VERSION 2
 
 enum {
   RESLIC_OK = 0,
@@ -96,7 +96,10 @@ typedef struct reslic_gc_desc {
   float* lik;    int64_t lik_bs;           /* bounded likelihood                          */
   int32_t* sym;  int64_t sym_bs;           /* int32(round(y-mu))                          */
   int32_t* idx;  int64_t idx_bs;           /* scale-table / CDF index, 0..table_len-1     */
-  double* bits;                            /* [B] -sum_i log2 L  (OVERWRITTEN, not +=)    */
+  double* bits;                            /* [B] -sum_i log2 L per image                 */
+  int32_t bits_accumulate;                 /* 0: bits[b] = sum;  1: bits[b] += sum (lets  */
+                                           /* the z and the 5 slice launches of one batch */
+                                           /* share one rate vector, loss.py:24-27)       */
   void* workspace; int64_t workspace_bytes;/* required iff bits != NULL                   */
   uint64_t philox_seed, philox_offset;
 } reslic_gc_desc;
@@ -136,6 +139,7 @@ typedef struct reslic_eb_desc {
   float* lik;   int64_t lik_bs;
   int32_t* sym; int64_t sym_bs;            /* int32(round(z-med))                         */
   double* bits;                            /* [B]                                         */
+  int32_t bits_accumulate;                 /* as in reslic_gc_desc                        */
   void* workspace; int64_t workspace_bytes;
   uint64_t philox_seed, philox_offset;
 } reslic_eb_desc;

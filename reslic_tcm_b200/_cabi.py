@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -40,7 +40,7 @@ class GcDesc(C.Structure):
         ("lik", C.c_void_p), ("lik_bs", C.c_int64),
         ("sym", C.c_void_p), ("sym_bs", C.c_int64),
         ("idx", C.c_void_p), ("idx_bs", C.c_int64),
-        ("bits", C.c_void_p),
+        ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
     ]
@@ -60,7 +60,7 @@ class EbDesc(C.Structure):
         ("ste", C.c_void_p), ("ste_bs", C.c_int64),
         ("lik", C.c_void_p), ("lik_bs", C.c_int64),
         ("sym", C.c_void_p), ("sym_bs", C.c_int64),
-        ("bits", C.c_void_p),
+        ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
     ]

@@ -99,7 +99,7 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
 // All 32 lanes of a warp must call.  acc = this warp's sum of log2(L) over elements of `image`;
 // `expected` = number of warps (over the whole grid) that commit to `image`.
 __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
-                                            unsigned long long* ws, double* bits_out) {
+                                            unsigned long long* ws, double* bits_out, bool accumulate) {
   const float v = warp_sum_f32(acc);
   if ((threadIdx.x & 31) == 0) {
     const bool finite = fabsf(v) <= 1e30f;                       // false for NaN
@@ -118,7 +118,7 @@ __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int e
       double bits = static_cast<double>(sum) * (1.0 / 65536.0);
       if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
       else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
-      bits_out[image] = bits;
+      bits_out[image] = accumulate ? bits_out[image] + bits : bits;   // single writer per image
       ws[image] = 0ull;
       if (flag) ws[B + image] = 0ull;
     }

@@ -26,9 +26,9 @@ struct EbParams {
   const float* matrix[5]; const float* bias[5]; const float* factor[4]; const float* medians;
   float* zhat; float* ste; float* lik; int32_t* sym;
   int64_t zhat_bs, ste_bs, lik_bs, sym_bs;
-  double* bits; unsigned long long* workspace; int64_t B;
+  double* bits; unsigned long long* workspace; int bits_accumulate; int64_t B;
   int64_t ne;       // elements per image = C*hw
-  int hw, C, tile, bpi, noise_mode;
+  int hw, C, tile, bpi, noise_mode, splits;
   float lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
@@ -67,6 +67,138 @@ __device__ __forceinline__ float logits_cumulative(const float* __restrict__ P, 
   return __fadd_rn(t, P[oB4]);
 }
 
+// transformed parameter j of channel c (softplus on matrices, tanh on factors, median last)
+__device__ __forceinline__ float eb_staged_param(const EbParams& p, int c, int j) {
+  if (j < oB0) return softplus_ref(p.matrix[0][c * 3 + j]);
+  if (j < oF0) return p.bias[0][c * 3 + (j - oB0)];
+  if (j < oM1) return tanhf(p.factor[0][c * 3 + (j - oF0)]);
+  if (j < oM4) {
+    const int l = (j - oM1) / 15, r = (j - oM1) - l * 15;
+    if (r < 9) return softplus_ref(p.matrix[1 + l][c * 9 + r]);
+    if (r < 12) return p.bias[1 + l][c * 3 + (r - 9)];
+    return tanhf(p.factor[1 + l][c * 3 + (r - 12)]);
+  }
+  if (j < oB4) return softplus_ref(p.matrix[4][c * 3 + (j - oM4)]);
+  if (j == oB4) return p.bias[4][c];
+  return p.medians[c];
+}
+
+// sign-trick likelihood from the two cumulative logits, adaptive_entropy_bottleneck.py:658-666
+__device__ __forceinline__ float eb_combine(float lower, float upper, float lik_bound) {
+  const float sum = lower + upper;
+  const float sg = (sum < 0.0f) ? 1.0f : ((sum > 0.0f) ? -1.0f : 0.0f);  // -torch.sign(sum); NaN -> 0
+  float L = fabsf(sigmoid_ref(sg * upper) - sigmoid_ref(sg * lower));
+  if (lik_bound > 0.0f) L = max_nan(L, lik_bound);
+  return L;
+}
+__device__ __forceinline__ float eb_likelihood(const float* __restrict__ P, float x, float lik_bound) {
+  return eb_combine(logits_cumulative(P, x - 0.5f), logits_cumulative(P, x + 0.5f), lik_bound);
+}
+
+// ------------------------------------------------------------------ eval mode: per-channel LUT
+// In "dequantize" mode z_hat = k + median with k = round(z - median) an integer, so the
+// likelihood is a function of (channel, k) only.  One CTA serves one channel (x a split of the
+// batch): it stages the channel's parameters, evaluates the 2*kLutK+1 likelihoods of
+// k = -kLutK..kLutK ONCE with exactly the per-element code path (bit-identical results), then
+// every element is a rounding, a table lookup and a log2 — ~15 instructions instead of ~800.
+// |k| > kLutK (and NaN) fall back to the direct evaluation.  Each (image, channel) run of hw
+// contiguous floats is walked by one warp, so the rate commit stays per (warp, image).
+constexpr int kLutK = 32;
+
+constexpr int kLutN = 2 * kLutK + 1;
+constexpr int kEbChunk = 4;      // values per lane held in registers: one chunk = 128 contiguous floats
+
+__global__ void __launch_bounds__(kThreads) eb_lut_kernel(const EbParams p) {
+  __shared__ float s_par[kEbStride + 1];
+  __shared__ float s_half[2 * kLutN];     // lower / upper cumulative logits of the table symbols
+  __shared__ float s_lut[kLutN];
+  __shared__ float s_lg[kLutN];           // log2 of the table likelihoods
+  griddep_wait();
+  griddep_launch_dependents();
+  const int c = blockIdx.x / p.splits;
+  const int split = blockIdx.x - c * p.splits;
+  const bool need_lik = p.lik || p.bits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wstride = p.splits * (kThreads / 32);
+  const int64_t base_c = static_cast<int64_t>(c) * p.hw;
+  // work items of a warp: (image b, chunk of 128 floats of the (b, c) run), b strided over warps
+  const int chunks = (p.hw + 32 * kEbChunk - 1) / (32 * kEbChunk);
+  int64_t b = split * (kThreads / 32) + warp;
+  int ch = 0;
+  float zv[kEbChunk];
+  auto load_chunk = [&](int64_t bb, int cc) {
+    const float* __restrict__ z = p.z + bb * p.z_bs + base_c + cc * (32 * kEbChunk);
+    const int rem = p.hw - cc * (32 * kEbChunk);
+#pragma unroll
+    for (int j = 0; j < kEbChunk; ++j) zv[j] = (lane + 32 * j < rem) ? ld_stream1(z + lane + 32 * j) : 0.0f;
+  };
+  if (b < p.B) load_chunk(b, 0);                 // in flight while the table is built
+
+  if (threadIdx.x < kEbStride) s_par[threadIdx.x] = eb_staged_param(p, c, threadIdx.x);
+  __syncthreads();
+  const float med = s_par[oMed];
+  if (need_lik) {
+    // 2*kLutN independent cumulative-logit evaluations, one per thread
+    if (threadIdx.x < 2 * kLutN) {
+      const int k = static_cast<int>(threadIdx.x % kLutN) - kLutK;
+      const float x = static_cast<float>(k) + med;             // == round(z - med) + med for that symbol
+      s_half[threadIdx.x] = logits_cumulative(s_par, threadIdx.x < kLutN ? x - 0.5f : x + 0.5f);
+    }
+    __syncthreads();
+    if (threadIdx.x < kLutN) {
+      const float lower = s_half[threadIdx.x], upper = s_half[kLutN + threadIdx.x];
+      const float L = eb_combine(lower, upper, p.lik_bound);
+      s_lut[threadIdx.x] = L;
+      s_lg[threadIdx.x] = log2f(L);
+    }
+    __syncthreads();
+  }
+  while (b < p.B) {
+    float acc = 0.0f;
+    for (;;) {
+      const int64_t off = base_c + ch * (32 * kEbChunk);
+      const int rem = p.hw - ch * (32 * kEbChunk);
+      float cur[kEbChunk];
+#pragma unroll
+      for (int j = 0; j < kEbChunk; ++j) cur[j] = zv[j];
+      // next work item's loads before this one's math
+      const bool last_chunk = (ch + 1 >= chunks);
+      const int64_t nb = last_chunk ? b + wstride : b;
+      const int nch = last_chunk ? 0 : ch + 1;
+      if (nb < p.B) load_chunk(nb, nch);
+#pragma unroll
+      for (int j = 0; j < kEbChunk; ++j) {
+        const int i = lane + 32 * j;
+        if (i < rem) {
+          const float q = rintf(cur[j] - med);
+          const float st = q + med;                   // "dequantize" == ste_round(z - med) + med
+          if (p.zhat) st_stream1(p.zhat + b * p.zhat_bs + off + i, st);
+          if (p.ste) st_stream1(p.ste + b * p.ste_bs + off + i, st);
+          if (p.sym) st_stream1(p.sym + b * p.sym_bs + off + i, __float2int_rn(q));
+          if (need_lik) {
+            float L, lg;
+            if (fabsf(q) <= static_cast<float>(kLutK)) {
+              const int k = __float2int_rn(q) + kLutK;
+              L = s_lut[k]; lg = s_lg[k];
+            } else {
+              L = eb_likelihood(s_par, st, p.lik_bound);
+              lg = log2f(L);
+            }
+            if (p.lik) st_stream1(p.lik + b * p.lik_bs + off + i, L);
+            acc += lg;
+          }
+        }
+      }
+      ch = nch;
+      if (last_chunk) break;
+    }
+    if (p.bits) rate_commit(acc, static_cast<int>(b), static_cast<unsigned int>(p.C), p.B, p.workspace, p.bits,
+                            p.bits_accumulate != 0);
+    b += wstride;
+  }
+}
+
+// ------------------------------------------------------------------ noise mode: direct evaluation
 __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
   __shared__ float s_par[kEbMaxCh * kEbStride];
   const int image = blockIdx.x / p.bpi;
@@ -89,19 +221,8 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
     const int nch = c_hi - c_lo + 1;
     __syncthreads();  // previous tile's readers are done with s_par
     for (int i = threadIdx.x; i < nch * kEbStride; i += kThreads) {
-      const int cl = i / kEbStride, j = i - cl * kEbStride, c = c_lo + cl;
-      float v;
-      if (j < oB0) v = softplus_ref(p.matrix[0][c * 3 + j]);
-      else if (j < oF0) v = p.bias[0][c * 3 + (j - oB0)];
-      else if (j < oM1) v = tanhf(p.factor[0][c * 3 + (j - oF0)]);
-      else if (j < oM4) {
-        const int l = (j - oM1) / 15, r = (j - oM1) - l * 15;
-        if (r < 9) v = softplus_ref(p.matrix[1 + l][c * 9 + r]);
-        else if (r < 12) v = p.bias[1 + l][c * 3 + (r - 9)];
-        else v = tanhf(p.factor[1 + l][c * 3 + (r - 12)]);
-      } else if (j < oB4) v = softplus_ref(p.matrix[4][c * 3 + (j - oM4)]);
-      else if (j == oB4) v = p.bias[4][c];
-      else v = p.medians[c];
+      const int cl = i / kEbStride, j = i - cl * kEbStride;
+      const float v = eb_staged_param(p, c_lo + cl, j);
       s_par[i] = v;
     }
     __syncthreads();
@@ -131,18 +252,13 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
       if (ste) st_stream1(ste + e, s);
       if (sym) st_stream1(sym + e, __float2int_rn(q));
       if (need_lik) {
-        const float lower = logits_cumulative(P, out - 0.5f);
-        const float upper = logits_cumulative(P, out + 0.5f);
-        const float sum = lower + upper;
-        const float sg = (sum < 0.0f) ? 1.0f : ((sum > 0.0f) ? -1.0f : 0.0f);  // -torch.sign(sum); NaN -> 0
-        float L = fabsf(sigmoid_ref(sg * upper) - sigmoid_ref(sg * lower));
-        if (p.lik_bound > 0.0f) L = max_nan(L, p.lik_bound);
+        const float L = eb_likelihood(P, out, p.lik_bound);
         if (lik) st_stream1(lik + e, L);
         acc += log2f(L);
       }
     }
   }
-  if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits);
+  if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits, p.bits_accumulate != 0);
 }
 
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
@@ -186,14 +302,37 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
       return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace missing or too small for `bits`");
     p.bits = d->bits;
+    p.bits_accumulate = d->bits_accumulate;
     if (reinterpret_cast<uintptr_t>(d->workspace) & 7u)
       return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace must be 8-byte aligned");
     p.workspace = static_cast<unsigned long long*>(d->workspace);
   }
-  const int64_t grid64 = bpi * d->B;
-  if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
-  eb_fwd_kernel<<<static_cast<int>(grid64), kThreads, 0, st>>>(p);
-  cudaError_t err = cudaGetLastError();
+  cudaError_t err;
+  if (!p.noise_mode) {
+    // eval: per-channel LUT kernel, one CTA per (channel, batch split)
+    // one (image, channel) run per warp where the machine has room for it (<= 8 CTAs per SM)
+    int64_t splits = (d->B + (kThreads / 32) - 1) / (kThreads / 32);
+    const int64_t cap = (8 * static_cast<int64_t>(sm_count()) + d->C - 1) / d->C;
+    if (splits > cap) splits = cap;
+    if (splits < 1) splits = 1;
+    p.splits = static_cast<int>(splits);
+    if (d->C * splits > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(d->C * splits));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
+    err = cudaLaunchKernelEx(&cfg, eb_lut_kernel, p);
+  } else {
+    const int64_t grid64 = bpi * d->B;
+    if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
+    eb_fwd_kernel<<<static_cast<int>(grid64), kThreads, 0, st>>>(p);
+    err = cudaGetLastError();
+  }
   if (err != cudaSuccess) return set_cuda_error(err, "eb_fwd launch");
   return RESLIC_OK;
 }

@@ -24,7 +24,7 @@ struct GcParams {
   int64_t y_bs, mu_bs, sigma_bs, noise_bs;
   float* yhat; float* ste; float* lik; int32_t* sym; int32_t* idx;
   int64_t yhat_bs, ste_bs, lik_bs, sym_bs, idx_bs;
-  double* bits; unsigned long long* workspace;
+  double* bits; unsigned long long* workspace; int bits_accumulate;
   const float* table; int table_len;
   int64_t n;          // elements per image
   int64_t B;          // images
@@ -37,71 +37,89 @@ struct GcParams {
 // Mirrors the reference op order: every line is one IEEE fp32 op there.
 //   a = (0.5 - v)/s, b = (-0.5 - v)/s   (true divides)
 //   L = 0.5*erfc(-2^-0.5 * a) - 0.5*erfc(-2^-0.5 * b)
-// The two divides share one reciprocal and use the Markstein residual correction, which
-// returns the correctly rounded quotient for the operand range left after the clamps
-// (checked against __fdiv_rn in tests/test_gc_parity.py).
-__device__ __forceinline__ void div2_rn(float n1, float n2, float s, float& q1, float& q2) {
-  float r = rcp_approx(s);
-  const float e = fmaf(-s, r, 1.0f);
-  r = fmaf(r, e, r);
-  float q = n1 * r;
-  float rem = fmaf(-s, q, n1);
-  q1 = fmaf(rem, r, q);
-  q = n2 * r;
-  rem = fmaf(-s, q, n2);
-  q2 = fmaf(rem, r, q);
+//
+// All FP32 add/mul/fma work is issued as Blackwell packed f32x2 instructions (FFMA2 / FMUL2 /
+// FADD2: two IEEE-rounded fp32 lanes per issue slot, sm_100+), two elements per lane pair.
+// Results are bit-identical to the scalar ops; what halves is the number of issue slots, which
+// is what bounds this kernel next to HBM.
+typedef float2 F2;
+__device__ __forceinline__ F2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ F2 neg2(F2 a) { return make_float2(-a.x, -a.y); }   // folds into an operand modifier
+__device__ __forceinline__ F2 abs2(F2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ F2 rcp2(F2 a) { return make_float2(rcp_approx(a.x), rcp_approx(a.y)); }
+__device__ __forceinline__ F2 min_nan2(F2 a, float b) { return make_float2(min_nan(a.x, b), min_nan(a.y, b)); }
+__device__ __forceinline__ F2 max_nan2(F2 a, float b) { return make_float2(max_nan(a.x, b), max_nan(a.y, b)); }
+
+// The two divides of an element share one reciprocal and use the Markstein residual
+// correction, which returns the correctly rounded quotient for the operand range left after
+// the clamps (cross-checked against the MIRROR build and the oracle in tests/test_gc_parity.py).
+__device__ __forceinline__ void div2_rn(F2 n1, F2 n2, F2 s, F2& q1, F2& q2) {
+  F2 r = rcp2(s);
+  const F2 ns = neg2(s);
+  const F2 e = fma2(ns, r, f2(1.0f));
+  r = fma2(r, e, r);
+  F2 q = mul2(n1, r);
+  F2 rem = fma2(ns, q, n1);
+  q1 = fma2(rem, r, q);
+  q = mul2(n2, r);
+  rem = fma2(ns, q, n2);
+  q2 = fma2(rem, r, q);
 }
 
-// erfc(x) for 0 <= x <= 12 as exp(-x^2) * (1-u) * Q(u), u = x/(x+2.5): one MUFU.RCP, one
-// MUFU.EX2, 21 FP32 ops (CUDA's erfcf: 3 MUFU + FRND + ~44).  Q is a degree-9 near-minimax
-// fit (|rel err| < 1.4e-8 in exact arithmetic); u = x*r keeps small x free of cancellation
-// and (1-u) carries the 1/x decay so Horner stays well conditioned.  exp(-x^2) gets the
-// rounding errors of x*x and of the log2(e) product back as a first-order correction, so
-// the relative error stays ~3e-7 out to the likelihood floor (x^2 ~ 20).
-__device__ __forceinline__ float erfc_pos_fast(float x) {
-  const float r = rcp_approx(x + 2.5f);
-  const float u = x * r;
-  const float w = fmaf(-x, r, 1.0f);
-  float q = 2.651532926e-02f;
-  q = fmaf(q, u, -5.741734803e-02f);
-  q = fmaf(q, u, -3.597635776e-02f);
-  q = fmaf(q, u, 1.268966794e-01f);
-  q = fmaf(q, u, 1.091585010e-01f);
-  q = fmaf(q, u, -2.630832791e-01f);
-  q = fmaf(q, u, -4.676126838e-01f);
-  q = fmaf(q, u, 1.608165503e+00f);
-  q = fmaf(q, u, -1.820949554e+00f);
-  q = fmaf(q, u, 1.0f);
-  const float L2E = 1.44269502162933349609375f;       // fp32(log2 e)
-  const float s2 = x * x;
-  const float e = fmaf(x, x, -s2);                    // exact low part of x*x
-  const float t = s2 * L2E;
-  float tl = fmaf(s2, L2E, -t);                       // exact low part of s2*L2E
-  tl = fmaf(e, L2E, tl);                              // (s2*L2E_LO <= 4e-7 at the floor: dropped)
-  const float E0 = ex2_approx(-t);
-  const float E = fmaf(E0 * tl, -0.693147182464599609375f, E0);   // 2^-(t+tl) ~ E0*(1 - ln2*tl)
-  return E * (w * q);
+// erfc(x) for 0 <= x <= 12 as exp(-x^2) * (1-u) * Q(u), u = x/(x+2.5): per element one
+// MUFU.RCP, one MUFU.EX2 and 19 FP32 ops (CUDA's erfcf: 3 MUFU + FRND + ~44).  Q is a
+// degree-9 near-minimax fit (|rel err| < 1.4e-8 in exact arithmetic); u = x*r keeps small x
+// free of cancellation and (1-u) carries the 1/x decay so Horner stays well conditioned.
+// exp(-x^2) gets the rounding errors of x*x and of the log2(e) product back as a first-order
+// correction, so the relative error stays ~3e-7 out to the likelihood floor (x^2 ~ 20).
+__device__ __forceinline__ F2 erfc_pos_fast(F2 x) {
+  const F2 r = rcp2(add2(x, f2(2.5f)));
+  const F2 u = mul2(x, r);
+  const F2 w = fma2(neg2(x), r, f2(1.0f));
+  F2 q = f2(2.651532926e-02f);
+  q = fma2(q, u, f2(-5.741734803e-02f));
+  q = fma2(q, u, f2(-3.597635776e-02f));
+  q = fma2(q, u, f2(1.268966794e-01f));
+  q = fma2(q, u, f2(1.091585010e-01f));
+  q = fma2(q, u, f2(-2.630832791e-01f));
+  q = fma2(q, u, f2(-4.676126838e-01f));
+  q = fma2(q, u, f2(1.608165503e+00f));
+  q = fma2(q, u, f2(-1.820949554e+00f));
+  q = fma2(q, u, f2(1.0f));
+  const F2 L2E = f2(1.44269502162933349609375f);      // fp32(log2 e)
+  const F2 s2 = mul2(x, x);
+  const F2 e = fma2(x, x, neg2(s2));                  // exact low part of x*x
+  const F2 t = mul2(s2, L2E);
+  F2 tl = fma2(s2, L2E, neg2(t));                     // exact low part of s2*L2E
+  tl = fma2(e, L2E, tl);                              // (s2*L2E_LO <= 4e-7 at the floor: dropped)
+  const F2 E0 = make_float2(ex2_approx(-t.x), ex2_approx(-t.y));
+  const F2 E = fma2(mul2(E0, tl), f2(-0.693147182464599609375f), E0);   // 2^-(t+tl) ~ E0*(1 - ln2*tl)
+  return mul2(E, mul2(w, q));
 }
 
 template <bool FAST>
-__device__ __forceinline__ float gc_likelihood(float v, float s) {
+__device__ __forceinline__ F2 gc_likelihood(F2 v, F2 s) {
   // clamps keep every intermediate finite (inf/inf, 0*inf); they change no result for
   // |y-mu|, sigma <= 1e30 and give the reference's limit values (L -> 0 -> bound) beyond.
-  const float vc = min_nan(v, 1e30f);
-  const float sc = min_nan(s, 1e30f);
-  float a, b;
-  div2_rn(0.5f - vc, -0.5f - vc, sc, a, b);
-  const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5)) cast to fp32
-  const float xa = c * a, xb = c * b;        // xb > 0 always; xa < 0 iff v < 0.5
+  const F2 vc = min_nan2(v, 1e30f);
+  const F2 sc = min_nan2(s, 1e30f);
+  F2 a, b;
+  div2_rn(add2(f2(0.5f), neg2(vc)), add2(f2(-0.5f), neg2(vc)), sc, a, b);
+  const F2 c = f2(-0.70710678118654752440f);  // float(-(2 ** -0.5)) cast to fp32
+  const F2 xa = mul2(c, a), xb = mul2(c, b);  // xb > 0 always; xa < 0 iff v < 0.5
   if (FAST) {
-    float ea = erfc_pos_fast(min_nan(fabsf(xa), 12.0f));
-    const float eb = erfc_pos_fast(min_nan(xb, 12.0f));
-    ea = (xa < 0.0f) ? 2.0f - ea : ea;
-    return fmaf(0.5f, ea, -0.5f * eb);
+    F2 ea = erfc_pos_fast(min_nan2(abs2(xa), 12.0f));
+    const F2 eb = erfc_pos_fast(min_nan2(xb, 12.0f));
+    ea.x = (xa.x < 0.0f) ? 2.0f - ea.x : ea.x;
+    ea.y = (xa.y < 0.0f) ? 2.0f - ea.y : ea.y;
+    return fma2(f2(0.5f), ea, mul2(f2(-0.5f), eb));
   }
-  const float upper = 0.5f * erfcf(xa);
-  const float lower = 0.5f * erfcf(xb);
-  return upper - lower;
+  const F2 upper = make_float2(0.5f * erfcf(xa.x), 0.5f * erfcf(xa.y));
+  const F2 lower = make_float2(0.5f * erfcf(xb.x), 0.5f * erfcf(xb.y));
+  return add2(upper, neg2(lower));
 }
 
 // build_indexes: idx = #{ j < len-1 : !(s <= table[j]) } = (len-1) - sum_j [s <= table[j]].
@@ -135,34 +153,47 @@ __device__ __forceinline__ int scale_index(float s, const float* pad, float g_sc
   return g;
 }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, int STEPS, bool FAST>
-struct GcElem {
+// One pair of elements.  `prod` accumulates the product of the pair's (bounded) likelihoods
+// so that the rate needs one MUFU.LG2 per four elements (see the caller); `acc` is used
+// directly when the bound is too small for that.
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, int STEPS, bool FAST, bool PAIR>
+struct GcPair {
   __device__ __forceinline__ static void run(const GcParams& p, const float* pad, float g_scale, float g_off,
-                                             float y, float mu, float sg, float u, float& yhat,
-                                             float& ste, float& lik, int& sym, int& idx, float& acc) {
-    const float d = y - mu;
+                                             F2 y, F2 mu, F2 sg, F2 u, F2& yhat, F2& ste, F2& lik,
+                                             int2& sym, int2& idx, float& prod, float& acc, bool use_prod) {
+    const F2 d = add2(y, neg2(mu));
     // torch.round (half to even) and the int32 symbol: for |d| < 2^22 adding 1.5*2^23 rounds d to
     // an integer in the FMA pipe and leaves that integer in the low mantissa bits; larger |d|
     // (never seen in latents, exercised by the edge-case tests) takes the FRND/F2I path.
-    const float tq = d + 12582912.0f;
-    float q = tq - 12582912.0f;
-    sym = __float_as_int(tq) - 0x4B400000;
-    if (!(fabsf(d) < 4194304.0f)) {
-      q = rintf(d);
-      sym = __float2int_rn(q);
+    const F2 tq = add2(d, f2(12582912.0f));
+    F2 q = add2(tq, f2(-12582912.0f));
+    sym.x = __float_as_int(tq.x) - 0x4B400000;
+    sym.y = __float_as_int(tq.y) - 0x4B400000;
+    if (!(fmaxf(fabsf(d.x), fabsf(d.y)) < 4194304.0f) || d.x != d.x) {
+      q.x = rintf(d.x); q.y = rintf(d.y);
+      sym.x = __float2int_rn(q.x); sym.y = __float2int_rn(q.y);
     }
-    ste = q + mu;
-    yhat = NOISE ? (y + u) : ste;
-    const float s = max_nan(sg, p.scale_bound);
+    ste = add2(q, mu);
+    yhat = NOISE ? add2(y, u) : ste;
+    const F2 s = max_nan2(sg, p.scale_bound);
     if (NEED_LIK) {
-      const float v = fabsf(yhat - mu);  // reference re-subtracts mu from the quantized value
-      float L = gc_likelihood<FAST>(v, s);
-      if (p.lik_bound > 0.0f) L = max_nan(L, p.lik_bound);
+      const F2 v = abs2(add2(yhat, neg2(mu)));   // reference re-subtracts mu from the quantized value
+      F2 L = gc_likelihood<FAST>(v, s);
+      if (p.lik_bound > 0.0f) L = max_nan2(L, p.lik_bound);
       lik = L;
-      // FAST: MUFU.LG2 (abs err <= 2^-22 for L in (0.5,2), rel err 2^-22 elsewhere)
-      acc += FAST ? lg2_approx(L) : log2f(L);
+      if (!PAIR) {                       // scalar path: lane y is a dummy
+        acc += FAST ? lg2_approx(L.x) : log2f(L.x);
+      } else if (FAST) {
+        if (use_prod) prod *= L.x * L.y;
+        else acc += lg2_approx(L.x) + lg2_approx(L.y);
+      } else {
+        acc += log2f(L.x) + log2f(L.y);
+      }
     }
-    if (NEED_IDX) idx = scale_index<STEPS>(s, pad, g_scale, g_off, p.table_len - 1);
+    if (NEED_IDX) {
+      idx.x = scale_index<STEPS>(s.x, pad, g_scale, g_off, p.table_len - 1);
+      idx.y = PAIR ? scale_index<STEPS>(s.y, pad, g_scale, g_off, p.table_len - 1) : 0;
+    }
   }
 };
 
@@ -273,10 +304,23 @@ gc_fwd_kernel(const GcParams p) {
           }
         }
         float oy[4], os[4], ol[4]; int osym[4], oidx[4];
+        // rate: FAST mode multiplies the four bounded likelihoods of a group and takes ONE
+        // MUFU.LG2 (abs err <= 2^-22 for arguments in (0.5,2), rel err 2^-22 elsewhere); the
+        // product cannot underflow while the bound is >= 1e-9 (1e-36 > FLT_MIN).
+        const bool use_prod = FAST && p.lik_bound >= 1e-9f;
+        float prod = 1.0f;
 #pragma unroll
-        for (int j = 0; j < W; ++j)
-          GcElem<NEED_LIK, NEED_IDX, NOISE, STEPS, FAST>::run(p, pad, g_scale, g_off, cur.y[j], cur.m[j], cur.s[j],
-                                                              cur.u[j], oy[j], os[j], ol[j], osym[j], oidx[j], acc);
+        for (int j = 0; j < (VEC ? 2 : 1); ++j) {
+          const int j0 = 2 * j, j1 = 2 * j + 1;
+          F2 yh, st, lk; int2 sy, ix;
+          GcPair<NEED_LIK, NEED_IDX, NOISE, STEPS, FAST, VEC>::run(
+              p, pad, g_scale, g_off, make_float2(cur.y[j0], cur.y[j1]), make_float2(cur.m[j0], cur.m[j1]),
+              make_float2(cur.s[j0], cur.s[j1]), make_float2(cur.u[j0], cur.u[j1]), yh, st, lk, sy, ix, prod, acc,
+              use_prod && VEC);
+          oy[j0] = yh.x; os[j0] = st.x; ol[j0] = lk.x; osym[j0] = sy.x; oidx[j0] = ix.x;
+          if (VEC) { oy[j1] = yh.y; os[j1] = st.y; ol[j1] = lk.y; osym[j1] = sy.y; oidx[j1] = ix.y; }
+        }
+        if (NEED_LIK && use_prod && VEC) acc += lg2_approx(prod);
         if (VEC) {
           if (yhat) st_stream4(yhat + off, make_float4(oy[0], oy[1], oy[2], oy[3]));
           if (ste) st_stream4(ste + off, make_float4(os[0], os[1], os[2], os[3]));
@@ -301,7 +345,7 @@ gc_fwd_kernel(const GcParams p) {
       const int64_t first = image * p.tiles_per_image, last = first + p.tiles_per_image - 1;
       const int64_t c_lo = ((first + 1) * G + total - 1) / total - 1;
       const int64_t c_hi = ((last + 1) * G + total - 1) / total - 1;
-      rate_commit(acc, image, static_cast<unsigned int>((c_hi - c_lo + 1) * (kThreads / 32)), p.B, p.workspace, p.bits);
+      rate_commit(acc, image, static_cast<unsigned int>((c_hi - c_lo + 1) * (kThreads / 32)), p.B, p.workspace, p.bits, p.bits_accumulate != 0);
     }
   }
 }
@@ -413,6 +457,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
     if (reinterpret_cast<uintptr_t>(d->workspace) & 7u)
       return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace must be 8-byte aligned");
     p.bits = d->bits;
+    p.bits_accumulate = d->bits_accumulate;
     p.workspace = static_cast<unsigned long long*>(d->workspace);
   }
   int steps = 6;

@@ -181,6 +181,7 @@ def gc_forward(
         if ws is None:
             ws = _cabi.workspace(y.device, B)
         d.bits = bits.data_ptr()
+        d.bits_accumulate = 1 if out.get("bits_accumulate") else 0
         d.workspace = ws.data_ptr()
         d.workspace_bytes = ws.numel()
         keep.append(ws)
@@ -315,6 +316,7 @@ def eb_forward(
         if ws is None:
             ws = _cabi.workspace(z.device, B)
         d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
+        d.bits_accumulate = 1 if out.get("bits_accumulate") else 0
         keep.append(ws)
         res.bits = bits
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF

@@ -10,9 +10,9 @@
     for each of the 5 channel slices of y (sequential in the real model: mu, sigma of
     slice k depend on y_hat of slices < k):
         GaussianConditional fused pass -> y_hat slice, L_y slice, [symbols, indexes], bits_y[B]
-    bpp[B] = (bits_y + bits_z) / num_pixels
+    bits[B] = bits_z + sum_k bits_y,k   (accumulated by the kernels themselves; bpp = bits / num_pixels)
 
-= 1 + 5 kernel launches per batch.  Static output buffers make the pass CUDA-graph
+= 1 + 5 kernel launches per batch and nothing else (no torch glue kernels).  Static output buffers make the pass CUDA-graph
 capturable (``capture()``), which removes the Python/launch overhead from steady state.
 """
 from __future__ import annotations
@@ -46,7 +46,6 @@ class TcmEntropyPath(nn.Module):
                 "y_lik": torch.empty_like(y),
                 "z_hat": torch.empty_like(z),
                 "z_lik": torch.empty_like(z),
-                "bits_slices": torch.zeros(self.num_slices + 1, B, dtype=torch.float64, device=dev),
                 "bits": torch.zeros(B, dtype=torch.float64, device=dev),
                 "workspace": torch.zeros(max(int(_cabi.load().reslic_workspace_bytes(B)), 16),
                                          dtype=torch.uint8, device=dev),
@@ -63,27 +62,34 @@ class TcmEntropyPath(nn.Module):
     @torch.no_grad()
     def forward(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, *, training: bool = False,
                 with_indexes: bool = False, num_pixels: Optional[int] = None, seed: int = 0,
-                offset: int = 0, noise_y: Optional[Tensor] = None, noise_z: Optional[Tensor] = None
-                ) -> Dict[str, Tensor]:
+                offset: int = 0, noise_y: Optional[Tensor] = None, noise_z: Optional[Tensor] = None,
+                fuse_slices: bool = False, skip_z: bool = False) -> Dict[str, Tensor]:
         """All tensors on the GPU, NCHW fp32: y/mu/sigma [B, 320, h, w], z [B, 192, h/4, w/4].
-        Returns views of static buffers (valid until the next call)."""
+        Returns views of static buffers (valid until the next call).
+
+        ``fuse_slices`` runs all channels of y in ONE launch: what a model whose mu/sigma are
+        available for every channel at once does (e.g. the reference's ScaleHyperprior,
+        src/models/Balle2018.py: one gaussian_conditional call on the whole y); TCM itself needs
+        the per-slice mode because slice k's parameters depend on y_hat of slices < k."""
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         b = self.buffers(y, z, with_indexes, training)
         C = y.shape[1]
         if C % self.num_slices:
             raise ValueError(f"{C} channels do not split into {self.num_slices} slices")
-        cs = C // self.num_slices
+        n_launch = 1 if fuse_slices else self.num_slices
+        cs = C // n_launch
         m, bi, f = eb._params()
-        ez = ops.eb_forward(z, m, bi, f, eb.quantiles[:, 0, 1], training=training, noise=noise_z,
-                            likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"),
-                            out={"ste": b["z_hat"], "lik": b["z_lik"], "bits": b["bits_slices"][0],
-                                 "workspace": b["workspace"]}, seed=seed, offset=offset)
-        del ez
+        if not skip_z:
+            ops.eb_forward(z, m, bi, f, eb.quantiles[:, 0, 1], training=training, noise=noise_z,
+                               likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"),
+                               out={"ste": b["z_hat"], "lik": b["z_lik"], "bits": b["bits"],
+                                    "workspace": b["workspace"]}, seed=seed, offset=offset)   # bits[b]  = z bits
         want = ["ste", "lik", "bits"] + (["sym", "idx"] if with_indexes else []) + (["yhat"] if training else [])
-        for k in range(self.num_slices):
+        for k in range(n_launch):
             sl = slice(cs * k, cs * (k + 1))
-            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits": b["bits_slices"][k + 1],
-                   "workspace": b["workspace"]}
+            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits": b["bits"],
+                   "bits_accumulate": not (skip_z and k == 0),
+                   "workspace": b["workspace"]}                                          # bits[b] += slice bits
             if with_indexes:
                 out["sym"], out["idx"] = b["symbols"][:, sl], b["indexes"][:, sl]
             if training:
@@ -93,15 +99,13 @@ class TcmEntropyPath(nn.Module):
                            scale_table=gc.scale_table if with_indexes else None, scale_bound=gc._scale_bound,
                            likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
                            offset=offset + 1 + k)
-        torch.sum(b["bits_slices"], dim=0, out=b["bits"])
         res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
                "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
         if with_indexes:
             res["symbols"], res["indexes"] = b["symbols"], b["indexes"]
         if training:
             res["y_noisy"] = b["y_noisy"]
-        if num_pixels is not None:
-            res["bpp"] = b["bits"] / float(num_pixels)
+        res["num_pixels"] = num_pixels      # bpp[b] = bits[b] / num_pixels (loss.py:24-27), left to the reader
         return res
 
     # ------------------------------------------------------------------ CUDA graph
