@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 2
+#define RESLIC_ABI_VERSION 3
 
 enum {
   RESLIC_OK = 0,
@@ -145,6 +145,64 @@ typedef struct reslic_eb_desc {
 } reslic_eb_desc;
 
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream);
+
+/* ----------------------------------------------------------------------------------
+ * STanH ("sum of tanh") quantizer family.
+ * Tables are the state the reference's NonSymStanH / SymStanH modules keep
+ * (src/quantization/activation.py:57-98, 214-234): K thresholds, K weights, K+1 levels,
+ * K level mid-points and K half-gaps, all fp32 DEVICE arrays.
+ * -------------------------------------------------------------------------------- */
+typedef struct reslic_stanh_tables {
+  const float* b;                /* [K] thresholds ASCENDING: sort(stanh.b) / sort(stanh.sym_b)        */
+  const float* w;                /* [K] weights as the module pairs them with the sorted thresholds   */
+                                 /*     (stanh.w, or stanh.sym_w for the symmetric form)              */
+  const float* cum_w;            /* [K+1] levels (stanh.cum_w)                                        */
+  const float* average_points;   /* [K] (stanh.average_points)                                        */
+  const float* distance_points;  /* [K] (stanh.distance_points)                                       */
+  int32_t K;                     /* 1..1024                                                           */
+  int32_t symmetric;             /* 0: NonSymStanH (strict >), 1: SymStanH (sign(), half level at ties)*/
+  float beta;                    /* soft-form temperature; -1 = hard form (activation.py:142-143)     */
+} reslic_stanh_tables;
+
+/* Fused GaussianConditionalStanh.forward / quantize / _likelihood
+ * (src/entropy_models/adaptive_gaussian_conditional.py:588-603, 95-157, 541-580; call sites
+ * src/models/stanh/tcm_stanh.py:432, wacnn_stanh.py:305, balle18_stanh.py:126):
+ *   training != 0 : y_hat = stanh_beta(y - mu*[removing_mean]) + mu*[removing_mean]   (:108-117)
+ *   training == 0 : y_hat = stanh_hard(y - mu) + mu                                   (:119-137)
+ *   training == 2 : y_hat = y (no quantization: _likelihood of already-quantised values, :541)
+ *   L = mass of the level cell of (y_hat - mu) under N(0, max(sigma, scale_bound)), bounded below
+ *   sym = level index of stanh_hard(y - mu): 0..K (non-symmetric) or -K/2..K/2 (symmetric),
+ *         i.e. stanh.map_sos_cdf without the per-element Python loop (:144-157)
+ * Layout conventions as reslic_gc_desc. */
+typedef struct reslic_stanh_gc_desc {
+  const float* y;      int64_t y_bs;
+  const float* mu;     int64_t mu_bs;      /* NULL = no means                              */
+  const float* sigma;  int64_t sigma_bs;
+  int64_t B, n;
+  int32_t training;                        /* forward(..., training=...)                   */
+  int32_t removing_mean;                   /* gaussian_configuration["removing_mean"]      */
+  float scale_bound, likelihood_bound;
+  reslic_stanh_tables tables;
+  float* yhat;   int64_t yhat_bs;
+  float* lik;    int64_t lik_bs;
+  int32_t* sym;  int64_t sym_bs;
+  double* bits;  int32_t bits_accumulate;
+  void* workspace; int64_t workspace_bytes;  /* as reslic_gc_desc                           */
+} reslic_stanh_gc_desc;
+
+int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream);
+
+/* The activation alone, flat over n elements (NonSymStanH/SymStanH.forward,
+ * activation.py:135-150, 294-304) and the two sums compute_gap needs
+ * (src/models/stanh/tcm_stanh.py:465-478):
+ *   out_soft[i] = stanh_beta(x[i])   (nullable)      out_hard[i] = stanh_hard(x[i])  (nullable)
+ *   gap2[0] = sum_i (x - stanh_beta(x))^2,  gap2[1] = sum_i (x - stanh_hard(x))^2   (nullable, fp64;
+ *   gap = |gap2[0] - gap2[1]| / n).  `gap_workspace`: >= reslic_stanh_gap_workspace_bytes() bytes,
+ *   zero-filled once, NOT shared with the rate workspace. */
+int64_t reslic_stanh_gap_workspace_bytes(void);
+int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft,
+                         float* out_hard, double* gap2, void* gap_workspace, int64_t gap_workspace_bytes,
+                         void* stream);
 
 /* ----------------------------------------------------------------------------------
  * Host-side setup helper (no GPU work): pmf[n] -> cdf[n+1] with 2^precision total mass

@@ -117,9 +117,68 @@ def gen_eb():
     return out
 
 
+def gen_stanh():
+    """The reference's own STanH modules (src/quantization/activation.py,
+    src/entropy_models/adaptive_gaussian_conditional.py) on CPU: activation (hard / soft), forward
+    in eval and training mode, quantize modes incl. the per-element "symbols" loop, and the
+    compute_gap formula of src/models/stanh/tcm_stanh.py:465-478."""
+    import contextlib
+    import io
+
+    import torch.nn.functional as F
+
+    em, q = shim.load_stanh_modules()
+    cases = {
+        "A": dict(symmetry=False, extrema=80, beta=10, removing_mean=True, perturb=False),
+        "B": dict(symmetry=False, extrema=10, beta=3, removing_mean=False, perturb=True),
+        "C": dict(symmetry=True, extrema=6, beta=5, removing_mean=True, perturb=True),
+    }
+    out = {}
+    for tag, c in cases.items():
+        g = torch.Generator().manual_seed(900 + ord(tag))
+        cfg = dict(beta=c["beta"], num_sigmoids=0, extrema=c["extrema"], trainable=True,
+                   removing_mean=c["removing_mean"], symmetry=c["symmetry"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            gcs = em.GaussianConditionalStanh(None, channels=8, gaussian_configuration=cfg)
+            if c["perturb"]:
+                with torch.no_grad():
+                    gcs.stanh.w.mul_(1.0 + 0.2 * torch.rand(gcs.stanh.w.shape, generator=g))
+            gcs.stanh.update_state(torch.device("cpu"))
+            gcs.stanh.define_channels_map()
+        shape = (2, 8, 6, 6)
+        mu = torch.randn(shape, generator=g)
+        sigma = torch.exp(torch.empty(shape).uniform_(math.log(0.05), math.log(40.0), generator=g))
+        y = mu + torch.minimum(sigma, torch.tensor(0.4 * c["extrema"])) * torch.randn(shape, generator=g)
+        # keep clear of exact ties with the thresholds (hard form is discontinuous there)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            st = gcs.stanh
+            b_all = st.sym_b if c["symmetry"] else st.b
+            w_all = st.sym_w if c["symmetry"] else st.w
+            flat = y.reshape(1, 1, -1)
+            hard = st(flat, -1).reshape(shape)
+            soft = st(flat, c["beta"]).reshape(shape)
+            gap = torch.abs(F.mse_loss(flat, st(flat, c["beta"])) - F.mse_loss(flat, st(flat, -1)))
+            yh_eval, lik_eval = gcs(y, sigma, training=False, means=mu)
+            yh_train, lik_train = gcs(y, sigma, training=True, means=mu)
+            sym = gcs.quantize(y.clone(), "symbols", means=mu)
+            lik_only = gcs._likelihood(yh_train, sigma, means=mu)
+        for k, v in dict(y=y, mu=mu, sigma=sigma, w=w_all.detach(), b=torch.sort(b_all.detach())[0],
+                         w_param=st.w.detach(), b_param=st.b.detach(),
+                         cum_w=st.cum_w, avg=st.average_points, dist=st.distance_points, hard=hard, soft=soft,
+                         gap=gap.reshape(1), yhat_eval=yh_eval, lik_eval=lik_eval, yhat_train=yh_train,
+                         lik_train=lik_train, sym=sym, lik_unbounded_train=lik_only,
+                         meta=torch.tensor([float(c["symmetry"]), c["extrema"], c["beta"], float(c["removing_mean"])])
+                         ).items():
+            out[f"{tag}_{k}"] = v.detach()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "stanh_golden.npz"), **{k: v.numpy() for k, v in out.items()})
+    return out
+
+
 if __name__ == "__main__":
     if not shim.available():
         raise SystemExit("reference not available: golden vectors can only be generated in the build container")
     a = gen_gc()
     b = gen_eb()
+    c = gen_stanh()
+    print("stanh:", len(c), "arrays")
     print("wrote", GOLDEN_DIR, {k: tuple(v.shape) for k, v in a.items()}, {k: tuple(v.shape) for k, v in b.items()})

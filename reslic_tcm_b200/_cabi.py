@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -66,6 +66,34 @@ class EbDesc(C.Structure):
     ]
 
 
+class StanhTables(C.Structure):
+    """struct reslic_stanh_tables."""
+
+    _fields_ = [
+        ("b", C.c_void_p), ("w", C.c_void_p), ("cum_w", C.c_void_p), ("average_points", C.c_void_p),
+        ("distance_points", C.c_void_p), ("K", C.c_int32), ("symmetric", C.c_int32), ("beta", C.c_float),
+    ]
+
+
+class StanhGcDesc(C.Structure):
+    """struct reslic_stanh_gc_desc."""
+
+    _fields_ = [
+        ("y", C.c_void_p), ("y_bs", C.c_int64),
+        ("mu", C.c_void_p), ("mu_bs", C.c_int64),
+        ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
+        ("B", C.c_int64), ("n", C.c_int64),
+        ("training", C.c_int32), ("removing_mean", C.c_int32),
+        ("scale_bound", C.c_float), ("likelihood_bound", C.c_float),
+        ("tables", StanhTables),
+        ("yhat", C.c_void_p), ("yhat_bs", C.c_int64),
+        ("lik", C.c_void_p), ("lik_bs", C.c_int64),
+        ("sym", C.c_void_p), ("sym_bs", C.c_int64),
+        ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 # every symbol include/reslic_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {
     "reslic_abi_version": (C.c_int, []),
@@ -79,6 +107,10 @@ EXPORTS = {
                                            C.c_void_p, C.c_void_p]),
     "reslic_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
+    "reslic_stanh_gc_fwd_f32": (C.c_int, [C.POINTER(StanhGcDesc), C.c_void_p]),
+    "reslic_stanh_gap_workspace_bytes": (C.c_int64, []),
+    "reslic_stanh_act_f32": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StanhTables), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "reslic_pmf_to_quantized_cdf": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

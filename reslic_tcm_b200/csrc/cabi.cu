@@ -101,6 +101,16 @@ int reslic_dequantize_f32(const int32_t* sym, const float* mu, int64_t n, float*
   return reslic::dequantize_launch(sym, mu, n, out, static_cast<cudaStream_t>(stream));
 }
 
+int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream) {
+  return reslic::stanh_gc_fwd_launch(d, static_cast<cudaStream_t>(stream));
+}
+int64_t reslic_stanh_gap_workspace_bytes(void) { return 16 + static_cast<int64_t>(reslic::sm_count()) * 8 * 16; }
+int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft, float* out_hard,
+                         double* gap2, void* gap_workspace, int64_t gap_workspace_bytes, void* stream) {
+  return reslic::stanh_act_launch(x, n, t, out_soft, out_hard, gap2, gap_workspace, gap_workspace_bytes,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
   return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,327 @@
+// stanh_fused.cu — fused STanH ("sum of tanh") quantizer + variable-bin Gaussian likelihood
+// (sm_100a).  Replaces the reference's GaussianConditionalStanh.forward / quantize / _likelihood
+// (src/entropy_models/adaptive_gaussian_conditional.py:95-157, 495-603), the STanH activation
+// itself (src/quantization/activation.py:135-150 NonSym, :294-304 Sym) and compute_gap
+// (src/models/stanh/tcm_stanh.py:465-478).
+//
+// The reference evaluates the quantizer as a dense [1, K, N] broadcast (K = 2*extrema = 160
+// thresholds per element: O(K*N) flops AND memory) and finds the likelihood bin with two
+// [N, K+1] one-hot matrices.  Here every element does
+//   * hard form (beta = -1): one binary search over the sorted thresholds in shared memory
+//     (value = level[#{k : x > b_k}]);
+//   * soft form (finite beta): tanh(beta*(x-b_k)) is exactly +-1 in fp32 once |beta*(x-b_k)| > 9.1
+//     (SURVEY.md §7.4 H1), so only the thresholds inside that window are evaluated and the
+//     saturated rest comes from the prefix sums the module already keeps (cum_w);
+//   * likelihood bin: one more binary search over the level mid-points (average_points), then the
+//     same exact-division + erfc arithmetic as the plain Gaussian-conditional kernel.
+// O(log K + window) per element, 12 B read + 8 B written, no intermediate tensors.
+#include "common.cuh"
+#include "gc_math.cuh"
+#include "reslic_internal.h"
+
+namespace reslic {
+
+constexpr int kStanhMaxK = 1024;          // thresholds (extrema <= 512)
+constexpr float kSatT = 9.1f;             // |t| beyond which 2*sigmoid(2t)-1 == +-1 in fp32
+
+struct StanhParams {
+  const float* y; const float* mu; const float* sigma;
+  int64_t y_bs, mu_bs, sigma_bs;
+  float* yhat; float* lik; int32_t* sym;
+  int64_t yhat_bs, lik_bs, sym_bs;
+  double* bits; unsigned long long* workspace; int bits_accumulate;
+  const float* b; const float* w; const float* cum_w; const float* avg; const float* dist;
+  int K, steps, symmetric, removing_mean, training, sym_offset;
+  float beta, scale_bound, lik_bound;
+  int64_t n, B, tiles_per_image;
+  double* gap;       // activation/gap kernel: [0] sum (x - soft)^2, [1] sum (x - hard)^2
+};
+
+struct StanhTables {
+  const float* b; const float* w; const float* cw; const float* avg; const float* dist;
+  int K, steps;
+};
+
+// #{k < K : x > t[k]} for ascending t (NaN -> 0)
+__device__ __forceinline__ int count_gt(float x, const float* t, int K, int steps) {
+  int lo = 0;
+  for (int step = 1 << (steps - 1); step > 0; step >>= 1) {
+    const int i = lo + step;
+    if (i <= K && x > t[i - 1]) lo = i;
+  }
+  return lo;
+}
+// #{k < K : x >= t[k]}
+__device__ __forceinline__ int count_ge(float x, const float* t, int K, int steps) {
+  int lo = 0;
+  for (int step = 1 << (steps - 1); step > 0; step >>= 1) {
+    const int i = lo + step;
+    if (i <= K && x >= t[i - 1]) lo = i;
+  }
+  return lo;
+}
+
+// activation.py:143 (NonSym: sum_k w_k*relu(sign(x-b_k)) - w_k/2) and :298 (Sym: sum_k w_k/2*sign(x-b_k)).
+// Both equal the level cum_w[c] with c = #{k : x > b_k}; the symmetric form gives the mean of the two
+// adjacent levels at an exact tie x == b_k (sign(0) = 0).  `c_out` is the level index ("symbols").
+__device__ __forceinline__ float stanh_hard(float x, const StanhTables& T, bool symmetric, int& c_out) {
+  const int c = count_gt(x, T.b, T.K, T.steps);
+  c_out = c;
+  float v = T.cw[c];
+  if (symmetric) {
+    const int ce = count_ge(x, T.b, T.K, T.steps);
+    v = 0.5f * (v + T.cw[ce]);
+  }
+  // NaN input: torch.sign(NaN) == 0, so the reference lands on the lowest level (NonSym: every
+  // relu(sign) term is 0) or on 0 (Sym: every sign term is 0) — not on NaN.
+  return (symmetric && x != x) ? 0.0f : v;
+}
+
+// activation.py:146-149 / :301-304: sum_k (w_k/2) * (2*sigmoid(2*beta*(x-b_k)) - 1)
+__device__ __forceinline__ float stanh_soft(float x, float beta, const StanhTables& T) {
+  int lo = 0, hi = T.K;
+  float sat = 0.0f;
+  if (beta > 0.0f) {
+    const float r = kSatT / beta;
+    lo = count_ge(x - r, T.b, T.K, T.steps);      // k < lo : beta*(x-b_k) >= T  -> +1
+    hi = count_gt(x + r, T.b, T.K, T.steps);      // k >= hi: beta*(x-b_k) <= -T -> -1
+    if (hi < lo) hi = lo;
+    // sum_{k<lo} w_k/2 - sum_{k>=hi} w_k/2 from the prefix sums W(c) = cum_w[c] - cum_w[0]
+    sat = 0.5f * ((T.cw[lo] - T.cw[0]) - (T.cw[T.K] - T.cw[hi]));
+  }
+  float acc = 0.0f;
+  for (int k = lo; k < hi; ++k) {
+    const float t = beta * (x - T.b[k]);
+    const float sg = 1.0f / (1.0f + expf(-(2.0f * t)));
+    acc = fmaf(T.w[k] * 0.5f, 2.0f * sg - 1.0f, acc);
+  }
+  return (x != x) ? x : sat + acc;
+}
+
+// adaptive_gaussian_conditional.py:495-580: half-widths (low, up) of the level cell that contains v,
+// then the mass of [level-low, level+up] under N(0, s) in the sign-dependent form of :564-567.
+template <bool FAST>
+__device__ __forceinline__ float stanh_likelihood(float v, float s, const StanhTables& T) {
+  const int j = count_gt(v, T.avg, T.K, T.steps);          // avg_left[j] < v <= avg_right[j]
+  const bool inside = (v > -1000.0f) && (v <= 1000.0f);    // the reference's +-1000 sentinels (:506,:511)
+  const float low = (inside && j > 0) ? T.dist[j - 1] : 0.0f;
+  const float up = (inside && j < T.K) ? T.dist[j] : 0.0f;
+  float n1, n2;
+  if (v >= 0.0f) { n1 = low - v; n2 = -up - v; }
+  else { n1 = v + up; n2 = v - low; }                       // NaN v lands here and stays NaN
+  n1 = max_nan(min_nan(n1, 1e30f), -1e30f);
+  n2 = max_nan(min_nan(n2, 1e30f), -1e30f);
+  return gauss_interval_mass<FAST>(n1, n2, s);
+}
+
+__device__ __forceinline__ void stage_tables(const StanhParams& p, float* sm, StanhTables& T) {
+  float* sb = sm; float* sw = sb + p.K; float* scw = sw + p.K; float* savg = scw + p.K + 1; float* sdist = savg + p.K;
+  for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
+    sb[i] = p.b[i]; sw[i] = p.w[i]; savg[i] = p.avg[i]; sdist[i] = p.dist[i];
+  }
+  for (int i = threadIdx.x; i <= p.K; i += blockDim.x) scw[i] = p.cum_w[i];
+  __syncthreads();
+  T.b = sb; T.w = sw; T.cw = scw; T.avg = savg; T.dist = sdist; T.K = p.K; T.steps = p.steps;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads) stanh_gc_fwd_kernel(const StanhParams p) {
+  extern __shared__ float sm[];
+  StanhTables T;
+  stage_tables(p, sm, T);
+  const bool need_lik = p.lik || p.bits;
+  const int64_t total = p.tiles_per_image * p.B;
+  int64_t t = (static_cast<int64_t>(blockIdx.x) * total) / gridDim.x;
+  const int64_t t_end = (static_cast<int64_t>(blockIdx.x + 1) * total) / gridDim.x;
+  while (t < t_end) {
+    const int image = static_cast<int>(t / p.tiles_per_image);
+    const int64_t seg_end = (static_cast<int64_t>(image) + 1) * p.tiles_per_image;
+    const int64_t stop = seg_end < t_end ? seg_end : t_end;
+    float acc = 0.0f;
+    for (; t < stop; ++t) {
+      const int64_t e = (t - image * p.tiles_per_image) * kThreads + threadIdx.x;
+      if (e >= p.n) continue;
+      const float y = ld_stream1(p.y + image * p.y_bs + e);
+      const float mu = p.mu ? ld_stream1(p.mu + image * p.mu_bs + e) : 0.0f;
+      float yhat; int level = 0;
+      if (p.training == 2) {
+        yhat = y;                                            // likelihood of given values (_likelihood)
+      } else if (p.training) {
+        // quantize(..., "training"): honours removing_mean (:108-117)
+        const float x = (p.mu && p.removing_mean) ? y - mu : y;
+        const float q = (p.beta == -1.0f) ? stanh_hard(x, T, p.symmetric, level) : stanh_soft(x, p.beta, T);
+        yhat = (p.mu && p.removing_mean) ? q + mu : q;
+        if (p.sym) { int c; stanh_hard(y - mu, T, p.symmetric, c); level = c; }
+      } else {
+        // "dequantize" / "symbols": always about the mean, hard levels (:119-137)
+        const float q = stanh_hard(y - mu, T, p.symmetric, level);
+        yhat = p.mu ? q + mu : q;
+      }
+      if (p.yhat) st_stream1(p.yhat + image * p.yhat_bs + e, yhat);
+      if (p.sym) st_stream1(p.sym + image * p.sym_bs + e, level + p.sym_offset);
+      if (need_lik) {
+        const float s = max_nan(ld_stream1(p.sigma + image * p.sigma_bs + e), p.scale_bound);
+        const float v = p.mu ? yhat - mu : yhat;             // :547-550
+        float L = stanh_likelihood<FAST>(v, s, T);
+        if (p.lik_bound > 0.0f) L = max_nan(L, p.lik_bound);
+        if (p.lik) st_stream1(p.lik + image * p.lik_bs + e, L);
+        acc += FAST ? lg2_approx(L) : log2f(L);
+      }
+    }
+    if (p.bits) {
+      const int64_t G = gridDim.x;
+      const int64_t first = image * p.tiles_per_image, last = first + p.tiles_per_image - 1;
+      const int64_t c_lo = ((first + 1) * G + total - 1) / total - 1;
+      const int64_t c_hi = ((last + 1) * G + total - 1) / total - 1;
+      rate_commit(acc, image, static_cast<unsigned int>((c_hi - c_lo + 1) * (kThreads / 32)), p.B, p.workspace,
+                  p.bits, p.bits_accumulate != 0);
+    }
+  }
+}
+
+// Activation alone (module forward) and the two squared-error sums compute_gap needs, in one pass:
+// out_soft / out_hard nullable; gap[0] += sum (x - soft)^2, gap[1] += sum (x - hard)^2.
+__global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p, float* out_soft, float* out_hard,
+                                                             double* partials, unsigned int* counter) {
+  extern __shared__ float sm[];
+  __shared__ double s_red[2][kThreads / 32];
+  __shared__ bool s_last;
+  StanhTables T;
+  stage_tables(p, sm, T);
+  const bool want_soft = out_soft || p.gap, want_hard = out_hard || p.gap;
+  double se_soft = 0.0, se_hard = 0.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < p.n;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const float x = p.y[i];
+    int c;
+    if (want_soft) {
+      const float q = (p.beta == -1.0f) ? stanh_hard(x, T, p.symmetric, c) : stanh_soft(x, p.beta, T);
+      if (out_soft) out_soft[i] = q;
+      const float d = x - q;
+      se_soft += static_cast<double>(d * d);
+    }
+    if (want_hard) {
+      const float q = stanh_hard(x, T, p.symmetric, c);
+      if (out_hard) out_hard[i] = q;
+      const float d = x - q;
+      se_hard += static_cast<double>(d * d);
+    }
+  }
+  if (!p.gap) return;
+  // deterministic: fixed tree inside the CTA, one partial pair per CTA, last CTA adds them in order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se_soft += __shfl_xor_sync(0xffffffffu, se_soft, o);
+    se_hard += __shfl_xor_sync(0xffffffffu, se_hard, o);
+  }
+  if (lane == 0) { s_red[0][warp] = se_soft; s_red[1][warp] = se_hard; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) { a += s_red[0][i]; b += s_red[1][i]; }
+    partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    const volatile double* pp = partials;
+    double a = 0.0, b = 0.0;
+    for (unsigned int i = 0; i < gridDim.x; ++i) { a += pp[2 * i]; b += pp[2 * i + 1]; }
+    p.gap[0] = a; p.gap[1] = b;
+    *counter = 0u;
+  }
+}
+
+static int steps_for(int K) { int s = 1; while ((1 << s) <= K) ++s; return s; }
+
+static int check_tables(const reslic_stanh_tables* t, const char* who) {
+  if (!t || !t->b || !t->w || !t->cum_w || !t->average_points || !t->distance_points) {
+    set_error(RESLIC_ERR_ARG, "stanh: a table pointer is null");
+    return RESLIC_ERR_ARG;
+  }
+  if (t->K < 1 || t->K > kStanhMaxK) {
+    set_error(RESLIC_ERR_ARG, "stanh: K outside 1..1024");
+    return RESLIC_ERR_ARG;
+  }
+  (void)who;
+  return RESLIC_OK;
+}
+
+static void fill_tables(StanhParams& p, const reslic_stanh_tables* t) {
+  p.b = t->b; p.w = t->w; p.cum_w = t->cum_w; p.avg = t->average_points; p.dist = t->distance_points;
+  p.K = t->K; p.steps = steps_for(t->K); p.symmetric = t->symmetric; p.beta = t->beta;
+  p.sym_offset = t->symmetric ? -(t->K / 2) : 0;
+}
+
+static size_t tables_smem(int K) { return static_cast<size_t>(5 * K + 1) * sizeof(float); }
+
+int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
+  if (!d) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: null descriptor");
+  if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: negative size");
+  if (d->B == 0 || d->n == 0) return RESLIC_OK;
+  if (int rc = check_tables(&d->tables, "stanh_gc_fwd")) return rc;
+  if (!d->y) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: y is null");
+  const bool need_lik = d->lik || d->bits;
+  if (need_lik && !d->sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: sigma is null");
+  if (!d->yhat && !d->sym && !need_lik) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: no output requested");
+  if (need_lik && !(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: scale_bound must be > 0");
+  if (d->n >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: more than 2^31 elements per image");
+  StanhParams p{};
+  p.y = d->y; p.mu = d->mu; p.sigma = d->sigma; p.y_bs = d->y_bs; p.mu_bs = d->mu_bs; p.sigma_bs = d->sigma_bs;
+  p.yhat = d->yhat; p.lik = d->lik; p.sym = d->sym; p.yhat_bs = d->yhat_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs;
+  fill_tables(p, &d->tables);
+  p.removing_mean = d->removing_mean; p.training = d->training;
+  p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
+  p.n = d->n; p.B = d->B; p.tiles_per_image = (d->n + kThreads - 1) / kThreads;
+  if (d->bits) {
+    if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B) ||
+        (reinterpret_cast<uintptr_t>(d->workspace) & 7u))
+      return set_error(RESLIC_ERR_WORKSPACE, "stanh_gc_fwd: workspace missing, misaligned or too small for `bits`");
+    p.bits = d->bits; p.bits_accumulate = d->bits_accumulate;
+    p.workspace = static_cast<unsigned long long*>(d->workspace);
+  }
+  const int64_t total = p.tiles_per_image * p.B;
+  int64_t grid = static_cast<int64_t>(sm_count()) * 8;
+  if (grid > total) grid = total;
+  const size_t smem = tables_smem(p.K);
+  if (math_mode() == RESLIC_MATH_MIRROR) stanh_gc_fwd_kernel<false><<<static_cast<int>(grid), kThreads, smem, st>>>(p);
+  else stanh_gc_fwd_kernel<true><<<static_cast<int>(grid), kThreads, smem, st>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "stanh_gc_fwd launch");
+  return RESLIC_OK;
+}
+
+int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft, float* out_hard,
+                     double* gap, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (n < 0) return set_error(RESLIC_ERR_ARG, "stanh_act: negative size");
+  if (int rc = check_tables(t, "stanh_act")) return rc;
+  if (n == 0) {
+    if (gap) cudaMemsetAsync(gap, 0, 2 * sizeof(double), st);
+    return RESLIC_OK;
+  }
+  if (!x) return set_error(RESLIC_ERR_ARG, "stanh_act: x is null");
+  if (!out_soft && !out_hard && !gap) return set_error(RESLIC_ERR_ARG, "stanh_act: no output requested");
+  StanhParams p{};
+  p.y = x; p.n = n; p.gap = gap;
+  fill_tables(p, t);
+  int64_t grid = (n + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  double* partials = nullptr; unsigned int* counter = nullptr;
+  if (gap) {
+    const int64_t need = 16 + static_cast<int64_t>(grid) * 2 * sizeof(double);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 7u))
+      return set_error(RESLIC_ERR_WORKSPACE, "stanh_act: workspace missing, misaligned or too small (need 16 + 16*8*SMs bytes)");
+    counter = static_cast<unsigned int*>(workspace);
+    partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
+  }
+  stanh_act_kernel<<<static_cast<int>(grid), kThreads, tables_smem(p.K), st>>>(p, out_soft, out_hard, partials, counter);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "stanh_act launch");
+  return RESLIC_OK;
+}
+
+}  // namespace reslic

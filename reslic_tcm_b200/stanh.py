@@ -1,0 +1,547 @@
+"""STanH ("sum of tanh") quantizers and the STanH Gaussian-conditional entropy model, backed
+by the fused sm_100a kernel in ``csrc/stanh_fused.cu``.
+
+Host-side mirror of the reference's in-repo modules (same class names, constructor
+arguments, attribute names and method names, so the STanH models call them unchanged):
+
+* ``NonSymStanH`` / ``SymStanH`` ........ src/quantization/activation.py:7-150 / 157-304
+* ``GaussianConditionalStanh`` ......... src/entropy_models/adaptive_gaussian_conditional.py:312-725
+  (base class ``HypeEntropyModelSoS`` :17-300); call sites src/models/stanh/tcm_stanh.py:331-337,432,
+  wacnn_stanh.py:166-171,305, balle18_stanh.py:31-34,126
+* ``compute_gap`` ...................... src/models/stanh/tcm_stanh.py:465-478
+
+Reference defects that are NOT replicated: debug prints in hot functions,
+the hard-wired ``device=cuda`` defaults, the per-element Python loops of the "symbols" mode
+and of ``dequantize``; semantics and API are kept.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, List, Optional, Tuple, Union
+
+import numpy as np
+import scipy.stats
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _cabi, ops
+from .entropy_models import EntropyModel, LowerBound, _no_grad_path
+
+__all__ = ["NonSymStanH", "SymStanH", "GaussianConditionalStanh", "compute_gap"]
+
+
+# ----------------------------------------------------------------------------- activation
+class _StanHBase(nn.Module):
+    symmetric = False
+
+    def _tables(self, beta: float):
+        """(struct reslic_stanh_tables, keepalive tensors) for the current state."""
+        dev = self.w.device
+        key = (self.w._version, self.b._version, id(self.cum_w), dev)
+        cached = getattr(self, "_tables_cache", None)
+        if cached is not None and cached[0] == key:
+            b_sorted, w, cw, avg, dist = cached[1]
+            t = _cabi.StanhTables(b_sorted.data_ptr(), w.data_ptr(), cw.data_ptr(), avg.data_ptr(), dist.data_ptr(),
+                                  b_sorted.numel(), 1 if self.symmetric else 0, float(beta))
+            return t, cached[1]
+        b_sorted = torch.sort(self._all_b().detach())[0].to(dev, torch.float32).contiguous()
+        w = self._all_w().detach().to(dev, torch.float32).contiguous()
+        cw = self.cum_w.detach().to(dev, torch.float32).contiguous()
+        avg = self.average_points.detach().to(dev, torch.float32).contiguous()
+        dist = self.distance_points.detach().to(dev, torch.float32).contiguous()
+        t = _cabi.StanhTables(b_sorted.data_ptr(), w.data_ptr(), cw.data_ptr(), avg.data_ptr(), dist.data_ptr(),
+                              b_sorted.numel(), 1 if self.symmetric else 0, float(beta))
+        self._tables_cache = (key, (b_sorted, w, cw, avg, dist))
+        return t, (b_sorted, w, cw, avg, dist)
+
+    def calculate_average_points(self):
+        self.average_points = torch.add(self.cum_w[1:], self.cum_w[:-1]) / 2
+
+    def calculate_distance_points(self):
+        self.distance_points = torch.sub(self.cum_w[1:], self.cum_w[:-1]) / 2
+
+    def f(self, x):
+        return 2 * torch.sigmoid(2 * x) - 1
+
+    def forward(self, x: Tensor, beta=None) -> Tensor:
+        """activation.py:135-150 / 294-304: hard levels for beta == -1, else sum of tanh."""
+        if beta is None:
+            beta = self.beta
+        _no_grad_path(x, self.w, self.b)
+        return stanh_activation(self, x, beta)
+
+    def gap_sums(self, x: Tensor, beta=None) -> Tensor:
+        """[sum (x - stanh_beta(x))^2, sum (x - stanh_hard(x))^2] as a float64 GPU tensor."""
+        if beta is None:
+            beta = self.beta
+        return _stanh_act(self, x, beta, want_soft=False, want_hard=False, want_gap=True)[2]
+
+
+def _stanh_act(mod: _StanHBase, x: Tensor, beta, want_soft: bool, want_hard: bool, want_gap: bool):
+    lib = _cabi.load()
+    ops._require_cuda("x", x)
+    xc = x.contiguous()
+    t, keep = mod._tables(beta)
+    soft = torch.empty_like(xc) if want_soft else None
+    hard = torch.empty_like(xc) if want_hard else None
+    gap = ws = None
+    if want_gap:
+        gap = torch.empty(2, dtype=torch.float64, device=x.device)
+        ws = _gap_workspace(x.device)
+    with torch.cuda.device(x.device):
+        code = lib.reslic_stanh_act_f32(xc.data_ptr(), xc.numel(), C.byref(t), _cabi.ptr(soft), _cabi.ptr(hard),
+                                        _cabi.ptr(gap), _cabi.ptr(ws), 0 if ws is None else ws.numel(),
+                                        _cabi.current_stream_ptr(x.device))
+    _cabi.check(code, "reslic_stanh_act_f32")
+    del keep
+    return soft, hard, gap
+
+
+_gap_ws = {}
+
+
+def _gap_workspace(device: torch.device) -> Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _gap_ws:
+        _gap_ws[key] = torch.zeros(int(_cabi.load().reslic_stanh_gap_workspace_bytes()), dtype=torch.uint8, device=device)
+    return _gap_ws[key]
+
+
+def stanh_activation(mod: _StanHBase, x: Tensor, beta) -> Tensor:
+    if beta == -1:
+        return _stanh_act(mod, x, -1.0, False, True, False)[1].view_as(x)
+    return _stanh_act(mod, x, float(beta), True, False, False)[0].view_as(x)
+
+
+class NonSymStanH(_StanHBase):
+    """activation.py:7-150."""
+
+    symmetric = False
+
+    def __init__(self, beta, num_sigmoids, extrema=5, trainable=True):
+        super().__init__()
+        self.num_sigmoids = int(num_sigmoids)
+        self.beta = beta
+        self.extrema = extrema
+        self.minimo = -extrema
+        self.massimo = extrema
+        self.range_num = torch.arange(self.minimo + 0.5, self.massimo).type(torch.FloatTensor)
+        if self.num_sigmoids > 0:
+            self.jump = len(self.range_num) / self.num_sigmoids
+            self.levels = num_sigmoids + 1
+        else:
+            self.levels = extrema * 2 + 1
+        if self.num_sigmoids == 0:
+            self.b = nn.Parameter(self.range_num.type(torch.FloatTensor), requires_grad=trainable)
+            self.w = nn.Parameter(torch.ones(len(self.range_num)), requires_grad=trainable)
+        else:
+            c = len(self.range_num) / self.num_sigmoids
+            self.b = nn.Parameter(torch.arange(self.minimo + self.jump / 2, self.massimo + self.jump / 2, c))
+            self.w = nn.Parameter(torch.zeros(self.num_sigmoids) + self.jump)
+        self.tr_parameters = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        self.length = len(self.range_num) if self.num_sigmoids == 0 else self.num_sigmoids
+        self.map_sos_cdf = {}
+        self.map_cdf_sos = {}
+        self.update_state()
+
+    def _all_b(self):
+        return self.b
+
+    def _all_w(self):
+        return self.w
+
+    def update_state(self, device=None):
+        device = self.w.device if device is None else device
+        before = getattr(self, "_cum_key", None)
+        self.update_cumulative_weights(device=device)
+        if before == self._cum_key and hasattr(self, "average_points"):
+            return                       # nothing changed: the reference calls this every forward
+        self.calculate_average_points()
+        self.average_points = self.average_points.to(device)
+        self.calculate_distance_points()
+        self.distance_points = self.distance_points.to(device)
+        self.define_channels_map()
+
+    def update_cumulative_weights(self, device=None):
+        """activation.py:91-98.  K <= 1024 numbers: summed sequentially on the host so that the levels
+        do not depend on the device's scan order (a GPU cumsum differs from the CPU one in the last
+        bit); skipped when w has not changed since the last call."""
+        device = self.w.device if device is None else device
+        key = (self.w._version, str(device))
+        if getattr(self, "_cum_key", None) == key:
+            return
+        with torch.no_grad():
+            w = self.w.detach().cpu()
+            n = (torch.sum(w) / 2).item()
+            cum_w = torch.zeros(self.length + 1)
+            cum_w[0] = 0.0
+            cum_w[1:] = torch.cumsum(w, dim=0)
+            self.cum_w = torch.sub(cum_w, n).to(device)
+        self._cum_key = key
+
+    def reinitialize_weights_and_bias(self):
+        if self.num_sigmoids == 0:
+            self.w = nn.Parameter(torch.ones(len(self.range_num)))
+            self.b = nn.Parameter(self.range_num.type(torch.FloatTensor))
+        else:
+            self.w = nn.Parameter(torch.zeros(self.num_sigmoids) + self.jump)
+            c = len(self.range_num) / self.num_sigmoids
+            self.b = nn.Parameter(torch.arange(self.minimo + self.jump / 2, self.massimo + self.jump / 2, c))
+
+    def define_channels_map(self):
+        levels = list(self.cum_w.detach().cpu().numpy())
+        mapping = list(np.arange(0, len(levels), 1))
+        self.map_sos_cdf = dict(zip(levels, mapping))
+        self.map_cdf_sos = dict(zip(mapping, levels))
+
+    @property
+    def symbol_offset(self) -> int:
+        return 0
+
+
+class SymStanH(_StanHBase):
+    """activation.py:157-304."""
+
+    symmetric = True
+
+    def __init__(self, beta, num_sigmoids, extrema=5, trainable=True):
+        super().__init__()
+        self.num_sigmoids = int(num_sigmoids)
+        self.beta = beta
+        self.minimo = -extrema
+        self.massimo = extrema
+        self.range_num = torch.arange(0.5, self.massimo).type(torch.FloatTensor)
+        if self.num_sigmoids > 0:
+            self.jump = len(self.range_num) / self.num_sigmoids
+            self.levels = num_sigmoids + 1
+        else:
+            self.levels = extrema * 2 + 1
+        if self.num_sigmoids == 0:
+            self.b = nn.Parameter(self.range_num.type(torch.FloatTensor), requires_grad=trainable)
+            self.w = nn.Parameter(torch.ones(len(self.range_num)), requires_grad=trainable)
+        else:
+            c = len(self.range_num) / self.num_sigmoids
+            self.b = nn.Parameter(torch.arange(self.jump / 2, self.massimo + self.jump / 2, c), requires_grad=trainable)
+            self.w = nn.Parameter(torch.zeros(self.num_sigmoids) + self.jump, requires_grad=trainable)
+        self.tr_parameters = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        self.length = len(self.range_num) if self.num_sigmoids == 0 else self.num_sigmoids
+        self.map_sos_cdf = {}
+        self.map_cdf_sos = {}
+        self.update_state()
+
+    def _all_b(self):
+        return self.sym_b
+
+    def _all_w(self):
+        return self.sym_w
+
+    def update_weights(self):
+        self.sym_w = torch.cat((torch.flip(self.w, [0]), self.w), 0)
+        self.sym_b = torch.cat((torch.flip(-self.b, [0]), self.b), 0)
+
+    def update_state(self, device=None):
+        device = self.w.device if device is None else device
+        key = (self.w._version, self.b._version, str(device))
+        if getattr(self, "_cum_key", None) == key and hasattr(self, "average_points"):
+            return                       # nothing changed: the reference calls this every forward
+        self._cum_key = key
+        with torch.no_grad():
+            self.update_weights()
+            self.update_cumulative_weights()
+        self.cum_w = self.cum_w.to(device)
+        self.calculate_average_points()
+        self.average_points = self.average_points.to(device)
+        self.calculate_distance_points()
+        self.distance_points = self.distance_points.to(device)
+
+    def update_cumulative_weights(self):
+        cum_w = torch.zeros(self.length + 1)
+        cum_w[1:] = torch.cumsum(self.w.detach().cpu(), dim=0)      # host-side, see NonSymStanH
+        self.cum_w = torch.cat((-torch.flip(cum_w[1:], dims=[0]), cum_w), dim=0)
+
+    def reinitialize_weights_and_bias(self):
+        if self.num_sigmoids == 0:
+            self.w = nn.Parameter(torch.ones(len(self.range_num)))
+            self.b = nn.Parameter(self.range_num.type(torch.FloatTensor))
+        else:
+            self.w = nn.Parameter(torch.zeros(self.num_sigmoids) + self.jump)
+            c = len(self.range_num) / self.num_sigmoids
+            self.b = nn.Parameter(torch.arange(self.minimo + self.jump / 2, self.massimo + self.jump / 2, c))
+
+    def define_channels_map(self):
+        levels = list(self.cum_w.detach().cpu().numpy())
+        minimum = -int(self.cum_w.shape[0]) // 2
+        mapping = list(np.arange(minimum, -minimum, 1).astype(int) + 1)
+        self.map_sos_cdf = dict(zip(levels, mapping))
+        self.map_cdf_sos = dict(zip(mapping, levels))
+
+    def define_channels_map2(self):
+        levels = list(self.cum_w.detach().cpu().numpy())
+        mapping = list(np.arange(0, len(levels), 1))
+        self.map_sos_cdf = dict(zip(levels, mapping))
+        self.map_cdf_sos = dict(zip(mapping, levels))
+
+    @property
+    def symbol_offset(self) -> int:
+        return -(2 * self.length // 2)
+
+
+def compute_gap(stanh: _StanHBase, inputs: Tensor, beta=None) -> Tensor:
+    """tcm_stanh.py:465-478 in one pass over y: |MSE(y, stanh_beta(y)) - MSE(y, stanh_hard(y))|
+    (drives the beta annealing, src/training/step.py:46-54).  Returns a 0-d float32 GPU tensor."""
+    sums = stanh.gap_sums(inputs, beta)
+    n = max(inputs.numel(), 1)
+    return torch.abs(sums[0] / n - sums[1] / n).to(torch.float32)
+
+
+# ----------------------------------------------------------------------------- entropy model
+class HypeEntropyModelSoS(EntropyModel):
+    """adaptive_gaussian_conditional.py:17-300: EntropyModel whose quantizer is ``self.stanh``."""
+
+    def __init__(self, removing_mean=True, likelihood_bound: float = 1e-9, entropy_coder: Optional[str] = None,
+                 entropy_coder_precision: int = 16):
+        super().__init__(likelihood_bound=likelihood_bound, entropy_coder=entropy_coder,
+                         entropy_coder_precision=entropy_coder_precision)
+        self.removing_mean = removing_mean
+
+    def define_permutation(self, x):
+        perm = np.arange(len(x.shape))
+        perm[0], perm[1] = perm[1], perm[0]
+        inv_perm = np.arange(len(x.shape))[np.argsort(perm)]
+        return perm, inv_perm
+
+    def _stanh_fused(self, inputs: Tensor, scales: Optional[Tensor], means: Optional[Tensor], training: bool,
+                     want, beta=None):
+        lib = _cabi.load()
+        ops._require_cuda("inputs", inputs)
+        _no_grad_path(inputs, scales, means, self.stanh.w, self.stanh.b)
+        want = set(want)
+        d = _cabi.StanhGcDesc()
+        keep = []
+
+        def bind(name, t):
+            t, bs, n = ops.image_major(t)
+            keep.append(t)
+            setattr(d, name, t.data_ptr())
+            setattr(d, name + "_bs", bs)
+            return n
+
+        n = bind("y", inputs)
+        if means is not None:
+            ops._require_cuda("means", means)
+            bind("mu", means.expand_as(inputs) if means.shape != inputs.shape else means)
+        if want & {"lik", "bits"}:
+            if scales is None:
+                raise ValueError("scales are required for the likelihood")
+            ops._require_cuda("scales", scales)
+            if scales.shape != inputs.shape:
+                raise ValueError("scales shape must match inputs")
+            bind("sigma", scales)
+        B = inputs.shape[0] if inputs.dim() > 0 else 1
+        d.B, d.n = B, n
+        d.training = int(training) if training in (0, 1, 2) else (1 if training else 0)
+        d.removing_mean = 1 if self.removing_mean else 0
+        d.scale_bound = float(getattr(self, "_scale_bound", 0.11))
+        d.likelihood_bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
+        d.tables, tk = self.stanh._tables(self.stanh.beta if beta is None else beta)
+        keep.append(tk)
+        res = {}
+        for name, dtype in (("yhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32)):
+            if name in want:
+                t = torch.empty(inputs.shape, dtype=dtype, device=inputs.device)
+                setattr(d, name, t.data_ptr())
+                setattr(d, name + "_bs", t.stride(0) if (B > 1) else n)
+                res[name] = t
+        if "bits" in want:
+            bits = torch.empty(B, dtype=torch.float64, device=inputs.device)
+            ws = _cabi.workspace(inputs.device, B)
+            d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
+            keep.append(ws)
+            res["bits"] = bits
+        with torch.cuda.device(inputs.device):
+            code = lib.reslic_stanh_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
+        _cabi.check(code, "reslic_stanh_gc_fwd_f32")
+        return res
+
+    def quantize(self, inputs, mode, means=None, perms=None):
+        """modes "training" | "dequantize" | "symbols" (:95-157).  ``perms`` is accepted for API
+        compatibility; the op is elementwise so no permutation is needed."""
+        if mode == "training":
+            return self._stanh_fused(inputs, None, means, True, ("yhat",))["yhat"]
+        if mode == "dequantize":
+            return self._stanh_fused(inputs, None, means, False, ("yhat",))["yhat"]
+        assert mode == "symbols", mode
+        return self._stanh_fused(inputs, None, means, False, ("sym",))["sym"]
+
+    def dequantize(self, inputs, means=None, dtype=torch.float):
+        """Level index -> level value (+ means) (:174-193), as one gather instead of a Python loop."""
+        levels = self.stanh.cum_w.to(inputs.device)
+        idx = (inputs.long() - self.stanh.symbol_offset).clamp_(0, levels.numel() - 1)
+        outputs = levels[idx].to(dtype)
+        if means is not None:
+            outputs = outputs.type_as(means) + means
+        return outputs.type(dtype)
+
+    def compress(self, symbols, indexes):
+        """:268-300 — takes SYMBOLS (the caller quantizes first)."""
+        if len(symbols.size()) < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if symbols.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        from . import rans
+
+        return rans.encode_with_indexes_batch(symbols.int(), indexes, self._quantized_cdf,
+                                              self._cdf_length.reshape(-1), self._offset.reshape(-1))
+
+
+class GaussianConditionalStanh(HypeEntropyModelSoS):
+    """adaptive_gaussian_conditional.py:312-725."""
+
+    def __init__(self, scale_table: Optional[Union[List, Tuple]], *args: Any, scale_bound: float = 0.11,
+                 tail_mass: float = 1e-9, gaussian_configuration=None, channels: int = 128, **kwargs: Any):
+        super().__init__(removing_mean=gaussian_configuration["removing_mean"], *args, **kwargs)
+        if not isinstance(scale_table, (type(None), list, tuple)):
+            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
+        if isinstance(scale_table, (list, tuple)) and len(scale_table) < 1:
+            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
+        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
+            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        self.tail_mass = float(tail_mass)
+        if scale_bound is None and scale_table:
+            scale_bound = self.scale_table[0]
+        if scale_bound <= 0:
+            raise ValueError("Invalid parameters")
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self._scale_bound = float(scale_bound)
+        self.register_buffer("scale_table", self._prepare_scale_table(scale_table) if scale_table else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]) if scale_bound is not None else None)
+        self.channels = int(channels)
+        self.M = int(channels)
+        self.num_sigmoids = int(gaussian_configuration["num_sigmoids"])
+        self.extrema = gaussian_configuration["extrema"]
+        self.symmetry = gaussian_configuration["symmetry"]
+        cls = SymStanH if self.symmetry else NonSymStanH
+        self.stanh = cls(gaussian_configuration["beta"], self.num_sigmoids, extrema=self.extrema,
+                         trainable=gaussian_configuration["trainable"])
+
+    @staticmethod
+    def _prepare_scale_table(scale_table):
+        return torch.Tensor(tuple(float(s) for s in scale_table))
+
+    def _standardized_cumulative(self, inputs):
+        half = float(0.5)
+        const = float(-(2 ** -0.5))
+        return half * torch.erfc(const * inputs)
+
+    @staticmethod
+    def _standardized_quantile(quantile):
+        return scipy.stats.norm.ppf(quantile)
+
+    def update_scale_table(self, scale_table):
+        device = self.scale_table.device
+        self.scale_table = self._prepare_scale_table(scale_table).to(device)
+        self.update(device)
+        return True
+
+    def define_v0_and_v1(self, inputs, average_points, distance_points):
+        """Setup-time (update()) restatement of :495-537: half-widths of each value's level cell."""
+        shape = inputs.shape
+        v = inputs.reshape(-1)
+        avg = average_points.to(v.device)
+        dist = distance_points.to(v.device)
+        j = torch.searchsorted(avg.contiguous(), v.contiguous(), right=False)      # #{k : avg_k < v}
+        inside = (v > -1000) & (v <= 1000)
+        zero = torch.zeros(1, device=v.device, dtype=dist.dtype)
+        left = torch.cat((zero, dist))
+        right = torch.cat((dist, zero))
+        v0 = torch.where(inside, left[j], torch.zeros_like(v)).reshape(shape)
+        v1 = torch.where(inside, right[j], torch.zeros_like(v)).reshape(shape)
+        return v0, v1
+
+    def update(self, device=None):
+        """CDF tables over the STanH levels (:397-454); setup code, once per model."""
+        device = self.scale_table.device if device is None else device
+        self.stanh.update_state(device)
+        max_length = self.stanh.cum_w.shape[0]
+        pmf_length = (torch.zeros(self.scale_table.shape[0]).int().to(device) + max_length)
+        self.stanh.define_channels_map()
+        samples = self.stanh.cum_w.repeat(self.scale_table.shape[0], 1).to(device).float()
+        # symbol - offset indexes the CDF row: level indexes start at stanh.symbol_offset
+        # (the reference stores -cum_w[0] here, which only matches for integer-spaced levels)
+        self._offset = torch.full((self.scale_table.shape[0],), self.stanh.symbol_offset, dtype=torch.int32,
+                                  device=device)
+        low, up = self.define_v0_and_v1(samples, self.stanh.average_points, self.stanh.distance_points)
+        samples_scale = self.scale_table.unsqueeze(1).float()
+        upper_pos = self._standardized_cumulative((low - samples) / samples_scale) * (samples >= 0)
+        upper_neg = self._standardized_cumulative((samples + up) / samples_scale) * (samples < 0)
+        lower_pos = self._standardized_cumulative((-up - samples) / samples_scale) * (samples >= 0)
+        lower_neg = self._standardized_cumulative((samples - low) / samples_scale) * (samples < 0)
+        upper = upper_pos + upper_neg
+        lower = lower_pos + lower_neg
+        pmf = upper - lower
+        self.pmf = pmf
+        self.cdf = self.pmf_to_cdf()
+        tail_mass = 2 * lower[:, :1]
+        self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._cdf_length = (pmf_length + 2).int()
+
+    def pmf_to_cdf(self):
+        cdf = self.pmf.cumsum(dim=-1)
+        zeros = torch.zeros(self.pmf.shape[:-1] + (1,), dtype=self.pmf.dtype, device=self.pmf.device)
+        return torch.cat([zeros, cdf], dim=-1).clamp(max=1.0)
+
+    # ---- per-element path: fused kernel -------------------------------------------------
+    def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None):
+        """Unbounded variable-bin likelihood of already-quantised ``inputs`` (:541-580): the fused
+        pass with the quantizer switched off (y_hat = inputs)."""
+        saved = self.use_likelihood_bound
+        self.use_likelihood_bound = False
+        try:
+            return self._stanh_fused(inputs, scales, means, 2, ("lik",))["lik"]
+        finally:
+            self.use_likelihood_bound = saved
+
+    def forward(self, values, scales, training=True, means=None):
+        """:588-603 — note the reference's argument order and default ``training=True``."""
+        if training is None:
+            training = self.training
+        r = self._stanh_fused(values, scales, means, bool(training), ("yhat", "lik"))
+        return r["yhat"], r["lik"]
+
+    def forward_fused(self, values, scales, training=True, means=None, want=("yhat", "lik", "bits")):
+        return self._stanh_fused(values, scales, means, bool(training), want)
+
+    def build_indexes(self, scales: Tensor):
+        if self.scale_table.numel() == 0:
+            raise ValueError("Uninitialized scale_table. Run update_scale_table() first")
+        return ops.build_indexes(scales, self.scale_table, self._scale_bound)
+
+    def permutation_function(self, x):
+        return self.define_permutation(x)
+
+    def compress(self, x, indexes, perms=None, means=None):
+        x = self.quantize(x, "symbols", means=means, perms=perms)
+        return super().compress(x, indexes)
+
+    def decompress(self, strings, indexes, means=None, flag=1):
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if len(indexes.size()) < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        if means is not None:
+            if means.size()[:2] != indexes.size()[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size():
+                for i in range(2, len(indexes.size())):
+                    if means.size(i) != 1:
+                        raise ValueError("Invalid means parameters")
+        from . import rans
+
+        symbols = rans.decode_with_indexes_batch(strings, indexes, self._quantized_cdf,
+                                                 self._cdf_length.reshape(-1), self._offset.reshape(-1))
+        return self.dequantize(symbols, means=means)
