@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 3
+#define RESLIC_ABI_VERSION 4
 
 enum {
   RESLIC_OK = 0,
@@ -105,6 +105,36 @@ typedef struct reslic_gc_desc {
 } reslic_gc_desc;
 
 int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream);
+
+/* ----------------------------------------------------------------------------------
+ * Gaussian conditional, backward of reslic_gc_fwd_f32 — what autograd does
+ * through compressai GaussianConditional.forward + ste_round in the reference's training step
+ * (src/training/step.py:38-43): erfc/abs/divide chain, both LowerBound gradient rules
+ * (pass where x >= bound or grad < 0, App. A.4), identity through the additive noise,
+ * zero through round(), identity through ste_round.
+ * Inputs are the forward's inputs (the noise is regenerated from the same seed/offset or re-read)
+ * plus the upstream gradients (each nullable = zero).  Outputs nullable.
+ *   mode NOISE      : g_y = g_yhat + g_ste + gv,  g_mu = -gv,          g_sigma = gs*pass
+ *   mode DEQUANTIZE : g_y = g_ste,                g_mu = g_yhat,       g_sigma = gs*pass
+ *   with gv = gL*pass_L * dL/dv * sign(yhat - mu), gs = gL*pass_L * dL/ds. */
+typedef struct reslic_gc_bwd_desc {
+  const float* y;       int64_t y_bs;
+  const float* mu;      int64_t mu_bs;     /* NULL = no means                              */
+  const float* sigma;   int64_t sigma_bs;
+  const float* noise;   int64_t noise_bs;  /* NULL = Philox(seed, offset) as in the forward */
+  int64_t B, n;
+  int32_t mode;
+  float scale_bound, likelihood_bound;
+  const float* g_yhat;  int64_t g_yhat_bs; /* d loss / d (quantize output)                  */
+  const float* g_ste;   int64_t g_ste_bs;  /* d loss / d (ste_round output)                 */
+  const float* g_lik;   int64_t g_lik_bs;  /* d loss / d (bounded likelihood)               */
+  float* g_y;     int64_t g_y_bs;
+  float* g_mu;    int64_t g_mu_bs;
+  float* g_sigma; int64_t g_sigma_bs;
+  uint64_t philox_seed, philox_offset;
+} reslic_gc_bwd_desc;
+
+int reslic_gc_bwd_f32(const reslic_gc_bwd_desc* d, void* stream);
 
 /* build_indexes alone (adaptive_gaussian_conditional.py:606-617): flat, n elements. */
 int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound,

@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -42,6 +42,26 @@ class GcDesc(C.Structure):
         ("idx", C.c_void_p), ("idx_bs", C.c_int64),
         ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+    ]
+
+
+class GcBwdDesc(C.Structure):
+    """struct reslic_gc_bwd_desc."""
+
+    _fields_ = [
+        ("y", C.c_void_p), ("y_bs", C.c_int64),
+        ("mu", C.c_void_p), ("mu_bs", C.c_int64),
+        ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
+        ("noise", C.c_void_p), ("noise_bs", C.c_int64),
+        ("B", C.c_int64), ("n", C.c_int64),
+        ("mode", C.c_int32), ("scale_bound", C.c_float), ("likelihood_bound", C.c_float),
+        ("g_yhat", C.c_void_p), ("g_yhat_bs", C.c_int64),
+        ("g_ste", C.c_void_p), ("g_ste_bs", C.c_int64),
+        ("g_lik", C.c_void_p), ("g_lik_bs", C.c_int64),
+        ("g_y", C.c_void_p), ("g_y_bs", C.c_int64),
+        ("g_mu", C.c_void_p), ("g_mu_bs", C.c_int64),
+        ("g_sigma", C.c_void_p), ("g_sigma_bs", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
     ]
 
@@ -103,6 +123,7 @@ EXPORTS = {
     "reslic_get_math_mode": (C.c_int, []),
     "reslic_workspace_bytes": (C.c_int64, [C.c_int64]),
     "reslic_gc_fwd_f32": (C.c_int, [C.POINTER(GcDesc), C.c_void_p]),
+    "reslic_gc_bwd_f32": (C.c_int, [C.POINTER(GcBwdDesc), C.c_void_p]),
     "reslic_build_indexes_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_void_p]),
     "reslic_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

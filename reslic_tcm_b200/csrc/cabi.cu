@@ -86,6 +86,10 @@ int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream) {
   return reslic::gc_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }
 
+int reslic_gc_bwd_f32(const reslic_gc_bwd_desc* d, void* stream) {
+  return reslic::gc_bwd_launch(d, static_cast<cudaStream_t>(stream));
+}
+
 int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound, const float* scale_table,
                              int32_t table_len, int32_t* idx, void* stream) {
   reslic_gc_desc d;

@@ -1,0 +1,118 @@
+// gc_bwd.cu — backward of the fused Gaussian-conditional forward (sm_100a).
+//
+// One elementwise pass: re-derives v, s, a, b from the forward's inputs (the noise is re-read or
+// regenerated from the same Philox counter) and applies the chain rule autograd applies to the
+// reference's op sequence (compressai GaussianConditional.forward + LowerBound + ste_round;
+// call sites src/models/reference/tcm.py:455-457, driven by src/training/step.py:38-43):
+//   dL/dv = (phi(b) - phi(a)) / s        dL/ds = (b*phi(b) - a*phi(a)) / s,   phi = N(0,1) pdf
+// HBM-bound: up to 28 B read + 12 B written per element.
+#include "common.cuh"
+#include "gc_math.cuh"
+#include "reslic_internal.h"
+
+namespace reslic {
+
+struct GcBwdParams {
+  const float* y; const float* mu; const float* sigma; const float* noise;
+  const float* g_yhat; const float* g_ste; const float* g_lik;
+  float* g_y; float* g_mu; float* g_sigma;
+  int64_t y_bs, mu_bs, sigma_bs, noise_bs, g_yhat_bs, g_ste_bs, g_lik_bs, g_y_bs, g_mu_bs, g_sigma_bs;
+  int64_t n, B, tiles_per_image;
+  int noise_mode;
+  float scale_bound, lik_bound;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi;
+};
+
+__device__ __forceinline__ void gc_bwd_elem(const GcBwdParams& p, float y, float mu, float sg, float u, float gyh,
+                                            float gst, float gl, float& gy, float& gmu, float& gsg) {
+  const float d = y - mu;
+  const float yhat = p.noise_mode ? y + u : rintf(d) + mu;
+  const float values = yhat - mu;
+  const float v = fabsf(values);
+  const float s = max_nan(sg, p.scale_bound);
+  float gv = 0.0f, gs = 0.0f;
+  if (p.g_lik) {
+    const float L = gauss_interval_mass<true>(0.5f - min_nan(v, 1e30f), -0.5f - min_nan(v, 1e30f), s);
+    // LowerBound backward (App. A.4): pass where x >= bound or the gradient pushes x up
+    const bool pass_l = !(p.lik_bound > 0.0f) || (L >= p.lik_bound) || (gl < 0.0f);
+    const float g = pass_l ? gl : 0.0f;
+    const float rs = 1.0f / s;
+    const float a = (0.5f - v) * rs, b = (-0.5f - v) * rs;
+    const float k = 0.3989422804014327f;                      // 1/sqrt(2 pi)
+    const float pa = k * expf(-0.5f * a * a), pb = k * expf(-0.5f * b * b);
+    const float dLdv = (pb - pa) * rs;
+    const float dLds = (b * pb - a * pa) * rs;
+    const float sgn = (values > 0.0f) ? 1.0f : ((values < 0.0f) ? -1.0f : 0.0f);   // torch.abs backward
+    gv = g * dLdv * sgn;
+    gs = g * dLds;
+    const bool pass_s = (sg >= p.scale_bound) || (gs < 0.0f);
+    gs = pass_s ? gs : 0.0f;
+  }
+  if (p.noise_mode) { gy = gyh + gst + gv; gmu = -gv; }
+  else { gy = gst; gmu = gyh; }            // round() has zero gradient; "+= means" passes g_yhat to mu
+  gsg = gs;
+}
+
+__global__ void __launch_bounds__(kThreads) gc_bwd_kernel(const GcBwdParams p) {
+  const int64_t total = p.tiles_per_image * p.B;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int image = static_cast<int>(t / p.tiles_per_image);
+    const int64_t e = (t - image * p.tiles_per_image) * kThreads + threadIdx.x;
+    if (e >= p.n) continue;
+    const float y = ld_stream1(p.y + image * p.y_bs + e);
+    const float mu = p.mu ? ld_stream1(p.mu + image * p.mu_bs + e) : 0.0f;
+    const float sg = p.sigma ? ld_stream1(p.sigma + image * p.sigma_bs + e) : 1.0f;
+    float u = 0.0f;
+    if (p.noise_mode) {
+      if (p.noise) u = ld_stream1(p.noise + image * p.noise_bs + e);
+      else {
+        const uint64_t gid = static_cast<uint64_t>(image) * static_cast<uint64_t>((p.n + 3) >> 2) +
+                             (static_cast<uint64_t>(e) >> 2);
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                        p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+        const int k = static_cast<int>(e & 3);
+        u = u32_to_centered_uniform(k == 0 ? r.x : k == 1 ? r.y : k == 2 ? r.z : r.w);
+      }
+    }
+    const float gyh = p.g_yhat ? ld_stream1(p.g_yhat + image * p.g_yhat_bs + e) : 0.0f;
+    const float gst = p.g_ste ? ld_stream1(p.g_ste + image * p.g_ste_bs + e) : 0.0f;
+    const float gl = p.g_lik ? ld_stream1(p.g_lik + image * p.g_lik_bs + e) : 0.0f;
+    float gy, gmu, gsg;
+    gc_bwd_elem(p, y, mu, sg, u, gyh, gst, gl, gy, gmu, gsg);
+    if (p.g_y) st_stream1(p.g_y + image * p.g_y_bs + e, gy);
+    if (p.g_mu) st_stream1(p.g_mu + image * p.g_mu_bs + e, gmu);
+    if (p.g_sigma) st_stream1(p.g_sigma + image * p.g_sigma_bs + e, gsg);
+  }
+}
+
+int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st) {
+  if (!d) return set_error(RESLIC_ERR_ARG, "gc_bwd: null descriptor");
+  if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "gc_bwd: negative size");
+  if (d->B == 0 || d->n == 0) return RESLIC_OK;
+  if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE)
+    return set_error(RESLIC_ERR_ARG, "gc_bwd: invalid quantization mode");
+  if (!d->y) return set_error(RESLIC_ERR_ARG, "gc_bwd: y is null");
+  if (d->g_lik && !d->sigma) return set_error(RESLIC_ERR_ARG, "gc_bwd: sigma is null");
+  if (!d->g_y && !d->g_mu && !d->g_sigma) return set_error(RESLIC_ERR_ARG, "gc_bwd: no output requested");
+  if (!(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "gc_bwd: scale_bound must be > 0");
+  if (d->n >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "gc_bwd: more than 2^31 elements per image");
+  GcBwdParams p{};
+  p.y = d->y; p.mu = d->mu; p.sigma = d->sigma; p.noise = d->noise;
+  p.g_yhat = d->g_yhat; p.g_ste = d->g_ste; p.g_lik = d->g_lik; p.g_y = d->g_y; p.g_mu = d->g_mu; p.g_sigma = d->g_sigma;
+  p.y_bs = d->y_bs; p.mu_bs = d->mu_bs; p.sigma_bs = d->sigma_bs; p.noise_bs = d->noise_bs;
+  p.g_yhat_bs = d->g_yhat_bs; p.g_ste_bs = d->g_ste_bs; p.g_lik_bs = d->g_lik_bs;
+  p.g_y_bs = d->g_y_bs; p.g_mu_bs = d->g_mu_bs; p.g_sigma_bs = d->g_sigma_bs;
+  p.n = d->n; p.B = d->B; p.tiles_per_image = (d->n + kThreads - 1) / kThreads;
+  p.noise_mode = d->mode == RESLIC_Q_NOISE; p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
+  p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
+  p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
+  int64_t grid = p.tiles_per_image * p.B;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+  if (grid > cap) grid = cap;
+  gc_bwd_kernel<<<static_cast<int>(grid), kThreads, 0, st>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "gc_bwd launch");
+  return RESLIC_OK;
+}
+
+}  // namespace reslic

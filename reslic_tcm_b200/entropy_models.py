@@ -77,6 +77,30 @@ def _no_grad_path(*tensors):
         )
 
 
+class _GaussianConditionalFn(torch.autograd.Function):
+    """Autograd node around the fused forward / backward kernels (one launch each)."""
+
+    @staticmethod
+    def forward(ctx, inputs, scales, means, noise, training, scale_bound, lik_bound, seed, offset):
+        r = ops.gc_forward(inputs, scales, means, training=training, noise=noise, scale_bound=scale_bound,
+                           likelihood_bound=lik_bound, want=("yhat", "lik", "ste"), seed=seed, offset=offset)
+        ctx.save_for_backward(inputs, scales, means, noise)
+        ctx.cfg = (bool(training), float(scale_bound), float(lik_bound), int(seed), int(offset))
+        ctx.set_materialize_grads(False)
+        return r.yhat, r.lik, r.ste
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik, g_ste):
+        inputs, scales, means, noise = ctx.saved_tensors
+        training, scale_bound, lik_bound, seed, offset = ctx.cfg
+        need = (ctx.needs_input_grad[0], means is not None and ctx.needs_input_grad[2], ctx.needs_input_grad[1])
+        c = lambda t: None if t is None else t.contiguous()
+        g_y, g_mu, g_sigma = ops.gc_backward(inputs, scales, means, training=training, noise=noise,
+                                             scale_bound=scale_bound, likelihood_bound=lik_bound, g_yhat=c(g_yhat),
+                                             g_ste=c(g_ste), g_lik=c(g_lik), need=need, seed=seed, offset=offset)
+        return g_y, g_sigma, g_mu, None, None, None, None, None, None
+
+
 class EntropyModel(nn.Module):
     """Base class: CDF buffers + quantize/dequantize (reference copy of the upstream
     class: src/entropy_models/adaptive_gaussian_conditional.py:17-61)."""
@@ -174,10 +198,8 @@ class EntropyModel(nn.Module):
         self._check_cdf_size()
         self._check_cdf_length()
         self._check_offsets_size()
-        from . import rans
-
-        return rans.encode_with_indexes_batch(symbols, indexes, self._quantized_cdf, self._cdf_length,
-                                              self._offset)
+        return _rans().encode_with_indexes_batch(symbols, indexes, self._quantized_cdf, self._cdf_length,
+                                                 self._offset)
 
     def decompress(self, strings, indexes, dtype: torch.dtype = torch.float, means: Optional[Tensor] = None):
         if not isinstance(strings, (tuple, list)):
@@ -196,11 +218,21 @@ class EntropyModel(nn.Module):
                 for i in range(2, len(indexes.size())):
                     if means.size(i) != 1:
                         raise ValueError("Invalid means parameters")
-        from . import rans
-
-        symbols = rans.decode_with_indexes_batch(strings, indexes, self._quantized_cdf, self._cdf_length,
-                                                 self._offset)
+        symbols = _rans().decode_with_indexes_batch(strings, indexes, self._quantized_cdf, self._cdf_length,
+                                                    self._offset)
         return self.dequantize(symbols, means, dtype)
+
+
+def _rans():
+    """The entropy coder is the next-row component N3: the symbols and CDF
+    indexes it consumes are produced on the GPU by this package, the coder itself is not part of
+    the path yet."""
+    try:
+        from . import rans
+    except ImportError as exc:  # pragma: no cover
+        raise ReslicError("rANS coder not built yet (SURVEY.md §8f N3): compress()/decompress() stop at the "
+                          "coder; use quantize(..., 'symbols') + build_indexes() for its inputs") from exc
+    return rans
 
 
 _philox_counter = [0]
@@ -301,8 +333,25 @@ class GaussianConditional(EntropyModel):
 
     def forward(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None,
                 training: Optional[bool] = None) -> Tuple[Tensor, Tensor]:
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (inputs, scales, means)):
+            y_hat, lik, _ = self.forward_with_ste(inputs, scales, means, training)
+            return y_hat, lik
         r = self.forward_fused(inputs, scales, means, training, want=("yhat", "lik"))
         return r.yhat, r.lik
+
+    def forward_with_ste(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None,
+                         training: Optional[bool] = None, noise: Optional[Tensor] = None
+                         ) -> Tuple[Tensor, Tensor, Tensor]:
+        """Differentiable (y_hat, likelihood, ste_round(y - mu) + mu) from one launch: the pair of
+        calls at tcm.py:455 and :457, with the fused backward kernel behind autograd."""
+        if training is None:
+            training = self.training
+        seed, offset = (0, 0)
+        if training and noise is None:
+            seed, offset = _philox_state(inputs.numel())
+        return _GaussianConditionalFn.apply(
+            inputs, scales, means, noise, bool(training), self._scale_bound,
+            self._likelihood_bound if self.use_likelihood_bound else 0.0, seed, offset)
 
     def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None) -> Tensor:
         """Unbounded likelihood of already-quantised ``inputs`` (tcm.py:570-582).  Served by
@@ -357,6 +406,16 @@ class EntropyBottleneck(EntropyModel):
     def _get_medians(self) -> Tensor:
         medians = self.quantiles[:, :, 1:2]
         return medians
+
+    def _medians_flat(self) -> Tensor:
+        """Contiguous [C] copy of the medians for the kernel, refreshed only when `quantiles`
+        changes (keeps a strided-copy kernel out of every forward / CUDA graph)."""
+        q = self.quantiles
+        key = (q._version, q.data_ptr(), q.device)
+        if getattr(self, "_med_key", None) != key:
+            self._med_flat = q.detach()[:, 0, 1].contiguous()
+            self._med_key = key
+        return self._med_flat
 
     def _params(self):
         n = len(self.filters) + 1
@@ -431,7 +490,7 @@ class EntropyBottleneck(EntropyModel):
         if training and noise is None:
             seed, offset = _philox_state(x.numel())
         return ops.eb_forward(
-            x, m, b, f, self.quantiles[:, 0, 1], training=training, noise=noise,
+            x, m, b, f, self._medians_flat(), training=training, noise=noise,
             likelihood_bound=self._likelihood_bound if self.use_likelihood_bound else 0.0,
             want=want, seed=seed, offset=offset)
 

@@ -196,6 +196,68 @@ def gc_forward(
     return res
 
 
+def gc_backward(
+    y: Tensor,
+    scales: Tensor,
+    means: Optional[Tensor],
+    *,
+    training: bool,
+    noise: Optional[Tensor] = None,
+    scale_bound: float = 0.11,
+    likelihood_bound: float = 1e-9,
+    g_yhat: Optional[Tensor] = None,
+    g_ste: Optional[Tensor] = None,
+    g_lik: Optional[Tensor] = None,
+    need: Sequence[bool] = (True, True, True),
+    seed: int = 0,
+    offset: int = 0,
+) -> Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]:
+    """Backward of gc_forward: (g_y, g_mu, g_sigma) from the upstream gradients of the quantize
+    output, the ste_round output and the bounded likelihood (each may be None = zero)."""
+    lib = _cabi.load()
+    _require_cuda("inputs", y)
+    d = _cabi.GcBwdDesc()
+    keep = []
+
+    def bind(name, t):
+        if t is None:
+            return
+        _require_cuda(name, t)
+        if t.shape != y.shape:
+            t = t.expand_as(y)
+        t, bs, _ = image_major(t)
+        keep.append(t)
+        setattr(d, name, t.data_ptr())
+        setattr(d, name + "_bs", bs)
+
+    _, _, n = image_major(y)
+    bind("y", y)
+    bind("mu", means)
+    bind("sigma", scales)
+    bind("noise", noise)
+    bind("g_yhat", g_yhat)
+    bind("g_ste", g_ste)
+    bind("g_lik", g_lik)
+    d.B, d.n = (y.shape[0] if y.dim() > 0 else 1), n
+    d.mode = _cabi.Q_NOISE if training else _cabi.Q_DEQUANTIZE
+    d.scale_bound, d.likelihood_bound = float(scale_bound), float(likelihood_bound)
+    outs = []
+    for name, want in zip(("g_y", "g_mu", "g_sigma"), need):
+        t = torch.empty_like(y, memory_format=torch.contiguous_format) if want else None
+        if t is not None:
+            setattr(d, name, t.data_ptr())
+            setattr(d, name + "_bs", n)
+        outs.append(t)
+    if not any(o is not None for o in outs):
+        return None, None, None
+    d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    with torch.cuda.device(y.device):
+        code = lib.reslic_gc_bwd_f32(C.byref(d), _cabi.current_stream_ptr(y.device))
+    _cabi.check(code, "reslic_gc_bwd_f32")
+    return tuple(outs)
+
+
 def build_indexes(scales: Tensor, scale_table: Tensor, scale_bound: float = 0.11) -> Tensor:
     """adaptive_gaussian_conditional.py:606-617 as one launch (int32, same shape)."""
     lib = _cabi.load()

@@ -80,7 +80,7 @@ class TcmEntropyPath(nn.Module):
         cs = C // n_launch
         m, bi, f = eb._params()
         if not skip_z:
-            ops.eb_forward(z, m, bi, f, eb.quantiles[:, 0, 1], training=training, noise=noise_z,
+            ops.eb_forward(z, m, bi, f, eb._medians_flat(), training=training, noise=noise_z,
                                likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"),
                                out={"ste": b["z_hat"], "lik": b["z_lik"], "bits": b["bits"],
                                     "workspace": b["workspace"]}, seed=seed, offset=offset)   # bits[b]  = z bits

@@ -391,9 +391,9 @@ class HypeEntropyModelSoS(EntropyModel):
             raise ValueError("`inputs` and `indexes` should have the same size.")
         self._check_cdf_size()
         self._check_cdf_length()
-        from . import rans
+        from .entropy_models import _rans
 
-        return rans.encode_with_indexes_batch(symbols.int(), indexes, self._quantized_cdf,
+        return _rans().encode_with_indexes_batch(symbols.int(), indexes, self._quantized_cdf,
                                               self._cdf_length.reshape(-1), self._offset.reshape(-1))
 
 
@@ -540,8 +540,8 @@ class GaussianConditionalStanh(HypeEntropyModelSoS):
                 for i in range(2, len(indexes.size())):
                     if means.size(i) != 1:
                         raise ValueError("Invalid means parameters")
-        from . import rans
+        from .entropy_models import _rans
 
-        symbols = rans.decode_with_indexes_batch(strings, indexes, self._quantized_cdf,
+        symbols = _rans().decode_with_indexes_batch(strings, indexes, self._quantized_cdf,
                                                  self._cdf_length.reshape(-1), self._offset.reshape(-1))
         return self.dequantize(symbols, means=means)
