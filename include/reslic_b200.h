@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 4
+#define RESLIC_ABI_VERSION 5
 
 enum {
   RESLIC_OK = 0,
@@ -175,6 +175,29 @@ typedef struct reslic_eb_desc {
 } reslic_eb_desc;
 
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream);
+
+/* Backward of reslic_eb_fwd_f32: gradients of the bounded likelihood (and of the
+ * quantize output) w.r.t. z and w.r.t. every bottleneck parameter — what autograd does through
+ * _logits_cumulative x2 + the sign trick + LowerBound (adaptive_entropy_bottleneck.py:525-543,
+ * 658-666) in the reference's training step.  Parameter gradients are per-channel reductions over
+ * all B*hw elements of the channel; they are OVERWRITTEN (raw-parameter space: softplus' / tanh'
+ * already applied).  g_medians is non-zero only in DEQUANTIZE mode (z_hat = round(z-med)+med). */
+typedef struct reslic_eb_bwd_desc {
+  const float* z;      int64_t z_bs;
+  const float* noise;  int64_t noise_bs;   /* NULL = Philox(seed, offset) as in the forward   */
+  int64_t B, C, hw;
+  int32_t mode;
+  float likelihood_bound;
+  const float* matrix[5]; const float* bias[5]; const float* factor[4]; const float* medians;
+  const float* g_zhat; int64_t g_zhat_bs;  /* d loss / d (quantize output), nullable          */
+  const float* g_lik;  int64_t g_lik_bs;   /* d loss / d (bounded likelihood), nullable       */
+  float* g_z;  int64_t g_z_bs;             /* nullable                                        */
+  float* g_matrix[5]; float* g_bias[5]; float* g_factor[4];   /* same shapes as the parameters, nullable as a set */
+  float* g_medians;                        /* [C], nullable                                   */
+  uint64_t philox_seed, philox_offset;
+} reslic_eb_bwd_desc;
+
+int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream);
 
 /* ----------------------------------------------------------------------------------
  * STanH ("sum of tanh") quantizer family.

@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -86,6 +86,25 @@ class EbDesc(C.Structure):
     ]
 
 
+class EbBwdDesc(C.Structure):
+    """struct reslic_eb_bwd_desc."""
+
+    _fields_ = [
+        ("z", C.c_void_p), ("z_bs", C.c_int64),
+        ("noise", C.c_void_p), ("noise_bs", C.c_int64),
+        ("B", C.c_int64), ("C", C.c_int64), ("hw", C.c_int64),
+        ("mode", C.c_int32), ("likelihood_bound", C.c_float),
+        ("matrix", C.c_void_p * 5), ("bias", C.c_void_p * 5), ("factor", C.c_void_p * 4),
+        ("medians", C.c_void_p),
+        ("g_zhat", C.c_void_p), ("g_zhat_bs", C.c_int64),
+        ("g_lik", C.c_void_p), ("g_lik_bs", C.c_int64),
+        ("g_z", C.c_void_p), ("g_z_bs", C.c_int64),
+        ("g_matrix", C.c_void_p * 5), ("g_bias", C.c_void_p * 5), ("g_factor", C.c_void_p * 4),
+        ("g_medians", C.c_void_p),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+    ]
+
+
 class StanhTables(C.Structure):
     """struct reslic_stanh_tables."""
 
@@ -127,6 +146,7 @@ EXPORTS = {
     "reslic_build_indexes_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_void_p]),
     "reslic_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "reslic_eb_bwd_f32": (C.c_int, [C.POINTER(EbBwdDesc), C.c_void_p]),
     "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
     "reslic_stanh_gc_fwd_f32": (C.c_int, [C.POINTER(StanhGcDesc), C.c_void_p]),
     "reslic_stanh_gap_workspace_bytes": (C.c_int64, []),

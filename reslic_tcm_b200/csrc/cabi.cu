@@ -115,6 +115,10 @@ int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t
                                   static_cast<cudaStream_t>(stream));
 }
 
+int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream) {
+  return reslic::eb_bwd_launch(d, static_cast<cudaStream_t>(stream));
+}
+
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
   return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }

@@ -15,6 +15,7 @@ int math_mode();                                          // RESLIC_MATH_*      
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);
 int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st);
+int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st);
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st);
 int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st);
 int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft, float* out_hard,

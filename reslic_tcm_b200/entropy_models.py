@@ -101,6 +101,38 @@ class _GaussianConditionalFn(torch.autograd.Function):
         return g_y, g_sigma, g_mu, None, None, None, None, None, None
 
 
+class _EntropyBottleneckFn(torch.autograd.Function):
+    """Autograd node around the fused bottleneck forward / backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, noise, training, lik_bound, seed, offset, quantiles, *params):
+        m, b, f = params[:5], params[5:10], params[10:14]
+        med = quantiles.detach()[:, 0, 1].contiguous()
+        r = ops.eb_forward(x, m, b, f, med, training=training, noise=noise, likelihood_bound=lik_bound,
+                           want=("zhat", "lik"), seed=seed, offset=offset)
+        ctx.save_for_backward(x, noise, quantiles, *params)
+        ctx.cfg = (bool(training), float(lik_bound), int(seed), int(offset))
+        ctx.set_materialize_grads(False)
+        return r.zhat, r.lik
+
+    @staticmethod
+    def backward(ctx, g_zhat, g_lik):
+        x, noise, quantiles, *params = ctx.saved_tensors
+        training, lik_bound, seed, offset = ctx.cfg
+        m, b, f = params[:5], params[5:10], params[10:14]
+        c = lambda t: None if t is None else t.contiguous()
+        g_z, gm, gb, gf, g_med = ops.eb_backward(
+            x, m, b, f, quantiles.detach()[:, 0, 1], training=training, noise=noise, likelihood_bound=lik_bound,
+            g_zhat=c(g_zhat), g_lik=c(g_lik), need_z=ctx.needs_input_grad[0],
+            need_params=any(ctx.needs_input_grad[7:]), seed=seed, offset=offset)
+        g_q = None
+        if ctx.needs_input_grad[6]:
+            g_q = torch.zeros_like(quantiles)
+            g_q[:, 0, 1] = g_med
+        gp = (list(gm) + list(gb) + list(gf)) if gm else [None] * 14
+        return (g_z, None, None, None, None, None, g_q, *gp)
+
+
 class EntropyModel(nn.Module):
     """Base class: CDF buffers + quantize/dequantize (reference copy of the upstream
     class: src/entropy_models/adaptive_gaussian_conditional.py:17-61)."""
@@ -494,8 +526,21 @@ class EntropyBottleneck(EntropyModel):
             likelihood_bound=self._likelihood_bound if self.use_likelihood_bound else 0.0,
             want=want, seed=seed, offset=offset)
 
-    def forward(self, x: Tensor, training: Optional[bool] = None) -> Tuple[Tensor, Tensor]:
-        r = self.forward_fused(x, training, want=("zhat", "lik"))
+    def forward(self, x: Tensor, training: Optional[bool] = None, noise: Optional[Tensor] = None
+                ) -> Tuple[Tensor, Tensor]:
+        if training is None:
+            training = self.training
+        m, b, f = self._params()
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, self.quantiles, *m, *b, *f)):
+            if self.filters != (3, 3, 3, 3):
+                raise ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
+            seed, offset = (0, 0)
+            if training and noise is None:
+                seed, offset = _philox_state(x.numel())
+            return _EntropyBottleneckFn.apply(
+                x, noise, bool(training), self._likelihood_bound if self.use_likelihood_bound else 0.0, seed, offset,
+                self.quantiles, *m, *b, *f)
+        r = self.forward_fused(x, training, want=("zhat", "lik"), noise=noise)
         return r.zhat, r.lik
 
     @staticmethod

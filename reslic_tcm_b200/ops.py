@@ -387,3 +387,72 @@ def eb_forward(
         code = lib.reslic_eb_fwd_f32(C.byref(d), _cabi.current_stream_ptr(z.device))
     _cabi.check(code, "reslic_eb_fwd_f32")
     return res
+
+
+def eb_backward(
+    z: Tensor,
+    matrices: Sequence[Tensor],
+    biases: Sequence[Tensor],
+    factors: Sequence[Tensor],
+    medians: Tensor,
+    *,
+    training: bool,
+    noise: Optional[Tensor] = None,
+    likelihood_bound: float = 1e-9,
+    g_zhat: Optional[Tensor] = None,
+    g_lik: Optional[Tensor] = None,
+    need_z: bool = True,
+    need_params: bool = True,
+    seed: int = 0,
+    offset: int = 0,
+):
+    """Backward of eb_forward: (g_z, [g_matrix]*5, [g_bias]*5, [g_factor]*4, g_medians)."""
+    lib = _cabi.load()
+    _require_cuda("z", z)
+    B, Cc = z.shape[0], z.shape[1]
+    hw = 1
+    for s_ in z.shape[2:]:
+        hw *= s_
+    zc = z.contiguous()
+    d = _cabi.EbBwdDesc()
+    keep = [zc]
+    d.z, d.z_bs = zc.data_ptr(), Cc * hw
+    for name, t in (("noise", noise), ("g_zhat", g_zhat), ("g_lik", g_lik)):
+        if t is not None:
+            _require_cuda(name, t)
+            tc = t.contiguous()
+            keep.append(tc)
+            setattr(d, name, tc.data_ptr())
+            setattr(d, name + "_bs", Cc * hw)
+    d.B, d.C, d.hw = B, Cc, hw
+    d.mode = _cabi.Q_NOISE if training else _cabi.Q_DEQUANTIZE
+    d.likelihood_bound = float(likelihood_bound)
+    gm, gb, gf = [], [], []
+    for i in range(5):
+        m, b = matrices[i].detach().contiguous(), biases[i].detach().contiguous()
+        keep += [m, b]
+        d.matrix[i], d.bias[i] = m.data_ptr(), b.data_ptr()
+        if need_params:
+            gm.append(torch.empty_like(m)); gb.append(torch.empty_like(b))
+            d.g_matrix[i], d.g_bias[i] = gm[-1].data_ptr(), gb[-1].data_ptr()
+    for i in range(4):
+        f = factors[i].detach().contiguous()
+        keep.append(f)
+        d.factor[i] = f.data_ptr()
+        if need_params:
+            gf.append(torch.empty_like(f))
+            d.g_factor[i] = gf[-1].data_ptr()
+    med = medians.detach().reshape(-1).contiguous()
+    keep.append(med)
+    d.medians = med.data_ptr()
+    g_med = torch.zeros(Cc, dtype=torch.float32, device=z.device)
+    d.g_medians = g_med.data_ptr()
+    g_z = torch.empty_like(zc) if need_z else None
+    if g_z is not None:
+        d.g_z, d.g_z_bs = g_z.data_ptr(), Cc * hw
+    d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    with torch.cuda.device(z.device):
+        code = lib.reslic_eb_bwd_f32(C.byref(d), _cabi.current_stream_ptr(z.device))
+    _cabi.check(code, "reslic_eb_bwd_f32")
+    return g_z, gm, gb, gf, g_med

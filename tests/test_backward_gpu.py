@@ -72,3 +72,55 @@ def test_module_forward_is_differentiable_and_philox_backward_is_consistent():
     (-(torch.log2(lik2)).sum() + (yh2 ** 2).sum()).backward()
     for a, b in ((y.grad, y2.grad), (s.grad, s2.grad), (m.grad, m2.grad)):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_eb_backward_matches_autograd(training):
+    from reslic_tcm_b200 import EntropyBottleneck, synthetic
+
+    C, shape = 6, (3, 6, 5, 4)
+    params = synthetic.eb_parameters(C, trained_like=True, seed=99)
+    g = torch.Generator().manual_seed(5)
+    z = 2.5 * torch.randn(shape, generator=g)
+    z.view(-1)[:3] = torch.tensor([60.0, -60.0, 0.0])          # likelihood floor on the first two
+    noise = torch.empty(shape).uniform_(-0.5, 0.5, generator=g)
+    wz, wl = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+
+    # reference: the oracle's op sequence under torch autograd, with the LowerBound gradient rule
+    ref = cr.EntropyBottleneckRef(C)
+    ref.matrices = [params[f"_matrix{i}"].clone().requires_grad_(True) for i in range(5)]
+    ref.biases = [params[f"_bias{i}"].clone().requires_grad_(True) for i in range(5)]
+    ref.factors = [params[f"_factor{i}"].clone().requires_grad_(True) for i in range(4)]
+    ref.quantiles = params["quantiles"].clone().requires_grad_(True)
+    zr = z.clone().requires_grad_(True)
+    xp = zr.permute(1, 0, 2, 3).reshape(C, 1, -1)
+    if training:
+        outputs = xp + noise.permute(1, 0, 2, 3).reshape(C, 1, -1)
+    else:
+        med = ref._get_medians()
+        outputs = torch.round(xp - med) + med
+    lik = RefLowerBound(1e-9)(ref._likelihood(outputs))
+    back = lambda t: t.reshape(C, shape[0], shape[2], shape[3]).permute(1, 0, 2, 3)
+    loss = (back(outputs) * wz).sum() + (torch.log(back(lik)) * wl).sum()
+    loss.backward()
+
+    mod = EntropyBottleneck(C).to(DEV).train(training)
+    synthetic.load_eb_parameters(mod, params)
+    zd = z.clone().to(DEV).requires_grad_(True)
+    zh, lk = mod(zd, training=training, noise=noise.to(DEV) if training else None)
+    ((zh * wz.to(DEV)).sum() + (torch.log(lk) * wl.to(DEV)).sum()).backward()
+
+    def check(name, a, r):
+        a, r = a.detach().cpu(), (torch.zeros_like(a.cpu()) if r is None else r)
+        scale = max(r.abs().max().item(), 1e-3)
+        err = (a - r).abs().max().item()
+        assert err <= 3e-4 * scale, f"{name}: max err {err:.3g} vs scale {scale:.3g}"
+
+    check("d/dz", zd.grad, zr.grad)
+    for i in range(5):
+        check(f"d/d_matrix{i}", getattr(mod, f"_matrix{i}").grad, ref.matrices[i].grad)
+        check(f"d/d_bias{i}", getattr(mod, f"_bias{i}").grad, ref.biases[i].grad)
+        if i < 4:
+            check(f"d/d_factor{i}", getattr(mod, f"_factor{i}").grad, ref.factors[i].grad)
+    if not training:
+        check("d/dquantiles", mod.quantiles.grad, ref.quantiles.grad)
