@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 5
+#define RESLIC_ABI_VERSION 6
 
 enum {
   RESLIC_OK = 0,
@@ -263,6 +263,28 @@ int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t
  * (src/entropy_models/coder.py:53-56; adaptive_gaussian_conditional.py:197-205).
  * HOST pointers. */
 int reslic_pmf_to_quantized_cdf(const float* pmf, int32_t n, int32_t precision, uint32_t* cdf);
+
+/* ----------------------------------------------------------------------------------
+ * Host-side rANS coder with CDF indexes.  HOST pointers, no GPU work.
+ * Replaces compressai.ans.{RansEncoder, BufferedRansEncoder, RansDecoder}
+ * (src/models/reference/tcm.py:522,564-565,604-605,621;
+ *  src/entropy_models/adaptive_gaussian_conditional.py:291-299,711-721).
+ * cdfs: int32 [n_cdfs, cdf_stride] row-major (= module._quantized_cdf), cdf_sizes / offsets
+ * [n_cdfs] (= _cdf_length / _offset).  value = symbol - offset[idx]; values outside
+ * [0, cdf_size-2) are escaped through 4-bit bypass groups. */
+void* reslic_rans_encoder_create(void);
+void reslic_rans_encoder_destroy(void* enc);
+int reslic_rans_encoder_push(void* enc, const int32_t* symbols, const int32_t* indexes, int64_t n,
+                             const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
+                             const int32_t* cdf_sizes, const int32_t* offsets);
+/* returns the byte count (or -1); *data stays owned by the encoder until its next call */
+int64_t reslic_rans_encoder_flush(void* enc, const uint8_t** data);
+void* reslic_rans_decoder_create(const uint8_t* data, int64_t nbytes);
+void reslic_rans_decoder_destroy(void* dec);
+/* decodes the NEXT n symbols of the stream (decode_stream semantics) */
+int reslic_rans_decoder_decode(void* dec, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                               int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes,
+                               const int32_t* offsets, int32_t* out_symbols);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -152,6 +152,15 @@ EXPORTS = {
     "reslic_stanh_gap_workspace_bytes": (C.c_int64, []),
     "reslic_stanh_act_f32": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StanhTables), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "reslic_rans_encoder_create": (C.c_void_p, []),
+    "reslic_rans_encoder_destroy": (None, [C.c_void_p]),
+    "reslic_rans_encoder_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                           C.c_int32, C.c_void_p, C.c_void_p]),
+    "reslic_rans_encoder_flush": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "reslic_rans_decoder_create": (C.c_void_p, [C.c_void_p, C.c_int64]),
+    "reslic_rans_decoder_destroy": (None, [C.c_void_p]),
+    "reslic_rans_decoder_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "reslic_pmf_to_quantized_cdf": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

@@ -1,0 +1,102 @@
+"""CPU: host rANS coder — exact encode/decode round trips incl. the bypass escape, the
+stream-continuation (decode_stream) semantics TCM.decompress relies on (tcm.py:604-621), error
+behaviour, and compression close to the model entropy."""
+import math
+
+import pytest
+import torch
+
+from oracle import compressai_ref as cr
+from reslic_tcm_b200 import rans
+
+
+@pytest.fixture(scope="module")
+def tables():
+    cdf, offset, length = cr.gc_update(cr.get_scale_table())
+    return cdf, length, offset
+
+
+def _draw(tables, n, seed, sigma_hi=40.0):
+    g = torch.Generator().manual_seed(seed)
+    sigma = torch.exp(torch.empty(n).uniform_(math.log(0.05), math.log(sigma_hi), generator=g))
+    sym = torch.round(sigma * torch.randn(n, generator=g)).int()
+    idx = cr.build_indexes(sigma, cr.get_scale_table())
+    return sym, idx, sigma
+
+
+def test_round_trip_one_shot_and_list_inputs(tables):
+    cdf, length, offset = tables
+    sym, idx, _ = _draw(tables, 20000, 1)
+    enc = rans.RansEncoder()
+    s = enc.encode_with_indexes(sym.tolist(), idx.tolist(), cdf.tolist(), length.tolist(), offset.tolist())
+    s2 = enc.encode_with_indexes(sym, idx, cdf, length, offset)
+    assert s == s2 and isinstance(s, bytes) and len(s) % 4 == 0
+    out = rans.RansDecoder().decode_with_indexes(s, idx.tolist(), cdf.tolist(), length.tolist(), offset.tolist())
+    assert out == sym.tolist()
+
+
+def test_bypass_escape_for_out_of_range_symbols(tables):
+    cdf, length, offset = tables
+    idx = torch.zeros(64, dtype=torch.int32)                      # narrowest CDF: every large value escapes
+    sym = torch.tensor([0, 1, -1, 5, -5, 100, -100, 32767, -32768, 2 ** 20, -(2 ** 20), 2 ** 30, -(2 ** 30)] * 4 +
+                       [0] * 12, dtype=torch.int32)
+    s = rans.RansEncoder().encode_with_indexes(sym, idx, cdf, length, offset)
+    out = rans.RansDecoder().decode_with_indexes(s, idx, cdf, length, offset)
+    assert out == sym.tolist()
+
+
+def test_buffered_encoder_and_stream_continuation(tables):
+    """TCM.compress pushes all slices into one BufferedRansEncoder (tcm.py:551-565); TCM.decompress
+    reads them back slice by slice from one stream (tcm.py:604-621)."""
+    cdf, length, offset = tables
+    parts = [_draw(tables, n, 10 + k) for k, n in enumerate((3000, 1, 0, 777, 4096))]
+    enc = rans.BufferedRansEncoder()
+    enc.encode_with_indexes(torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), cdf, length, offset)
+    stream = enc.flush()
+    dec = rans.RansDecoder()
+    dec.set_stream(stream)
+    for sym, idx, _ in parts:
+        assert dec.decode_stream(idx, cdf, length, offset) == sym.tolist()
+    # pushing in several calls gives the same stream as one call
+    enc2 = rans.BufferedRansEncoder()
+    for sym, idx, _ in parts:
+        enc2.encode_with_indexes(sym, idx, cdf, length, offset)
+    assert enc2.flush() == stream
+
+
+def test_rate_is_close_to_model_entropy(tables):
+    cdf, length, offset = tables
+    sym, idx, sigma = _draw(tables, 200000, 3, sigma_hi=20.0)
+    s = rans.RansEncoder().encode_with_indexes(sym, idx, cdf, length, offset)
+    table = cr.get_scale_table()
+    lik = cr.lower_bound(cr.gc_likelihood(sym.float(), table[idx.long()], None), 1e-9)   # model at the table scale
+    bits_model = float(-torch.log2(lik.double()).sum())
+    assert len(s) * 8 <= 1.01 * bits_model + 64
+
+
+def test_errors(tables):
+    cdf, length, offset = tables
+    enc = rans.RansEncoder()
+    with pytest.raises(ValueError):
+        enc.encode_with_indexes([1, 2], [0], cdf, length, offset)
+    with pytest.raises(ValueError):
+        enc.encode_with_indexes([1], [64], cdf, length, offset)          # index out of range
+    with pytest.raises(ValueError):
+        rans.RansDecoder().set_stream(b"abc")
+    dec = rans.RansDecoder()
+    with pytest.raises(ValueError):
+        dec.decode_stream([0], cdf, length, offset)                       # no stream
+    s = enc.encode_with_indexes([3, -2, 7], [5, 5, 5], cdf, length, offset)
+    with pytest.raises(ValueError):
+        rans.RansDecoder().decode_with_indexes(s, [5] * 100000, cdf, length, offset)   # reads past the end
+
+
+def test_entropy_model_compress_decompress_cpu_buffers(tables):
+    """EntropyModel-level batch helpers (one string per image)."""
+    cdf, length, offset = tables
+    sym = torch.stack([_draw(tables, 512, 20 + b)[0] for b in range(3)]).reshape(3, 8, 8, 8)
+    idx = torch.stack([_draw(tables, 512, 20 + b)[1] for b in range(3)]).reshape(3, 8, 8, 8)
+    strings = rans.encode_with_indexes_batch(sym, idx, cdf, length, offset)
+    assert len(strings) == 3
+    back = rans.decode_with_indexes_batch(strings, idx, cdf, length, offset)
+    assert torch.equal(back, sym)
