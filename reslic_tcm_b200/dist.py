@@ -66,6 +66,15 @@ class RateReducer:
         self.packed[3] = float(bits_per_image.numel())
         return self.packed
 
+    def set_static(self, sq_err: float, pixels: float, images: float) -> None:
+        """Fill the fields that do not change from step to step (once, outside the hot loop)."""
+        self.packed[1], self.packed[2], self.packed[3] = float(sq_err), float(pixels), float(images)
+
+    def pack_bits(self, bits_per_image: torch.Tensor) -> torch.Tensor:
+        """Hot-loop form: ONE tiny kernel writes sum(bits) into the packed vector."""
+        torch.sum(bits_per_image, dim=0, keepdim=True, out=self.packed[0:1])
+        return self.packed
+
     def all_reduce(self, async_op: bool = False):
         if dist.is_initialized() and dist.get_world_size() > 1:
             return dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, async_op=async_op)
