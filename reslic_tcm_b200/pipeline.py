@@ -123,3 +123,76 @@ class TcmEntropyPath(nn.Module):
         with torch.cuda.graph(graph):
             res = self.forward(y, mu, sigma, z, **kw)
         return graph, res
+
+
+class HostPipeline:
+    """End-to-end pass for latents that live in HOST memory: pinned host y/mu/sigma/z in, host
+    symbols/indexes/bits out.  The batch is cut into image chunks (contiguous in NCHW); chunk c's
+    H2D copy, its 1 + 5 kernel launches and its D2H copy run on three streams chained by events,
+    so PCIe traffic in both directions overlaps and the kernels hide entirely under the copies.
+    This is what a caller whose dense transforms run elsewhere (or the CPU rANS coder consuming the
+    symbols, tcm.py:551-565) sees; when the latents are produced on the GPU use TcmEntropyPath."""
+
+    def __init__(self, path: TcmEntropyPath, batch: int, y_hw, z_hw, *, with_indexes: bool, training: bool = False,
+                 chunks: int = 4, device=None, num_pixels: Optional[int] = None):
+        self.path, self.with_indexes, self.training, self.num_pixels = path, with_indexes, training, num_pixels
+        dev = torch.device(device if device is not None else "cuda")
+        self.dev = dev
+        B = batch
+        chunks = max(1, min(chunks, B))
+        base, extra = divmod(B, chunks)
+        self.ranges = []
+        start = 0
+        for c in range(chunks):
+            n = base + (1 if c < extra else 0)
+            self.ranges.append((start, start + n))
+            start += n
+        C, Cz = synthetic.M_LATENT, synthetic.Z_CHANNELS
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.d_in = {k: torch.empty(B, C, *y_hw, **f32) for k in ("y", "mu", "sigma")}
+        self.d_in["z"] = torch.empty(B, Cz, *z_hw, **f32)
+        # one sub-path (static output buffers) per chunk, sharing the parameters of `path`
+        self.sub = []
+        for (a, b) in self.ranges:
+            p = TcmEntropyPath.__new__(TcmEntropyPath)
+            nn.Module.__init__(p)
+            p.num_slices = path.num_slices
+            p.entropy_bottleneck, p.gaussian_conditional = path.entropy_bottleneck, path.gaussian_conditional
+            p._bufs, p._key = None, None
+            self.sub.append(p)
+        self.out_names = ["bits"] + (["symbols", "indexes"] if with_indexes else [])
+        self.h_out = {"bits": torch.empty(B, dtype=torch.float64).pin_memory()}
+        if with_indexes:
+            for k in ("symbols", "indexes"):
+                self.h_out[k] = torch.empty(B, C, *y_hw, dtype=torch.int32).pin_memory()
+        self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in self.ranges]
+        self.ev_out = [torch.cuda.Event() for _ in self.ranges]
+        self.ev_free = [torch.cuda.Event() for _ in self.ranges]
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.d_in.values())
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out.values())
+
+    @torch.no_grad()
+    def run(self, host: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """host: pinned CPU tensors y, mu, sigma, z (full batch).  Returns pinned host outputs;
+        the call returns after enqueueing — synchronise `self.s_d2h` (or the device) before reading."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st in (self.s_h2d, self.s_comp, self.s_d2h):
+            st.wait_stream(cur)
+        for c, (a, b) in enumerate(self.ranges):
+            with torch.cuda.stream(self.s_h2d):
+                for k in ("y", "mu", "sigma", "z"):
+                    self.d_in[k][a:b].copy_(host[k][a:b], non_blocking=True)
+                self.ev_in[c].record(self.s_h2d)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(self.ev_in[c])
+                res = self.sub[c].forward(self.d_in["y"][a:b], self.d_in["mu"][a:b], self.d_in["sigma"][a:b],
+                                          self.d_in["z"][a:b], training=self.training, with_indexes=self.with_indexes,
+                                          num_pixels=self.num_pixels)
+                self.ev_out[c].record(self.s_comp)
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(self.ev_out[c])
+                for k in self.out_names:
+                    self.h_out[k][a:b].copy_(res[k], non_blocking=True)
+        cur.wait_stream(self.s_d2h)
+        return self.h_out
