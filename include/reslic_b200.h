@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 6
+#define RESLIC_ABI_VERSION 7
 
 enum {
   RESLIC_OK = 0,
@@ -244,6 +244,26 @@ typedef struct reslic_stanh_gc_desc {
 } reslic_stanh_gc_desc;
 
 int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream);
+
+/* Fused EntropyBottleneckStanh.forward (src/entropy_models/adaptive_entropy_bottleneck.py:679-708;
+ * call sites src/models/stanh/wacnn_stanh.py:160-161, balle18_stanh.py:26,124): STanH quantization of
+ * z without medians (training != 0: soft, beta; == 0: hard), variable-bin sign-trick likelihood
+ * (:551-603, :643-666), level index, per-image rate.  z is [B, C, hw]; filters (3,3,3,3). */
+typedef struct reslic_eb_stanh_desc {
+  const float* z;  int64_t z_bs;
+  int64_t B, C, hw;
+  int32_t training;
+  float likelihood_bound;
+  const float* matrix[5]; const float* bias[5]; const float* factor[4];
+  reslic_stanh_tables tables;
+  float* zhat;  int64_t zhat_bs;
+  float* lik;   int64_t lik_bs;
+  int32_t* sym; int64_t sym_bs;
+  double* bits; int32_t bits_accumulate;
+  void* workspace; int64_t workspace_bytes;
+} reslic_eb_stanh_desc;
+
+int reslic_eb_stanh_fwd_f32(const reslic_eb_stanh_desc* d, void* stream);
 
 /* The activation alone, flat over n elements (NonSymStanH/SymStanH.forward,
  * activation.py:135-150, 294-304) and the two sums compute_gap needs

@@ -174,11 +174,55 @@ def gen_stanh():
     return out
 
 
+def gen_eb_stanh():
+    """The reference's own EntropyBottleneckStanh with perturbed STanH weights, eval and training."""
+    import contextlib
+    import io
+
+    em, _ = shim.load_stanh_modules()
+    out = {}
+    for tag, sym in (("N", False), ("S", True)):
+        torch.manual_seed(31 + int(sym))
+        g = torch.Generator().manual_seed(32 + int(sym))
+        cfg = dict(beta=4, num_sigmoids=0, extrema=6, trainable=True, symmetry=sym)
+        C = 5
+        with contextlib.redirect_stdout(io.StringIO()):
+            eb = em.EntropyBottleneckStanh(C, factorized_configuration=cfg)
+            with torch.no_grad():
+                eb.stanh.w.mul_(1.0 + 0.2 * torch.rand(eb.stanh.w.shape, generator=g))
+                for i in range(5):
+                    m = getattr(eb, f"_matrix{i}")
+                    m.add_(0.3 * torch.randn(m.shape, generator=g))
+                    if i < 4:
+                        f = getattr(eb, f"_factor{i}")
+                        f.copy_(0.5 * torch.randn(f.shape, generator=g))
+            eb.stanh.update_state(torch.device("cpu"))
+        z = 2.5 * torch.randn((2, C, 3, 7), generator=g)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            zh_e, lik_e = eb(z, training=False)
+            zh_t, lik_t = eb(z, training=True)
+            st = eb.stanh
+            b_all = st.sym_b if sym else st.b
+            w_all = st.sym_w if sym else st.w
+        d = dict(z=z, zhat_eval=zh_e, lik_eval=lik_e, zhat_train=zh_t, lik_train=lik_t, w=w_all.detach(),
+                 b=torch.sort(b_all.detach())[0], w_param=st.w.detach(), b_param=st.b.detach(), cum_w=st.cum_w)
+        for i in range(5):
+            d[f"_matrix{i}"] = getattr(eb, f"_matrix{i}").detach()
+            d[f"_bias{i}"] = getattr(eb, f"_bias{i}").detach()
+            if i < 4:
+                d[f"_factor{i}"] = getattr(eb, f"_factor{i}").detach()
+        for k, v in d.items():
+            out[f"{tag}_{k}"] = v.detach()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "eb_stanh_golden.npz"), **{k: v.numpy() for k, v in out.items()})
+    return out
+
+
 if __name__ == "__main__":
     if not shim.available():
         raise SystemExit("reference not available: golden vectors can only be generated in the build container")
     a = gen_gc()
     b = gen_eb()
     c = gen_stanh()
+    gen_eb_stanh()
     print("stanh:", len(c), "arrays")
     print("wrote", GOLDEN_DIR, {k: tuple(v.shape) for k, v in a.items()}, {k: tuple(v.shape) for k, v in b.items()})

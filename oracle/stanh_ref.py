@@ -133,3 +133,31 @@ def gap(y: Tensor, w: Tensor, b_sorted: Tensor, beta: float, symmetric: bool) ->
     flat = y.reshape(1, 1, -1)
     return torch.abs(F.mse_loss(flat, stanh(flat, w, b_sorted, beta, symmetric)) -
                      F.mse_loss(flat, stanh(flat, w, b_sorted, -1, symmetric)))
+
+
+def eb_stanh_forward(x: Tensor, eb, w: Tensor, b_sorted: Tensor, cum_w: Tensor, beta: float, symmetric: bool,
+                     training: bool, likelihood_bound: float = 1e-9) -> Tuple[Tensor, Tensor]:
+    """EntropyBottleneckStanh.forward (src/entropy_models/adaptive_entropy_bottleneck.py:679-708):
+    STanH quantization of z WITHOUT medians (EntropyModelSoS.quantize :113-177 with means=None), bins
+    [x - low, x + up] from define_v0_and_v1 (:551-603), the same cumulative-logit MLP and sign trick.
+    `eb` is a compressai_ref.EntropyBottleneckRef holding the parameters."""
+    avg, dist = mid_and_half_gaps(cum_w)
+    C = x.shape[1]
+    perm = list(range(x.dim()))
+    perm[0], perm[1] = perm[1], perm[0]
+    xp = x.permute(*perm).contiguous()
+    shape = xp.size()
+    values = xp.reshape(C, 1, -1)
+    flat = values.reshape(1, 1, -1)
+    out = stanh(flat, w, b_sorted, beta if training else -1, symmetric).reshape(C, 1, -1)
+    low, up = define_v0_and_v1(out.reshape(-1), avg, dist)
+    v0 = (out.reshape(-1) - low).reshape(C, 1, -1)
+    v1 = (out.reshape(-1) + up).reshape(C, 1, -1)
+    lower = eb._logits_cumulative(v0)
+    upper = eb._logits_cumulative(v1)
+    sign = -torch.sign(lower + upper)
+    lik = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+    if likelihood_bound > 0:
+        lik = lower_bound(lik, likelihood_bound)
+    inv = [perm.index(i) for i in range(len(perm))]
+    return out.reshape(shape).permute(*inv).contiguous(), lik.reshape(shape).permute(*inv).contiguous()

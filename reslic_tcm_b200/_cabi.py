@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -133,6 +133,23 @@ class StanhGcDesc(C.Structure):
     ]
 
 
+class EbStanhDesc(C.Structure):
+    """struct reslic_eb_stanh_desc."""
+
+    _fields_ = [
+        ("z", C.c_void_p), ("z_bs", C.c_int64),
+        ("B", C.c_int64), ("C", C.c_int64), ("hw", C.c_int64),
+        ("training", C.c_int32), ("likelihood_bound", C.c_float),
+        ("matrix", C.c_void_p * 5), ("bias", C.c_void_p * 5), ("factor", C.c_void_p * 4),
+        ("tables", StanhTables),
+        ("zhat", C.c_void_p), ("zhat_bs", C.c_int64),
+        ("lik", C.c_void_p), ("lik_bs", C.c_int64),
+        ("sym", C.c_void_p), ("sym_bs", C.c_int64),
+        ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 # every symbol include/reslic_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {
     "reslic_abi_version": (C.c_int, []),
@@ -149,6 +166,7 @@ EXPORTS = {
     "reslic_eb_bwd_f32": (C.c_int, [C.POINTER(EbBwdDesc), C.c_void_p]),
     "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
     "reslic_stanh_gc_fwd_f32": (C.c_int, [C.POINTER(StanhGcDesc), C.c_void_p]),
+    "reslic_eb_stanh_fwd_f32": (C.c_int, [C.POINTER(EbStanhDesc), C.c_void_p]),
     "reslic_stanh_gap_workspace_bytes": (C.c_int64, []),
     "reslic_stanh_act_f32": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StanhTables), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

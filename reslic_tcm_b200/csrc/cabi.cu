@@ -108,6 +108,9 @@ int reslic_dequantize_f32(const int32_t* sym, const float* mu, int64_t n, float*
 int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream) {
   return reslic::stanh_gc_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }
+int reslic_eb_stanh_fwd_f32(const reslic_eb_stanh_desc* d, void* stream) {
+  return reslic::eb_stanh_fwd_launch(d, static_cast<cudaStream_t>(stream));
+}
 int64_t reslic_stanh_gap_workspace_bytes(void) { return 16 + static_cast<int64_t>(reslic::sm_count()) * 8 * 16; }
 int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft, float* out_hard,
                          double* gap2, void* gap_workspace, int64_t gap_workspace_bytes, void* stream) {

@@ -16,6 +16,7 @@
 //     same exact-division + erfc arithmetic as the plain Gaussian-conditional kernel.
 // O(log K + window) per element, 12 B read + 8 B written, no intermediate tensors.
 #include "common.cuh"
+#include "eb_math.cuh"
 #include "gc_math.cuh"
 #include "reslic_internal.h"
 
@@ -235,6 +236,73 @@ __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p
   }
 }
 
+// ------------------------------------------------------------------ factorized bottleneck + STanH
+// EntropyBottleneckStanh.forward (src/entropy_models/adaptive_entropy_bottleneck.py:679-708): z is
+// quantized by the STanH activation WITHOUT medians (:113-177 with means=None), the likelihood is the
+// sign-trick sigmoid difference of the cumulative-logit MLP over the level cell [x - low, x + up]
+// (:551-603, :643-666).  Same tiling as eb_fwd_kernel: the parameters of the few channels a
+// 256-element tile touches are staged per tile; the STanH tables are staged once per CTA.
+struct EbStanhParams {
+  const float* z; int64_t z_bs;
+  const float* matrix[5]; const float* bias[5]; const float* factor[4]; const float* medians;   // medians unused (zeros)
+  float* zhat; float* lik; int32_t* sym; int64_t zhat_bs, lik_bs, sym_bs;
+  double* bits; unsigned long long* workspace; int bits_accumulate;
+  StanhParams st;            // tables + beta/symmetric (tensor fields unused)
+  int64_t B, ne; int hw, C, tile, bpi, training;
+  float lik_bound;
+};
+
+__global__ void __launch_bounds__(kThreads) eb_stanh_fwd_kernel(const EbStanhParams p) {
+  extern __shared__ float sm[];
+  __shared__ float s_par[kEbMaxCh * kEbStride];
+  StanhTables T;
+  stage_tables(p.st, sm, T);
+  const int image = blockIdx.x / p.bpi;
+  const int chunk = blockIdx.x - image * p.bpi;
+  const bool need_lik = p.lik || p.bits;
+  float acc = 0.0f;
+  const int64_t ntiles = (p.ne + p.tile - 1) / p.tile;
+  for (int64_t t = chunk; t < ntiles; t += p.bpi) {
+    const int64_t e0 = t * p.tile;
+    const int64_t e1 = min(p.ne, e0 + static_cast<int64_t>(p.tile));
+    const int c_lo = static_cast<int>(e0 / p.hw);
+    const int nch = static_cast<int>((e1 - 1) / p.hw) - c_lo + 1;
+    __syncthreads();
+    if (need_lik)
+      for (int i = threadIdx.x; i < nch * kEbStride; i += kThreads) {
+        const int cl = i / kEbStride, j = i - cl * kEbStride;
+        s_par[i] = (j == oMed) ? 0.0f : eb_staged_param(p, c_lo + cl, j);
+      }
+    __syncthreads();
+    const int64_t e = e0 + threadIdx.x;
+    if (threadIdx.x < p.tile && e < e1) {
+      const float zv = ld_stream1(p.z + image * p.z_bs + e);
+      int level = 0;
+      float x;
+      if (p.training && p.st.beta != -1.0f) {
+        x = stanh_soft(zv, p.st.beta, T);
+        if (p.sym) { int c2; stanh_hard(zv, T, p.st.symmetric, c2); level = c2; }
+      } else {
+        x = stanh_hard(zv, T, p.st.symmetric, level);
+      }
+      if (p.zhat) st_stream1(p.zhat + image * p.zhat_bs + e, x);
+      if (p.sym) st_stream1(p.sym + image * p.sym_bs + e, level + p.st.sym_offset);
+      if (need_lik) {
+        const float* P = s_par + (static_cast<int>(e / p.hw) - c_lo) * kEbStride;
+        const int j = count_gt(x, T.avg, T.K, T.steps);
+        const bool inside = (x > -1000.0f) && (x <= 1000.0f);
+        const float low = (inside && j > 0) ? T.dist[j - 1] : 0.0f;
+        const float up = (inside && j < T.K) ? T.dist[j] : 0.0f;
+        const float L = eb_combine(logits_cumulative(P, x - low), logits_cumulative(P, x + up), p.lik_bound);
+        if (p.lik) st_stream1(p.lik + image * p.lik_bs + e, L);
+        acc += log2f(L);
+      }
+    }
+  }
+  if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits,
+                          p.bits_accumulate != 0);
+}
+
 static int steps_for(int K) { int s = 1; while ((1 << s) <= K) ++s; return s; }
 
 static int check_tables(const reslic_stanh_tables* t, const char* who) {
@@ -321,6 +389,47 @@ int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, fl
   stanh_act_kernel<<<static_cast<int>(grid), kThreads, tables_smem(p.K), st>>>(p, out_soft, out_hard, partials, counter);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_act launch");
+  return RESLIC_OK;
+}
+
+int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st) {
+  if (!d) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: null descriptor");
+  if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: negative size");
+  if (d->B == 0 || d->C == 0 || d->hw == 0) return RESLIC_OK;
+  if (int rc = check_tables(&d->tables, "eb_stanh_fwd")) return rc;
+  if (!d->z) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: z is null");
+  for (int i = 0; i < 5; ++i)
+    if (!d->matrix[i] || !d->bias[i] || (i < 4 && !d->factor[i]))
+      return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: a parameter pointer is null");
+  if (!d->zhat && !d->lik && !d->sym && !d->bits) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: no output requested");
+  EbStanhParams p{};
+  p.z = d->z; p.z_bs = d->z_bs;
+  for (int i = 0; i < 5; ++i) { p.matrix[i] = d->matrix[i]; p.bias[i] = d->bias[i]; }
+  for (int i = 0; i < 4; ++i) p.factor[i] = d->factor[i];
+  p.medians = nullptr;
+  p.zhat = d->zhat; p.lik = d->lik; p.sym = d->sym; p.zhat_bs = d->zhat_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs;
+  fill_tables(p.st, &d->tables);
+  p.B = d->B; p.ne = d->C * d->hw; p.hw = static_cast<int>(d->hw); p.C = static_cast<int>(d->C);
+  p.training = d->training; p.lik_bound = d->likelihood_bound;
+  int64_t tile = kThreads;
+  if ((kEbMaxCh - 1) * d->hw < tile) tile = (kEbMaxCh - 1) * d->hw;
+  p.tile = static_cast<int>(tile);
+  int64_t bpi = (p.ne + tile - 1) / tile;
+  const int64_t max_ctas = static_cast<int64_t>(sm_count()) * 64;
+  if (bpi * d->B > max_ctas) bpi = (max_ctas + d->B - 1) / d->B;
+  if (bpi < 1) bpi = 1;
+  if (bpi * (kThreads / 32) > 60000) bpi = 60000 / (kThreads / 32);     // arrival count field is 16 bits
+  p.bpi = static_cast<int>(bpi);
+  if (d->bits) {
+    if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B) ||
+        (reinterpret_cast<uintptr_t>(d->workspace) & 7u))
+      return set_error(RESLIC_ERR_WORKSPACE, "eb_stanh_fwd: workspace missing, misaligned or too small for `bits`");
+    p.bits = d->bits; p.bits_accumulate = d->bits_accumulate;
+    p.workspace = static_cast<unsigned long long*>(d->workspace);
+  }
+  eb_stanh_fwd_kernel<<<static_cast<int>(bpi * d->B), kThreads, tables_smem(p.st.K), st>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "eb_stanh_fwd launch");
   return RESLIC_OK;
 }
 

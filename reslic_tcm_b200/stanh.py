@@ -28,7 +28,7 @@ from torch import Tensor
 from . import _cabi, ops
 from .entropy_models import EntropyModel, LowerBound, _no_grad_path
 
-__all__ = ["NonSymStanH", "SymStanH", "GaussianConditionalStanh", "compute_gap"]
+__all__ = ["NonSymStanH", "SymStanH", "GaussianConditionalStanh", "EntropyBottleneckStanh", "compute_gap"]
 
 
 # ----------------------------------------------------------------------------- activation
@@ -545,3 +545,170 @@ class GaussianConditionalStanh(HypeEntropyModelSoS):
         symbols = _rans().decode_with_indexes_batch(strings, indexes, self._quantized_cdf,
                                                  self._cdf_length.reshape(-1), self._offset.reshape(-1))
         return self.dequantize(symbols, means=means)
+
+
+class EntropyBottleneckStanh(EntropyModel):
+    """src/entropy_models/adaptive_entropy_bottleneck.py:299-771 (base EntropyModelSoS :24-296): the
+    factorized bottleneck whose quantizer is a STanH (no medians) and whose bins follow the STanH
+    levels.  forward() is one fused kernel launch; update() keeps the reference's float pmf/cdf.
+    The reference's compress()/decompress() for this class reference undefined names (SURVEY.md
+    App. B) and are not reproduced."""
+
+    def __init__(self, channels: int, *args: Any, tail_mass: float = 1e-9, pretrained_entropy_model=None,
+                 factorized_configuration=None, init_scale: float = 10, filters: Tuple[int, ...] = (3, 3, 3, 3),
+                 **kwargs: Any):
+        super().__init__(*args, **kwargs)
+        self.channels = int(channels)
+        self.M = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        self.pmf_length = None
+        self.num_sigmoids = int(factorized_configuration["num_sigmoids"])
+        self.extrema = factorized_configuration["extrema"]
+        self.symmetry = factorized_configuration["symmetry"]
+        cls = SymStanH if self.symmetry else NonSymStanH
+        self.stanh = cls(factorized_configuration["beta"], self.num_sigmoids, extrema=self.extrema,
+                         trainable=factorized_configuration["trainable"])
+        filt = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for i in range(len(self.filters) + 1):
+            if pretrained_entropy_model is None:
+                init = np.log(np.expm1(1 / scale / filt[i + 1]))
+                matrix = torch.Tensor(self.channels, filt[i + 1], filt[i])
+                matrix.data.fill_(init)
+                bias = torch.Tensor(self.channels, filt[i + 1], 1)
+                nn.init.uniform_(bias, -0.5, 0.5)
+                factor = torch.zeros(self.channels, filt[i + 1], 1) if i < len(self.filters) else None
+            else:
+                matrix = getattr(pretrained_entropy_model, f"_matrix{i:d}").data.clone()
+                bias = getattr(pretrained_entropy_model, f"_bias{i:d}").data.clone()
+                factor = getattr(pretrained_entropy_model, f"_factor{i:d}").data.clone() if i < len(self.filters) else None
+            self.register_parameter(f"_matrix{i:d}", nn.Parameter(matrix))
+            self.register_parameter(f"_bias{i:d}", nn.Parameter(bias))
+            if factor is not None:
+                self.register_parameter(f"_factor{i:d}", nn.Parameter(factor))
+        target = np.log(2 / 1e-9 - 1)
+        self.target = torch.Tensor([-target, 0, target])
+
+    def _params(self):
+        n = len(self.filters) + 1
+        return ([getattr(self, f"_matrix{i:d}") for i in range(n)], [getattr(self, f"_bias{i:d}") for i in range(n)],
+                [getattr(self, f"_factor{i:d}") for i in range(n - 1)])
+
+    def define_permutation(self, x):
+        perm = np.arange(len(x.shape))
+        perm[0], perm[1] = perm[1], perm[0]
+        inv_perm = np.arange(len(x.shape))[np.argsort(perm)]
+        return perm, inv_perm
+
+    def _logits_cumulative(self, inputs: Tensor, stop_gradient: bool) -> Tensor:
+        """Setup-time evaluation (update()); the per-element path is the fused kernel (:525-543)."""
+        logits = inputs
+        for i in range(len(self.filters) + 1):
+            matrix = getattr(self, f"_matrix{i:d}")
+            bias = getattr(self, f"_bias{i:d}")
+            if stop_gradient:
+                matrix, bias = matrix.detach(), bias.detach()
+            logits = torch.matmul(torch.nn.functional.softplus(matrix), logits) + bias
+            if i < len(self.filters):
+                factor = getattr(self, f"_factor{i:d}")
+                if stop_gradient:
+                    factor = factor.detach()
+                logits = logits + torch.tanh(factor) * torch.tanh(logits)
+        return logits
+
+    def _fused(self, x: Tensor, training: bool, want, beta=None):
+        lib = _cabi.load()
+        ops._require_cuda("x", x)
+        if self.filters != (3, 3, 3, 3):
+            raise _cabi.ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
+        m, b, f = self._params()
+        _no_grad_path(x, *m, *b, *f, self.stanh.w, self.stanh.b)
+        xc = x.contiguous()
+        B, Cc = xc.shape[0], xc.shape[1]
+        hw = 1
+        for s_ in xc.shape[2:]:
+            hw *= s_
+        d = _cabi.EbStanhDesc()
+        keep = [xc]
+        d.z, d.z_bs = xc.data_ptr(), Cc * hw
+        d.B, d.C, d.hw = B, Cc, hw
+        d.training = 1 if training else 0
+        d.likelihood_bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
+        for i in range(5):
+            mi, bi = m[i].detach().contiguous(), b[i].detach().contiguous()
+            keep += [mi, bi]
+            d.matrix[i], d.bias[i] = mi.data_ptr(), bi.data_ptr()
+        for i in range(4):
+            fi = f[i].detach().contiguous()
+            keep.append(fi)
+            d.factor[i] = fi.data_ptr()
+        d.tables, tk = self.stanh._tables(self.stanh.beta if beta is None else beta)
+        keep.append(tk)
+        res = {}
+        for name, dtype in (("zhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32)):
+            if name in want:
+                t = torch.empty(xc.shape, dtype=dtype, device=x.device)
+                setattr(d, name, t.data_ptr())
+                setattr(d, name + "_bs", Cc * hw)
+                res[name] = t
+        if "bits" in want:
+            bits = torch.empty(B, dtype=torch.float64, device=x.device)
+            ws = _cabi.workspace(x.device, B)
+            d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
+            keep.append(ws)
+            res["bits"] = bits
+        with torch.cuda.device(x.device):
+            code = lib.reslic_eb_stanh_fwd_f32(C.byref(d), _cabi.current_stream_ptr(x.device))
+        _cabi.check(code, "reslic_eb_stanh_fwd_f32")
+        return res
+
+    def quantize(self, inputs, mode, means=None, perms=None):
+        """EntropyModelSoS.quantize (:113-177): "training" (soft STanH, means ignored as in the
+        reference), "dequantize" (hard levels about the means), "symbols" (level index)."""
+        if mode == "training":
+            return self._fused(inputs, True, ("zhat",))["zhat"]
+        x = inputs - means if means is not None else inputs
+        if mode == "dequantize":
+            out = self._fused(x, False, ("zhat",))["zhat"]
+            return out + means if means is not None else out
+        assert mode == "symbols", mode
+        return self._fused(x, False, ("sym",))["sym"]
+
+    def forward(self, x: Tensor, training: bool = True):
+        """:679-708 — note the reference default ``training=True``."""
+        r = self._fused(x, bool(training), ("zhat", "lik"))
+        return r["zhat"], r["lik"]
+
+    def forward_fused(self, x: Tensor, training: bool = True, want=("zhat", "lik", "bits")):
+        return self._fused(x, bool(training), want)
+
+    def update(self, device=None):
+        """Float pmf / cdf over the STanH levels per channel (:481-514)."""
+        device = self._matrix0.device if device is None else device
+        self.stanh.update_state(device)
+        with torch.no_grad():
+            samples = self.stanh.cum_w.repeat(self.M, 1).unsqueeze(1).to(device)
+            avg, dist = self.stanh.average_points.to(device), self.stanh.distance_points.to(device)
+            flat = samples.reshape(-1)
+            j = torch.searchsorted(avg.contiguous(), flat.contiguous(), right=False)
+            inside = (flat > -1000) & (flat <= 1000)
+            zero = torch.zeros(1, device=device, dtype=dist.dtype)
+            low = torch.where(inside, torch.cat((zero, dist))[j], torch.zeros_like(flat))
+            up = torch.where(inside, torch.cat((dist, zero))[j], torch.zeros_like(flat))
+            v0 = (flat - low).reshape(samples.shape)
+            v1 = (flat + up).reshape(samples.shape)
+            lower = self._logits_cumulative(v0, stop_gradient=True)
+            upper = self._logits_cumulative(v1, stop_gradient=True)
+            sign = -torch.sign(lower + upper)
+            pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+            self.pmf = pmf
+            cdf = pmf.cumsum(dim=-1)
+            self.cdf = torch.cat([torch.zeros(pmf.shape[:-1] + (1,), dtype=pmf.dtype, device=device), cdf],
+                                 dim=-1).clamp(max=1.0)
+        return True
+
+    def order_pars(self):
+        self.stanh.w = nn.Parameter(torch.sort(self.stanh.w)[0])
+        self.stanh.b = nn.Parameter(torch.sort(self.stanh.b)[0])

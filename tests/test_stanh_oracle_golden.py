@@ -52,3 +52,21 @@ def test_symbols_and_unbounded_likelihood(g, tag):
     avg, dist = sr.mid_and_half_gaps(c["cum_w"])
     lik = sr.likelihood(g[f"{tag}_yhat_train"], c["sigma"], c["mu"], avg, dist)
     assert_equal_exact(lik, g[f"{tag}_lik_unbounded_train"], "_likelihood on given values")
+
+
+@pytest.mark.parametrize("tag", ["N", "S"])
+@pytest.mark.parametrize("training", [False, True])
+def test_eb_stanh_forward(tag, training):
+    from oracle import compressai_ref as cr
+
+    g = load_golden("eb_stanh_golden.npz")
+    C = g[f"{tag}_z"].shape[1]
+    eb = cr.EntropyBottleneckRef(C)
+    eb.matrices = [g[f"{tag}__matrix{i}"] for i in range(5)]
+    eb.biases = [g[f"{tag}__bias{i}"] for i in range(5)]
+    eb.factors = [g[f"{tag}__factor{i}"] for i in range(4)]
+    zh, lik = sr.eb_stanh_forward(g[f"{tag}_z"], eb, g[f"{tag}_w"], g[f"{tag}_b"], g[f"{tag}_cum_w"], 4.0, tag == "S",
+                                  training)
+    key = "train" if training else "eval"
+    assert_equal_exact(zh, g[f"{tag}_zhat_{key}"], "z_hat vs reference EntropyBottleneckStanh")
+    assert_equal_exact(lik, g[f"{tag}_lik_{key}"], "likelihood vs reference EntropyBottleneckStanh")

@@ -150,3 +150,47 @@ def test_large_random_against_oracle_and_edge_values():
     ties = ((d - torch.floor(d)) - 0.5).abs() < 1e-6
     ok = inside & ~ties
     assert torch.equal(sym[ok] - 80, torch.round(d[ok]).int())
+
+
+@pytest.mark.parametrize("tag", ["N", "S"])
+@pytest.mark.parametrize("training", [False, True])
+def test_entropy_bottleneck_stanh(tag, training):
+    from oracle import compressai_ref as cr
+
+    g = load_golden("eb_stanh_golden.npz")
+    C = g[f"{tag}_z"].shape[1]
+    cfg = dict(beta=4, num_sigmoids=0, extrema=6, trainable=True, symmetry=(tag == "S"))
+    mod = stanh.EntropyBottleneckStanh(C, factorized_configuration=cfg).to(DEV)
+    ref = cr.EntropyBottleneckRef(C)
+    with torch.no_grad():
+        mod.stanh.w.copy_(g[f"{tag}_w_param"])
+        mod.stanh.b.copy_(g[f"{tag}_b_param"])
+        for i in range(5):
+            getattr(mod, f"_matrix{i}").copy_(g[f"{tag}__matrix{i}"])
+            getattr(mod, f"_bias{i}").copy_(g[f"{tag}__bias{i}"])
+            if i < 4:
+                getattr(mod, f"_factor{i}").copy_(g[f"{tag}__factor{i}"])
+    mod.stanh.update_state(torch.device(DEV))
+    ref.matrices = [g[f"{tag}__matrix{i}"] for i in range(5)]
+    ref.biases = [g[f"{tag}__bias{i}"] for i in range(5)]
+    ref.factors = [g[f"{tag}__factor{i}"] for i in range(4)]
+    key = "train" if training else "eval"
+    with torch.no_grad():
+        zh, lik = mod(g[f"{tag}_z"].to(DEV), training=training)
+        r = mod.forward_fused(g[f"{tag}_z"].to(DEV), training=training)
+    c = dict(w=g[f"{tag}_w"])
+    _close(zh, g[f"{tag}_zhat_{key}"], _soft_tol(c), "z_hat vs reference EntropyBottleneckStanh")
+    # likelihood of the kernel's own z_hat through the oracle's MLP (the reference's z_hat differs in
+    # the last bits; the cumulative logits amplify that in the tails)
+    avg, dist = sr.mid_and_half_gaps(g[f"{tag}_cum_w"])
+    x = zh.cpu().permute(1, 0, 2, 3).reshape(C, 1, -1)
+    low, up = sr.define_v0_and_v1(x.reshape(-1), avg, dist)
+    lower = ref._logits_cumulative((x.reshape(-1) - low).reshape(C, 1, -1))
+    upper = ref._logits_cumulative((x.reshape(-1) + up).reshape(C, 1, -1))
+    sign = -torch.sign(lower + upper)
+    lik_ref = cr_bound(torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower)))
+    lik_ref = lik_ref.reshape(C, zh.shape[0], zh.shape[2], zh.shape[3]).permute(1, 0, 2, 3)
+    assert_lik_close(lik, lik_ref, what="likelihood vs oracle on the same z_hat")
+    assert_lik_close(lik, g[f"{tag}_lik_{key}"], rtol=5e-4, what="likelihood vs reference module")
+    own = -(torch.log2(lik.double()).reshape(lik.shape[0], -1).sum(1))
+    assert torch.allclose(r["bits"], own, rtol=2e-6)
