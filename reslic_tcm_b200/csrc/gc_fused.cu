@@ -30,6 +30,7 @@ struct GcParams {
   int64_t n;          // elements per image
   int64_t B;          // images
   int64_t tiles_per_image;
+  unsigned int tpi, total_tiles, q_tiles, r_tiles;   // 32-bit partition: CTA c owns q (+1 if c < r) tiles
   float scale_bound, lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
@@ -150,16 +151,18 @@ gc_fwd_kernel(const GcParams p) {
   constexpr int W = VEC ? 4 : 1;
   constexpr int kTileElems = kThreads * W;
   const int groups = static_cast<int>(VEC ? (p.n >> 2) : p.n);      // per image (n < 2^31 checked on host)
-  const int64_t total = p.tiles_per_image * p.B;
-  int64_t t = (static_cast<int64_t>(blockIdx.x) * total) / gridDim.x;
-  const int64_t t_end = (static_cast<int64_t>(blockIdx.x + 1) * total) / gridDim.x;
+  // CTA c owns tiles [c*q + min(c,r), ...) — q = T / G, r = T % G precomputed on the host, all in
+  // 32-bit arithmetic (64-bit divisions here sat on the critical path of short launches)
+  const unsigned int cta = blockIdx.x;
+  unsigned int t = cta * p.q_tiles + min(cta, p.r_tiles);
+  const unsigned int t_end = t + p.q_tiles + (cta < p.r_tiles ? 1u : 0u);
 
   struct In { float y[4], m[4], s[4], u[4]; };
   while (t < t_end) {
-    const int image = static_cast<int>(t / p.tiles_per_image);
-    const int chunk0 = static_cast<int>(t - image * p.tiles_per_image);
-    const int64_t seg_end64 = (static_cast<int64_t>(image) + 1) * p.tiles_per_image;
-    const int ntiles = static_cast<int>((seg_end64 < t_end ? seg_end64 : t_end) - t);
+    const int image = static_cast<int>(t / p.tpi);
+    const int chunk0 = static_cast<int>(t - image * p.tpi);
+    const unsigned int seg_end = (static_cast<unsigned int>(image) + 1u) * p.tpi;
+    const int ntiles = static_cast<int>(min(seg_end, t_end) - t);
     t += ntiles;
     int g = chunk0 * kThreads + threadIdx.x;                       // element group inside the image
     const int64_t e0 = static_cast<int64_t>(g) * W;
@@ -253,11 +256,14 @@ gc_fwd_kernel(const GcParams p) {
     if (NEED_LIK && p.bits) {
       // warps committing to this image = (CTAs whose tile range meets the image) * warps per CTA;
       // tile tau belongs to CTA ceil((tau+1)*G/T) - 1.
-      const int64_t G = gridDim.x;
-      const int64_t first = image * p.tiles_per_image, last = first + p.tiles_per_image - 1;
-      const int64_t c_lo = ((first + 1) * G + total - 1) / total - 1;
-      const int64_t c_hi = ((last + 1) * G + total - 1) / total - 1;
-      rate_commit(acc, image, static_cast<unsigned int>((c_hi - c_lo + 1) * (kThreads / 32)), p.B, p.workspace, p.bits, p.bits_accumulate != 0);
+      // owner of tile tau: the first r CTAs hold q+1 tiles each, the rest q
+      auto owner = [&](unsigned int tau) -> unsigned int {
+        const unsigned int big = p.r_tiles * (p.q_tiles + 1u);
+        return tau < big ? tau / (p.q_tiles + 1u) : p.r_tiles + (tau - big) / p.q_tiles;
+      };
+      const unsigned int first = static_cast<unsigned int>(image) * p.tpi;
+      const unsigned int n_ctas = owner(first + p.tpi - 1u) - owner(first) + 1u;
+      rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate != 0);
     }
   }
 }
@@ -286,6 +292,10 @@ static cudaError_t launch_pf(GcParams& p, cudaStream_t st) {
   if (waves > 0) grid = static_cast<int64_t>(waves) * sm_count();
   else if (waves < 0) grid = static_cast<int64_t>(resident_ctas(kernel, &occ)) * sm_count();
   if (grid > total) grid = total;
+  p.tpi = static_cast<unsigned int>(p.tiles_per_image);
+  p.total_tiles = static_cast<unsigned int>(total);
+  p.q_tiles = static_cast<unsigned int>(total / grid);
+  p.r_tiles = static_cast<unsigned int>(total % grid);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
@@ -362,7 +372,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   const int64_t groups = vec ? d->n / 4 : d->n;
   p.tiles_per_image = (groups + kThreads - 1) / kThreads;
   if (d->n >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "gc_fwd: more than 2^31 elements per image");
-  if (p.tiles_per_image * d->B > (1LL << 40)) return set_error(RESLIC_ERR_ARG, "gc_fwd: input too large");
+  if (p.tiles_per_image * d->B >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "gc_fwd: input too large (>= 2^31 tiles)");
   if (d->bits) {
     if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
       return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace missing or too small for `bits`");
