@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 7
+#define RESLIC_ABI_VERSION 8
 
 enum {
   RESLIC_OK = 0,
@@ -135,6 +135,11 @@ typedef struct reslic_gc_bwd_desc {
 } reslic_gc_bwd_desc;
 
 int reslic_gc_bwd_f32(const reslic_gc_bwd_desc* d, void* stream);
+
+/* Latent-residual-prediction tail of the slice loop (tcm.py:461-464):
+ *   y_hat += 0.5 * tanh(lrp)   in place, image-major like reslic_gc_desc (3 launches -> 1). */
+int reslic_lrp_tail_f32(float* y_hat, int64_t y_hat_bs, const float* lrp, int64_t lrp_bs, int64_t B, int64_t n,
+                        void* stream);
 
 /* build_indexes alone (adaptive_gaussian_conditional.py:606-617): flat, n elements. */
 int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound,
@@ -244,6 +249,26 @@ typedef struct reslic_stanh_gc_desc {
 } reslic_stanh_gc_desc;
 
 int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream);
+
+/* Backward of reslic_stanh_gc_fwd_f32 for FIXED STanH parameters (gaussian_configuration
+ * ["trainable"] = False, the reference default): gradients w.r.t. y, mu, sigma of the quantize
+ * output and of the bounded likelihood.  Gradients w.r.t. stanh.w / stanh.b are not produced. */
+typedef struct reslic_stanh_gc_bwd_desc {
+  const float* y;      int64_t y_bs;
+  const float* mu;     int64_t mu_bs;
+  const float* sigma;  int64_t sigma_bs;
+  int64_t B, n;
+  int32_t training, removing_mean;
+  float scale_bound, likelihood_bound;
+  reslic_stanh_tables tables;
+  const float* g_yhat; int64_t g_yhat_bs;
+  const float* g_lik;  int64_t g_lik_bs;
+  float* g_y;     int64_t g_y_bs;
+  float* g_mu;    int64_t g_mu_bs;
+  float* g_sigma; int64_t g_sigma_bs;
+} reslic_stanh_gc_bwd_desc;
+
+int reslic_stanh_gc_bwd_f32(const reslic_stanh_gc_bwd_desc* d, void* stream);
 
 /* Fused EntropyBottleneckStanh.forward (src/entropy_models/adaptive_entropy_bottleneck.py:679-708;
  * call sites src/models/stanh/wacnn_stanh.py:160-161, balle18_stanh.py:26,124): STanH quantization of

@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -133,6 +133,25 @@ class StanhGcDesc(C.Structure):
     ]
 
 
+class StanhGcBwdDesc(C.Structure):
+    """struct reslic_stanh_gc_bwd_desc."""
+
+    _fields_ = [
+        ("y", C.c_void_p), ("y_bs", C.c_int64),
+        ("mu", C.c_void_p), ("mu_bs", C.c_int64),
+        ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
+        ("B", C.c_int64), ("n", C.c_int64),
+        ("training", C.c_int32), ("removing_mean", C.c_int32),
+        ("scale_bound", C.c_float), ("likelihood_bound", C.c_float),
+        ("tables", StanhTables),
+        ("g_yhat", C.c_void_p), ("g_yhat_bs", C.c_int64),
+        ("g_lik", C.c_void_p), ("g_lik_bs", C.c_int64),
+        ("g_y", C.c_void_p), ("g_y_bs", C.c_int64),
+        ("g_mu", C.c_void_p), ("g_mu_bs", C.c_int64),
+        ("g_sigma", C.c_void_p), ("g_sigma_bs", C.c_int64),
+    ]
+
+
 class EbStanhDesc(C.Structure):
     """struct reslic_eb_stanh_desc."""
 
@@ -166,6 +185,8 @@ EXPORTS = {
     "reslic_eb_bwd_f32": (C.c_int, [C.POINTER(EbBwdDesc), C.c_void_p]),
     "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
     "reslic_stanh_gc_fwd_f32": (C.c_int, [C.POINTER(StanhGcDesc), C.c_void_p]),
+    "reslic_stanh_gc_bwd_f32": (C.c_int, [C.POINTER(StanhGcBwdDesc), C.c_void_p]),
+    "reslic_lrp_tail_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "reslic_eb_stanh_fwd_f32": (C.c_int, [C.POINTER(EbStanhDesc), C.c_void_p]),
     "reslic_stanh_gap_workspace_bytes": (C.c_int64, []),
     "reslic_stanh_act_f32": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StanhTables), C.c_void_p, C.c_void_p,

@@ -50,6 +50,30 @@ __global__ void __launch_bounds__(kThreads) dequantize_kernel(const int32_t* __r
   }
 }
 
+__global__ void __launch_bounds__(kThreads) lrp_tail_kernel(float* __restrict__ y_hat, int64_t y_bs,
+                                                           const float* __restrict__ lrp, int64_t l_bs, int64_t n,
+                                                           int64_t tiles_per_image, int64_t total) {
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t image = t / tiles_per_image;
+    const int64_t e = (t - image * tiles_per_image) * kThreads + threadIdx.x;
+    if (e < n) y_hat[image * y_bs + e] += 0.5f * tanhf(lrp[image * l_bs + e]);
+  }
+}
+
+int lrp_tail_launch(float* y_hat, int64_t y_bs, const float* lrp, int64_t l_bs, int64_t B, int64_t n, cudaStream_t st) {
+  if (B < 0 || n < 0) return set_error(RESLIC_ERR_ARG, "lrp_tail: negative size");
+  if (B == 0 || n == 0) return RESLIC_OK;
+  if (!y_hat || !lrp) return set_error(RESLIC_ERR_ARG, "lrp_tail: null pointer");
+  const int64_t tpi = (n + kThreads - 1) / kThreads, total = tpi * B;
+  int64_t grid = total;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+  if (grid > cap) grid = cap;
+  lrp_tail_kernel<<<static_cast<int>(grid), kThreads, 0, st>>>(y_hat, y_bs, lrp, l_bs, n, tpi, total);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "lrp_tail launch");
+  return RESLIC_OK;
+}
+
 int dequantize_launch(const int32_t* sym, const float* mu, int64_t n, float* out, cudaStream_t st) {
   if (n < 0) return set_error(RESLIC_ERR_ARG, "dequantize: negative size");
   if (n == 0) return RESLIC_OK;
@@ -101,6 +125,11 @@ int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound, c
   return reslic::gc_fwd_launch(&d, static_cast<cudaStream_t>(stream));
 }
 
+int reslic_lrp_tail_f32(float* y_hat, int64_t y_hat_bs, const float* lrp, int64_t lrp_bs, int64_t B, int64_t n,
+                        void* stream) {
+  return reslic::lrp_tail_launch(y_hat, y_hat_bs, lrp, lrp_bs, B, n, static_cast<cudaStream_t>(stream));
+}
+
 int reslic_dequantize_f32(const int32_t* sym, const float* mu, int64_t n, float* out, void* stream) {
   return reslic::dequantize_launch(sym, mu, n, out, static_cast<cudaStream_t>(stream));
 }
@@ -110,6 +139,9 @@ int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream) {
 }
 int reslic_eb_stanh_fwd_f32(const reslic_eb_stanh_desc* d, void* stream) {
   return reslic::eb_stanh_fwd_launch(d, static_cast<cudaStream_t>(stream));
+}
+int reslic_stanh_gc_bwd_f32(const reslic_stanh_gc_bwd_desc* d, void* stream) {
+  return reslic::stanh_gc_bwd_launch(d, static_cast<cudaStream_t>(stream));
 }
 int64_t reslic_stanh_gap_workspace_bytes(void) { return 16 + static_cast<int64_t>(reslic::sm_count()) * 8 * 16; }
 int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft, float* out_hard,

@@ -19,8 +19,10 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st);
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st);
 int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st);
 int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st);
+int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st);
 int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, float* out_soft, float* out_hard,
                      double* gap, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int lrp_tail_launch(float* y_hat, int64_t y_bs, const float* lrp, int64_t l_bs, int64_t B, int64_t n, cudaStream_t st);
 int dequantize_launch(const int32_t* sym, const float* mu, int64_t n, float* out, cudaStream_t st);
 
 }  // namespace reslic

@@ -433,4 +433,121 @@ int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st) {
   return RESLIC_OK;
 }
 
+// ------------------------------------------------------------------ backward (non-trainable STanH)
+// What autograd does through GaussianConditionalStanh.forward for fixed w, b
+// (gaussian_configuration["trainable"] = False, the reference default, src/utils/parser.py):
+//   soft form:  d stanh / dx = sum_k (w_k/2) * beta * (1 - tanh^2(beta (x - b_k)))   (window only)
+//   hard form:  zero (sign / relu)
+//   likelihood: bins (low, up) are piecewise constant in v; dL/dv = (phi(a1) - phi(a2)) * dir / s,
+//               dL/ds = -(a1 phi(a1) - a2 phi(a2)) / s, both LowerBound gradient rules.
+struct StanhBwdParams {
+  const float* y; const float* mu; const float* sigma; const float* g_yhat; const float* g_lik;
+  float* g_y; float* g_mu; float* g_sigma;
+  int64_t y_bs, mu_bs, sigma_bs, g_yhat_bs, g_lik_bs, g_y_bs, g_mu_bs, g_sigma_bs;
+  StanhParams st;
+  int64_t n, B, tiles_per_image;
+  int training, removing_mean;
+  float scale_bound, lik_bound;
+};
+
+__device__ __forceinline__ float stanh_soft_grad(float x, float beta, const StanhTables& T) {
+  int lo = 0, hi = T.K;
+  if (beta > 0.0f) {
+    const float r = kSatT / beta;
+    lo = count_ge(x - r, T.b, T.K, T.steps);
+    hi = count_gt(x + r, T.b, T.K, T.steps);
+    if (hi < lo) hi = lo;
+  }
+  float acc = 0.0f;
+  for (int k = lo; k < hi; ++k) {
+    const float t = beta * (x - T.b[k]);
+    const float sg = 1.0f / (1.0f + expf(-(2.0f * t)));
+    // d/dx [2 sigma(2t) - 1] = 4 beta sigma (1 - sigma)
+    acc = fmaf(T.w[k] * 0.5f, 4.0f * beta * sg * (1.0f - sg), acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdParams p) {
+  extern __shared__ float sm[];
+  StanhTables T;
+  stage_tables(p.st, sm, T);
+  const int64_t total = p.tiles_per_image * p.B;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int image = static_cast<int>(t / p.tiles_per_image);
+    const int64_t e = (t - image * p.tiles_per_image) * kThreads + threadIdx.x;
+    if (e >= p.n) continue;
+    const float y = p.y[image * p.y_bs + e];
+    const float mu = p.mu ? p.mu[image * p.mu_bs + e] : 0.0f;
+    const bool rm = p.mu && (p.training ? p.removing_mean != 0 : true);
+    const float x = rm ? y - mu : y;
+    const bool soft = p.training && p.st.beta != -1.0f;
+    int lvl;
+    const float q = soft ? stanh_soft(x, p.st.beta, T) : stanh_hard(x, T, p.st.symmetric, lvl);
+    const float dq = soft ? stanh_soft_grad(x, p.st.beta, T) : 0.0f;          // d q / d x
+    const float yhat = rm ? q + mu : q;
+    // d yhat/dy = dq ; d yhat/dmu = rm ? (1 - dq) : 0
+    const float gyh = p.g_yhat ? p.g_yhat[image * p.g_yhat_bs + e] : 0.0f;
+    float gv = 0.0f, gs = 0.0f;
+    if (p.g_lik) {
+      const float gl = p.g_lik[image * p.g_lik_bs + e];
+      const float sg_in = p.sigma[image * p.sigma_bs + e];
+      const float s = max_nan(sg_in, p.scale_bound);
+      const float v = p.mu ? yhat - mu : yhat;
+      const int j = count_gt(v, T.avg, T.K, T.steps);
+      const bool inside = (v > -1000.0f) && (v <= 1000.0f);
+      const float low = (inside && j > 0) ? T.dist[j - 1] : 0.0f;
+      const float up = (inside && j < T.K) ? T.dist[j] : 0.0f;
+      float n1, n2, dir;
+      if (v >= 0.0f) { n1 = low - v; n2 = -up - v; dir = -1.0f; }
+      else { n1 = v + up; n2 = v - low; dir = 1.0f; }
+      const float L = gauss_interval_mass<true>(max_nan(min_nan(n1, 1e30f), -1e30f), max_nan(min_nan(n2, 1e30f), -1e30f), s);
+      const bool pass_l = !(p.lik_bound > 0.0f) || (L >= p.lik_bound) || (gl < 0.0f);
+      const float g = pass_l ? gl : 0.0f;
+      const float rs = 1.0f / s;
+      const float a1 = n1 * rs, a2 = n2 * rs;
+      const float k = 0.3989422804014327f;
+      const float p1 = k * expf(-0.5f * a1 * a1), p2 = k * expf(-0.5f * a2 * a2);
+      gv = g * (p1 - p2) * dir * rs;
+      gs = -g * (a1 * p1 - a2 * p2) * rs;
+      const bool pass_s = (sg_in >= p.scale_bound) || (gs < 0.0f);
+      gs = pass_s ? gs : 0.0f;
+    }
+    // v = yhat - mu:  dv/dy = dq,  dv/dmu = (rm ? 1 - dq : 0) - (mu given ? 1 : 0)
+    const float dyhat_dmu = rm ? 1.0f - dq : 0.0f;
+    const float gy = (gyh + gv) * dq;
+    const float gmu = gyh * dyhat_dmu + gv * (dyhat_dmu - (p.mu ? 1.0f : 0.0f));
+    if (p.g_y) p.g_y[image * p.g_y_bs + e] = gy;
+    if (p.g_mu) p.g_mu[image * p.g_mu_bs + e] = gmu;
+    if (p.g_sigma) p.g_sigma[image * p.g_sigma_bs + e] = gs;
+  }
+}
+
+int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st) {
+  if (!d) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: null descriptor");
+  if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: negative size");
+  if (d->B == 0 || d->n == 0) return RESLIC_OK;
+  if (int rc = check_tables(&d->tables, "stanh_gc_bwd")) return rc;
+  if (!d->y) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: y is null");
+  if (d->g_lik && !d->sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: sigma is null");
+  if (!d->g_y && !d->g_mu && !d->g_sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: no output requested");
+  if (!(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: scale_bound must be > 0");
+  StanhBwdParams p{};
+  p.y = d->y; p.mu = d->mu; p.sigma = d->sigma; p.g_yhat = d->g_yhat; p.g_lik = d->g_lik;
+  p.g_y = d->g_y; p.g_mu = d->g_mu; p.g_sigma = d->g_sigma;
+  p.y_bs = d->y_bs; p.mu_bs = d->mu_bs; p.sigma_bs = d->sigma_bs; p.g_yhat_bs = d->g_yhat_bs; p.g_lik_bs = d->g_lik_bs;
+  p.g_y_bs = d->g_y_bs; p.g_mu_bs = d->g_mu_bs; p.g_sigma_bs = d->g_sigma_bs;
+  fill_tables(p.st, &d->tables);
+  p.n = d->n; p.B = d->B; p.tiles_per_image = (d->n + kThreads - 1) / kThreads;
+  p.training = d->training; p.removing_mean = d->removing_mean;
+  p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
+  int64_t grid = p.tiles_per_image * p.B;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (grid > cap) grid = cap;
+  stanh_gc_bwd_kernel<<<static_cast<int>(grid), kThreads, tables_smem(p.st.K), st>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "stanh_gc_bwd launch");
+  return RESLIC_OK;
+}
+
 }  // namespace reslic

@@ -456,3 +456,22 @@ def eb_backward(
         code = lib.reslic_eb_bwd_f32(C.byref(d), _cabi.current_stream_ptr(z.device))
     _cabi.check(code, "reslic_eb_bwd_f32")
     return g_z, gm, gb, gf, g_med
+
+
+def lrp_tail_(y_hat: Tensor, lrp: Tensor) -> Tensor:
+    """In place ``y_hat += 0.5 * tanh(lrp)`` (tcm.py:461-464) as one launch; y_hat may be a channel
+    slice of the full latent."""
+    lib = _cabi.load()
+    _require_cuda("y_hat", y_hat)
+    _require_cuda("lrp", lrp)
+    if lrp.shape != y_hat.shape:
+        raise ValueError("lrp shape must match y_hat")
+    yh, ybs, n = image_major(y_hat)
+    if yh is not y_hat:
+        raise ValueError("y_hat must be image-major (a channel slice of a contiguous NCHW tensor qualifies)")
+    lr, lbs, _ = image_major(lrp)
+    B = y_hat.shape[0] if y_hat.dim() > 0 else 1
+    with torch.cuda.device(y_hat.device):
+        code = lib.reslic_lrp_tail_f32(yh.data_ptr(), ybs, lr.data_ptr(), lbs, B, n, _cabi.current_stream_ptr(y_hat.device))
+    _cabi.check(code, "reslic_lrp_tail_f32")
+    return y_hat

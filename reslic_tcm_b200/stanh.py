@@ -296,6 +296,25 @@ def compute_gap(stanh: _StanHBase, inputs: Tensor, beta=None) -> Tensor:
 
 
 # ----------------------------------------------------------------------------- entropy model
+class _StanhGcFn(torch.autograd.Function):
+    """Autograd node around the fused STanH forward / backward kernels (fixed w, b)."""
+
+    @staticmethod
+    def forward(ctx, module, inputs, scales, means, training):
+        with torch.no_grad():
+            r = module._stanh_fused(inputs, scales, means, training, ("yhat", "lik"))
+        ctx.module, ctx.training = module, bool(training)
+        ctx.save_for_backward(inputs, scales, means)
+        ctx.set_materialize_grads(False)
+        return r["yhat"], r["lik"]
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik):
+        inputs, scales, means = ctx.saved_tensors
+        g_y, g_mu, g_sigma = ctx.module._stanh_backward(inputs, scales, means, ctx.training, g_yhat, g_lik)
+        return None, g_y, g_sigma, (g_mu if means is not None else None), None
+
+
 class HypeEntropyModelSoS(EntropyModel):
     """adaptive_gaussian_conditional.py:17-300: EntropyModel whose quantizer is ``self.stanh``."""
 
@@ -363,6 +382,41 @@ class HypeEntropyModelSoS(EntropyModel):
             code = lib.reslic_stanh_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
         _cabi.check(code, "reslic_stanh_gc_fwd_f32")
         return res
+
+    def _stanh_backward(self, inputs, scales, means, training, g_yhat, g_lik):
+        lib = _cabi.load()
+        d = _cabi.StanhGcBwdDesc()
+        keep = []
+
+        def bind(name, t):
+            if t is None:
+                return
+            if t.shape != inputs.shape:
+                t = t.expand_as(inputs)
+            t, bs, _ = ops.image_major(t.contiguous() if not t.is_contiguous() and name.startswith("g_") else t)
+            keep.append(t)
+            setattr(d, name, t.data_ptr())
+            setattr(d, name + "_bs", bs)
+
+        _, _, n = ops.image_major(inputs)
+        bind("y", inputs); bind("mu", means); bind("sigma", scales); bind("g_yhat", g_yhat); bind("g_lik", g_lik)
+        B = inputs.shape[0] if inputs.dim() > 0 else 1
+        d.B, d.n = B, n
+        d.training, d.removing_mean = (1 if training else 0), (1 if self.removing_mean else 0)
+        d.scale_bound = float(getattr(self, "_scale_bound", 0.11))
+        d.likelihood_bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
+        d.tables, tk = self.stanh._tables(self.stanh.beta)
+        keep.append(tk)
+        outs = []
+        for name in ("g_y", "g_mu", "g_sigma"):
+            t = torch.empty(inputs.shape, dtype=torch.float32, device=inputs.device)
+            setattr(d, name, t.data_ptr())
+            setattr(d, name + "_bs", n)
+            outs.append(t)
+        with torch.cuda.device(inputs.device):
+            code = lib.reslic_stanh_gc_bwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
+        _cabi.check(code, "reslic_stanh_gc_bwd_f32")
+        return tuple(outs)
 
     def quantize(self, inputs, mode, means=None, perms=None):
         """modes "training" | "dequantize" | "symbols" (:95-157).  ``perms`` is accepted for API
@@ -508,6 +562,11 @@ class GaussianConditionalStanh(HypeEntropyModelSoS):
         """:588-603 — note the reference's argument order and default ``training=True``."""
         if training is None:
             training = self.training
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (values, scales, means)):
+            if self.stanh.w.requires_grad or self.stanh.b.requires_grad:
+                raise _cabi.ReslicError("gradients w.r.t. the STanH parameters w/b (trainable=True) are not "
+                                        "implemented; build the module with trainable=False")
+            return _StanhGcFn.apply(self, values, scales, means, bool(training))
         r = self._stanh_fused(values, scales, means, bool(training), ("yhat", "lik"))
         return r["yhat"], r["lik"]
 

@@ -124,3 +124,63 @@ def test_eb_backward_matches_autograd(training):
             check(f"d/d_factor{i}", getattr(mod, f"_factor{i}").grad, ref.factors[i].grad)
     if not training:
         check("d/dquantiles", mod.quantiles.grad, ref.quantiles.grad)
+
+
+@pytest.mark.parametrize("training,removing_mean,symmetry", [(True, True, False), (True, False, False),
+                                                             (False, True, False), (True, True, True)])
+def test_stanh_backward_matches_autograd(training, removing_mean, symmetry):
+    from oracle import stanh_ref as sr
+    from reslic_tcm_b200 import stanh
+
+    beta, extrema = 3.0, 6
+    cfg = dict(beta=beta, num_sigmoids=0, extrema=extrema, trainable=False, removing_mean=removing_mean,
+               symmetry=symmetry)
+    mod = stanh.GaussianConditionalStanh(None, channels=4, gaussian_configuration=cfg).to(DEV)
+    g = torch.Generator().manual_seed(41)
+    with torch.no_grad():
+        mod.stanh.w.mul_((1.0 + 0.2 * torch.rand(mod.stanh.w.shape, generator=g)).to(DEV))
+    mod.stanh.update_state(torch.device(DEV))
+    st = mod.stanh
+    w = (st.sym_w if symmetry else st.w).detach().cpu()
+    b = torch.sort((st.sym_b if symmetry else st.b).detach().cpu())[0]
+    cum_w = st.cum_w.cpu()
+    shape = (2, 4, 5, 6)
+    mu = torch.randn(shape, generator=g)
+    sigma = torch.exp(torch.empty(shape).uniform_(-3.0, 2.0, generator=g))
+    y = mu + 2.0 * torch.randn(shape, generator=g)
+    wy, wl = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+
+    leaves = [t.clone().requires_grad_(True) for t in (y, sigma, mu)]
+    avg, dist = sr.mid_and_half_gaps(cum_w)
+    yh = sr.quantize(leaves[0], "training" if training else "dequantize", leaves[2], w, b, beta, symmetry, removing_mean)
+    values = yh - leaves[2]
+    low, up = sr.define_v0_and_v1(values.detach(), avg, dist)
+    s = RefLowerBound(0.11)(leaves[1])
+    upper = cr.standardized_cumulative((low - values) / s) * (values >= 0) + \
+        cr.standardized_cumulative((values + up) / s) * (values < 0)
+    lower = cr.standardized_cumulative((-up - values) / s) * (values >= 0) + \
+        cr.standardized_cumulative((values - low) / s) * (values < 0)
+    lik = RefLowerBound(1e-9)(upper - lower)
+    ((yh * wy).sum() + (torch.log(lik) * wl).sum()).backward()
+
+    dl = [t.clone().to(DEV).requires_grad_(True) for t in (y, sigma, mu)]
+    yh2, lik2 = mod(dl[0], dl[1], training=training, means=dl[2])
+    ((yh2 * wy.to(DEV)).sum() + (torch.log(lik2) * wl.to(DEV)).sum()).backward()
+    for name, a, r in zip(("d/dy", "d/dsigma", "d/dmu"), (t.grad for t in dl), (t.grad for t in leaves)):
+        r = torch.zeros(shape) if r is None else r
+        a = torch.zeros(shape) if a is None else a.cpu()
+        scale = max(r.abs().max().item(), 1.0)
+        err = (a - r).abs()
+        assert bool((err <= 5e-4 * r.abs() + 2e-5 * scale).all()), f"{name}: max err {err.max():.3g} (scale {scale:.3g})"
+
+
+def test_lrp_tail_in_place_on_a_slice():
+    from reslic_tcm_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    full = torch.randn(3, 320, 4, 4, generator=g).to(DEV)
+    lrp = torch.randn(3, 64, 4, 4, generator=g).to(DEV)
+    ref = full.clone()
+    ref[:, 64:128] += 0.5 * torch.tanh(lrp)
+    ops.lrp_tail_(full[:, 64:128], lrp)
+    assert torch.allclose(full, ref, rtol=0, atol=2e-7)
