@@ -111,7 +111,7 @@ def run_reference(args):
     if rank != 0:
         return
     c = synthetic.CONFIGS[args.config]
-    n_img = args.cpu_images or min(c.batch, 4)
+    n_img = args.cpu_images or min(c.batch, 8)
     from oracle import compressai_ref as cr
 
     cores = os.cpu_count() or 1
@@ -340,11 +340,20 @@ def run_ours(args):
         torch.cuda.synchronize()
         return r0.elapsed_time(r1) * 1e3 / (reps * n_launch), n_launch
 
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("gc_fwd_kernel", {})
+    except Exception:
+        pass
+
     def roof_obj(us, n_launch):
         elems = y_elems // n_launch
         achieved = bpe * elems / (us * 1e-6) / 1e9
+        traffic = None      # dram read+write bytes per launch from the committed ncu --set full capture
+        if traffic_db.get("config") == c.cfg and traffic_db.get("elems_per_launch") == elems:
+            traffic = traffic_db["dram_bytes_read"] + traffic_db["dram_bytes_write"]
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gc_fwd_kernel", "bytes_per_elem": bpe, "elems_per_launch": elems,
+                "traffic": traffic, "kernel": "gc_fwd_kernel", "bytes_per_elem": bpe, "elems_per_launch": elems,
                 "us_per_launch": us, "peak_source": peak_src, "gc_melem_per_s": elems / us}
 
     us_slice, n5 = gc_only_leg(False)
