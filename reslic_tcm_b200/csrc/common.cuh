@@ -96,11 +96,13 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
   return v;
 }
 
-// All 32 lanes of a warp must call.  acc = this warp's sum of log2(L) over elements of `image`;
-// `expected` = number of warps (over the whole grid) that commit to `image`.
-__device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
-                                            unsigned long long* ws, double* bits_out, bool accumulate) {
+// Split form: `rate_commit_issue` performs the warp reduction and lane 0's atomicAdd and returns
+// the post-add word (meaningful in lane 0 only); `rate_commit_finish` inspects it.  Calling finish
+// one tile later keeps the atomic's round trip off the warp's critical path.
+__device__ __forceinline__ unsigned long long rate_commit_issue(float acc, int image, int64_t B,
+                                                               unsigned long long* ws) {
   const float v = warp_sum_f32(acc);
+  unsigned long long now = 0ull;
   if ((threadIdx.x & 31) == 0) {
     const bool finite = fabsf(v) <= 1e30f;                       // false for NaN
     long long q = 0;
@@ -110,19 +112,33 @@ __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int e
       __threadfence();
     }
     const unsigned long long add = kArrOne + static_cast<unsigned long long>(q + kRateBias);
-    const unsigned long long now = atomicAdd(&ws[image], add) + add;
-    if ((now >> 48) == expected) {
-      __threadfence();
-      const long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
-      const unsigned long long flag = *reinterpret_cast<volatile unsigned long long*>(&ws[B + image]);
-      double bits = static_cast<double>(sum) * (1.0 / 65536.0);
-      if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
-      else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
-      bits_out[image] = accumulate ? bits_out[image] + bits : bits;   // single writer per image
-      ws[image] = 0ull;
-      if (flag) ws[B + image] = 0ull;
-    }
+    now = atomicAdd(&ws[image], add) + add;
   }
+  return now;
+}
+
+__device__ __forceinline__ void rate_commit_finish(unsigned long long now, int image, unsigned int expected,
+                                                   int64_t B, unsigned long long* ws, double* bits_out,
+                                                   bool accumulate) {
+  if ((threadIdx.x & 31) == 0 && (now >> 48) == expected) {
+    __threadfence();
+    const long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
+    const unsigned long long flag = *reinterpret_cast<volatile unsigned long long*>(&ws[B + image]);
+    double bits = static_cast<double>(sum) * (1.0 / 65536.0);
+    if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
+    else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
+    bits_out[image] = accumulate ? bits_out[image] + bits : bits;   // single writer per image
+    ws[image] = 0ull;
+    if (flag) ws[B + image] = 0ull;
+  }
+}
+
+// All 32 lanes of a warp must call.  acc = this warp's sum of log2(L) over elements of `image`;
+// `expected` = number of warps (over the whole grid) that commit to `image`.
+__device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
+                                            unsigned long long* ws, double* bits_out, bool accumulate) {
+  const unsigned long long now = rate_commit_issue(acc, image, B, ws);
+  rate_commit_finish(now, image, expected, B, ws, bits_out, accumulate);
 }
 
 }  // namespace reslic
