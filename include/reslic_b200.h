@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 8
+#define RESLIC_ABI_VERSION 9
 
 enum {
   RESLIC_OK = 0,
@@ -62,8 +62,22 @@ int reslic_abi_version(void);
 const char* reslic_last_error(void);
 /* Number of SMs of the current device (grid sizing is done inside the library). */
 int reslic_device_sm_count(void);
-/* Scratch bytes needed by any *_fwd call with a `bits` output for B images. */
+/* Scratch bytes needed by any *_fwd call with a rate output for B images. */
 int64_t reslic_workspace_bytes(int64_t B);
+
+/* Rate output modes (the `bits_accumulate` field of every *_fwd descriptor):
+ *   0  bits[b]  = -sum log2 L of this launch       (written by the launch's last-arriving warp)
+ *   1  bits[b] += -sum log2 L of this launch
+ *   RESLIC_RATE_DEFERRED  the sum is added to the workspace only (`bits` may be NULL and is not
+ *      touched); any number of launches — the z launch and the five slice launches of one batch,
+ *      training/loss.py:24-27 — accumulate there, and ONE reslic_rate_finalize_f64 call turns the
+ *      workspace into bits and re-zeroes it.  The launches then end without the round trip to L2
+ *      that detecting the last arriver costs (about 1.3 us of a 15 us slice launch on B200). */
+#define RESLIC_RATE_DEFERRED 2
+/* bits[b] (accumulate ? += : =) the deferred rate of image b, for b < B; same B and workspace as the
+ * launches that accumulated.  Stream-ordered after them. */
+int reslic_rate_finalize_f64(void* workspace, int64_t workspace_bytes, int64_t B, double* bits,
+                             int32_t accumulate, void* stream);
 
 /* ----------------------------------------------------------------------------------
  * Gaussian conditional, fused forward.
@@ -99,8 +113,9 @@ typedef struct reslic_gc_desc {
   double* bits;                            /* [B] -sum_i log2 L per image                 */
   int32_t bits_accumulate;                 /* 0: bits[b] = sum;  1: bits[b] += sum (lets  */
                                            /* the z and the 5 slice launches of one batch */
-                                           /* share one rate vector, loss.py:24-27)       */
-  void* workspace; int64_t workspace_bytes;/* required iff bits != NULL                   */
+                                           /* share one rate vector, loss.py:24-27);      */
+                                           /* RESLIC_RATE_DEFERRED: see above             */
+  void* workspace; int64_t workspace_bytes;/* required iff a rate output is requested     */
   uint64_t philox_seed, philox_offset;
 } reslic_gc_desc;
 

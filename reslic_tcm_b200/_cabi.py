@@ -16,7 +16,8 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 8
+ABI_VERSION = 9
+RATE_DEFERRED = 2
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -177,6 +178,7 @@ EXPORTS = {
     "reslic_set_math_mode": (C.c_int, [C.c_int]),
     "reslic_get_math_mode": (C.c_int, []),
     "reslic_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "reslic_rate_finalize_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "reslic_gc_fwd_f32": (C.c_int, [C.POINTER(GcDesc), C.c_void_p]),
     "reslic_gc_bwd_f32": (C.c_int, [C.POINTER(GcBwdDesc), C.c_void_p]),
     "reslic_build_indexes_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int32,

@@ -12,9 +12,8 @@ static int g_math_mode = RESLIC_MATH_FAST;
 int math_mode() { return g_math_mode; }
 const GcTuning& gc_tuning() {
   static GcTuning t = [] {
-    GcTuning v{-1, 1, 1};
+    GcTuning v{-1, 1};
     if (const char* e = std::getenv("RESLIC_GC_CTAS_PER_SM")) v.ctas_per_sm = std::atoi(e);
-    if (const char* e = std::getenv("RESLIC_GC_PREFETCH")) v.prefetch = std::atoi(e) != 0;
     if (const char* e = std::getenv("RESLIC_PDL")) v.pdl = std::atoi(e) != 0;
     return v;
   }();
@@ -28,6 +27,64 @@ int set_cuda_error(cudaError_t err, const char* where) {
   std::snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(err), cudaGetErrorString(err));
   return static_cast<int>(err);
 }
+int rate_setup(const char* who, double* bits, int32_t mode, void* workspace, int64_t workspace_bytes, int64_t B,
+               double** bits_out, int* mode_out, unsigned long long** ws_out) {
+  char msg[160];
+  if (mode < 0 || mode > RESLIC_RATE_DEFERRED) {
+    std::snprintf(msg, sizeof(msg), "%s: bits_accumulate must be 0, 1 or RESLIC_RATE_DEFERRED", who);
+    return set_error(RESLIC_ERR_ARG, msg);
+  }
+  if (mode != RESLIC_RATE_DEFERRED && !bits) {
+    std::snprintf(msg, sizeof(msg), "%s: bits is null", who);
+    return set_error(RESLIC_ERR_ARG, msg);
+  }
+  if (!workspace || workspace_bytes < reslic_workspace_bytes(B) || (reinterpret_cast<uintptr_t>(workspace) & 7u)) {
+    std::snprintf(msg, sizeof(msg), "%s: workspace missing, misaligned or too small for the rate output", who);
+    return set_error(RESLIC_ERR_WORKSPACE, msg);
+  }
+  *ws_out = static_cast<unsigned long long*>(workspace);
+  *mode_out = mode;
+  *bits_out = bits ? bits : reinterpret_cast<double*>(workspace);   // deferred: sentinel, never dereferenced
+  return RESLIC_OK;
+}
+
+// bits[b] (= or +=) deferred sum of image b; leaves the deferred words zero.
+__global__ void rate_finalize_kernel(unsigned long long* ws, int64_t B, double* bits, int accumulate) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= B) return;
+  const long long sum = static_cast<long long>(ws[2 * B + i]);
+  const unsigned long long flag = ws[3 * B + i];
+  double v = static_cast<double>(sum) * (1.0 / 65536.0);
+  if (flag & 1ull) v = __longlong_as_double(0x7ff8000000000000LL);
+  else if (flag & 2ull) v = __longlong_as_double(0x7ff0000000000000LL);
+  bits[i] = accumulate ? bits[i] + v : v;
+  ws[2 * B + i] = 0ull;
+  if (flag) ws[3 * B + i] = 0ull;
+}
+int rate_finalize_launch(void* workspace, int64_t workspace_bytes, int64_t B, double* bits, int32_t accumulate,
+                         cudaStream_t st) {
+  if (B < 0) return set_error(RESLIC_ERR_ARG, "rate_finalize: negative B");
+  if (B == 0) return RESLIC_OK;
+  if (!bits) return set_error(RESLIC_ERR_ARG, "rate_finalize: bits is null");
+  if (!workspace || workspace_bytes < reslic_workspace_bytes(B) || (reinterpret_cast<uintptr_t>(workspace) & 7u))
+    return set_error(RESLIC_ERR_WORKSPACE, "rate_finalize: workspace missing, misaligned or too small");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>((B + 127) / 128));
+  cfg.blockDim = dim3(128);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, rate_finalize_kernel, static_cast<unsigned long long*>(workspace), B, bits,
+                                       static_cast<int>(accumulate != 0));
+  if (err != cudaSuccess) return set_cuda_error(err, "rate_finalize launch");
+  return RESLIC_OK;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -103,7 +160,11 @@ int reslic_set_math_mode(int mode) {
 int reslic_get_math_mode(void) { return reslic::g_math_mode; }
 int64_t reslic_workspace_bytes(int64_t B) {
   if (B <= 0) return 0;
-  return 2 * B * static_cast<int64_t>(sizeof(unsigned long long));
+  return 4 * B * static_cast<int64_t>(sizeof(unsigned long long));
+}
+int reslic_rate_finalize_f64(void* workspace, int64_t workspace_bytes, int64_t B, double* bits, int32_t accumulate,
+                             void* stream) {
+  return reslic::rate_finalize_launch(workspace, workspace_bytes, B, bits, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream) {

@@ -133,12 +133,29 @@ __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int i
   }
 }
 
+// Deferred form (mode RESLIC_RATE_DEFERRED): the warp's sum goes to the image's DEFERRED word with a
+// fire-and-forget reduction (no return value, so the warp retires without waiting for the round
+// trip to L2, which is what the immediate form pays to learn whether it was the last arriver);
+// reslic_rate_finalize_f64 later turns the words into bits and re-zeroes them.  Integer addition
+// commutes, so the result is still bit-reproducible and may accumulate over any number of launches.
+// Workspace layout (64-bit words): [0,B) immediate sum/arrival, [B,2B) immediate flags,
+// [2B,3B) deferred sums (signed fixed point, bits * 2^16), [3B,4B) deferred flags.
+__device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsigned long long* ws) {
+  const float v = warp_sum_f32(acc);
+  if ((threadIdx.x & 31) == 0) {
+    if (fabsf(v) <= 1e30f) atomicAdd(&ws[2 * B + image], static_cast<unsigned long long>(__float2ll_rn(-v * 65536.0f)));
+    else atomicOr(&ws[3 * B + image], (v != v) ? 1ull : 2ull);
+  }
+}
+
 // All 32 lanes of a warp must call.  acc = this warp's sum of log2(L) over elements of `image`;
-// `expected` = number of warps (over the whole grid) that commit to `image`.
+// `expected` = number of warps (over the whole grid) that commit to `image`;
+// mode = the descriptor's bits_accumulate (0 write, 1 accumulate, 2 deferred).
 __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
-                                            unsigned long long* ws, double* bits_out, bool accumulate) {
+                                            unsigned long long* ws, double* bits_out, int mode) {
+  if (mode == 2) { rate_defer(acc, image, B, ws); return; }
   const unsigned long long now = rate_commit_issue(acc, image, B, ws);
-  rate_commit_finish(now, image, expected, B, ws, bits_out, accumulate);
+  rate_commit_finish(now, image, expected, B, ws, bits_out, mode != 0);
 }
 
 }  // namespace reslic

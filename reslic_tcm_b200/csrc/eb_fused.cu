@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads) eb_lut_kernel(const EbParams p) {
       if (last_chunk) break;
     }
     if (p.bits) rate_commit(acc, static_cast<int>(b), static_cast<unsigned int>(p.C), p.B, p.workspace, p.bits,
-                            p.bits_accumulate != 0);
+                            p.bits_accumulate);
     b += wstride;
   }
 }
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
       }
     }
   }
-  if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits, p.bits_accumulate != 0);
+  if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits, p.bits_accumulate);
 }
 
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
@@ -209,7 +209,7 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   for (int i = 0; i < 5; ++i)
     if (!d->matrix[i] || !d->bias[i] || (i < 4 && !d->factor[i]))
       return set_error(RESLIC_ERR_ARG, "eb_fwd: a parameter pointer is null");
-  if (!d->zhat && !d->ste && !d->lik && !d->sym && !d->bits)
+  if (!d->zhat && !d->ste && !d->lik && !d->sym && !rate_requested(d->bits, d->bits_accumulate))
     return set_error(RESLIC_ERR_ARG, "eb_fwd: no output requested");
 
   EbParams p{};
@@ -234,14 +234,10 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   if (bpi * d->B > max_ctas) bpi = (max_ctas + d->B - 1) / d->B;
   if (bpi < 1) bpi = 1;
   p.bpi = static_cast<int>(bpi);
-  if (d->bits) {
-    if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
-      return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace missing or too small for `bits`");
-    p.bits = d->bits;
-    p.bits_accumulate = d->bits_accumulate;
-    if (reinterpret_cast<uintptr_t>(d->workspace) & 7u)
-      return set_error(RESLIC_ERR_WORKSPACE, "eb_fwd: workspace must be 8-byte aligned");
-    p.workspace = static_cast<unsigned long long*>(d->workspace);
+  if (rate_requested(d->bits, d->bits_accumulate)) {
+    const int rc = rate_setup("eb_fwd", d->bits, d->bits_accumulate, d->workspace, d->workspace_bytes, d->B,
+                              &p.bits, &p.bits_accumulate, &p.workspace);
+    if (rc != RESLIC_OK) return rc;
   }
   cudaError_t err;
   if (!p.noise_mode) {

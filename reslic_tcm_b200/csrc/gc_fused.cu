@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gc_math.cuh"
 #include "reslic_internal.h"
+#include <limits>
 
 namespace reslic {
 
@@ -31,89 +32,165 @@ struct GcParams {
   int64_t B;          // images
   int64_t tiles_per_image;
   unsigned int tpi, total_tiles, q_tiles, r_tiles;   // 32-bit partition: CTA c owns q (+1 if c < r) tiles
-  float scale_bound, lik_bound;
+  float scale_bound;
+  float lik_floor;    // the likelihood bound, or -inf when the bound is disabled (max with it is then a no-op)
+  float d_limit;      // groups with max(|y-mu|, sigma) < d_limit take the clamp-free path; 0 sends every group to the general one
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
 
 // build_indexes: idx = #{ j < len-1 : !(s <= table[j]) } = (len-1) - sum_j [s <= table[j]].
-// Shared-memory layout `pad`: pad[0] = -inf, pad[1+j] = table[j] (j < len-1), +inf beyond, so
-// idx = g  <=>  pad[g] < s <= pad[g+1].  The scale table is log-spaced
-// (exp(linspace(ln .11, ln 256, 64)), tcm.py:26-34), so g is GUESSED from one MUFU.LG2 and
-// a fused multiply-add, then PROVEN with the two exact comparisons the reference makes; a
-// failed proof (s within rounding of a table value, a table that is not log-spaced, NaN)
+// Shared-memory layout: pad2[g] = (lo_g, hi_g) with lo_0 = -inf, lo_g = table[g-1], hi_g = lo_{g+1}
+// and +inf beyond table[len-2], so   idx = g  <=>  lo_g < s <= hi_g.   The scale table is log-spaced
+// (exp(linspace(ln .11, ln 256, 64)), tcm.py:26-34), so g is GUESSED from one MUFU.LG2 and a fused
+// multiply-add, then PROVEN with the two exact comparisons the reference makes (one 64-bit shared
+// load); a failed proof (s within rounding of a table value, a table that is not log-spaced, NaN)
 // falls back to the branch-free binary search.  The result is bit-exact for any table.
-constexpr int kPadLen = 260;
+constexpr int kPadLen = 256;
 
-template <int STEPS>
-__device__ __forceinline__ int scale_index_search(float s, const float* pad) {
+__device__ __forceinline__ int scale_index_search(float s, const float2* pad2) {
   int lo = 0;
 #pragma unroll
-  for (int step = 1 << (STEPS - 1); step > 0; step >>= 1) {
-    const float t = pad[lo + step];            // == table[lo + step - 1]
+  for (int step = 128; step > 0; step >>= 1) {
+    const float t = pad2[lo + step].x;         // == table[lo + step - 1], +inf past the table
     lo += (!(s <= t)) ? step : 0;
   }
-  return lo;  // NaN walks to 2^STEPS - 1; the caller clamps to table_len - 1
+  return lo;  // NaN walks to 255; the caller clamps to table_len - 1
+}
+__device__ __noinline__ int scale_index_cold(float s, const float2* pad2, int last) {
+  return min(scale_index_search(s, pad2), last);
+}
+// the guess: round-to-nearest of (x + 0.5 - bias) ~ ceil(x - bias), read off the mantissa of
+// x + 1.5*2^23 (no F2I: the XU pipe is the scarce one here); a wrong or wild guess fails the proof.
+__device__ __forceinline__ int scale_index_guess(float s, float g_scale, float g_off, int last) {
+  const int g = __float_as_int(fmaf(lg2_approx(s), g_scale, g_off) + 12582912.0f) - 0x4B400000;
+  return max(0, min(g, last));
 }
 
-template <int STEPS>
-__device__ __forceinline__ int scale_index(float s, const float* pad, float g_scale, float g_off, int last) {
-  // round-to-nearest of (x + 0.5 - bias) ~ ceil(x - bias), read off the mantissa of x + 1.5*2^23
-  // (no F2I: the XU pipe is the scarce one here); any wrong or wild guess is caught by the proof.
-  int g = __float_as_int(fmaf(lg2_approx(s), g_scale, g_off) + 12582912.0f) - 0x4B400000;
-  g = max(0, min(g, last));
-  const float lo = pad[g], hi = pad[g + 1];
-  if (!((lo < s) && (s <= hi))) g = min(scale_index_search<STEPS>(s, pad), last);
-  return g;
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
-// One pair of elements.  `prod` accumulates the product of the pair's (bounded) likelihoods
-// so that the rate needs one MUFU.LG2 per four elements (see the caller); `acc` is used
-// directly when the bound is too small for that.
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, int STEPS, bool FAST, bool PAIR>
-struct GcPair {
-  __device__ __forceinline__ static void run(const GcParams& p, const float* pad, float g_scale, float g_off,
-                                             F2 y, F2 mu, F2 sg, F2 u, F2& yhat, F2& ste, F2& lik,
-                                             int2& sym, int2& idx, float& prod, float& acc, bool use_prod) {
-    const F2 d = add2(y, neg2(mu));
-    // torch.round (half to even) and the int32 symbol: for |d| < 2^22 adding 1.5*2^23 rounds d to
-    // an integer in the FMA pipe and leaves that integer in the low mantissa bits; larger |d|
-    // (never seen in latents, exercised by the edge-case tests) takes the FRND/F2I path.
-    const F2 tq = add2(d, f2(12582912.0f));
-    F2 q = add2(tq, f2(-12582912.0f));
-    sym.x = __float_as_int(tq.x) - 0x4B400000;
-    sym.y = __float_as_int(tq.y) - 0x4B400000;
-    if (!(fmaxf(fabsf(d.x), fabsf(d.y)) < 4194304.0f) || d.x != d.x) {
-      q.x = rintf(d.x); q.y = rintf(d.y);
-      sym.x = __float2int_rn(q.x); sym.y = __float2int_rn(q.y);
-    }
-    ste = add2(q, mu);
-    yhat = NOISE ? add2(y, u) : ste;
-    const F2 s = max_nan2(sg, p.scale_bound);
-    if (NEED_LIK) {
-      const F2 v = abs2(add2(yhat, neg2(mu)));   // reference re-subtracts mu from the quantized value
-      F2 L = gc_likelihood<FAST>(v, s);
-      if (p.lik_bound > 0.0f) L = max_nan2(L, p.lik_bound);
-      lik = L;
-      if (!PAIR) {                       // scalar path: lane y is a dummy
-        acc += FAST ? lg2_approx(L.x) : log2f(L.x);
-      } else if (FAST) {
-        if (use_prod) prod *= L.x * L.y;
-        else acc += lg2_approx(L.x) + lg2_approx(L.y);
-      } else {
-        acc += log2f(L.x) + log2f(L.y);
-      }
-    }
-    if (NEED_IDX) {
-      idx.x = scale_index<STEPS>(s.x, pad, g_scale, g_off, p.table_len - 1);
-      idx.y = PAIR ? scale_index<STEPS>(s.y, pad, g_scale, g_off, p.table_len - 1) : 0;
-    }
+// ------------------------------------------------------------------ one element, any input
+// The general path: every operand class the reference accepts (|y-mu| >= 2^22, inf, NaN, huge or
+// denormal sigma) — used by the scalar kernel (unaligned tensors, n % 4 != 0) and, out of line,
+// by the vector kernel for the rare group that fails its range check.
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool FAST>
+__device__ __forceinline__ void gc_elem(float y, float mu, float sg, float u, float scale_bound, float lik_floor,
+                                        const float2* pad2, int last, float& yhat, float& ste, float& lik,
+                                        int& sym, int& idx, float& acc) {
+  const float q = rintf(y - mu);               // torch.round: half to even
+  sym = __float2int_rn(q);
+  ste = q + mu;
+  yhat = NOISE ? y + u : ste;
+  const float s = max_nan(sg, scale_bound);
+  lik = 0.0f; idx = 0;
+  if (NEED_LIK) {
+    const float v = fabsf(yhat - mu);          // the reference re-subtracts mu from the quantized value
+    const float L = max_nan(gc_likelihood<FAST>(f2(v), f2(s)).x, lik_floor);
+    lik = L;
+    acc += FAST ? lg2_approx(L) : log2f(L);
   }
-};
+  if (NEED_IDX) idx = min(scale_index_search(s, pad2), last);
+}
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST, bool PF>
-__global__ void __launch_bounds__(kThreads, PF ? 4 : 5)
+struct GcOutPtrs { float* yhat; float* ste; float* lik; int32_t* sym; int32_t* idx; };
+
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool FAST>
+__device__ __noinline__ float gc_group_cold(float4 y, float4 m, float4 s, float4 u, float scale_bound, float lik_floor,
+                                            const float2* pad2, int last, GcOutPtrs o) {
+  float acc = 0.0f;
+  float4 oy, os, ol; int4 osym, oidx;
+  gc_elem<NEED_LIK, NEED_IDX, NOISE, FAST>(y.x, m.x, s.x, u.x, scale_bound, lik_floor, pad2, last, oy.x, os.x, ol.x, osym.x, oidx.x, acc);
+  gc_elem<NEED_LIK, NEED_IDX, NOISE, FAST>(y.y, m.y, s.y, u.y, scale_bound, lik_floor, pad2, last, oy.y, os.y, ol.y, osym.y, oidx.y, acc);
+  gc_elem<NEED_LIK, NEED_IDX, NOISE, FAST>(y.z, m.z, s.z, u.z, scale_bound, lik_floor, pad2, last, oy.z, os.z, ol.z, osym.z, oidx.z, acc);
+  gc_elem<NEED_LIK, NEED_IDX, NOISE, FAST>(y.w, m.w, s.w, u.w, scale_bound, lik_floor, pad2, last, oy.w, os.w, ol.w, osym.w, oidx.w, acc);
+  if (o.yhat) st_stream4(o.yhat, oy);
+  if (o.ste) st_stream4(o.ste, os);
+  if (NEED_LIK && o.lik) st_stream4(o.lik, ol);
+  if (o.sym) st_stream4(o.sym, osym);
+  if (NEED_IDX && o.idx) st_stream4(o.idx, oidx);
+  return acc;
+}
+
+// ------------------------------------------------------------------ four elements, in range
+// One range check per group — max(|d_0..3|, s_0..3) < d_limit (2^22), NaN fails — proves that every
+// intermediate below is finite, so the hot path carries no clamp: round and symbol come from one
+// magic-number add (adding 1.5*2^23 rounds d to an integer, half to even, in the FMA pipe and
+// leaves that integer in the low mantissa bits), the likelihood from gc_likelihood_finite, and
+// the rate from ONE MUFU.LG2 of the product of the four bounded likelihoods (abs err <= 2^-22
+// for arguments in (0.5,2), rel err 2^-22 elsewhere; the host only enables this path while the
+// bound is >= 1e-9, so the product stays above 1e-36 > FLT_MIN).
+struct GcIn { float4 y, m, s, u; };
+
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool FAST>
+__device__ __forceinline__ void gc_group_vec(const GcParams& p, const float2* pad2, float g_scale, float g_off,
+                                             const GcIn& in, const GcOutPtrs& base, unsigned int bo, float& acc) {
+  auto at = [bo](auto* ptr) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + bo); };
+  const F2 y0 = make_float2(in.y.x, in.y.y), y1 = make_float2(in.y.z, in.y.w);
+  const F2 m0 = make_float2(in.m.x, in.m.y), m1 = make_float2(in.m.z, in.m.w);
+  const F2 d0 = add2(y0, neg2(m0)), d1 = add2(y1, neg2(m1));
+  const F2 s0 = max_nan2(make_float2(in.s.x, in.s.y), p.scale_bound);
+  const F2 s1 = max_nan2(make_float2(in.s.z, in.s.w), p.scale_bound);
+  float mx = max3_nan(fabsf(d0.x), fabsf(d0.y), fabsf(d1.x));
+  if (NEED_LIK || NEED_IDX) {
+    mx = max3_nan(mx, fabsf(d1.y), s0.x);
+    mx = max3_nan(mx, s0.y, s1.x);
+    mx = max_nan(mx, s1.y);
+  } else {
+    mx = max_nan(mx, fabsf(d1.y));
+  }
+  if (NOISE) {   // caller-supplied noise is data too
+    mx = max3_nan(mx, fabsf(in.u.x), fabsf(in.u.y));
+    mx = max3_nan(mx, fabsf(in.u.z), fabsf(in.u.w));
+  }
+  const int last = p.table_len - 1;
+  if (!(mx < p.d_limit)) {
+    GcOutPtrs o;
+    o.yhat = base.yhat ? at(base.yhat) : nullptr; o.ste = base.ste ? at(base.ste) : nullptr;
+    o.lik = base.lik ? at(base.lik) : nullptr; o.sym = base.sym ? at(base.sym) : nullptr;
+    o.idx = base.idx ? at(base.idx) : nullptr;
+    acc += gc_group_cold<NEED_LIK, NEED_IDX, NOISE, FAST>(in.y, in.m, in.s, in.u, p.scale_bound, p.lik_floor, pad2, last, o);
+    return;
+  }
+  const F2 magic = f2(12582912.0f);
+  const F2 t0 = add2(d0, magic), t1 = add2(d1, magic);
+  const F2 q0 = add2(t0, neg2(magic)), q1 = add2(t1, neg2(magic));
+  const F2 e0 = add2(q0, m0), e1 = add2(q1, m1);                 // ste_round output
+  F2 h0 = e0, h1 = e1;                                           // quantize() output
+  if (NOISE) { h0 = add2(y0, make_float2(in.u.x, in.u.y)); h1 = add2(y1, make_float2(in.u.z, in.u.w)); }
+  if (base.yhat) st_stream4(at(base.yhat), make_float4(h0.x, h0.y, h1.x, h1.y));
+  if (base.ste) st_stream4(at(base.ste), make_float4(e0.x, e0.y, e1.x, e1.y));
+  if (base.sym)
+    st_stream4(at(base.sym), make_int4(__float_as_int(t0.x) - 0x4B400000, __float_as_int(t0.y) - 0x4B400000,
+                                       __float_as_int(t1.x) - 0x4B400000, __float_as_int(t1.y) - 0x4B400000));
+  if (NEED_LIK) {
+    const F2 v0 = abs2(add2(h0, neg2(m0))), v1 = abs2(add2(h1, neg2(m1)));   // the reference re-subtracts mu
+    const F2 L0 = max_nan2(gc_likelihood_finite<FAST>(v0, s0), p.lik_floor);
+    const F2 L1 = max_nan2(gc_likelihood_finite<FAST>(v1, s1), p.lik_floor);
+    if (base.lik) st_stream4(at(base.lik), make_float4(L0.x, L0.y, L1.x, L1.y));
+    if (FAST) acc += lg2_approx((L0.x * L0.y) * (L1.x * L1.y));
+    else acc += (log2f(L0.x) + log2f(L0.y)) + (log2f(L1.x) + log2f(L1.y));
+  }
+  if (NEED_IDX) {
+    int g0 = scale_index_guess(s0.x, g_scale, g_off, last), g1 = scale_index_guess(s0.y, g_scale, g_off, last);
+    int g2 = scale_index_guess(s1.x, g_scale, g_off, last), g3 = scale_index_guess(s1.y, g_scale, g_off, last);
+    const float2 b0 = pad2[g0], b1 = pad2[g1], b2 = pad2[g2], b3 = pad2[g3];
+    const bool proven = (b0.x < s0.x) && (s0.x <= b0.y) && (b1.x < s0.y) && (s0.y <= b1.y) &&
+                        (b2.x < s1.x) && (s1.x <= b2.y) && (b3.x < s1.y) && (s1.y <= b3.y);
+    if (!proven) {
+      g0 = scale_index_cold(s0.x, pad2, last); g1 = scale_index_cold(s0.y, pad2, last);
+      g2 = scale_index_cold(s1.x, pad2, last); g3 = scale_index_cold(s1.y, pad2, last);
+    }
+    if (base.idx) st_stream4(at(base.idx), make_int4(g0, g1, g2, g3));
+  }
+}
+
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST>
+__global__ void __launch_bounds__(kThreads, 4)
 gc_fwd_kernel(const GcParams p) {
-  __shared__ float pad[NEED_IDX ? kPadLen : 1];
+  __shared__ float2 pad2[NEED_IDX ? kPadLen : 1];
   __shared__ float s_guess[2];
   float g_scale = 0.0f, g_off = 0.0f;
   // Programmatic dependent launch: this grid may have been scheduled while its predecessor
@@ -124,8 +201,9 @@ gc_fwd_kernel(const GcParams p) {
   bool table_staged = !NEED_IDX;
   auto stage_table = [&]() {
     const float inf = __int_as_float(0x7f800000);
-    for (int i = threadIdx.x; i < kPadLen; i += kThreads)
-      pad[i] = (i == 0) ? -inf : ((i <= p.table_len - 1) ? p.table[i - 1] : inf);
+    const int last = p.table_len - 1;
+    auto entry = [&](int i) { return (i == 0) ? -inf : ((i <= last) ? p.table[i - 1] : inf); };
+    for (int i = threadIdx.x; i < kPadLen; i += kThreads) pad2[i] = make_float2(entry(i), entry(i + 1));
     if (threadIdx.x == 0) {
       // guess(s) = ceil((log2 s - log2 t_0) * (len-2) / (log2 t_{len-2} - log2 t_0))
       float sc = 0.0f, off = 0.0f;
@@ -142,128 +220,116 @@ gc_fwd_kernel(const GcParams p) {
   };
 
   // Persistent CTAs: the slice is cut into tiles of kThreads element groups (a tile never
-  // straddles two images); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G), so all
-  // CTAs get the same work to within one tile and stay resident for the whole launch.  The
-  // range is walked image segment by image segment: inside a segment every tensor pointer
-  // just advances by one tile, and the next tile's loads are issued before the current tile
-  // is computed (register double buffer), so a CTA never alternates between an all-loads and
-  // an all-math phase.
+  // straddles two images); CTA c owns the contiguous tile range [c*q + min(c,r), ...) — q = T / G,
+  // r = T % G precomputed on the host in 32-bit arithmetic — so all CTAs get the same work to
+  // within one tile and stay resident for the whole launch.  The range is walked image segment by
+  // image segment.  Inside a segment every tensor is addressed as (segment base, uniform) +
+  // (32-bit byte offset, per thread): no per-thread pointer registers, two integer adds per access.
+  // Tiles are double-buffered in registers by a two-tile ping-pong (A computes while B loads and
+  // vice versa), so a CTA never alternates between an all-loads and an all-math phase and no
+  // register is ever copied from a "next" to a "current" buffer.
   constexpr int W = VEC ? 4 : 1;
-  constexpr int kTileElems = kThreads * W;
+  constexpr unsigned int kTileBytes = kThreads * W * 4;
   const int groups = static_cast<int>(VEC ? (p.n >> 2) : p.n);      // per image (n < 2^31 checked on host)
-  // CTA c owns tiles [c*q + min(c,r), ...) — q = T / G, r = T % G precomputed on the host, all in
-  // 32-bit arithmetic (64-bit divisions here sat on the critical path of short launches)
   const unsigned int cta = blockIdx.x;
   unsigned int t = cta * p.q_tiles + min(cta, p.r_tiles);
   const unsigned int t_end = t + p.q_tiles + (cta < p.r_tiles ? 1u : 0u);
+  const unsigned int tb = threadIdx.x * (W * 4);
 
-  struct In { float y[4], m[4], s[4], u[4]; };
+  GcIn a, b;
+  a.y = a.m = a.u = make_float4(0.f, 0.f, 0.f, 0.f); a.s = make_float4(1.f, 1.f, 1.f, 1.f);
+  b = a;                                     // absent inputs keep these defaults for the whole launch
   while (t < t_end) {
     const int image = static_cast<int>(t / p.tpi);
     const int chunk0 = static_cast<int>(t - image * p.tpi);
     const unsigned int seg_end = (static_cast<unsigned int>(image) + 1u) * p.tpi;
     const int ntiles = static_cast<int>(min(seg_end, t_end) - t);
     t += ntiles;
-    int g = chunk0 * kThreads + threadIdx.x;                       // element group inside the image
-    const int64_t e0 = static_cast<int64_t>(g) * W;
-    const float* __restrict__ y = p.y ? p.y + image * p.y_bs + e0 : nullptr;
-    const float* __restrict__ mu = p.mu ? p.mu + image * p.mu_bs + e0 : nullptr;
-    const float* __restrict__ sg = p.sigma ? p.sigma + image * p.sigma_bs + e0 : nullptr;
-    const float* __restrict__ nz = (NOISE && p.noise) ? p.noise + image * p.noise_bs + e0 : nullptr;
-    float* yhat = p.yhat ? p.yhat + image * p.yhat_bs + e0 : nullptr;
-    float* ste = p.ste ? p.ste + image * p.ste_bs + e0 : nullptr;
-    float* lik = (NEED_LIK && p.lik) ? p.lik + image * p.lik_bs + e0 : nullptr;
-    int32_t* sym = p.sym ? p.sym + image * p.sym_bs + e0 : nullptr;
-    int32_t* idx = (NEED_IDX && p.idx) ? p.idx + image * p.idx_bs + e0 : nullptr;
+    const int64_t seg = static_cast<int64_t>(chunk0) * (kThreads * W);          // element offset of tile 0 in the image
+    const float* y = p.y ? p.y + image * p.y_bs + seg : nullptr;
+    const float* mu = p.mu ? p.mu + image * p.mu_bs + seg : nullptr;
+    const float* sg = p.sigma ? p.sigma + image * p.sigma_bs + seg : nullptr;
+    const float* nz = (NOISE && p.noise) ? p.noise + image * p.noise_bs + seg : nullptr;
+    GcOutPtrs o;
+    o.yhat = p.yhat ? p.yhat + image * p.yhat_bs + seg : nullptr;
+    o.ste = p.ste ? p.ste + image * p.ste_bs + seg : nullptr;
+    o.lik = (NEED_LIK && p.lik) ? p.lik + image * p.lik_bs + seg : nullptr;
+    o.sym = p.sym ? p.sym + image * p.sym_bs + seg : nullptr;
+    o.idx = (NEED_IDX && p.idx) ? p.idx + image * p.idx_bs + seg : nullptr;
+    const int g = chunk0 * kThreads + threadIdx.x;                 // this thread's element group in tile 0
 
-    auto load = [&](In& r, int k) {          // tile k of this segment (k*kTileElems ahead of the base)
-      const int off = k * kTileElems;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { r.y[j] = 0.f; r.m[j] = 0.f; r.s[j] = 1.f; r.u[j] = 0.f; }
+    auto load = [&](GcIn& r, int k) {        // tile k of this segment
       if (g + k * kThreads >= groups) return;
+      const unsigned int bo = tb + static_cast<unsigned int>(k) * kTileBytes;
+      auto at = [bo](const float* ptr) { return reinterpret_cast<const float*>(reinterpret_cast<const char*>(ptr) + bo); };
       if (VEC) {
-        if (y) { const float4 v = ld_stream4(y + off); r.y[0] = v.x; r.y[1] = v.y; r.y[2] = v.z; r.y[3] = v.w; }
-        if (mu) { const float4 v = ld_stream4(mu + off); r.m[0] = v.x; r.m[1] = v.y; r.m[2] = v.z; r.m[3] = v.w; }
-        if (sg) { const float4 v = ld_stream4(sg + off); r.s[0] = v.x; r.s[1] = v.y; r.s[2] = v.z; r.s[3] = v.w; }
-        if (NOISE && nz) { const float4 v = ld_stream4(nz + off); r.u[0] = v.x; r.u[1] = v.y; r.u[2] = v.z; r.u[3] = v.w; }
+        if (y) r.y = ld_stream4(at(y));
+        if (mu) r.m = ld_stream4(at(mu));
+        if (sg) r.s = ld_stream4(at(sg));
+        if (NOISE && nz) r.u = ld_stream4(at(nz));
       } else {
-        if (y) r.y[0] = ld_stream1(y + off);
-        if (mu) r.m[0] = ld_stream1(mu + off);
-        if (sg) r.s[0] = ld_stream1(sg + off);
-        if (NOISE && nz) r.u[0] = ld_stream1(nz + off);
+        if (y) r.y.x = ld_stream1(at(y));
+        if (mu) r.m.x = ld_stream1(at(mu));
+        if (sg) r.s.x = ld_stream1(at(sg));
+        if (NOISE && nz) r.u.x = ld_stream1(at(nz));
+      }
+    };
+    float acc = 0.0f;
+    auto compute = [&](GcIn& r, int k) {
+      const int gk = g + k * kThreads;
+      if (gk >= groups) return;
+      const unsigned int bo = tb + static_cast<unsigned int>(k) * kTileBytes;
+      if (NOISE && !nz) {
+        // counter = global element-group id; one Philox call feeds 4 consecutive elements
+        const uint64_t gq = static_cast<uint64_t>(VEC ? gk : (gk >> 2));
+        const uint64_t gid = static_cast<uint64_t>(image) * static_cast<uint64_t>((p.n + 3) >> 2) + gq;
+        const Philox4 x = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                        p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+        if (VEC) {
+          r.u = make_float4(u32_to_centered_uniform(x.x), u32_to_centered_uniform(x.y),
+                            u32_to_centered_uniform(x.z), u32_to_centered_uniform(x.w));
+        } else {
+          const int q4 = gk & 3;
+          r.u.x = u32_to_centered_uniform(q4 == 0 ? x.x : q4 == 1 ? x.y : q4 == 2 ? x.z : x.w);
+        }
+      }
+      if (VEC) {
+        gc_group_vec<NEED_LIK, NEED_IDX, NOISE, FAST>(p, pad2, g_scale, g_off, r, o, bo, acc);
+      } else {
+        float yh, st, lk; int sy, ix;
+        gc_elem<NEED_LIK, NEED_IDX, NOISE, FAST>(r.y.x, r.m.x, r.s.x, r.u.x, p.scale_bound, p.lik_floor, pad2,
+                                                 p.table_len - 1, yh, st, lk, sy, ix, acc);
+        auto at = [bo](auto* ptr) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + bo); };
+        if (o.yhat) st_stream1(at(o.yhat), yh);
+        if (o.ste) st_stream1(at(o.ste), st);
+        if (o.lik) st_stream1(at(o.lik), lk);
+        if (o.sym) st_stream1(at(o.sym), sy);
+        if (o.idx) st_stream1(at(o.idx), ix);
       }
     };
 
-    float acc = 0.0f;
-    In cur;
-    load(cur, 0);
+    load(a, 0);
     if (!table_staged) stage_table();      // the first tile's loads are already in flight
-    for (int k = 0; k < ntiles; ++k) {
-      In nxt;
-      if (PF && k + 1 < ntiles) load(nxt, k + 1);
-      const int gk = g + k * kThreads;
-      if (gk < groups) {
-        const int off = k * kTileElems;
-        if (NOISE && !nz) {
-          // counter = global element-group id; one Philox call feeds 4 consecutive elements
-          const uint64_t gq = static_cast<uint64_t>(VEC ? gk : (gk >> 2));
-          const uint64_t gid = static_cast<uint64_t>(image) * static_cast<uint64_t>((p.n + 3) >> 2) + gq;
-          const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                          p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
-          if (VEC) {
-            cur.u[0] = u32_to_centered_uniform(r.x); cur.u[1] = u32_to_centered_uniform(r.y);
-            cur.u[2] = u32_to_centered_uniform(r.z); cur.u[3] = u32_to_centered_uniform(r.w);
-          } else {
-            const int q4 = gk & 3;
-            cur.u[0] = u32_to_centered_uniform(q4 == 0 ? r.x : q4 == 1 ? r.y : q4 == 2 ? r.z : r.w);
-          }
-        }
-        float oy[4], os[4], ol[4]; int osym[4], oidx[4];
-        // rate: FAST mode multiplies the four bounded likelihoods of a group and takes ONE
-        // MUFU.LG2 (abs err <= 2^-22 for arguments in (0.5,2), rel err 2^-22 elsewhere); the
-        // product cannot underflow while the bound is >= 1e-9 (1e-36 > FLT_MIN).
-        const bool use_prod = FAST && p.lik_bound >= 1e-9f;
-        float prod = 1.0f;
-#pragma unroll
-        for (int j = 0; j < (VEC ? 2 : 1); ++j) {
-          const int j0 = 2 * j, j1 = 2 * j + 1;
-          F2 yh, st, lk; int2 sy, ix;
-          GcPair<NEED_LIK, NEED_IDX, NOISE, STEPS, FAST, VEC>::run(
-              p, pad, g_scale, g_off, make_float2(cur.y[j0], cur.y[j1]), make_float2(cur.m[j0], cur.m[j1]),
-              make_float2(cur.s[j0], cur.s[j1]), make_float2(cur.u[j0], cur.u[j1]), yh, st, lk, sy, ix, prod, acc,
-              use_prod && VEC);
-          oy[j0] = yh.x; os[j0] = st.x; ol[j0] = lk.x; osym[j0] = sy.x; oidx[j0] = ix.x;
-          if (VEC) { oy[j1] = yh.y; os[j1] = st.y; ol[j1] = lk.y; osym[j1] = sy.y; oidx[j1] = ix.y; }
-        }
-        if (NEED_LIK && use_prod && VEC) acc += lg2_approx(prod);
-        if (VEC) {
-          if (yhat) st_stream4(yhat + off, make_float4(oy[0], oy[1], oy[2], oy[3]));
-          if (ste) st_stream4(ste + off, make_float4(os[0], os[1], os[2], os[3]));
-          if (lik) st_stream4(lik + off, make_float4(ol[0], ol[1], ol[2], ol[3]));
-          if (sym) st_stream4(sym + off, make_int4(osym[0], osym[1], osym[2], osym[3]));
-          if (idx) st_stream4(idx + off, make_int4(oidx[0], oidx[1], oidx[2], oidx[3]));
-        } else {
-          if (yhat) st_stream1(yhat + off, oy[0]);
-          if (ste) st_stream1(ste + off, os[0]);
-          if (lik) st_stream1(lik + off, ol[0]);
-          if (sym) st_stream1(sym + off, osym[0]);
-          if (idx) st_stream1(idx + off, oidx[0]);
-        }
-      }
-      if (PF) cur = nxt;
-      else if (k + 1 < ntiles) load(cur, k + 1);
+    for (int k = 0; k < ntiles; k += 2) {
+      if (k + 1 < ntiles) load(b, k + 1);
+      compute(a, k);
+      if (k + 2 < ntiles) load(a, k + 2);
+      if (k + 1 < ntiles) compute(b, k + 1);
     }
     if (NEED_LIK && p.bits) {
-      // warps committing to this image = (CTAs whose tile range meets the image) * warps per CTA;
-      // tile tau belongs to CTA ceil((tau+1)*G/T) - 1.
-      // owner of tile tau: the first r CTAs hold q+1 tiles each, the rest q
-      auto owner = [&](unsigned int tau) -> unsigned int {
-        const unsigned int big = p.r_tiles * (p.q_tiles + 1u);
-        return tau < big ? tau / (p.q_tiles + 1u) : p.r_tiles + (tau - big) / p.q_tiles;
-      };
-      const unsigned int first = static_cast<unsigned int>(image) * p.tpi;
-      const unsigned int n_ctas = owner(first + p.tpi - 1u) - owner(first) + 1u;
-      rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate != 0);
+      if (p.bits_accumulate == RESLIC_RATE_DEFERRED) {
+        rate_defer(acc, image, p.B, p.workspace);      // fire and forget: the warp retires without a round trip
+      } else {
+        // warps committing to this image = (CTAs whose tile range meets the image) * warps per CTA;
+        // owner of tile tau: the first r CTAs hold q+1 tiles each, the rest q
+        auto owner = [&](unsigned int tau) -> unsigned int {
+          const unsigned int big = p.r_tiles * (p.q_tiles + 1u);
+          return tau < big ? tau / (p.q_tiles + 1u) : p.r_tiles + (tau - big) / p.q_tiles;
+        };
+        const unsigned int first = static_cast<unsigned int>(image) * p.tpi;
+        const unsigned int n_ctas = owner(first + p.tpi - 1u) - owner(first) + 1u;
+        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate);
+      }
     }
   }
 }
@@ -282,10 +348,10 @@ static int resident_ctas(K kernel, int* cache) {
   return *cache;
 }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST, bool PF>
-static cudaError_t launch_pf(GcParams& p, cudaStream_t st) {
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST>
+static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
   static int occ = 0;
-  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, STEPS, FAST, PF>;
+  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, FAST>;
   const int64_t total = p.tiles_per_image * p.B;
   const int waves = gc_tuning().ctas_per_sm;   // 0: one tile per CTA; k>0: k CTAs per SM; <0: resident count
   int64_t grid = total;
@@ -296,6 +362,8 @@ static cudaError_t launch_pf(GcParams& p, cudaStream_t st) {
   p.total_tiles = static_cast<unsigned int>(total);
   p.q_tiles = static_cast<unsigned int>(total / grid);
   p.r_tiles = static_cast<unsigned int>(total % grid);
+  // per-thread byte offsets inside a CTA's tile range are 32-bit
+  if (static_cast<int64_t>(p.q_tiles) + 1 >= (1LL << 32) / (kThreads * 16)) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
@@ -308,29 +376,21 @@ static cudaError_t launch_pf(GcParams& p, cudaStream_t st) {
   cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, int STEPS, bool FAST>
-static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
-  return gc_tuning().prefetch ? launch_pf<NEED_LIK, NEED_IDX, NOISE, VEC, STEPS, FAST, true>(p, st)
-                              : launch_pf<NEED_LIK, NEED_IDX, NOISE, VEC, STEPS, FAST, false>(p, st);
-}
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
-static cudaError_t launch_steps(GcParams& p, int steps, bool fast, cudaStream_t st) {
+static cudaError_t launch_math(GcParams& p, bool fast, cudaStream_t st) {
   // the math policy only matters when a likelihood is computed
-  if (NEED_LIK && !fast)
-    return steps <= 6 ? launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 6, false>(p, st)
-                      : launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 8, false>(p, st);
-  return steps <= 6 ? launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 6, true>(p, st)
-                    : launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, 8, true>(p, st);
+  if (NEED_LIK && !fast) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, false>(p, st);
+  return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, true>(p, st);
 }
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE>
-static cudaError_t launch_vec(GcParams& p, int steps, bool vec, bool fast, cudaStream_t st) {
-  return vec ? launch_steps<NEED_LIK, NEED_IDX, NOISE, true>(p, steps, fast, st)
-             : launch_steps<NEED_LIK, NEED_IDX, NOISE, false>(p, steps, fast, st);
+static cudaError_t launch_vec(GcParams& p, bool vec, bool fast, cudaStream_t st) {
+  return vec ? launch_math<NEED_LIK, NEED_IDX, NOISE, true>(p, fast, st)
+             : launch_math<NEED_LIK, NEED_IDX, NOISE, false>(p, fast, st);
 }
 template <bool NEED_LIK, bool NEED_IDX>
-static cudaError_t launch_noise(GcParams& p, int steps, bool vec, bool noise, bool fast, cudaStream_t st) {
-  return noise ? launch_vec<NEED_LIK, NEED_IDX, true>(p, steps, vec, fast, st)
-               : launch_vec<NEED_LIK, NEED_IDX, false>(p, steps, vec, fast, st);
+static cudaError_t launch_noise(GcParams& p, bool vec, bool noise, bool fast, cudaStream_t st) {
+  return noise ? launch_vec<NEED_LIK, NEED_IDX, true>(p, vec, fast, st)
+               : launch_vec<NEED_LIK, NEED_IDX, false>(p, vec, fast, st);
 }
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
@@ -340,7 +400,8 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   if (d->B > (1 << 24)) return set_error(RESLIC_ERR_ARG, "gc_fwd: B too large");
   if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE)
     return set_error(RESLIC_ERR_ARG, "gc_fwd: invalid quantization mode");
-  const bool need_lik = d->lik || d->bits;
+  const bool want_rate = rate_requested(d->bits, d->bits_accumulate);
+  const bool need_lik = d->lik || want_rate;
   const bool need_idx = d->idx != nullptr;
   const bool need_y = d->yhat || d->ste || d->sym || need_lik;
   if (need_y && !d->y) return set_error(RESLIC_ERR_ARG, "gc_fwd: y is null");
@@ -357,7 +418,9 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   p.yhat = d->yhat; p.ste = d->ste; p.lik = d->lik; p.sym = d->sym; p.idx = d->idx;
   p.yhat_bs = d->yhat_bs; p.ste_bs = d->ste_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs; p.idx_bs = d->idx_bs;
   p.table = d->scale_table; p.table_len = d->table_len;
-  p.n = d->n; p.B = d->B; p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
+  p.n = d->n; p.B = d->B; p.scale_bound = d->scale_bound;
+  // compressai applies the likelihood bound only when it is > 0; max(L, -inf) is the branch-free "no bound"
+  p.lik_floor = d->likelihood_bound > 0.0f ? d->likelihood_bound : -std::numeric_limits<float>::infinity();
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
 
@@ -373,24 +436,22 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   p.tiles_per_image = (groups + kThreads - 1) / kThreads;
   if (d->n >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "gc_fwd: more than 2^31 elements per image");
   if (p.tiles_per_image * d->B >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "gc_fwd: input too large (>= 2^31 tiles)");
-  if (d->bits) {
-    if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B))
-      return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace missing or too small for `bits`");
-    if (reinterpret_cast<uintptr_t>(d->workspace) & 7u)
-      return set_error(RESLIC_ERR_WORKSPACE, "gc_fwd: workspace must be 8-byte aligned");
-    p.bits = d->bits;
-    p.bits_accumulate = d->bits_accumulate;
-    p.workspace = static_cast<unsigned long long*>(d->workspace);
+  if (want_rate) {
+    const int rc = rate_setup("gc_fwd", d->bits, d->bits_accumulate, d->workspace, d->workspace_bytes, d->B,
+                              &p.bits, &p.bits_accumulate, &p.workspace);
+    if (rc != RESLIC_OK) return rc;
   }
-  int steps = 6;
-  if (need_idx && d->table_len - 1 > 63) steps = 8;
   const bool noise = d->mode == RESLIC_Q_NOISE;
   const bool fast = math_mode() != RESLIC_MATH_MIRROR;
+  // The clamp-free path needs (2^22 + 1) / scale_bound far from overflow and, in FAST mode, a bound
+  // that keeps the product of four likelihoods normal; exotic settings run the general path throughout.
+  const bool product_ok = !need_lik || !fast || d->likelihood_bound >= 1e-9f;
+  p.d_limit = (d->scale_bound >= 1e-3f && product_ok) ? 4194304.0f : 0.0f;
   cudaError_t err;
-  if (need_lik) err = need_idx ? launch_noise<true, true>(p, steps, vec, noise, fast, st)
-                               : launch_noise<true, false>(p, steps, vec, noise, fast, st);
-  else err = need_idx ? launch_noise<false, true>(p, steps, vec, noise, fast, st)
-                      : launch_noise<false, false>(p, steps, vec, noise, fast, st);
+  if (need_lik) err = need_idx ? launch_noise<true, true>(p, vec, noise, fast, st)
+                               : launch_noise<true, false>(p, vec, noise, fast, st);
+  else err = need_idx ? launch_noise<false, true>(p, vec, noise, fast, st)
+                      : launch_noise<false, false>(p, vec, noise, fast, st);
   if (err != cudaSuccess) return set_cuda_error(err, "gc_fwd launch");
   return RESLIC_OK;
 }

@@ -72,6 +72,28 @@ __device__ __forceinline__ F2 erfc_pos_fast(F2 x) {
   return mul2(E, mul2(w, q));
 }
 
+// L for operands known to be finite and moderate: 0 <= v <= 2^23, scale_bound <= s < 2^22 with
+// scale_bound >= 1e-3 (the vector kernel's per-group range check).  |x| then stays below 1e10, x*x
+// is finite, ex2 flushes to zero beyond x ~ 9.4 and 0 * finite = 0: no clamp is needed and the
+// value equals gc_likelihood's bit for bit.
+template <bool FAST>
+__device__ __forceinline__ F2 gc_likelihood_finite(F2 v, F2 s) {
+  F2 a, b;
+  div2_rn(add2(f2(0.5f), neg2(v)), add2(f2(-0.5f), neg2(v)), s, a, b);
+  const F2 c = f2(-0.70710678118654752440f);
+  const F2 xa = mul2(c, a), xb = mul2(c, b);  // xb > 0 always; xa < 0 iff v < 0.5
+  if (FAST) {
+    F2 ea = erfc_pos_fast(abs2(xa));
+    const F2 eb = erfc_pos_fast(xb);
+    ea.x = (xa.x < 0.0f) ? 2.0f - ea.x : ea.x;
+    ea.y = (xa.y < 0.0f) ? 2.0f - ea.y : ea.y;
+    return fma2(f2(0.5f), ea, mul2(f2(-0.5f), eb));
+  }
+  const F2 upper = make_float2(0.5f * erfcf(xa.x), 0.5f * erfcf(xa.y));
+  const F2 lower = make_float2(0.5f * erfcf(xb.x), 0.5f * erfcf(xb.y));
+  return add2(upper, neg2(lower));
+}
+
 template <bool FAST>
 __device__ __forceinline__ F2 gc_likelihood(F2 v, F2 s) {
   // clamps keep every intermediate finite (inf/inf, 0*inf); they change no result for

@@ -9,8 +9,16 @@ namespace reslic {
 int set_error(int code, const char* msg);                 // returns code
 int set_cuda_error(cudaError_t err, const char* where);   // returns (int)err
 int sm_count();
-struct GcTuning { int ctas_per_sm; int prefetch; int pdl; };
+struct GcTuning { int ctas_per_sm; int pdl; };
 const GcTuning& gc_tuning();                              // launch-shape knobs (env overridable)
+// Rate outputs of a *_fwd descriptor: requested when `bits` is given or the mode is RESLIC_RATE_DEFERRED.
+inline bool rate_requested(const double* bits, int32_t mode) { return bits != nullptr || mode == 2; }
+// Validates mode/workspace and fills the kernel-side fields; in deferred mode *bits_out is a non-null
+// sentinel (never dereferenced) so that kernels keep one `if (p.bits)` gate.  Returns RESLIC_OK or an error.
+int rate_setup(const char* who, double* bits, int32_t mode, void* workspace, int64_t workspace_bytes, int64_t B,
+               double** bits_out, int* mode_out, unsigned long long** ws_out);
+int rate_finalize_launch(void* workspace, int64_t workspace_bytes, int64_t B, double* bits, int32_t accumulate,
+                         cudaStream_t st);
 int math_mode();                                          // RESLIC_MATH_*                                           // SMs of the current device (cached per device)
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);

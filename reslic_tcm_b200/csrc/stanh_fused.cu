@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) stanh_gc_fwd_kernel(const StanhParam
       const int64_t c_lo = ((first + 1) * G + total - 1) / total - 1;
       const int64_t c_hi = ((last + 1) * G + total - 1) / total - 1;
       rate_commit(acc, image, static_cast<unsigned int>((c_hi - c_lo + 1) * (kThreads / 32)), p.B, p.workspace,
-                  p.bits, p.bits_accumulate != 0);
+                  p.bits, p.bits_accumulate);
     }
   }
 }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) eb_stanh_fwd_kernel(const EbStanhPar
     }
   }
   if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits,
-                          p.bits_accumulate != 0);
+                          p.bits_accumulate);
 }
 
 static int steps_for(int K) { int s = 1; while ((1 << s) <= K) ++s; return s; }
@@ -332,7 +332,7 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
   if (d->B == 0 || d->n == 0) return RESLIC_OK;
   if (int rc = check_tables(&d->tables, "stanh_gc_fwd")) return rc;
   if (!d->y) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: y is null");
-  const bool need_lik = d->lik || d->bits;
+  const bool need_lik = d->lik || rate_requested(d->bits, d->bits_accumulate);
   if (need_lik && !d->sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: sigma is null");
   if (!d->yhat && !d->sym && !need_lik) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: no output requested");
   if (need_lik && !(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: scale_bound must be > 0");
@@ -344,12 +344,10 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
   p.removing_mean = d->removing_mean; p.training = d->training;
   p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
   p.n = d->n; p.B = d->B; p.tiles_per_image = (d->n + kThreads - 1) / kThreads;
-  if (d->bits) {
-    if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B) ||
-        (reinterpret_cast<uintptr_t>(d->workspace) & 7u))
-      return set_error(RESLIC_ERR_WORKSPACE, "stanh_gc_fwd: workspace missing, misaligned or too small for `bits`");
-    p.bits = d->bits; p.bits_accumulate = d->bits_accumulate;
-    p.workspace = static_cast<unsigned long long*>(d->workspace);
+  if (rate_requested(d->bits, d->bits_accumulate)) {
+    const int rc = rate_setup("stanh_gc_fwd", d->bits, d->bits_accumulate, d->workspace, d->workspace_bytes, d->B,
+                              &p.bits, &p.bits_accumulate, &p.workspace);
+    if (rc != RESLIC_OK) return rc;
   }
   const int64_t total = p.tiles_per_image * p.B;
   int64_t grid = static_cast<int64_t>(sm_count()) * 8;
@@ -401,7 +399,7 @@ int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st) {
   for (int i = 0; i < 5; ++i)
     if (!d->matrix[i] || !d->bias[i] || (i < 4 && !d->factor[i]))
       return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: a parameter pointer is null");
-  if (!d->zhat && !d->lik && !d->sym && !d->bits) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: no output requested");
+  if (!d->zhat && !d->lik && !d->sym && !rate_requested(d->bits, d->bits_accumulate)) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: no output requested");
   EbStanhParams p{};
   p.z = d->z; p.z_bs = d->z_bs;
   for (int i = 0; i < 5; ++i) { p.matrix[i] = d->matrix[i]; p.bias[i] = d->bias[i]; }
@@ -420,12 +418,10 @@ int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st) {
   if (bpi < 1) bpi = 1;
   if (bpi * (kThreads / 32) > 60000) bpi = 60000 / (kThreads / 32);     // arrival count field is 16 bits
   p.bpi = static_cast<int>(bpi);
-  if (d->bits) {
-    if (!d->workspace || d->workspace_bytes < reslic_workspace_bytes(d->B) ||
-        (reinterpret_cast<uintptr_t>(d->workspace) & 7u))
-      return set_error(RESLIC_ERR_WORKSPACE, "eb_stanh_fwd: workspace missing, misaligned or too small for `bits`");
-    p.bits = d->bits; p.bits_accumulate = d->bits_accumulate;
-    p.workspace = static_cast<unsigned long long*>(d->workspace);
+  if (rate_requested(d->bits, d->bits_accumulate)) {
+    const int rc = rate_setup("eb_stanh_fwd", d->bits, d->bits_accumulate, d->workspace, d->workspace_bytes, d->B,
+                              &p.bits, &p.bits_accumulate, &p.workspace);
+    if (rc != RESLIC_OK) return rc;
   }
   eb_stanh_fwd_kernel<<<static_cast<int>(bpi * d->B), kThreads, tables_smem(p.st.K), st>>>(p);
   cudaError_t err = cudaGetLastError();

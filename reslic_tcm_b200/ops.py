@@ -73,6 +73,49 @@ def _out_like(x: Tensor, dtype) -> Tensor:
     return torch.empty(x.shape, dtype=dtype, device=x.device)
 
 
+def _rate_outputs(d, out: dict, B: int, device, keep: list) -> Optional[Tensor]:
+    """Fill the rate fields of a *_fwd descriptor.  ``out["bits_deferred"]`` selects
+    RESLIC_RATE_DEFERRED: the sum stays in ``out["workspace"]`` (required then) until
+    :func:`rate_finalize`; otherwise ``out["bits"]`` (or a fresh tensor) receives it."""
+    ws = out.get("workspace")
+    if out.get("bits_deferred"):
+        if ws is None:
+            raise ValueError("out['bits_deferred'] needs the caller's out['workspace'] (it carries the sum)")
+        d.bits = None
+        d.bits_accumulate = _cabi.RATE_DEFERRED
+        bits = None
+    else:
+        bits = out.get("bits")
+        if bits is None:
+            bits = torch.empty(B, dtype=torch.float64, device=device)
+        elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
+            raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
+        d.bits = bits.data_ptr()
+        d.bits_accumulate = 1 if out.get("bits_accumulate") else 0
+    if ws is None:
+        ws = _cabi.workspace(device, B)
+    d.workspace = ws.data_ptr()
+    d.workspace_bytes = ws.numel()
+    keep.append(ws)
+    return bits
+
+
+def rate_finalize(workspace: Tensor, B: int, bits: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """bits[b] (= or +=) the rate the deferred launches left in ``workspace`` (reslic_rate_finalize_f64)."""
+    lib = _cabi.load()
+    if bits is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs the bits tensor to add to")
+        bits = torch.empty(B, dtype=torch.float64, device=workspace.device)
+    elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous() or not bits.is_cuda:
+        raise ValueError("bits must be a contiguous CUDA float64 [B] tensor")
+    with torch.cuda.device(workspace.device):
+        code = lib.reslic_rate_finalize_f64(workspace.data_ptr(), workspace.numel(), B, bits.data_ptr(),
+                                            1 if accumulate else 0, _cabi.current_stream_ptr(workspace.device))
+    _cabi.check(code, "reslic_rate_finalize_f64")
+    return bits
+
+
 def gc_forward(
     y: Tensor,
     scales: Optional[Tensor] = None,
@@ -172,20 +215,7 @@ def gc_forward(
         setattr(d, name + "_bs", bs)
         setattr(res, name, t)
     if "bits" in want:
-        bits = out.get("bits")
-        if bits is None:
-            bits = torch.empty(B, dtype=torch.float64, device=y.device)
-        elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
-            raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
-        ws = out.get("workspace")
-        if ws is None:
-            ws = _cabi.workspace(y.device, B)
-        d.bits = bits.data_ptr()
-        d.bits_accumulate = 1 if out.get("bits_accumulate") else 0
-        d.workspace = ws.data_ptr()
-        d.workspace_bytes = ws.numel()
-        keep.append(ws)
-        res.bits = bits
+        res.bits = _rate_outputs(d, out, B, y.device, keep)
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
     with torch.cuda.device(y.device):
@@ -369,18 +399,7 @@ def eb_forward(
             setattr(d, name + "_bs", Cc * hw)
             setattr(res, name, t)
     if "bits" in want:
-        bits = out.get("bits")
-        if bits is None:
-            bits = torch.empty(B, dtype=torch.float64, device=z.device)
-        elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
-            raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
-        ws = out.get("workspace")
-        if ws is None:
-            ws = _cabi.workspace(z.device, B)
-        d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
-        d.bits_accumulate = 1 if out.get("bits_accumulate") else 0
-        keep.append(ws)
-        res.bits = bits
+        res.bits = _rate_outputs(d, out, B, z.device, keep)
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
     with torch.cuda.device(z.device):

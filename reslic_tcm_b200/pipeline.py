@@ -10,7 +10,9 @@
     for each of the 5 channel slices of y (sequential in the real model: mu, sigma of
     slice k depend on y_hat of slices < k):
         GaussianConditional fused pass -> y_hat slice, L_y slice, [symbols, indexes], bits_y[B]
-    bits[B] = bits_z + sum_k bits_y,k   (accumulated by the kernels themselves; bpp = bits / num_pixels)
+    bits[B] = bits_z + sum_k bits_y,k   (each launch adds its fixed-point sum to the rate workspace with
+                                          fire-and-forget reductions; one finalize launch writes bits;
+                                          bpp = bits / num_pixels)
 
 = 1 + 5 kernel launches per batch and nothing else (no torch glue kernels).  Static output buffers make the pass CUDA-graph
 capturable (``capture()``), which removes the Python/launch overhead from steady state.
@@ -82,14 +84,13 @@ class TcmEntropyPath(nn.Module):
         if not skip_z:
             ops.eb_forward(z, m, bi, f, eb._medians_flat(), training=training, noise=noise_z,
                                likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"),
-                               out={"ste": b["z_hat"], "lik": b["z_lik"], "bits": b["bits"],
-                                    "workspace": b["workspace"]}, seed=seed, offset=offset)   # bits[b]  = z bits
+                               out={"ste": b["z_hat"], "lik": b["z_lik"], "bits_deferred": True,
+                                    "workspace": b["workspace"]}, seed=seed, offset=offset)   # workspace += z bits
         want = ["ste", "lik", "bits"] + (["sym", "idx"] if with_indexes else []) + (["yhat"] if training else [])
         for k in range(n_launch):
             sl = slice(cs * k, cs * (k + 1))
-            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits": b["bits"],
-                   "bits_accumulate": not (skip_z and k == 0),
-                   "workspace": b["workspace"]}                                          # bits[b] += slice bits
+            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits_deferred": True,
+                   "workspace": b["workspace"]}                                          # workspace += slice bits
             if with_indexes:
                 out["sym"], out["idx"] = b["symbols"][:, sl], b["indexes"][:, sl]
             if training:
@@ -99,6 +100,7 @@ class TcmEntropyPath(nn.Module):
                            scale_table=gc.scale_table if with_indexes else None, scale_bound=gc._scale_bound,
                            likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
                            offset=offset + 1 + k)
+        ops.rate_finalize(b["workspace"], y.shape[0], bits=b["bits"])                     # bits[b] = total
         res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
                "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
         if with_indexes:

@@ -21,7 +21,7 @@ __global__ void fill(float* y, float* mu, float* sg, size_t n, unsigned seed) {
 int main(int argc, char** argv) {
   int B = argc > 1 ? atoi(argv[1]) : 24; long n = argc > 2 ? atol(argv[2]) : 64 * 48 * 32;
   int with_idx = argc > 3 ? atoi(argv[3]) : 1; int noise = argc > 4 ? atoi(argv[4]) : 0;
-  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50;
+  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50; int deferred = argc > 6 ? atoi(argv[6]) : 0;
   size_t N = (size_t)B * n;
   std::vector<float*> y(nset), mu(nset), sg(nset), yh(nset), lk(nset), nz(nset); std::vector<int*> sym(nset), idx(nset);
   float tabh[64]; for (int i = 0; i < 64; ++i) tabh[i] = expf(logf(0.11f) + i * (logf(256.f) - logf(0.11f)) / 63.f);
@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
     d.ste = yh[s]; d.ste_bs = n; d.lik = lk[s]; d.lik_bs = n;
     if (noise) { d.yhat = nz[s]; d.yhat_bs = n; }
     if (with_idx) { d.scale_table = tab; d.table_len = 64; d.sym = sym[s]; d.sym_bs = n; d.idx = idx[s]; d.idx_bs = n; }
-    d.bits = bits; d.workspace = ws; d.workspace_bytes = wsb; d.philox_seed = 1;
+    d.bits = deferred ? nullptr : bits; d.bits_accumulate = deferred ? RESLIC_RATE_DEFERRED : 0; d.workspace = ws; d.workspace_bytes = wsb; d.philox_seed = 1;
     int rc = reslic_gc_fwd_f32(&d, st);
     if (rc) { printf("launch failed %d %s\n", rc, reslic_last_error()); exit(1); }
   };
@@ -62,7 +62,13 @@ int main(int argc, char** argv) {
   double us = ms * 1e3 / (reps * 5 * nset);
   int bpe = 12 + 8 + (with_idx ? 8 : 0) + (noise ? 4 : 0);
   double gbs = (double)N * bpe / (us * 1e-6) / 1e9;
+  if (deferred) {  // drain what the timed launches accumulated, then one clean launch
+    if (reslic_rate_finalize_f64(ws, wsb, B, bits, 0, st)) { printf("finalize failed %s\n", reslic_last_error()); exit(1); }
+    launch(0);
+    if (reslic_rate_finalize_f64(ws, wsb, B, bits, 0, st)) { printf("finalize failed %s\n", reslic_last_error()); exit(1); }
+    CK(cudaStreamSynchronize(st));
+  }
   double hb[4]; CK(cudaMemcpy(hb, bits, sizeof(double) * (B < 4 ? B : 4), cudaMemcpyDeviceToHost));
-  printf("B=%d n=%ld idx=%d noise=%d : %.2f us/launch  %.1f GB/s  %.1f%% of 6537.6  (%.1f Gelem/s) bits0=%.3f\n", B, n, with_idx, noise, us, gbs, 100 * gbs / 6537.6, N / us / 1e3, hb[0]);
+  printf("B=%d n=%ld idx=%d noise=%d def=%d : %.2f us/launch  %.1f GB/s  %.1f%% of 6537.6  (%.1f Gelem/s) bits0=%.3f\n", B, n, with_idx, noise, deferred, us, gbs, 100 * gbs / 6537.6, N / us / 1e3, hb[0]);
   return 0;
 }

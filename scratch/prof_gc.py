@@ -8,7 +8,7 @@ cfg = int(os.environ.get("CFG", "2"))
 c = synthetic.CONFIGS[cfg]
 B = c.batch
 g = torch.Generator(device=dev).manual_seed(1)
-shape = (B, 64, *c.y_hw)
+shape = (B, 320 if os.environ.get("WHOLE") else 64, *c.y_hw)
 mu = torch.randn(shape, device=dev, generator=g)
 sigma = torch.exp(torch.empty(shape, device=dev).uniform_(-3.0, 4.16, generator=g))
 y = mu + sigma * torch.randn(shape, device=dev, generator=g)
