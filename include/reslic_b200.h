@@ -74,6 +74,10 @@ int64_t reslic_workspace_bytes(int64_t B);
  *      workspace into bits and re-zeroes it.  The launches then end without the round trip to L2
  *      that detecting the last arriver costs (about 1.3 us of a 15 us slice launch on B200). */
 #define RESLIC_RATE_DEFERRED 2
+/*   RESLIC_RATE_COLLECT   bits[b] = this launch's sum + everything earlier RESLIC_RATE_DEFERRED launches
+ *      left in the workspace (which is re-zeroed): the LAST launch of a batch collects, so the batch
+ *      needs no finalize launch and pays the last-arriver round trip once instead of per launch. */
+#define RESLIC_RATE_COLLECT 3
 /* bits[b] (accumulate ? += : =) the deferred rate of image b, for b < B; same B and workspace as the
  * launches that accumulated.  Stream-ordered after them. */
 int reslic_rate_finalize_f64(void* workspace, int64_t workspace_bytes, int64_t B, double* bits,

@@ -18,6 +18,7 @@ from . import _build
 
 ABI_VERSION = 9
 RATE_DEFERRED = 2
+RATE_COLLECT = 3
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 

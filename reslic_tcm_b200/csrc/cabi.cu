@@ -12,9 +12,10 @@ static int g_math_mode = RESLIC_MATH_FAST;
 int math_mode() { return g_math_mode; }
 const GcTuning& gc_tuning() {
   static GcTuning t = [] {
-    GcTuning v{-1, 1};
+    GcTuning v{-1, 1, 0};
     if (const char* e = std::getenv("RESLIC_GC_CTAS_PER_SM")) v.ctas_per_sm = std::atoi(e);
     if (const char* e = std::getenv("RESLIC_PDL")) v.pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RESLIC_GC_MIN_CTAS")) v.min_ctas = std::atoi(e);   // 4 / 5: force one build; 0: by launch size
     return v;
   }();
   return t;
@@ -30,8 +31,8 @@ int set_cuda_error(cudaError_t err, const char* where) {
 int rate_setup(const char* who, double* bits, int32_t mode, void* workspace, int64_t workspace_bytes, int64_t B,
                double** bits_out, int* mode_out, unsigned long long** ws_out) {
   char msg[160];
-  if (mode < 0 || mode > RESLIC_RATE_DEFERRED) {
-    std::snprintf(msg, sizeof(msg), "%s: bits_accumulate must be 0, 1 or RESLIC_RATE_DEFERRED", who);
+  if (mode < 0 || mode > RESLIC_RATE_COLLECT) {
+    std::snprintf(msg, sizeof(msg), "%s: bits_accumulate must be 0, 1, RESLIC_RATE_DEFERRED or RESLIC_RATE_COLLECT", who);
     return set_error(RESLIC_ERR_ARG, msg);
   }
   if (mode != RESLIC_RATE_DEFERRED && !bits) {

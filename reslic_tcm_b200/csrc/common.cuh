@@ -119,11 +119,18 @@ __device__ __forceinline__ unsigned long long rate_commit_issue(float acc, int i
 
 __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int image, unsigned int expected,
                                                    int64_t B, unsigned long long* ws, double* bits_out,
-                                                   bool accumulate) {
+                                                   bool accumulate, bool collect = false) {
   if ((threadIdx.x & 31) == 0 && (now >> 48) == expected) {
     __threadfence();
-    const long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
-    const unsigned long long flag = *reinterpret_cast<volatile unsigned long long*>(&ws[B + image]);
+    long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
+    unsigned long long flag = *reinterpret_cast<volatile unsigned long long*>(&ws[B + image]);
+    if (collect) {   // fold in what earlier RESLIC_RATE_DEFERRED launches of this stream left behind
+      sum += static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&ws[2 * B + image]));
+      const unsigned long long dflag = *reinterpret_cast<volatile unsigned long long*>(&ws[3 * B + image]);
+      ws[2 * B + image] = 0ull;
+      if (dflag) ws[3 * B + image] = 0ull;
+      flag |= dflag;
+    }
     double bits = static_cast<double>(sum) * (1.0 / 65536.0);
     if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
     else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
@@ -150,12 +157,12 @@ __device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsi
 
 // All 32 lanes of a warp must call.  acc = this warp's sum of log2(L) over elements of `image`;
 // `expected` = number of warps (over the whole grid) that commit to `image`;
-// mode = the descriptor's bits_accumulate (0 write, 1 accumulate, 2 deferred).
+// mode = the descriptor's bits_accumulate (0 write, 1 accumulate, 2 deferred, 3 write + collect deferred).
 __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
                                             unsigned long long* ws, double* bits_out, int mode) {
   if (mode == 2) { rate_defer(acc, image, B, ws); return; }
   const unsigned long long now = rate_commit_issue(acc, image, B, ws);
-  rate_commit_finish(now, image, expected, B, ws, bits_out, mode != 0);
+  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3);
 }
 
 }  // namespace reslic

@@ -23,9 +23,9 @@ namespace reslic {
 
 struct GcParams {
   const float* y; const float* mu; const float* sigma; const float* noise;
-  int64_t y_bs, mu_bs, sigma_bs, noise_bs;
+  uint32_t y_bs, mu_bs, sigma_bs, noise_bs;   // batch strides in elements (< 2^32, checked on the host)
   float* yhat; float* ste; float* lik; int32_t* sym; int32_t* idx;
-  int64_t yhat_bs, ste_bs, lik_bs, sym_bs, idx_bs;
+  uint32_t yhat_bs, ste_bs, lik_bs, sym_bs, idx_bs;
   double* bits; unsigned long long* workspace; int bits_accumulate;
   const float* table; int table_len;
   int64_t n;          // elements per image
@@ -187,8 +187,12 @@ __device__ __forceinline__ void gc_group_vec(const GcParams& p, const float2* pa
   }
 }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST>
-__global__ void __launch_bounds__(kThreads, 4)
+// MINB = resident CTAs per SM the register budget is cut for: 4 (64 registers, no spill in the loop) is
+// the faster build for long launches; 5 (48 registers, a few spilled scalars, 25 % more warps to hide
+// the first-tile latency) wins on short ones (a TCM slice: < 4 tiles per CTA) — measured 14.1 vs 14.5 us
+// on 24 x 98304 and 66.8 vs 57.3 us on 24 x 491520, so the host picks by launch size.
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 gc_fwd_kernel(const GcParams p) {
   __shared__ float2 pad2[NEED_IDX ? kPadLen : 1];
   __shared__ float s_guess[2];
@@ -208,9 +212,10 @@ gc_fwd_kernel(const GcParams p) {
       // guess(s) = ceil((log2 s - log2 t_0) * (len-2) / (log2 t_{len-2} - log2 t_0))
       float sc = 0.0f, off = 0.0f;
       if (p.table_len >= 3) {
-        const float l0 = log2f(p.table[0]), l1 = log2f(p.table[p.table_len - 2]);
+        // approximate log/divide are enough: this only seeds the guess, the proof is exact
+        const float l0 = lg2_approx(p.table[0]), l1 = lg2_approx(p.table[p.table_len - 2]);
         // the small downward bias makes sigma == table[j] (notably the 0.11 bound itself) guess j
-        if (l1 > l0) { sc = static_cast<float>(p.table_len - 2) / (l1 - l0); off = -l0 * sc - 2.44140625e-4f + 0.5f; }
+        if (l1 > l0) { sc = __fdividef(static_cast<float>(p.table_len - 2), l1 - l0); off = -l0 * sc - 2.44140625e-4f + 0.5f; }
       }
       s_guess[0] = sc; s_guess[1] = off;
     }
@@ -246,16 +251,20 @@ gc_fwd_kernel(const GcParams p) {
     const int ntiles = static_cast<int>(min(seg_end, t_end) - t);
     t += ntiles;
     const int64_t seg = static_cast<int64_t>(chunk0) * (kThreads * W);          // element offset of tile 0 in the image
-    const float* y = p.y ? p.y + image * p.y_bs + seg : nullptr;
-    const float* mu = p.mu ? p.mu + image * p.mu_bs + seg : nullptr;
-    const float* sg = p.sigma ? p.sigma + image * p.sigma_bs + seg : nullptr;
-    const float* nz = (NOISE && p.noise) ? p.noise + image * p.noise_bs + seg : nullptr;
+    // image base + segment start: one 32x32->64 multiply-add per tensor on the uniform datapath
+    auto at_seg = [&](auto* base, uint32_t bs) {
+      return base + (static_cast<uint64_t>(static_cast<uint32_t>(image)) * bs + static_cast<uint64_t>(seg));
+    };
+    const float* y = p.y ? at_seg(p.y, p.y_bs) : nullptr;
+    const float* mu = p.mu ? at_seg(p.mu, p.mu_bs) : nullptr;
+    const float* sg = p.sigma ? at_seg(p.sigma, p.sigma_bs) : nullptr;
+    const float* nz = (NOISE && p.noise) ? at_seg(p.noise, p.noise_bs) : nullptr;
     GcOutPtrs o;
-    o.yhat = p.yhat ? p.yhat + image * p.yhat_bs + seg : nullptr;
-    o.ste = p.ste ? p.ste + image * p.ste_bs + seg : nullptr;
-    o.lik = (NEED_LIK && p.lik) ? p.lik + image * p.lik_bs + seg : nullptr;
-    o.sym = p.sym ? p.sym + image * p.sym_bs + seg : nullptr;
-    o.idx = (NEED_IDX && p.idx) ? p.idx + image * p.idx_bs + seg : nullptr;
+    o.yhat = p.yhat ? at_seg(p.yhat, p.yhat_bs) : nullptr;
+    o.ste = p.ste ? at_seg(p.ste, p.ste_bs) : nullptr;
+    o.lik = (NEED_LIK && p.lik) ? at_seg(p.lik, p.lik_bs) : nullptr;
+    o.sym = p.sym ? at_seg(p.sym, p.sym_bs) : nullptr;
+    o.idx = (NEED_IDX && p.idx) ? at_seg(p.idx, p.idx_bs) : nullptr;
     const int g = chunk0 * kThreads + threadIdx.x;                 // this thread's element group in tile 0
 
     auto load = [&](GcIn& r, int k) {        // tile k of this segment
@@ -348,15 +357,21 @@ static int resident_ctas(K kernel, int* cache) {
   return *cache;
 }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST>
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST, int MINB>
 static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
   static int occ = 0;
-  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, FAST>;
+  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, FAST, MINB>;
   const int64_t total = p.tiles_per_image * p.B;
   const int waves = gc_tuning().ctas_per_sm;   // 0: one tile per CTA; k>0: k CTAs per SM; <0: resident count
   int64_t grid = total;
   if (waves > 0) grid = static_cast<int64_t>(waves) * sm_count();
-  else if (waves < 0) grid = static_cast<int64_t>(resident_ctas(kernel, &occ)) * sm_count();
+  else if (waves < 0) {
+    // one resident wave; long launches (>= 16 tiles per CTA) are cut into two waves of half-length
+    // ranges instead, so that the hardware scheduler evens out the spread in CTA completion times
+    // (measured: 61.5 -> 57.3 us on 24 x 491520; shorter launches lose more to the second prologue)
+    grid = static_cast<int64_t>(resident_ctas(kernel, &occ)) * sm_count();
+    if (total >= 16 * grid) grid *= 2;
+  }
   if (grid > total) grid = total;
   p.tpi = static_cast<unsigned int>(p.tiles_per_image);
   p.total_tiles = static_cast<unsigned int>(total);
@@ -379,8 +394,11 @@ static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
 static cudaError_t launch_math(GcParams& p, bool fast, cudaStream_t st) {
   // the math policy only matters when a likelihood is computed
-  if (NEED_LIK && !fast) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, false>(p, st);
-  return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, true>(p, st);
+  if (NEED_LIK && !fast) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, false, 4>(p, st);
+  // short launches (at most 8 tiles per CTA slot of the 4-per-SM build) take the 5-per-SM build
+  const bool short_launch = VEC && p.tiles_per_image * p.B <= 8LL * 4 * sm_count() && gc_tuning().min_ctas != 4;
+  if (short_launch || gc_tuning().min_ctas == 5) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, true, VEC ? 5 : 4>(p, st);
+  return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, true, 4>(p, st);
 }
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE>
 static cudaError_t launch_vec(GcParams& p, bool vec, bool fast, cudaStream_t st) {
@@ -412,11 +430,18 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   if (!(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "gc_fwd: scale_bound must be > 0");
 
   GcParams p{};
-  p.y = d->y; p.y_bs = d->y_bs;
-  p.mu = d->mu; p.mu_bs = d->mu_bs; p.sigma = d->sigma; p.sigma_bs = d->sigma_bs;
-  p.noise = d->noise; p.noise_bs = d->noise_bs;
+  bool stride_ok = true;
+  auto bs32 = [&](const void* ptr, int64_t bs) -> uint32_t {
+    if (ptr && d->B > 1 && (bs < 0 || bs >= (1LL << 32))) stride_ok = false;
+    return static_cast<uint32_t>(bs);
+  };
+  p.y = d->y; p.y_bs = bs32(d->y, d->y_bs);
+  p.mu = d->mu; p.mu_bs = bs32(d->mu, d->mu_bs); p.sigma = d->sigma; p.sigma_bs = bs32(d->sigma, d->sigma_bs);
+  p.noise = d->noise; p.noise_bs = bs32(d->noise, d->noise_bs);
   p.yhat = d->yhat; p.ste = d->ste; p.lik = d->lik; p.sym = d->sym; p.idx = d->idx;
-  p.yhat_bs = d->yhat_bs; p.ste_bs = d->ste_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs; p.idx_bs = d->idx_bs;
+  p.yhat_bs = bs32(d->yhat, d->yhat_bs); p.ste_bs = bs32(d->ste, d->ste_bs); p.lik_bs = bs32(d->lik, d->lik_bs);
+  p.sym_bs = bs32(d->sym, d->sym_bs); p.idx_bs = bs32(d->idx, d->idx_bs);
+  if (!stride_ok) return set_error(RESLIC_ERR_ARG, "gc_fwd: batch stride outside [0, 2^32) elements");
   p.table = d->scale_table; p.table_len = d->table_len;
   p.n = d->n; p.B = d->B; p.scale_bound = d->scale_bound;
   // compressai applies the likelihood bound only when it is > 0; max(L, -inf) is the branch-free "no bound"

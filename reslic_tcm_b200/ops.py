@@ -76,7 +76,9 @@ def _out_like(x: Tensor, dtype) -> Tensor:
 def _rate_outputs(d, out: dict, B: int, device, keep: list) -> Optional[Tensor]:
     """Fill the rate fields of a *_fwd descriptor.  ``out["bits_deferred"]`` selects
     RESLIC_RATE_DEFERRED: the sum stays in ``out["workspace"]`` (required then) until
-    :func:`rate_finalize`; otherwise ``out["bits"]`` (or a fresh tensor) receives it."""
+    :func:`rate_finalize` or a later launch with ``out["bits_collect"]`` (RESLIC_RATE_COLLECT: its
+    bits = its own sum + everything deferred); otherwise ``out["bits"]`` (or a fresh tensor) receives
+    this launch's sum."""
     ws = out.get("workspace")
     if out.get("bits_deferred"):
         if ws is None:
@@ -91,7 +93,7 @@ def _rate_outputs(d, out: dict, B: int, device, keep: list) -> Optional[Tensor]:
         elif bits.shape != (B,) or bits.dtype != torch.float64 or not bits.is_contiguous():
             raise ValueError("out['bits'] must be a contiguous float64 [B] tensor")
         d.bits = bits.data_ptr()
-        d.bits_accumulate = 1 if out.get("bits_accumulate") else 0
+        d.bits_accumulate = _cabi.RATE_COLLECT if out.get("bits_collect") else (1 if out.get("bits_accumulate") else 0)
     if ws is None:
         ws = _cabi.workspace(device, B)
     d.workspace = ws.data_ptr()

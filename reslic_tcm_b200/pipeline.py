@@ -11,8 +11,8 @@
     slice k depend on y_hat of slices < k):
         GaussianConditional fused pass -> y_hat slice, L_y slice, [symbols, indexes], bits_y[B]
     bits[B] = bits_z + sum_k bits_y,k   (each launch adds its fixed-point sum to the rate workspace with
-                                          fire-and-forget reductions; one finalize launch writes bits;
-                                          bpp = bits / num_pixels)
+                                          fire-and-forget reductions; the last launch collects them into
+                                          bits; bpp = bits / num_pixels)
 
 = 1 + 5 kernel launches per batch and nothing else (no torch glue kernels).  Static output buffers make the pass CUDA-graph
 capturable (``capture()``), which removes the Python/launch overhead from steady state.
@@ -65,14 +65,16 @@ class TcmEntropyPath(nn.Module):
     def forward(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, *, training: bool = False,
                 with_indexes: bool = False, num_pixels: Optional[int] = None, seed: int = 0,
                 offset: int = 0, noise_y: Optional[Tensor] = None, noise_z: Optional[Tensor] = None,
-                fuse_slices: bool = False, skip_z: bool = False) -> Dict[str, Tensor]:
+                fuse_slices: bool = False, skip_z: bool = False, defer_rate: bool = False) -> Dict[str, Tensor]:
         """All tensors on the GPU, NCHW fp32: y/mu/sigma [B, 320, h, w], z [B, 192, h/4, w/4].
         Returns views of static buffers (valid until the next call).
 
         ``fuse_slices`` runs all channels of y in ONE launch: what a model whose mu/sigma are
         available for every channel at once does (e.g. the reference's ScaleHyperprior,
         src/models/Balle2018.py: one gaussian_conditional call on the whole y); TCM itself needs
-        the per-slice mode because slice k's parameters depend on y_hat of slices < k."""
+        the per-slice mode because slice k's parameters depend on y_hat of slices < k.
+        ``defer_rate`` leaves the pass's rate in the workspace (no launch collects; ``bits`` is not
+        written): the caller sums several passes and calls ``ops.rate_finalize`` once."""
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         b = self.buffers(y, z, with_indexes, training)
         C = y.shape[1]
@@ -81,16 +83,18 @@ class TcmEntropyPath(nn.Module):
         n_launch = 1 if fuse_slices else self.num_slices
         cs = C // n_launch
         m, bi, f = eb._params()
-        if not skip_z:
-            ops.eb_forward(z, m, bi, f, eb._medians_flat(), training=training, noise=noise_z,
-                               likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"),
-                               out={"ste": b["z_hat"], "lik": b["z_lik"], "bits_deferred": True,
-                                    "workspace": b["workspace"]}, seed=seed, offset=offset)   # workspace += z bits
+        # Rate: every launch but the last adds its fixed-point sum to the workspace (fire-and-forget
+        # reductions: the launch ends without the round trip that finding the last-arriving warp costs);
+        # the LAST launch collects workspace + own sum into bits[b].  The small z launch is put last so
+        # that the collector's round trip is paid by the cheapest kernel (z and y are independent here).
         want = ["ste", "lik", "bits"] + (["sym", "idx"] if with_indexes else []) + (["yhat"] if training else [])
         for k in range(n_launch):
             sl = slice(cs * k, cs * (k + 1))
-            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "bits_deferred": True,
-                   "workspace": b["workspace"]}                                          # workspace += slice bits
+            out = {"ste": b["y_hat"][:, sl], "lik": b["y_lik"][:, sl], "workspace": b["workspace"]}
+            if k + 1 < n_launch or not skip_z or defer_rate:
+                out["bits_deferred"] = True                                              # workspace += slice bits
+            else:
+                out["bits"], out["bits_collect"] = b["bits"], True                       # bits = slice + workspace
             if with_indexes:
                 out["sym"], out["idx"] = b["symbols"][:, sl], b["indexes"][:, sl]
             if training:
@@ -100,7 +104,15 @@ class TcmEntropyPath(nn.Module):
                            scale_table=gc.scale_table if with_indexes else None, scale_bound=gc._scale_bound,
                            likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
                            offset=offset + 1 + k)
-        ops.rate_finalize(b["workspace"], y.shape[0], bits=b["bits"])                     # bits[b] = total
+        if not skip_z:
+            out = {"ste": b["z_hat"], "lik": b["z_lik"], "workspace": b["workspace"]}
+            if defer_rate:
+                out["bits_deferred"] = True
+            else:
+                out["bits"], out["bits_collect"] = b["bits"], True                       # bits = z + workspace
+            ops.eb_forward(z, m, bi, f, eb._medians_flat(), training=training, noise=noise_z,
+                           likelihood_bound=eb._likelihood_bound, want=("ste", "lik", "bits"), out=out,
+                           seed=seed, offset=offset)
         res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
                "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
         if with_indexes:

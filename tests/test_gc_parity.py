@@ -243,6 +243,51 @@ def test_workspace_reuse_across_batch_sizes(gc):
         own = -(torch.log2(r.lik.double()).reshape(B, -1).sum(1))
         assert torch.allclose(r.bits, own, rtol=2e-6), (B, C)
 
+def test_deferred_rate_modes_equal_the_immediate_sum(gc):
+    """RESLIC_RATE_DEFERRED launches leave fixed-point sums in the workspace; reslic_rate_finalize_f64 or a
+    last RESLIC_RATE_COLLECT launch turns them into bits.  Integer accumulation: the total equals the sum
+    of the per-launch immediate results exactly (both are multiples of 2^-16), the workspace ends zeroed,
+    and non-finite partials (NaN input) survive the deferral."""
+    B = 6
+    parts = []
+    ws = torch.zeros(int(_cabi.load().reslic_workspace_bytes(B)), dtype=torch.uint8, device=DEV)
+    total = torch.zeros(B, dtype=torch.float64, device=DEV)
+    for k in range(3):
+        y, mu, sigma, _ = _rand((B, 64, 16, 16), 700 + k)
+        parts.append((y.to(DEV), sigma.to(DEV), mu.to(DEV)))
+        total += ops.gc_forward(*parts[-1], want=("bits",)).bits
+    # (a) three deferred launches + finalize
+    for a in parts:
+        r = ops.gc_forward(*a, want=("lik", "bits"), out={"bits_deferred": True, "workspace": ws})
+        assert r.bits is None
+    got = ops.rate_finalize(ws, B)
+    assert torch.equal(got, total)
+    assert int(ws.view(torch.int64).abs().sum()) == 0
+    # (b) accumulate into an existing vector
+    for a in parts[:2]:
+        ops.gc_forward(*a, want=("bits",), out={"bits_deferred": True, "workspace": ws})
+    base = torch.full((B,), 10.0, dtype=torch.float64, device=DEV)
+    ops.rate_finalize(ws, B, bits=base, accumulate=True)
+    two = ops.gc_forward(*parts[0], want=("bits",)).bits + ops.gc_forward(*parts[1], want=("bits",)).bits
+    assert torch.equal(base, two + 10.0)
+    # (c) two deferred launches, the third collects
+    for a in parts[:2]:
+        ops.gc_forward(*a, want=("bits",), out={"bits_deferred": True, "workspace": ws})
+    out_bits = torch.empty(B, dtype=torch.float64, device=DEV)
+    r = ops.gc_forward(*parts[2], want=("bits",), out={"bits": out_bits, "bits_collect": True, "workspace": ws})
+    assert torch.equal(r.bits, total)
+    assert int(ws.view(torch.int64).abs().sum()) == 0
+    # (d) a NaN in image 2 of a deferred launch is carried to the collected result
+    y, sg, mu = parts[0]
+    y_bad = y.clone(); y_bad[2, 3, 4, 5] = float("nan")
+    ops.gc_forward(y_bad, sg, mu, want=("bits",), out={"bits_deferred": True, "workspace": ws})
+    r = ops.gc_forward(*parts[1], want=("bits",), out={"bits_collect": True, "workspace": ws})
+    assert torch.isnan(r.bits[2]) and torch.isfinite(r.bits[[0, 1, 3, 4, 5]]).all()
+    assert int(ws.view(torch.int64).abs().sum()) == 0
+    # (e) misuse
+    with pytest.raises(ValueError):
+        ops.gc_forward(*parts[0], want=("bits",), out={"bits_deferred": True})
+
 
 def test_mirror_mode_matches_oracle_and_fast_mode(gc):
     """MIRROR arithmetic (CUDA erfcf/log2f = what the reference's torch CUDA kernels run) and
