@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 9
+#define RESLIC_ABI_VERSION 10
 
 enum {
   RESLIC_OK = 0,
@@ -196,9 +196,20 @@ typedef struct reslic_eb_desc {
   int32_t bits_accumulate;                 /* as in reslic_gc_desc                        */
   void* workspace; int64_t workspace_bytes;
   uint64_t philox_seed, philox_offset;
+  const float* lut;                        /* optional, DEQUANTIZE mode: [C, RESLIC_EB_LUT_STRIDE] table  */
+                                           /* from reslic_eb_build_lut_f32 for THESE parameters and bound */
 } reslic_eb_desc;
 
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream);
+
+/* In DEQUANTIZE mode z_hat - median is an integer k, so the likelihood is a function of (channel, k).
+ * reslic_eb_fwd_f32 builds that table (|k| <= 32) in every launch; a caller whose parameters do not
+ * change between launches (evaluation, compress) builds it ONCE here and passes it as `lut`, which
+ * takes the 5-layer cumulative-logit evaluation off the launch's latency chain.  The table holds, per
+ * channel, 65 bounded likelihoods followed by their 65 log2 values — bit-identical to what the launch
+ * computes itself.  Uses d->C, matrix/bias/factor/medians and likelihood_bound only. */
+#define RESLIC_EB_LUT_STRIDE 130
+int reslic_eb_build_lut_f32(const reslic_eb_desc* d, float* lut, void* stream);
 
 /* Backward of reslic_eb_fwd_f32: gradients of the bounded likelihood (and of the
  * quantize output) w.r.t. z and w.r.t. every bottleneck parameter — what autograd does through

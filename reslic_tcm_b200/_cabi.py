@@ -16,9 +16,10 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
+EB_LUT_STRIDE = 130
 Q_DEQUANTIZE, Q_NOISE = 0, 1
 MATH_FAST, MATH_MIRROR = 0, 1
 
@@ -85,6 +86,7 @@ class EbDesc(C.Structure):
         ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("lut", C.c_void_p),
     ]
 
 
@@ -187,6 +189,7 @@ EXPORTS = {
     "reslic_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "reslic_eb_bwd_f32": (C.c_int, [C.POINTER(EbBwdDesc), C.c_void_p]),
     "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
+    "reslic_eb_build_lut_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p, C.c_void_p]),
     "reslic_stanh_gc_fwd_f32": (C.c_int, [C.POINTER(StanhGcDesc), C.c_void_p]),
     "reslic_stanh_gc_bwd_f32": (C.c_int, [C.POINTER(StanhGcBwdDesc), C.c_void_p]),
     "reslic_lrp_tail_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),

@@ -219,5 +219,8 @@ int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream) {
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
   return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }
+int reslic_eb_build_lut_f32(const reslic_eb_desc* d, float* lut, void* stream) {
+  return reslic::eb_build_lut_launch(d, lut, static_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

@@ -29,6 +29,8 @@ struct EbParams {
   int hw, C, tile, bpi, noise_mode, splits;
   float lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  const float* lut;     // optional prebuilt [C, 2*kLutN] table (eval mode)
+  float* lut_out;       // eb_build_lut_kernel's destination
 };
 
 // ------------------------------------------------------------------ eval mode: per-channel LUT
@@ -43,6 +45,41 @@ constexpr int kLutK = 32;
 
 constexpr int kLutN = 2 * kLutK + 1;
 constexpr int kEbChunk = 4;      // values per lane held in registers: one chunk = 128 contiguous floats
+
+// The channel's table: 2*kLutN independent cumulative-logit evaluations (one per thread) with exactly
+// the per-element code path, combined into kLutN bounded likelihoods and their log2.  All threads call.
+__device__ __forceinline__ void eb_build_table(const EbParams& p, const float* s_par, float med, float* s_half,
+                                               float* s_lut, float* s_lg) {
+  if (threadIdx.x < 2 * kLutN) {
+    const int k = static_cast<int>(threadIdx.x % kLutN) - kLutK;
+    const float x = static_cast<float>(k) + med;             // == round(z - med) + med for that symbol
+    s_half[threadIdx.x] = logits_cumulative(s_par, threadIdx.x < kLutN ? x - 0.5f : x + 0.5f);
+  }
+  __syncthreads();
+  if (threadIdx.x < kLutN) {
+    const float lower = s_half[threadIdx.x], upper = s_half[kLutN + threadIdx.x];
+    const float L = eb_combine(lower, upper, p.lik_bound);
+    s_lut[threadIdx.x] = L;
+    s_lg[threadIdx.x] = log2f(L);
+  }
+  __syncthreads();
+}
+
+// One CTA per channel: the table of eb_lut_kernel written to global memory (reslic_eb_build_lut_f32).
+__global__ void __launch_bounds__(kThreads) eb_build_lut_kernel(const EbParams p) {
+  __shared__ float s_par[kEbStride + 1];
+  __shared__ float s_half[2 * kLutN];
+  __shared__ float s_lut[kLutN];
+  __shared__ float s_lg[kLutN];
+  const int c = blockIdx.x;
+  if (threadIdx.x < kEbStride) s_par[threadIdx.x] = eb_staged_param(p, c, threadIdx.x);
+  __syncthreads();
+  eb_build_table(p, s_par, s_par[oMed], s_half, s_lut, s_lg);
+  if (threadIdx.x < kLutN) {
+    p.lut_out[static_cast<int64_t>(c) * (2 * kLutN) + threadIdx.x] = s_lut[threadIdx.x];
+    p.lut_out[static_cast<int64_t>(c) * (2 * kLutN) + kLutN + threadIdx.x] = s_lg[threadIdx.x];
+  }
+}
 
 __global__ void __launch_bounds__(kThreads) eb_lut_kernel(const EbParams p) {
   __shared__ float s_par[kEbStride + 1];
@@ -71,24 +108,15 @@ __global__ void __launch_bounds__(kThreads) eb_lut_kernel(const EbParams p) {
   if (b < p.B) load_chunk(b, 0);                 // in flight while the table is built
 
   if (threadIdx.x < kEbStride) s_par[threadIdx.x] = eb_staged_param(p, c, threadIdx.x);
+  const bool have_table = need_lik && p.lut != nullptr;    // built once by eb_build_lut_kernel for these parameters
+  if (have_table && threadIdx.x >= kThreads - kLutN) {     // the upper warps: their loads overlap the parameter staging
+    const int t = threadIdx.x - (kThreads - kLutN);
+    s_lut[t] = p.lut[static_cast<int64_t>(c) * (2 * kLutN) + t];
+    s_lg[t] = p.lut[static_cast<int64_t>(c) * (2 * kLutN) + kLutN + t];
+  }
   __syncthreads();
   const float med = s_par[oMed];
-  if (need_lik) {
-    // 2*kLutN independent cumulative-logit evaluations, one per thread
-    if (threadIdx.x < 2 * kLutN) {
-      const int k = static_cast<int>(threadIdx.x % kLutN) - kLutK;
-      const float x = static_cast<float>(k) + med;             // == round(z - med) + med for that symbol
-      s_half[threadIdx.x] = logits_cumulative(s_par, threadIdx.x < kLutN ? x - 0.5f : x + 0.5f);
-    }
-    __syncthreads();
-    if (threadIdx.x < kLutN) {
-      const float lower = s_half[threadIdx.x], upper = s_half[kLutN + threadIdx.x];
-      const float L = eb_combine(lower, upper, p.lik_bound);
-      s_lut[threadIdx.x] = L;
-      s_lg[threadIdx.x] = log2f(L);
-    }
-    __syncthreads();
-  }
+  if (need_lik && !have_table) eb_build_table(p, s_par, med, s_half, s_lut, s_lg);
   while (b < p.B) {
     float acc = 0.0f;
     for (;;) {
@@ -131,6 +159,102 @@ __global__ void __launch_bounds__(kThreads) eb_lut_kernel(const EbParams p) {
     if (p.bits) rate_commit(acc, static_cast<int>(b), static_cast<unsigned int>(p.C), p.B, p.workspace, p.bits,
                             p.bits_accumulate);
     b += wstride;
+  }
+}
+
+// ------------------------------------------------------------------ eval mode with a prebuilt table
+// With the table built once (reslic_eb_build_lut_f32) nothing ties a CTA to one channel any more, so
+// the work is cut the other way: one CTA per (image, 8 consecutive channels), one warp per channel run.
+// A warp copies its channel's 2 x 65 table entries to shared memory behind a __syncwarp only; the
+// parameters are staged lazily, by the warp that meets an out-of-table symbol (|k| > 32 or NaN).  The
+// eight warps' partial rates meet in shared memory and ONE thread commits for the CTA: C/8 arrivals
+// per image instead of C (192 same-word atomics per image arriving together made this launch's commit
+// cost more than its arithmetic).
+constexpr int kEbWarps = kThreads / 32;
+__global__ void __launch_bounds__(kThreads) eb_lut8_kernel(const EbParams p) {
+  __shared__ float s_lut[kEbWarps][kLutN + 1];
+  __shared__ float s_lg[kEbWarps][kLutN + 1];
+  __shared__ float s_par[kEbWarps][kEbStride + 1];
+  __shared__ float s_red[kEbWarps];
+  griddep_wait();
+  griddep_launch_dependents();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int octets = (p.C + kEbWarps - 1) / kEbWarps;
+  const int image = blockIdx.x / octets;
+  const int c = (blockIdx.x - image * octets) * kEbWarps + warp;
+  const bool need_lik = p.lik || p.bits;
+  float acc = 0.0f;
+  if (c < p.C) {
+    const int64_t base_c = static_cast<int64_t>(c) * p.hw;
+    const float* __restrict__ z = p.z + image * p.z_bs + base_c;
+    const int chunks = (p.hw + 32 * kEbChunk - 1) / (32 * kEbChunk);
+    float zv[kEbChunk];
+    auto load_chunk = [&](int cc) {
+      const int rem = p.hw - cc * (32 * kEbChunk);
+#pragma unroll
+      for (int j = 0; j < kEbChunk; ++j) zv[j] = (lane + 32 * j < rem) ? ld_stream1(z + cc * (32 * kEbChunk) + lane + 32 * j) : 0.0f;
+    };
+    load_chunk(0);
+    const float med = p.medians[c];
+    if (need_lik) {
+      for (int t = lane; t < kLutN; t += 32) {
+        s_lut[warp][t] = p.lut[static_cast<int64_t>(c) * (2 * kLutN) + t];
+        s_lg[warp][t] = p.lut[static_cast<int64_t>(c) * (2 * kLutN) + kLutN + t];
+      }
+      __syncwarp();
+    }
+    bool staged = false;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const int64_t off = base_c + ch * (32 * kEbChunk);
+      const int rem = p.hw - ch * (32 * kEbChunk);
+      float cur[kEbChunk];
+#pragma unroll
+      for (int j = 0; j < kEbChunk; ++j) cur[j] = zv[j];
+      if (ch + 1 < chunks) load_chunk(ch + 1);
+#pragma unroll
+      for (int j = 0; j < kEbChunk; ++j) {
+        const int i = lane + 32 * j;
+        const bool valid = i < rem;
+        const float q = rintf(cur[j] - med);
+        const float st = q + med;                   // "dequantize" == ste_round(z - med) + med
+        const bool far = need_lik && valid && !(fabsf(q) <= static_cast<float>(kLutK));
+        if (__any_sync(0xffffffffu, far) && !staged) {
+          for (int t = lane; t < kEbStride; t += 32) s_par[warp][t] = eb_staged_param(p, c, t);
+          __syncwarp();
+          staged = true;
+        }
+        if (valid) {
+          if (p.zhat) st_stream1(p.zhat + image * p.zhat_bs + off + i, st);
+          if (p.ste) st_stream1(p.ste + image * p.ste_bs + off + i, st);
+          if (p.sym) st_stream1(p.sym + image * p.sym_bs + off + i, __float2int_rn(q));
+          if (need_lik) {
+            float L, lg;
+            if (!far) {
+              const int k = __float2int_rn(q) + kLutK;
+              L = s_lut[warp][k]; lg = s_lg[warp][k];
+            } else {
+              L = eb_likelihood(s_par[warp], st, p.lik_bound);
+              lg = log2f(L);
+            }
+            if (p.lik) st_stream1(p.lik + image * p.lik_bs + off + i, L);
+            acc += lg;
+          }
+        }
+      }
+    }
+  }
+  if (p.bits) {
+    const float v = warp_sum_f32(acc);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      float total = 0.0f;
+      if (lane == 0) {
+#pragma unroll
+        for (int w = 0; w < kEbWarps; ++w) total += s_red[w];     // fixed order: reproducible
+      }
+      rate_commit(total, image, static_cast<unsigned int>(octets), p.B, p.workspace, p.bits, p.bits_accumulate);
+    }
   }
 }
 
@@ -222,6 +346,7 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   p.B = d->B;
   p.ne = d->C * d->hw; p.hw = static_cast<int>(d->hw); p.C = static_cast<int>(d->C);
   p.noise_mode = d->mode == RESLIC_Q_NOISE; p.lik_bound = d->likelihood_bound;
+  p.lut = p.noise_mode ? nullptr : d->lut;
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
   // a tile may touch at most kEbMaxCh channels: tile <= (kEbMaxCh - 1) * hw
@@ -240,7 +365,22 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     if (rc != RESLIC_OK) return rc;
   }
   cudaError_t err;
-  if (!p.noise_mode) {
+  if (!p.noise_mode && p.lut) {
+    // eval with a prebuilt table: one CTA per (image, 8 channels)
+    const int64_t octets = (d->C + kEbWarps - 1) / kEbWarps;
+    if (octets * d->B > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
+    if (octets > 60000) return set_error(RESLIC_ERR_ARG, "eb_fwd: too many channels for the rate arrival count");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(octets * d->B));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
+    err = cudaLaunchKernelEx(&cfg, eb_lut8_kernel, p);
+  } else if (!p.noise_mode) {
     // eval: per-channel LUT kernel, one CTA per (channel, batch split)
     // one (image, channel) run per warp where the machine has room for it (<= 8 CTAs per SM)
     int64_t splits = (d->B + (kThreads / 32) - 1) / (kThreads / 32);
@@ -266,6 +406,27 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     err = cudaGetLastError();
   }
   if (err != cudaSuccess) return set_cuda_error(err, "eb_fwd launch");
+  return RESLIC_OK;
+}
+
+int eb_build_lut_launch(const reslic_eb_desc* d, float* lut, cudaStream_t st) {
+  if (!d || !lut) return set_error(RESLIC_ERR_ARG, "eb_build_lut: null descriptor or table");
+  if (d->C < 0 || d->C > (1 << 20)) return set_error(RESLIC_ERR_ARG, "eb_build_lut: C out of range");
+  if (d->C == 0) return RESLIC_OK;
+  if (!d->medians) return set_error(RESLIC_ERR_ARG, "eb_build_lut: medians is null");
+  for (int i = 0; i < 5; ++i)
+    if (!d->matrix[i] || !d->bias[i] || (i < 4 && !d->factor[i]))
+      return set_error(RESLIC_ERR_ARG, "eb_build_lut: a parameter pointer is null");
+  EbParams p{};
+  for (int i = 0; i < 5; ++i) { p.matrix[i] = d->matrix[i]; p.bias[i] = d->bias[i]; }
+  for (int i = 0; i < 4; ++i) p.factor[i] = d->factor[i];
+  p.medians = d->medians;
+  p.C = static_cast<int>(d->C);
+  p.lik_bound = d->likelihood_bound;
+  p.lut_out = lut;
+  eb_build_lut_kernel<<<static_cast<int>(d->C), kThreads, 0, st>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error(err, "eb_build_lut launch");
   return RESLIC_OK;
 }
 

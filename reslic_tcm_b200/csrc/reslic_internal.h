@@ -25,6 +25,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);
 int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st);
 int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st);
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st);
+int eb_build_lut_launch(const reslic_eb_desc* d, float* lut, cudaStream_t st);
 int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st);
 int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st);
 int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st);

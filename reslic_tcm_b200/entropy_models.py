@@ -449,6 +449,18 @@ class EntropyBottleneck(EntropyModel):
             self._med_key = key
         return self._med_flat
 
+    def _eval_lut(self) -> Tensor:
+        """[C, 130] table of the eval-mode likelihoods (ops.eb_build_lut), rebuilt only when a
+        parameter, the medians or the bound changes (tensor version counters): evaluation and
+        compress loops then launch the bottleneck without its 5-layer table construction."""
+        m, b, f = self._params()
+        bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
+        key = tuple((t._version, t.data_ptr()) for t in (*m, *b, *f, self.quantiles)) + (bound,)
+        if getattr(self, "_lut_key", None) != key:
+            self._lut = ops.eb_build_lut(m, b, f, self._medians_flat(), likelihood_bound=bound)
+            self._lut_key = key
+        return self._lut
+
     def _params(self):
         n = len(self.filters) + 1
         return ([getattr(self, f"_matrix{i:d}") for i in range(n)],
@@ -524,7 +536,7 @@ class EntropyBottleneck(EntropyModel):
         return ops.eb_forward(
             x, m, b, f, self._medians_flat(), training=training, noise=noise,
             likelihood_bound=self._likelihood_bound if self.use_likelihood_bound else 0.0,
-            want=want, seed=seed, offset=offset)
+            want=want, seed=seed, offset=offset, lut=None if training else self._eval_lut())
 
     def forward(self, x: Tensor, training: Optional[bool] = None, noise: Optional[Tensor] = None
                 ) -> Tuple[Tensor, Tensor]:

@@ -322,6 +322,50 @@ def dequantize(symbols: Tensor, means: Optional[Tensor] = None) -> Tensor:
     return out
 
 
+def _eb_fill_params(d, matrices, biases, factors, medians, Cc: int, keep: list) -> None:
+    for i in range(5):
+        m = matrices[i].detach().contiguous()
+        b = biases[i].detach().contiguous()
+        _require_cuda(f"_matrix{i}", m)
+        _require_cuda(f"_bias{i}", b)
+        keep += [m, b]
+        d.matrix[i] = m.data_ptr()
+        d.bias[i] = b.data_ptr()
+    for i in range(4):
+        f = factors[i].detach().contiguous()
+        _require_cuda(f"_factor{i}", f)
+        keep.append(f)
+        d.factor[i] = f.data_ptr()
+    med = medians.detach().reshape(-1).contiguous()
+    _require_cuda("medians", med)
+    if med.numel() != Cc:
+        raise ValueError("medians must have one entry per channel")
+    keep.append(med)
+    d.medians = med.data_ptr()
+
+
+def eb_build_lut(matrices: Sequence[Tensor], biases: Sequence[Tensor], factors: Sequence[Tensor], medians: Tensor,
+                 *, likelihood_bound: float = 1e-9) -> Tensor:
+    """[C, 130] eval-mode table of the bottleneck (reslic_eb_build_lut_f32): per channel the bounded
+    likelihoods of round(z - median) = -32..32 and their log2, bit-identical to what eb_forward computes
+    itself.  Valid until a parameter, the medians or the bound changes."""
+    lib = _cabi.load()
+    if len(matrices) != 5 or len(biases) != 5 or len(factors) != 4:
+        raise _cabi.ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
+    Cc = matrices[0].shape[0]
+    d = _cabi.EbDesc()
+    keep: list = []
+    _eb_fill_params(d, matrices, biases, factors, medians, Cc, keep)
+    d.C = Cc
+    d.likelihood_bound = float(likelihood_bound)
+    dev = matrices[0].device
+    lut = torch.empty((Cc, _cabi.EB_LUT_STRIDE), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        code = lib.reslic_eb_build_lut_f32(C.byref(d), lut.data_ptr(), _cabi.current_stream_ptr(dev))
+    _cabi.check(code, "reslic_eb_build_lut_f32")
+    return lut
+
+
 def eb_forward(
     z: Tensor,
     matrices: Sequence[Tensor],
@@ -336,8 +380,11 @@ def eb_forward(
     out: Optional[dict] = None,
     seed: int = 0,
     offset: int = 0,
+    lut: Optional[Tensor] = None,
 ) -> EbOutputs:
-    """One fused pass of the factorized bottleneck over z [B, C, *spatial] (tcm.py:429-433)."""
+    """One fused pass of the factorized bottleneck over z [B, C, *spatial] (tcm.py:429-433).
+    ``lut``: the table from :func:`eb_build_lut` for these very parameters (eval mode only; ignored
+    when ``training``) — takes the table construction off the launch."""
     lib = _cabi.load()
     _require_cuda("z", z)
     if z.dim() < 2:
@@ -368,25 +415,13 @@ def eb_forward(
     d.B, d.C, d.hw = B, Cc, hw
     d.mode = _cabi.Q_NOISE if training else _cabi.Q_DEQUANTIZE
     d.likelihood_bound = float(likelihood_bound)
-    for i in range(5):
-        m = matrices[i].detach().contiguous()
-        b = biases[i].detach().contiguous()
-        _require_cuda(f"_matrix{i}", m)
-        _require_cuda(f"_bias{i}", b)
-        keep += [m, b]
-        d.matrix[i] = m.data_ptr()
-        d.bias[i] = b.data_ptr()
-    for i in range(4):
-        f = factors[i].detach().contiguous()
-        _require_cuda(f"_factor{i}", f)
-        keep.append(f)
-        d.factor[i] = f.data_ptr()
-    med = medians.detach().reshape(-1).contiguous()
-    _require_cuda("medians", med)
-    if med.numel() != Cc:
-        raise ValueError("medians must have one entry per channel")
-    keep.append(med)
-    d.medians = med.data_ptr()
+    _eb_fill_params(d, matrices, biases, factors, medians, Cc, keep)
+    if lut is not None and not training:
+        _require_cuda("lut", lut)
+        if lut.shape != (Cc, _cabi.EB_LUT_STRIDE) or lut.dtype != torch.float32 or not lut.is_contiguous():
+            raise ValueError(f"lut must be a contiguous float32 [C, {_cabi.EB_LUT_STRIDE}] tensor from eb_build_lut")
+        keep.append(lut)
+        d.lut = lut.data_ptr()
     res = EbOutputs()
     out = dict(out or {})
     for name, dtype in (("zhat", torch.float32), ("ste", torch.float32), ("lik", torch.float32),

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import compressai_ref as cr
-from reslic_tcm_b200 import EntropyBottleneck, synthetic
+from reslic_tcm_b200 import EntropyBottleneck, ops, synthetic
 from tests.util import assert_equal_exact, assert_lik_close, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -112,6 +112,46 @@ def test_full_size_config2_properties():
     assert torch.allclose(r.bits, own, rtol=2e-6)
     _, lik_ref = ref.forward(z[:2])
     assert_lik_close(r.lik[:2], lik_ref)
+
+
+def test_cached_eval_table_is_bit_identical_and_tracks_parameters():
+    """reslic_eb_build_lut_f32: the table built once equals the one every launch builds for itself (same
+    code path), so likelihoods and symbols with and without `lut` are bit-identical (bits to fp32 summation order); the module
+    rebuilds its cached table when a parameter changes in place."""
+    mod, ref = _pair(192, True, seed=77)
+    z = (torch.randn(3, 192, 12, 8, generator=torch.Generator().manual_seed(5)) * 6.0).to(DEV)
+    z[0, 0, 0, 0] = 40.0          # beyond the table: direct evaluation
+    m, b, f = mod._params()
+    want = ("zhat", "lik", "sym", "bits")
+    with torch.no_grad():
+        plain = ops.eb_forward(z, m, b, f, mod._medians_flat(), want=want, likelihood_bound=1e-9)
+        lut = ops.eb_build_lut(m, b, f, mod._medians_flat(), likelihood_bound=1e-9)
+        fast = ops.eb_forward(z, m, b, f, mod._medians_flat(), want=want, likelihood_bound=1e-9, lut=lut)
+    assert lut.shape == (192, 130)
+    for name in ("zhat", "lik", "sym"):
+        assert torch.equal(getattr(plain, name), getattr(fast, name)), name
+    # the table launch sums the fp32 partials per (image, 8 channels) instead of per (image, channel)
+    assert torch.allclose(plain.bits, fast.bits, rtol=2e-6)
+    # the table is the likelihood of the integer offsets about the median
+    k = torch.arange(-32, 33, device=DEV, dtype=torch.float32)
+    zz = (mod._medians_flat()[None, :, None] + k[None, None, :]).contiguous()          # [1, C, 65]
+    with torch.no_grad():
+        direct = ops.eb_forward(zz, m, b, f, mod._medians_flat(), want=("lik",), likelihood_bound=1e-9).lik[0]
+    assert torch.equal(direct, lut[:, :65])
+    assert torch.equal(torch.log2(lut[:, :65]).float(), lut[:, 65:]) or torch.allclose(torch.log2(lut[:, :65]), lut[:, 65:], rtol=2e-7, atol=1e-7)
+    # cache invalidation
+    t0 = mod._eval_lut()
+    assert mod._eval_lut() is t0
+    with torch.no_grad():
+        mod._bias0.add_(0.25)
+    t1 = mod._eval_lut()
+    assert t1 is not t0 and not torch.equal(t0, t1)
+    with torch.no_grad():
+        r = mod.forward_fused(z, training=False, want=("lik",))
+        again = ops.eb_forward(z, *mod._params(), mod._medians_flat(), want=("lik",), likelihood_bound=1e-9)
+    assert torch.equal(r.lik, again.lik)
+    with pytest.raises(ValueError):
+        ops.eb_forward(z, m, b, f, mod._medians_flat(), want=("lik",), lut=lut[:, :100].contiguous())
 
 
 def test_unsupported_filters_fail_loudly():
