@@ -142,11 +142,14 @@ class HostPipeline:
     symbols/indexes/bits out.  The batch is cut into image chunks (contiguous in NCHW); chunk c's
     H2D copy, its 1 + 5 kernel launches and its D2H copy run on three streams chained by events,
     so PCIe traffic in both directions overlaps and the kernels hide entirely under the copies.
+    Device and host output buffers exist ``depth`` (2) times over, so consecutive ``run`` calls
+    overlap too: batch i+1 is uploading while batch i's symbols are still going back, and the
+    steady state is bounded by the larger of the two PCIe directions, not by their sum.
     This is what a caller whose dense transforms run elsewhere (or the CPU rANS coder consuming the
     symbols, tcm.py:551-565) sees; when the latents are produced on the GPU use TcmEntropyPath."""
 
     def __init__(self, path: TcmEntropyPath, batch: int, y_hw, z_hw, *, with_indexes: bool, training: bool = False,
-                 chunks: int = 4, device=None, num_pixels: Optional[int] = None):
+                 chunks: int = 4, device=None, num_pixels: Optional[int] = None, depth: int = 2):
         self.path, self.with_indexes, self.training, self.num_pixels = path, with_indexes, training, num_pixels
         dev = torch.device(device if device is not None else "cuda")
         self.dev = dev
@@ -159,52 +162,78 @@ class HostPipeline:
             n = base + (1 if c < extra else 0)
             self.ranges.append((start, start + n))
             start += n
+        self.depth = max(1, int(depth))
         C, Cz = synthetic.M_LATENT, synthetic.Z_CHANNELS
         f32 = dict(dtype=torch.float32, device=dev)
-        self.d_in = {k: torch.empty(B, C, *y_hw, **f32) for k in ("y", "mu", "sigma")}
-        self.d_in["z"] = torch.empty(B, Cz, *z_hw, **f32)
-        # one sub-path (static output buffers) per chunk, sharing the parameters of `path`
-        self.sub = []
-        for (a, b) in self.ranges:
-            p = TcmEntropyPath.__new__(TcmEntropyPath)
-            nn.Module.__init__(p)
-            p.num_slices = path.num_slices
-            p.entropy_bottleneck, p.gaussian_conditional = path.entropy_bottleneck, path.gaussian_conditional
-            p._bufs, p._key = None, None
-            self.sub.append(p)
         self.out_names = ["bits"] + (["symbols", "indexes"] if with_indexes else [])
-        self.h_out = {"bits": torch.empty(B, dtype=torch.float64).pin_memory()}
-        if with_indexes:
-            for k in ("symbols", "indexes"):
-                self.h_out[k] = torch.empty(B, C, *y_hw, dtype=torch.int32).pin_memory()
+        self.slots = []
+        for _ in range(self.depth):
+            d_in = {k: torch.empty(B, C, *y_hw, **f32) for k in ("y", "mu", "sigma")}
+            d_in["z"] = torch.empty(B, Cz, *z_hw, **f32)
+            # one sub-path (static output buffers) per chunk, sharing the parameters of `path`
+            sub = []
+            for _r in self.ranges:
+                p = TcmEntropyPath.__new__(TcmEntropyPath)
+                nn.Module.__init__(p)
+                p.num_slices = path.num_slices
+                p.entropy_bottleneck, p.gaussian_conditional = path.entropy_bottleneck, path.gaussian_conditional
+                p._bufs, p._key = None, None
+                sub.append(p)
+            h_out = {"bits": torch.empty(B, dtype=torch.float64).pin_memory()}
+            if with_indexes:
+                for k in ("symbols", "indexes"):
+                    h_out[k] = torch.empty(B, C, *y_hw, dtype=torch.int32).pin_memory()
+            self.slots.append({
+                "d_in": d_in, "sub": sub, "h_out": h_out, "used": False,
+                "ev_in": [torch.cuda.Event() for _r in self.ranges],      # chunk uploaded
+                "ev_comp": [torch.cuda.Event() for _r in self.ranges],    # chunk computed (inputs free, outputs ready)
+                "ev_out": [torch.cuda.Event() for _r in self.ranges],     # chunk downloaded (device outputs free)
+                "done": torch.cuda.Event(),                               # whole batch on the host
+            })
         self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
-        self.ev_in = [torch.cuda.Event() for _ in self.ranges]
-        self.ev_out = [torch.cuda.Event() for _ in self.ranges]
-        self.ev_free = [torch.cuda.Event() for _ in self.ranges]
-        self.h2d_bytes = sum(t.numel() * 4 for t in self.d_in.values())
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out.values())
+        self._turn = 0
+        one = self.slots[0]
+        self.h2d_bytes = sum(t.numel() * 4 for t in one["d_in"].values())
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in one["h_out"].values())
 
     @torch.no_grad()
     def run(self, host: Dict[str, Tensor]) -> Dict[str, Tensor]:
-        """host: pinned CPU tensors y, mu, sigma, z (full batch).  Returns pinned host outputs;
-        the call returns after enqueueing — synchronise `self.s_d2h` (or the device) before reading."""
-        cur = torch.cuda.current_stream(self.dev)
-        for st in (self.s_h2d, self.s_comp, self.s_d2h):
-            st.wait_stream(cur)
+        """host: pinned CPU tensors y, mu, sigma, z (full batch).  Enqueues the batch and returns its
+        pinned host outputs plus ``"done"``, the event to synchronise before reading them; the buffers
+        are reused ``depth`` calls later.  ``host`` must stay unchanged until the upload has run."""
+        slot = self.slots[self._turn % self.depth]
+        self._turn += 1
+        if not slot["used"]:      # first use: order after whatever the caller has enqueued so far
+            cur = torch.cuda.current_stream(self.dev)
+            for st in (self.s_h2d, self.s_comp, self.s_d2h):
+                st.wait_stream(cur)
+        d_in, h_out = slot["d_in"], slot["h_out"]
         for c, (a, b) in enumerate(self.ranges):
             with torch.cuda.stream(self.s_h2d):
+                if slot["used"]:
+                    self.s_h2d.wait_event(slot["ev_comp"][c])          # the previous tenant's kernels have read the inputs
                 for k in ("y", "mu", "sigma", "z"):
-                    self.d_in[k][a:b].copy_(host[k][a:b], non_blocking=True)
-                self.ev_in[c].record(self.s_h2d)
+                    d_in[k][a:b].copy_(host[k][a:b], non_blocking=True)
+                slot["ev_in"][c].record(self.s_h2d)
             with torch.cuda.stream(self.s_comp):
-                self.s_comp.wait_event(self.ev_in[c])
-                res = self.sub[c].forward(self.d_in["y"][a:b], self.d_in["mu"][a:b], self.d_in["sigma"][a:b],
-                                          self.d_in["z"][a:b], training=self.training, with_indexes=self.with_indexes,
-                                          num_pixels=self.num_pixels)
-                self.ev_out[c].record(self.s_comp)
+                self.s_comp.wait_event(slot["ev_in"][c])
+                if slot["used"]:
+                    self.s_comp.wait_event(slot["ev_out"][c])          # ... and its outputs have left the device
+                res = slot["sub"][c].forward(d_in["y"][a:b], d_in["mu"][a:b], d_in["sigma"][a:b], d_in["z"][a:b],
+                                             training=self.training, with_indexes=self.with_indexes,
+                                             num_pixels=self.num_pixels)
+                slot["ev_comp"][c].record(self.s_comp)
             with torch.cuda.stream(self.s_d2h):
-                self.s_d2h.wait_event(self.ev_out[c])
+                self.s_d2h.wait_event(slot["ev_comp"][c])
                 for k in self.out_names:
-                    self.h_out[k][a:b].copy_(res[k], non_blocking=True)
-        cur.wait_stream(self.s_d2h)
-        return self.h_out
+                    h_out[k][a:b].copy_(res[k], non_blocking=True)
+                slot["ev_out"][c].record(self.s_d2h)
+        slot["done"].record(self.s_d2h)
+        slot["used"] = True
+        out = dict(h_out)
+        out["done"] = slot["done"]
+        return out
+
+    def synchronize(self) -> None:
+        """Wait until every enqueued batch is on the host."""
+        self.s_d2h.synchronize()

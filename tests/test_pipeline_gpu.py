@@ -6,7 +6,7 @@ import torch
 
 from oracle import compressai_ref as cr
 from reslic_tcm_b200 import ops, synthetic
-from reslic_tcm_b200.pipeline import TcmEntropyPath
+from reslic_tcm_b200.pipeline import HostPipeline, TcmEntropyPath
 from tests.util import assert_equal_exact, assert_lik_close
 
 pytestmark = pytest.mark.gpu
@@ -91,3 +91,29 @@ def test_bits_accumulate_flag():
     assert torch.allclose(bits, one + 100.0, rtol=1e-12)
     ops.gc_forward(y, s, None, want=("bits",), out={"bits": bits})
     assert torch.equal(bits, one)
+
+
+def test_host_pipeline_streams_batches_and_matches_the_device_pass():
+    """HostPipeline: pinned host latents in, host symbols/indexes/bits out, chunked over images and
+    double-buffered over consecutive batches.  Four different batches are enqueued back to back without
+    a synchronisation in between (so uploads, kernels and downloads of neighbouring batches overlap and
+    every buffer slot is reused); each must equal the device-resident pass on the same data."""
+    B, y_hw, z_hw = 5, (16, 8), (4, 2)
+    _, path, _ = _setup(2, B, y_hw, z_hw)
+    hp = HostPipeline(path, B, y_hw, z_hw, with_indexes=True, chunks=3, device=DEV)
+    batches = [synthetic.make_batch(2, range(10 * k, 10 * k + B), y_hw=y_hw, z_hw=z_hw, pin=True) for k in range(4)]
+    got = []
+    for k, host in enumerate(batches):
+        got.append(hp.run(host))
+        # results of a slot stay valid until `depth` further calls: copy batch k-1 before it is overwritten
+        if k >= 1:
+            got[k - 1]["done"].synchronize()
+            got[k - 1] = {n: got[k - 1][n].clone() for n in ("bits", "symbols", "indexes")}
+    hp.synchronize()
+    got[-1] = {n: got[-1][n].clone() for n in ("bits", "symbols", "indexes")}
+    for k, host in enumerate(batches):
+        ref = path.forward(host["y"].to(DEV), host["mu"].to(DEV), host["sigma"].to(DEV), host["z"].to(DEV),
+                           with_indexes=True)
+        assert torch.equal(got[k]["symbols"], ref["symbols"].cpu()), k
+        assert torch.equal(got[k]["indexes"], ref["indexes"].cpu()), k
+        assert torch.allclose(got[k]["bits"], ref["bits"].cpu(), rtol=1e-6), k      # chunking regroups fp32 partials
