@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-whole-y", action="store_true")
+    ap.add_argument("--rotations-per-graph", type=int, default=2,
+                    help="consecutive steps chained in one CUDA graph = this many rotations of the buffer sets (0: one graph per step)")
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="image chunks per batch in the host pipeline (batches are double-buffered, so 1 streams best; more chunks cut per-batch latency)")
     return ap.parse_args()
@@ -229,6 +231,11 @@ def run_ours(args):
     from reslic_tcm_b200.pipeline import TcmEntropyPath
 
     _cabi.load()  # no extension -> loud failure, never a fallback
+    # stdout carries exactly ONE JSON line: libraries that write banners to fd 1 (NCCL prints its version
+    # there at the first collective) are sent to stderr until that line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, local, world = rdist.init_from_env()
     if world != args.gpus and rank == 0:
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
@@ -251,42 +258,55 @@ def run_ours(args):
         torch.cuda.synchronize()
         graph, res = path.capture(inp["y"], inp["mu"], inp["sigma"], inp["z"], **kw)
         sets.append({"path": path, "inp": inp, "graph": graph, "res": res})
-    reducers = [rdist.RateReducer(dev) for _ in range(2)]     # alternate: step i+1 never waits on step i's reduce
-    for r_ in reducers:
+    # rate exchange: steps that are enqueued together (one graph of `group` steps) share ONE packed
+    # all-reduce of a [group, 4] float64 matrix; two reducers alternate so that group g+1 never waits
+    # on group g's collective
+    group = len(sets) * max(1, args.rotations_per_graph)
+    reducers = [rdist.RateReducer(dev, slots=group) for _ in range(2)]
+    single = rdist.RateReducer(dev)
+    for r_ in reducers + [single]:
         r_.set_static(0.0, B * c.num_pixels_per_image, B)
     y_elems, z_elems = B * c.y_elems_per_image, B * c.z_elems_per_image
     elems_rank = y_elems + z_elems
     launches_per_step = 1 + synthetic.NUM_SLICES
 
-    # One graph per step (one batch), plus a graph of len(sets) consecutive steps — one per buffer set — so
-    # that back-to-back batches are chained by programmatic (PDL) edges instead of graph-replay boundaries.
-    group = len(sets)
-    super_graph = None
-    if group > 1:
-        super_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(super_graph):
-            for s in sets:
-                s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kw)
+    # One graph per step (one batch), plus graphs of `group` consecutive steps — one per buffer set — so
+    # that back-to-back batches are chained by programmatic (PDL) edges instead of graph-replay boundaries;
+    # the group graphs (one per reducer) end with the `group` tiny kernels that pack sum(bits) of each step.
+    super_graphs = []
+    if group > 1 and args.rotations_per_graph > 0:
+        for red in reducers:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for j in range(group):
+                    s = sets[j % len(sets)]
+                    s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kw)
+                    if world > 1:
+                        red.pack_bits(s["res"]["bits"], slot=j)
+            super_graphs.append(g)
 
-    def reduce_step(i):  # the path's only exchange: one packed-scalar all-reduce per step
-        red = reducers[i % 2]
-        red.pack_bits(sets[i % group]["res"]["bits"])
-        red.all_reduce(async_op=True)
+    works = [None, None, None]
 
     def step(i, collective=True):
-        sets[i % group]["graph"].replay()
-        if world > 1 and collective:
-            reduce_step(i)
+        sets[i % len(sets)]["graph"].replay()
+        if world > 1 and collective:  # the path's only exchange: one packed-scalar all-reduce
+            if works[2] is not None:
+                works[2].wait()
+            single.pack_bits(sets[i % len(sets)]["res"]["bits"])
+            works[2] = single.all_reduce(async_op=True)
 
     def run_steps(i0, n, collective=True):
         """Steps i0 .. i0+n-1, in groups of `group` where they line up with the buffer rotation."""
         i, end = i0, i0 + n
         while i < end:
-            if super_graph is not None and i % group == 0 and i + group <= end:
-                super_graph.replay()
+            if super_graphs and i % group == 0 and i + group <= end:
+                k = (i // group) % 2
+                if works[k] is not None:       # stream-level wait: this reducer's previous collective has read its matrix
+                    works[k].wait()
+                    works[k] = None
+                super_graphs[k].replay()
                 if world > 1 and collective:
-                    for j in range(group):
-                        reduce_step(i + j)
+                    works[k] = reducers[k].all_reduce(async_op=True)
                 i += group
             else:
                 step(i, collective)
@@ -454,13 +474,16 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": c.name, "cfg": c.cfg, "images_per_gpu": B, "y_shape": [B, 320, *c.y_hw],
                        "z_shape": [B, 192, *c.z_hw], "launches_per_step": launches_per_step,
-                       "mode": "per-slice launches (1 EB + 5 GC per step) replayed as CUDA graphs, steps chained in groups of the buffer rotation",
+                       "mode": f"per-slice launches (1 EB + 5 GC per step) replayed as CUDA graphs, steps chained in graphs of {group} (one packed rate all-reduce per graph when N > 1)",
                        "l2": f"{len(sets)} rotating buffer sets of {(bpe * y_elems + 12 * z_elems) / 1e6:.0f} MB each (> 126 MB L2)",
                        "bpp_mean_image0_set": float(bits.mean()) / c.num_pixels_per_image},
             "roofline": roof, "whole_y": whole, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

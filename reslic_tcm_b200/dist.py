@@ -52,27 +52,34 @@ class RateReducer:
 
     FIELDS = ("bits", "sq_err", "pixels", "images")
 
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, slots: int = 1):
+        """``slots`` > 1 batches that many consecutive steps into ONE all-reduce (a [slots, 4] matrix):
+        the exchange is latency-bound, and a collective kernel that lands in the middle of a
+        persistent-CTA launch costs that launch a second wave, so steps that are enqueued together
+        share one collective."""
         self.device = device
-        self.packed = torch.zeros(len(self.FIELDS), dtype=torch.float64, device=device)
+        self.slots = int(slots)
+        self.packed = torch.zeros(self.slots, len(self.FIELDS), dtype=torch.float64, device=device)
 
-    def pack(self, bits_per_image: torch.Tensor, sq_err: Optional[torch.Tensor], pixels: float) -> torch.Tensor:
-        self.packed[0] = bits_per_image.sum()
+    def pack(self, bits_per_image: torch.Tensor, sq_err: Optional[torch.Tensor], pixels: float, slot: int = 0
+             ) -> torch.Tensor:
+        row = self.packed[slot]
+        row[0] = bits_per_image.sum()
         if sq_err is not None:
-            self.packed[1] = sq_err
+            row[1] = sq_err
         else:
-            self.packed[1] = 0.0
-        self.packed[2] = float(pixels)
-        self.packed[3] = float(bits_per_image.numel())
+            row[1] = 0.0
+        row[2] = float(pixels)
+        row[3] = float(bits_per_image.numel())
         return self.packed
 
     def set_static(self, sq_err: float, pixels: float, images: float) -> None:
         """Fill the fields that do not change from step to step (once, outside the hot loop)."""
-        self.packed[1], self.packed[2], self.packed[3] = float(sq_err), float(pixels), float(images)
+        self.packed[:, 1], self.packed[:, 2], self.packed[:, 3] = float(sq_err), float(pixels), float(images)
 
-    def pack_bits(self, bits_per_image: torch.Tensor) -> torch.Tensor:
-        """Hot-loop form: ONE tiny kernel writes sum(bits) into the packed vector."""
-        torch.sum(bits_per_image, dim=0, keepdim=True, out=self.packed[0:1])
+    def pack_bits(self, bits_per_image: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """Hot-loop form: ONE tiny kernel writes sum(bits) into the packed matrix (graph-capturable)."""
+        torch.sum(bits_per_image, dim=0, keepdim=True, out=self.packed[slot, 0:1])
         return self.packed
 
     def all_reduce(self, async_op: bool = False):
@@ -80,8 +87,8 @@ class RateReducer:
             return dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, async_op=async_op)
         return None
 
-    def result(self) -> dict:
-        v = self.packed.tolist()
+    def result(self, slot: int = 0) -> dict:
+        v = self.packed[slot].tolist()
         pixels = max(v[2], 1.0)
         return {"bits": v[0], "sq_err": v[1], "pixels": v[2], "images": v[3],
                 "bpp": v[0] / pixels, "mse": v[1] / pixels}

@@ -83,3 +83,30 @@ def test_single_process_reducer_is_a_noop_wrapper():
     red.pack(torch.tensor([10.0, 6.0], dtype=torch.float64), None, 32)
     assert red.all_reduce() is None
     assert red.result() == {"bits": 16.0, "sq_err": 0.0, "pixels": 32.0, "images": 2.0, "bpp": 0.5, "mse": 0.0}
+
+
+def _worker_slots(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    red = rdist.RateReducer(torch.device("cpu"), slots=3)
+    red.set_static(0.0, 100.0, 2.0)
+    for step in range(3):                       # three steps enqueued together share ONE all-reduce
+        bits = torch.tensor([1.0 + rank, 10.0 * (step + 1)], dtype=torch.float64)
+        red.pack_bits(bits, slot=step)
+    red.all_reduce()
+    torch.save([red.result(slot=k) for k in range(3)], os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_batched_steps_share_one_allreduce(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker_slots, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(tmp_path, f"s{r}.pt")) for r in range(world)]
+    assert outs[0] == outs[1]
+    for step in range(3):
+        r = outs[0][step]
+        assert r["bits"] == (1.0 + 10.0 * (step + 1)) + (2.0 + 10.0 * (step + 1))
+        assert r["pixels"] == 200.0 and r["images"] == 4.0
+        assert r["bpp"] == pytest.approx(r["bits"] / 200.0)
