@@ -340,13 +340,13 @@ def test_rate_is_deterministic(gc):
         assert torch.equal(ops.gc_forward(yd, sd, md, want=("bits",)).bits, ref)
 
 
-@pytest.mark.parametrize("cfg", [2, 5])
+@pytest.mark.parametrize("cfg", [2, 3, 4, 5])
 def test_full_size_properties(gc, cfg):
     """BASELINE.json sizes: size-independent properties instead of an elementwise oracle —
     sym/ste round trip, index monotone in sigma and consistent with the table, the fused
     rate equals the sum over the returned likelihoods, a 1-image oracle spot check."""
     c = synthetic.CONFIGS[cfg]
-    B = min(c.batch, 24)
+    B = min(c.batch, 64)
     batch = synthetic.make_batch(cfg, range(B), with_noise=c.training)
     y, mu, sg = (batch[k].to(DEV) for k in ("y", "mu", "sigma"))
     table = synthetic.scale_table(DEV)
