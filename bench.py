@@ -224,6 +224,25 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa(dev) -> None:
+    """Multi-rank runs: pin this process to the CPUs local to its GPU (sysfs local_cpulist) so that its
+    pinned host buffers are allocated on that NUMA node and the e2e copies do not cross sockets."""
+    try:
+        p = torch.cuda.get_device_properties(dev)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            print(f"[bench] rank on {bdf}: bound to {len(cpus)} local CPUs ({txt})", file=sys.stderr)
+    except Exception as e:      # topology not exposed in this container: run unbound
+        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -242,6 +261,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:
+        bind_to_gpu_numa(dev)      # before any pinned allocation: first touch puts the pages on the GPU's node
     c = synthetic.CONFIGS[args.config]
     B = c.batch                                   # weak scaling: every rank gets a full batch
     images = range(rank * B, (rank + 1) * B)      # of distinct images
