@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 10
+#define RESLIC_ABI_VERSION 11
 
 enum {
   RESLIC_OK = 0,
@@ -280,9 +280,21 @@ typedef struct reslic_stanh_gc_desc {
 
 int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream);
 
-/* Backward of reslic_stanh_gc_fwd_f32 for FIXED STanH parameters (gaussian_configuration
- * ["trainable"] = False, the reference default): gradients w.r.t. y, mu, sigma of the quantize
- * output and of the bounded likelihood.  Gradients w.r.t. stanh.w / stanh.b are not produced. */
+/* Backward of reslic_stanh_gc_fwd_f32: gradients w.r.t. y, mu, sigma of the quantize output and of the
+ * bounded likelihood, and — when `g_params` is given (gaussian_configuration["trainable"] = True) — the
+ * raw material of the gradients w.r.t. the STanH parameters, which autograd gets in the reference through
+ * the dense [1,K,N] soft quantizer (activation.py:146-149 / 301-304) and through distance_points inside
+ * _likelihood (adaptive_gaussian_conditional.py:544-567; update_state runs under grad, tcm_stanh.py:399).
+ * g_params (5K+2 doubles, overwritten) holds, over all elements with upstream gradient G on the quantizer
+ * output and saturation window [lo, hi) of the soft form:
+ *   A[K+1]  sum of G by lo          (every k <  lo has dq/dw_k = +1/2)
+ *   Bq[K+1] sum of G by hi          (every k >= hi has dq/dw_k = -1/2)
+ *   Ww[K]   sum of G * dq/dw_k  for lo <= k < hi
+ *   Wb[K]   sum of G * dq/db_k  for lo <= k < hi          (b = the SORTED thresholds of `tables`)
+ *   Hd[K]   sum of g_lik * dL/d distance_points[m]
+ * so that  dLoss/dw_k = (sum_{m>k} A[m] - sum_{m<=k} Bq[m]) / 2 + Ww[k]  (w as paired with the sorted
+ * thresholds), dLoss/db_k = Wb[k], dLoss/d distance_points[m] = Hd[m]; mapping those to the module's raw
+ * w / b (mirroring of the symmetric form, distance_points = diff(cum_w)/2) is K-sized host work. */
 typedef struct reslic_stanh_gc_bwd_desc {
   const float* y;      int64_t y_bs;
   const float* mu;     int64_t mu_bs;
@@ -296,6 +308,7 @@ typedef struct reslic_stanh_gc_bwd_desc {
   float* g_y;     int64_t g_y_bs;
   float* g_mu;    int64_t g_mu_bs;
   float* g_sigma; int64_t g_sigma_bs;
+  double* g_params; int64_t g_params_len;   /* optional, see above */
 } reslic_stanh_gc_bwd_desc;
 
 int reslic_stanh_gc_bwd_f32(const reslic_stanh_gc_bwd_desc* d, void* stream);

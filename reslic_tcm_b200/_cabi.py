@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
 EB_LUT_STRIDE = 130
@@ -153,6 +153,7 @@ class StanhGcBwdDesc(C.Structure):
         ("g_y", C.c_void_p), ("g_y_bs", C.c_int64),
         ("g_mu", C.c_void_p), ("g_mu_bs", C.c_int64),
         ("g_sigma", C.c_void_p), ("g_sigma_bs", C.c_int64),
+        ("g_params", C.c_void_p), ("g_params_len", C.c_int64),
     ]
 
 

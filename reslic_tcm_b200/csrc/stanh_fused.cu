@@ -444,6 +444,7 @@ struct StanhBwdParams {
   int64_t n, B, tiles_per_image;
   int training, removing_mean;
   float scale_bound, lik_bound;
+  double* g_par;       // optional [5K+2]: A[K+1] | Bq[K+1] | Ww[K] | Wb[K] | Hd[K] (see reslic_stanh_gc_bwd_desc)
 };
 
 __device__ __forceinline__ float stanh_soft_grad(float x, float beta, const StanhTables& T) {
@@ -464,10 +465,46 @@ __device__ __forceinline__ float stanh_soft_grad(float x, float beta, const Stan
   return acc;
 }
 
+// Parameter-gradient accumulators of one CTA (doubles in shared memory, flushed with one global atomic per
+// entry at the end).  For an element with upstream gradient G on the soft quantizer output q and
+// saturation window [lo, hi):  dq/dw_k = +1/2 for k < lo, -1/2 for k >= hi — recorded as ONE add to A[lo]
+// and ONE to Bq[hi] (the host turns the two histograms into per-k sums with a prefix sum) — and the exact
+// derivative inside the window, where also dq/db_k lives.
+struct StanhParAcc {
+  double* A; double* Bq; double* Ww; double* Wb; double* Hd;
+};
+__device__ __forceinline__ void stanh_soft_param_grad(float x, float beta, const StanhTables& T, float G,
+                                                      const StanhParAcc& acc) {
+  int lo = 0, hi = T.K;
+  if (beta > 0.0f) {
+    const float r = kSatT / beta;
+    lo = count_ge(x - r, T.b, T.K, T.steps);
+    hi = count_gt(x + r, T.b, T.K, T.steps);
+    if (hi < lo) hi = lo;
+  }
+  atomicAdd(&acc.A[lo], static_cast<double>(G));
+  atomicAdd(&acc.Bq[hi], static_cast<double>(G));
+  for (int k = lo; k < hi; ++k) {
+    const float t = beta * (x - T.b[k]);
+    const float sg = 1.0f / (1.0f + expf(-(2.0f * t)));
+    atomicAdd(&acc.Ww[k], static_cast<double>(G * 0.5f * (2.0f * sg - 1.0f)));
+    atomicAdd(&acc.Wb[k], static_cast<double>(G * (T.w[k] * 0.5f) * (-4.0f * beta * sg * (1.0f - sg))));
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdParams p) {
   extern __shared__ float sm[];
   StanhTables T;
   stage_tables(p.st, sm, T);
+  StanhParAcc acc{};
+  const int n_acc = 5 * p.st.K + 2;
+  if (p.g_par) {
+    // doubles behind the float tables (5K+1 floats, rounded up to an 8-byte boundary)
+    double* base = reinterpret_cast<double*>(sm + ((5 * p.st.K + 1 + 1) & ~1));
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) base[i] = 0.0;
+    acc.A = base; acc.Bq = acc.A + p.st.K + 1; acc.Ww = acc.Bq + p.st.K + 1; acc.Wb = acc.Ww + p.st.K; acc.Hd = acc.Wb + p.st.K;
+    __syncthreads();
+  }
   const int64_t total = p.tiles_per_image * p.B;
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     const int image = static_cast<int>(t / p.tiles_per_image);
@@ -506,6 +543,13 @@ __global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdPa
       const float p1 = k * expf(-0.5f * a1 * a1), p2 = k * expf(-0.5f * a2 * a2);
       gv = g * (p1 - p2) * dir * rs;
       gs = -g * (a1 * p1 - a2 * p2) * rs;
+      if (p.g_par && g != 0.0f) {
+        // L = Phi(a1) - Phi(a2): v >= 0: a1 = (low - v)/s, a2 = (-up - v)/s;  v < 0: a1 = (v + up)/s, a2 = (v - low)/s;
+        // low = dist[j-1], up = dist[j] (the half-widths depend on the weights)
+        const float dlow = (v >= 0.0f ? p1 : p2) * rs, dup = (v >= 0.0f ? p2 : p1) * rs;
+        if (inside && j > 0) atomicAdd(&acc.Hd[j - 1], static_cast<double>(g * dlow));
+        if (inside && j < T.K) atomicAdd(&acc.Hd[j], static_cast<double>(g * dup));
+      }
       const bool pass_s = (sg_in >= p.scale_bound) || (gs < 0.0f);
       gs = pass_s ? gs : 0.0f;
     }
@@ -513,9 +557,28 @@ __global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdPa
     const float dyhat_dmu = rm ? 1.0f - dq : 0.0f;
     const float gy = (gyh + gv) * dq;
     const float gmu = gyh * dyhat_dmu + gv * (dyhat_dmu - (p.mu ? 1.0f : 0.0f));
+    if (p.g_par && (gyh + gv) != 0.0f && x == x) {
+      if (soft) {
+        stanh_soft_param_grad(x, p.st.beta, T, gyh + gv, acc);
+      } else {
+        // hard form: the level is still linear in the weights — dq/dw_k = +1/2 where x > b_k, -1/2 where
+        // x < b_k; at an exact tie the non-symmetric form (relu(sign(0)) = 0) gives -1/2, the symmetric one 0
+        const int c_gt = count_gt(x, T.b, T.K, T.steps);
+        const int c_ge = p.st.symmetric ? count_ge(x, T.b, T.K, T.steps) : c_gt;
+        atomicAdd(&acc.A[c_gt], static_cast<double>(gyh + gv));
+        atomicAdd(&acc.Bq[c_ge], static_cast<double>(gyh + gv));
+      }
+    }
     if (p.g_y) p.g_y[image * p.g_y_bs + e] = gy;
     if (p.g_mu) p.g_mu[image * p.g_mu_bs + e] = gmu;
     if (p.g_sigma) p.g_sigma[image * p.g_sigma_bs + e] = gs;
+  }
+  if (p.g_par) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) {
+      const double v = acc.A[i];
+      if (v != 0.0) atomicAdd(&p.g_par[i], v);
+    }
   }
 }
 
@@ -526,7 +589,12 @@ int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st) {
   if (int rc = check_tables(&d->tables, "stanh_gc_bwd")) return rc;
   if (!d->y) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: y is null");
   if (d->g_lik && !d->sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: sigma is null");
-  if (!d->g_y && !d->g_mu && !d->g_sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: no output requested");
+  if (!d->g_y && !d->g_mu && !d->g_sigma && !d->g_params)
+    return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: no output requested");
+  if (d->g_params && d->g_params_len < 5 * static_cast<int64_t>(d->tables.K) + 2)
+    return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: g_params needs 5*K+2 doubles");
+  if (d->g_params && (reinterpret_cast<uintptr_t>(d->g_params) & 7u))
+    return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: g_params must be 8-byte aligned");
   if (!(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: scale_bound must be > 0");
   StanhBwdParams p{};
   p.y = d->y; p.mu = d->mu; p.sigma = d->sigma; p.g_yhat = d->g_yhat; p.g_lik = d->g_lik;
@@ -540,7 +608,16 @@ int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st) {
   int64_t grid = p.tiles_per_image * p.B;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   if (grid > cap) grid = cap;
-  stanh_gc_bwd_kernel<<<static_cast<int>(grid), kThreads, tables_smem(p.st.K), st>>>(p);
+  p.g_par = d->g_params;
+  size_t smem = tables_smem(p.st.K);
+  if (p.g_par) {
+    smem = static_cast<size_t>((5 * p.st.K + 2) & ~1) * sizeof(float) + static_cast<size_t>(5 * p.st.K + 2) * sizeof(double);
+    cudaError_t e = cudaMemsetAsync(p.g_par, 0, static_cast<size_t>(5 * p.st.K + 2) * sizeof(double), st);
+    if (e == cudaSuccess && smem > 48 * 1024)
+      e = cudaFuncSetAttribute(stanh_gc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error(e, "stanh_gc_bwd setup");
+  }
+  stanh_gc_bwd_kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_gc_bwd launch");
   return RESLIC_OK;

@@ -55,6 +55,12 @@ class _StanHBase(nn.Module):
         self._tables_cache = (key, (b_sorted, w, cw, avg, dist))
         return t, (b_sorted, w, cw, avg, dist)
 
+    def _effective(self, w: Tensor, b: Tensor):
+        """(w as paired with the sorted thresholds, sorted thresholds, distance_points) as DIFFERENTIABLE
+        functions of the raw parameters — the K-sized host mirror of update_state, used only to map the
+        kernel's parameter-gradient sums back to w / b."""
+        raise NotImplementedError
+
     def calculate_average_points(self):
         self.average_points = torch.add(self.cum_w[1:], self.cum_w[:-1]) / 2
 
@@ -151,6 +157,10 @@ class NonSymStanH(_StanHBase):
     def _all_w(self):
         return self.w
 
+    def _effective(self, w: Tensor, b: Tensor):
+        cum = torch.cat((w.new_zeros(1), torch.cumsum(w, dim=0)))          # the -sum(w)/2 shift cancels in the differences
+        return w, torch.sort(b)[0], (cum[1:] - cum[:-1]) / 2
+
     def update_state(self, device=None):
         device = self.w.device if device is None else device
         before = getattr(self, "_cum_key", None)
@@ -236,6 +246,13 @@ class SymStanH(_StanHBase):
     def _all_w(self):
         return self.sym_w
 
+    def _effective(self, w: Tensor, b: Tensor):
+        sym_w = torch.cat((torch.flip(w, [0]), w), 0)
+        sym_b = torch.cat((torch.flip(-b, [0]), b), 0)
+        half = torch.cat((w.new_zeros(1), torch.cumsum(w, dim=0)))
+        cum = torch.cat((-torch.flip(half[1:], dims=[0]), half), dim=0)
+        return sym_w, torch.sort(sym_b)[0], (cum[1:] - cum[:-1]) / 2
+
     def update_weights(self):
         self.sym_w = torch.cat((torch.flip(self.w, [0]), self.w), 0)
         self.sym_b = torch.cat((torch.flip(-self.b, [0]), self.b), 0)
@@ -297,22 +314,33 @@ def compute_gap(stanh: _StanHBase, inputs: Tensor, beta=None) -> Tensor:
 
 # ----------------------------------------------------------------------------- entropy model
 class _StanhGcFn(torch.autograd.Function):
-    """Autograd node around the fused STanH forward / backward kernels (fixed w, b)."""
+    """Autograd node around the fused STanH forward / backward kernels.  ``w`` and ``b`` are the module's
+    parameters: when either requires grad the backward kernel also accumulates the parameter-gradient
+    sums (reslic_stanh_gc_bwd_desc.g_params), which are mapped to w / b here with K-sized torch ops."""
 
     @staticmethod
-    def forward(ctx, module, inputs, scales, means, training):
+    def forward(ctx, module, inputs, scales, means, training, w, b):
         with torch.no_grad():
             r = module._stanh_fused(inputs, scales, means, training, ("yhat", "lik"))
         ctx.module, ctx.training = module, bool(training)
-        ctx.save_for_backward(inputs, scales, means)
+        ctx.save_for_backward(inputs, scales, means, w, b)
         ctx.set_materialize_grads(False)
         return r["yhat"], r["lik"]
 
     @staticmethod
     def backward(ctx, g_yhat, g_lik):
-        inputs, scales, means = ctx.saved_tensors
-        g_y, g_mu, g_sigma = ctx.module._stanh_backward(inputs, scales, means, ctx.training, g_yhat, g_lik)
-        return None, g_y, g_sigma, (g_mu if means is not None else None), None
+        inputs, scales, means, w, b = ctx.saved_tensors
+        want_par = ctx.needs_input_grad[5] or ctx.needs_input_grad[6]
+        g_y, g_mu, g_sigma, g_par = ctx.module._stanh_backward(inputs, scales, means, ctx.training, g_yhat, g_lik,
+                                                              want_params=want_par)
+        g_w = g_b = None
+        if want_par:
+            g_w, g_b = ctx.module._stanh_param_grads(g_par, w, b)
+            if not ctx.needs_input_grad[5]:
+                g_w = None
+            if not ctx.needs_input_grad[6]:
+                g_b = None
+        return None, g_y, g_sigma, (g_mu if means is not None else None), None, g_w, g_b
 
 
 class HypeEntropyModelSoS(EntropyModel):
@@ -383,7 +411,7 @@ class HypeEntropyModelSoS(EntropyModel):
         _cabi.check(code, "reslic_stanh_gc_fwd_f32")
         return res
 
-    def _stanh_backward(self, inputs, scales, means, training, g_yhat, g_lik):
+    def _stanh_backward(self, inputs, scales, means, training, g_yhat, g_lik, want_params: bool = False):
         lib = _cabi.load()
         d = _cabi.StanhGcBwdDesc()
         keep = []
@@ -413,10 +441,29 @@ class HypeEntropyModelSoS(EntropyModel):
             setattr(d, name, t.data_ptr())
             setattr(d, name + "_bs", n)
             outs.append(t)
+        g_par = None
+        if want_params:
+            g_par = torch.empty(5 * int(d.tables.K) + 2, dtype=torch.float64, device=inputs.device)
+            d.g_params, d.g_params_len = g_par.data_ptr(), g_par.numel()
         with torch.cuda.device(inputs.device):
             code = lib.reslic_stanh_gc_bwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
         _cabi.check(code, "reslic_stanh_gc_bwd_f32")
-        return tuple(outs)
+        return (*outs, g_par)
+
+    def _stanh_param_grads(self, g_par: Tensor, w: Tensor, b: Tensor):
+        """Kernel sums (A | Bq | Ww | Wb | Hd, see reslic_stanh_gc_bwd_desc) -> gradients of the raw w / b."""
+        K = (g_par.numel() - 2) // 5
+        A, Bq, Ww, Wb, Hd = torch.split(g_par, [K + 1, K + 1, K, K, K])
+        # dLoss/dw_eff[k] = (sum_{m>k} A[m] - sum_{m<=k} Bq[m]) / 2 + Ww[k]
+        g_weff = 0.5 * ((A.sum() - torch.cumsum(A, 0)[:K]) - torch.cumsum(Bq, 0)[:K]) + Ww
+        with torch.enable_grad():
+            wl = w.detach().double().requires_grad_(True)
+            bl = b.detach().double().requires_grad_(True)
+            w_eff, b_eff, dist = self.stanh._effective(wl, bl)
+            g_w, g_b = torch.autograd.grad([w_eff, b_eff, dist], [wl, bl], [g_weff, Wb, Hd], allow_unused=True)
+        g_w = torch.zeros_like(w) if g_w is None else g_w.to(w.dtype)
+        g_b = torch.zeros_like(b) if g_b is None else g_b.to(b.dtype)
+        return g_w, g_b
 
     def quantize(self, inputs, mode, means=None, perms=None):
         """modes "training" | "dequantize" | "symbols" (:95-157).  ``perms`` is accepted for API
@@ -562,11 +609,9 @@ class GaussianConditionalStanh(HypeEntropyModelSoS):
         """:588-603 — note the reference's argument order and default ``training=True``."""
         if training is None:
             training = self.training
-        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (values, scales, means)):
-            if self.stanh.w.requires_grad or self.stanh.b.requires_grad:
-                raise _cabi.ReslicError("gradients w.r.t. the STanH parameters w/b (trainable=True) are not "
-                                        "implemented; build the module with trainable=False")
-            return _StanhGcFn.apply(self, values, scales, means, bool(training))
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                           for t in (values, scales, means, self.stanh.w, self.stanh.b)):
+            return _StanhGcFn.apply(self, values, scales, means, bool(training), self.stanh.w, self.stanh.b)
         r = self._stanh_fused(values, scales, means, bool(training), ("yhat", "lik"))
         return r["yhat"], r["lik"]
 

@@ -173,6 +173,72 @@ def test_stanh_backward_matches_autograd(training, removing_mean, symmetry):
         err = (a - r).abs()
         assert bool((err <= 5e-4 * r.abs() + 2e-5 * scale).all()), f"{name}: max err {err.max():.3g} (scale {scale:.3g})"
 
+@pytest.mark.parametrize("training,symmetry,num_sigmoids", [(True, False, 0), (True, True, 0), (False, False, 0),
+                                                            (True, False, 6)])
+def test_stanh_parameter_gradients_match_autograd(training, symmetry, num_sigmoids):
+    """trainable=True (the reference default): d loss / d stanh.w and d stanh.b through the soft quantizer
+    (dense [1,K,N] sum in the reference) and through distance_points inside _likelihood, against fp64 torch
+    autograd on the oracle restatement built from leaf w / b exactly as the reference's update_state does."""
+    from oracle import stanh_ref as sr
+    from reslic_tcm_b200 import stanh
+
+    beta, extrema = 2.5, 5
+    cfg = dict(beta=beta, num_sigmoids=num_sigmoids, extrema=extrema, trainable=True, removing_mean=True,
+               symmetry=symmetry)
+    mod = stanh.GaussianConditionalStanh(None, channels=4, gaussian_configuration=cfg).to(DEV)
+    g = torch.Generator().manual_seed(43)
+    with torch.no_grad():
+        mod.stanh.w.mul_((1.0 + 0.2 * torch.rand(mod.stanh.w.shape, generator=g)).to(DEV))
+        mod.stanh.b.add_((0.1 * (torch.rand(mod.stanh.b.shape, generator=g) - 0.5)).to(DEV))
+    mod.stanh.update_state(torch.device(DEV))
+    assert mod.stanh.w.requires_grad and mod.stanh.b.requires_grad
+    shape = (3, 4, 9, 7)
+    mu = torch.randn(shape, generator=g)
+    sigma = torch.exp(torch.empty(shape).uniform_(-2.0, 1.5, generator=g))
+    y = mu + 2.5 * torch.randn(shape, generator=g)
+    wy, wl = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+
+    # ---- reference: fp64 autograd from leaf w, b
+    w_leaf = mod.stanh.w.detach().cpu().double().requires_grad_(True)
+    b_leaf = mod.stanh.b.detach().cpu().double().requires_grad_(True)
+    if symmetry:
+        w_eff = torch.cat((torch.flip(w_leaf, [0]), w_leaf), 0)
+        b_eff = torch.sort(torch.cat((torch.flip(-b_leaf, [0]), b_leaf), 0))[0]
+        half = torch.cat((torch.zeros(1, dtype=torch.float64), torch.cumsum(w_leaf, 0)))
+        cum_w = torch.cat((-torch.flip(half[1:], dims=[0]), half), dim=0)
+    else:
+        w_eff, b_eff = w_leaf, torch.sort(b_leaf)[0]
+        cum_w = torch.cat((torch.zeros(1, dtype=torch.float64), torch.cumsum(w_leaf, 0))) - w_leaf.sum().detach() / 2
+    avg, dist = sr.mid_and_half_gaps(cum_w)
+    yd, sd, md = y.double(), sigma.double(), mu.double()
+    yh = sr.quantize(yd, "training" if training else "dequantize", md, w_eff, b_eff, beta, symmetry, True)
+    values = yh - md
+    # one-hot cell selection in the fp32 tables the kernel uses (cell membership carries no gradient)
+    j = torch.bucketize(values.detach().float(), mod.stanh.average_points.detach().cpu().float(), right=False)
+    dl = torch.cat((torch.zeros(1, dtype=torch.float64), dist))
+    dr = torch.cat((dist, torch.zeros(1, dtype=torch.float64)))
+    low, up = dl[j], dr[j]
+    s = torch.clamp(sd, min=0.11)
+    upper = cr.standardized_cumulative((low - values) / s) * (values >= 0) + \
+        cr.standardized_cumulative((values + up) / s) * (values < 0)
+    lower = cr.standardized_cumulative((-up - values) / s) * (values >= 0) + \
+        cr.standardized_cumulative((values - low) / s) * (values < 0)
+    lik = RefLowerBound(1e-9)(upper - lower)      # compressai's rule: also passes gradients that push L up
+    ((yh * wy.double()).sum() + (torch.log(lik) * wl.double()).sum()).backward()
+
+    # ---- ours
+    yh2, lik2 = mod(y.to(DEV), sigma.to(DEV), training=training, means=mu.to(DEV))
+    assert yh2.requires_grad or lik2.requires_grad
+    ((yh2 * wy.to(DEV)).sum() + (torch.log(lik2) * wl.to(DEV)).sum()).backward()
+    for name, a, r in (("d/dw", mod.stanh.w.grad, w_leaf.grad), ("d/db", mod.stanh.b.grad, b_leaf.grad)):
+        r = torch.zeros_like(w_leaf) if r is None else r
+        a = torch.zeros_like(r) if a is None else a.detach().cpu().double()
+        scale = max(r.abs().max().item(), 1.0)
+        err = (a - r).abs()
+        assert bool((err <= 2e-3 * r.abs() + 2e-4 * scale).all()), f"{name}: max err {err.max():.3g} (scale {scale:.3g}) ours {a} ref {r}"
+    if training:
+        assert float(mod.stanh.b.grad.abs().max()) > 0 and float(mod.stanh.w.grad.abs().max()) > 0
+
 
 def test_lrp_tail_in_place_on_a_slice():
     from reslic_tcm_b200 import ops
