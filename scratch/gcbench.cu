@@ -21,28 +21,30 @@ __global__ void fill(float* y, float* mu, float* sg, size_t n, unsigned seed) {
 int main(int argc, char** argv) {
   int B = argc > 1 ? atoi(argv[1]) : 24; long n = argc > 2 ? atol(argv[2]) : 64 * 48 * 32;
   int with_idx = argc > 3 ? atoi(argv[3]) : 1; int noise = argc > 4 ? atoi(argv[4]) : 0;
-  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50; int deferred = argc > 6 ? atoi(argv[6]) : 0;
-  size_t N = (size_t)B * n;
+  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50; int deferred = argc > 6 ? atoi(argv[6]) : 0; int smul = argc > 7 ? atoi(argv[7]) : 1;  // smul: batch stride = smul * n (a channel slice of a wider tensor)
+  size_t N = (size_t)B * n; size_t NA = N * smul; long bs = n * smul;
   std::vector<float*> y(nset), mu(nset), sg(nset), yh(nset), lk(nset), nz(nset); std::vector<int*> sym(nset), idx(nset);
   float tabh[64]; for (int i = 0; i < 64; ++i) tabh[i] = expf(logf(0.11f) + i * (logf(256.f) - logf(0.11f)) / 63.f);
   float* tab; CK(cudaMalloc(&tab, 256)); CK(cudaMemcpy(tab, tabh, 256, cudaMemcpyHostToDevice));
   double* bits; CK(cudaMalloc(&bits, B * 8));
   void* ws; size_t wsb = reslic_workspace_bytes(B); CK(cudaMalloc(&ws, wsb)); CK(cudaMemset(ws, 0, wsb));
   for (int s = 0; s < nset; ++s) {
-    CK(cudaMalloc(&y[s], N * 4)); CK(cudaMalloc(&mu[s], N * 4)); CK(cudaMalloc(&sg[s], N * 4));
-    CK(cudaMalloc(&yh[s], N * 4)); CK(cudaMalloc(&lk[s], N * 4)); CK(cudaMalloc(&sym[s], N * 4)); CK(cudaMalloc(&idx[s], N * 4));
-    CK(cudaMalloc(&nz[s], N * 4));
-    fill<<<1024, 256>>>(y[s], mu[s], sg[s], N, 17u + s);
+    CK(cudaMalloc(&y[s], NA * 4)); CK(cudaMalloc(&mu[s], NA * 4)); CK(cudaMalloc(&sg[s], NA * 4));
+    CK(cudaMalloc(&yh[s], NA * 4)); CK(cudaMalloc(&lk[s], NA * 4)); CK(cudaMalloc(&sym[s], NA * 4)); CK(cudaMalloc(&idx[s], NA * 4));
+    CK(cudaMalloc(&nz[s], NA * 4));
+    fill<<<1024, 256>>>(y[s], mu[s], sg[s], NA, 17u + s);
   }
   CK(cudaDeviceSynchronize());
   cudaStream_t st; CK(cudaStreamCreate(&st));
+  long slice_ctr = 0;
   auto launch = [&](int s) {
     reslic_gc_desc d; memset(&d, 0, sizeof(d));
-    d.y = y[s]; d.y_bs = n; d.mu = mu[s]; d.mu_bs = n; d.sigma = sg[s]; d.sigma_bs = n; d.B = B; d.n = n;
+    const long so = (long)(smul > 1 ? ((slice_ctr++) % smul) : 0) * n;   // walk the slices of the wide tensor like TCM does
+    d.y = y[s] + so; d.y_bs = bs; d.mu = mu[s] + so; d.mu_bs = bs; d.sigma = sg[s] + so; d.sigma_bs = bs; d.B = B; d.n = n;
     d.mode = noise ? RESLIC_Q_NOISE : RESLIC_Q_DEQUANTIZE; d.scale_bound = 0.11f; d.likelihood_bound = 1e-9f;
-    d.ste = yh[s]; d.ste_bs = n; d.lik = lk[s]; d.lik_bs = n;
-    if (noise) { d.yhat = nz[s]; d.yhat_bs = n; }
-    if (with_idx) { d.scale_table = tab; d.table_len = 64; d.sym = sym[s]; d.sym_bs = n; d.idx = idx[s]; d.idx_bs = n; }
+    d.ste = yh[s] + so; d.ste_bs = bs; d.lik = lk[s] + so; d.lik_bs = bs;
+    if (noise) { d.yhat = nz[s] + so; d.yhat_bs = bs; }
+    if (with_idx) { d.scale_table = tab; d.table_len = 64; d.sym = sym[s] + so; d.sym_bs = bs; d.idx = idx[s] + so; d.idx_bs = bs; }
     d.bits = deferred ? nullptr : bits; d.bits_accumulate = deferred ? RESLIC_RATE_DEFERRED : 0; d.workspace = ws; d.workspace_bytes = wsb; d.philox_seed = 1;
     int rc = reslic_gc_fwd_f32(&d, st);
     if (rc) { printf("launch failed %d %s\n", rc, reslic_last_error()); exit(1); }
