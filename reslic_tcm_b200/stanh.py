@@ -359,7 +359,7 @@ class HypeEntropyModelSoS(EntropyModel):
         return perm, inv_perm
 
     def _stanh_fused(self, inputs: Tensor, scales: Optional[Tensor], means: Optional[Tensor], training: bool,
-                     want, beta=None):
+                     want, beta=None, out: Optional[dict] = None):
         lib = _cabi.load()
         ops._require_cuda("inputs", inputs)
         _no_grad_path(inputs, scales, means, self.stanh.w, self.stanh.b)
@@ -400,12 +400,8 @@ class HypeEntropyModelSoS(EntropyModel):
                 setattr(d, name, t.data_ptr())
                 setattr(d, name + "_bs", t.stride(0) if (B > 1) else n)
                 res[name] = t
-        if "bits" in want:
-            bits = torch.empty(B, dtype=torch.float64, device=inputs.device)
-            ws = _cabi.workspace(inputs.device, B)
-            d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
-            keep.append(ws)
-            res["bits"] = bits
+        if "bits" in want:      # out: the rate keys of ops.gc_forward (bits, bits_accumulate, bits_deferred, bits_collect, workspace)
+            res["bits"] = ops._rate_outputs(d, dict(out or {}), B, inputs.device, keep)
         with torch.cuda.device(inputs.device):
             code = lib.reslic_stanh_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
         _cabi.check(code, "reslic_stanh_gc_fwd_f32")
@@ -615,8 +611,8 @@ class GaussianConditionalStanh(HypeEntropyModelSoS):
         r = self._stanh_fused(values, scales, means, bool(training), ("yhat", "lik"))
         return r["yhat"], r["lik"]
 
-    def forward_fused(self, values, scales, training=True, means=None, want=("yhat", "lik", "bits")):
-        return self._stanh_fused(values, scales, means, bool(training), want)
+    def forward_fused(self, values, scales, training=True, means=None, want=("yhat", "lik", "bits"), out=None):
+        return self._stanh_fused(values, scales, means, bool(training), want, out=out)
 
     def build_indexes(self, scales: Tensor):
         if self.scale_table.numel() == 0:
@@ -722,7 +718,7 @@ class EntropyBottleneckStanh(EntropyModel):
                 logits = logits + torch.tanh(factor) * torch.tanh(logits)
         return logits
 
-    def _fused(self, x: Tensor, training: bool, want, beta=None):
+    def _fused(self, x: Tensor, training: bool, want, beta=None, out: Optional[dict] = None):
         lib = _cabi.load()
         ops._require_cuda("x", x)
         if self.filters != (3, 3, 3, 3):
@@ -758,11 +754,7 @@ class EntropyBottleneckStanh(EntropyModel):
                 setattr(d, name + "_bs", Cc * hw)
                 res[name] = t
         if "bits" in want:
-            bits = torch.empty(B, dtype=torch.float64, device=x.device)
-            ws = _cabi.workspace(x.device, B)
-            d.bits, d.workspace, d.workspace_bytes = bits.data_ptr(), ws.data_ptr(), ws.numel()
-            keep.append(ws)
-            res["bits"] = bits
+            res["bits"] = ops._rate_outputs(d, dict(out or {}), B, x.device, keep)
         with torch.cuda.device(x.device):
             code = lib.reslic_eb_stanh_fwd_f32(C.byref(d), _cabi.current_stream_ptr(x.device))
         _cabi.check(code, "reslic_eb_stanh_fwd_f32")
@@ -785,8 +777,8 @@ class EntropyBottleneckStanh(EntropyModel):
         r = self._fused(x, bool(training), ("zhat", "lik"))
         return r["zhat"], r["lik"]
 
-    def forward_fused(self, x: Tensor, training: bool = True, want=("zhat", "lik", "bits")):
-        return self._fused(x, bool(training), want)
+    def forward_fused(self, x: Tensor, training: bool = True, want=("zhat", "lik", "bits"), out=None):
+        return self._fused(x, bool(training), want, out=out)
 
     def update(self, device=None):
         """Float pmf / cdf over the STanH levels per channel (:481-514)."""

@@ -194,3 +194,54 @@ def test_entropy_bottleneck_stanh(tag, training):
     assert_lik_close(lik, g[f"{tag}_lik_{key}"], rtol=5e-4, what="likelihood vs reference module")
     own = -(torch.log2(lik.double()).reshape(lik.shape[0], -1).sum(1))
     assert torch.allclose(r["bits"], own, rtol=2e-6)
+
+
+def test_rate_modes_across_kernels_share_one_workspace():
+    """RESLIC_RATE_DEFERRED / RESLIC_RATE_COLLECT through the other kernels that emit a rate (STanH
+    conditional, STanH bottleneck, plain bottleneck in table / per-launch-table / noise mode): launches of
+    different kernels defer into ONE workspace and the last one collects; the total equals the sum of the
+    launches' immediate results exactly (integer accumulation of the same per-warp fixed-point terms)."""
+    from reslic_tcm_b200 import EntropyBottleneck, _cabi, ops, synthetic
+    from reslic_tcm_b200 import stanh as st
+
+    B = 3
+    g = torch.Generator().manual_seed(9)
+    ws = torch.zeros(int(_cabi.load().reslic_workspace_bytes(B)), dtype=torch.uint8, device=DEV)
+    cfg = dict(beta=3.0, num_sigmoids=0, extrema=6, trainable=False, removing_mean=True, symmetry=False)
+    gcs = st.GaussianConditionalStanh(None, channels=8, gaussian_configuration=cfg).to(DEV)
+    gcs.stanh.update_state(torch.device(DEV))
+    y = (3.0 * torch.randn(B, 8, 6, 5, generator=g)).to(DEV)
+    sg = torch.exp(torch.empty(B, 8, 6, 5).uniform_(-2.0, 1.0, generator=g)).to(DEV)
+    mu = torch.randn(B, 8, 6, 5, generator=g).to(DEV)
+    ebs = st.EntropyBottleneckStanh(16, factorized_configuration=dict(beta=3.0, num_sigmoids=0, extrema=6,
+                                                                       trainable=False, symmetry=False)).to(DEV)
+    ebs.stanh.update_state(torch.device(DEV))
+    eb = EntropyBottleneck(16).to(DEV).eval()
+    synthetic.load_eb_parameters(eb, synthetic.eb_parameters(16))
+    z = (2.0 * torch.randn(B, 16, 4, 3, generator=g)).to(DEV)
+    m, b, f = eb._params()
+    med = eb._medians_flat()
+
+    def launches(mode):
+        """mode(k, last) -> out dict for launch k."""
+        outs = []
+        with torch.no_grad():
+            outs.append(gcs.forward_fused(y, sg, training=False, means=mu, want=("bits",), out=mode(0)))
+            outs.append(ebs.forward_fused(z, training=False, want=("bits",), out=mode(1)))
+            outs.append(ops.eb_forward(z, m, b, f, med, want=("bits",), out=mode(2)))                       # per-launch table
+            outs.append(ops.eb_forward(z, m, b, f, med, want=("bits",), out=mode(3), lut=eb._eval_lut()))   # cached table
+            outs.append(ops.eb_forward(z, m, b, f, med, training=True, want=("bits",), out=mode(4), seed=5))  # noise mode
+        return outs
+
+    imm = launches(lambda k: {})
+    total = sum(o["bits"] if isinstance(o, dict) else o.bits for o in imm)
+    final = torch.empty(B, dtype=torch.float64, device=DEV)
+    res = launches(lambda k: {"workspace": ws, "bits_deferred": True} if k < 4
+                   else {"workspace": ws, "bits": final, "bits_collect": True})
+    assert all((o["bits"] if isinstance(o, dict) else o.bits) is None for o in res[:4])
+    assert torch.equal(final, total)
+    assert int(ws.view(torch.int64).abs().sum()) == 0
+    # all deferred + finalize
+    launches(lambda k: {"workspace": ws, "bits_deferred": True})
+    assert torch.equal(ops.rate_finalize(ws, B), total)
+    assert int(ws.view(torch.int64).abs().sum()) == 0
