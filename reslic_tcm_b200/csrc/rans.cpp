@@ -27,7 +27,7 @@ constexpr uint64_t kRansL = 1ull << 31;
 struct Sym { uint16_t start; uint16_t range; bool bypass; };
 
 struct Encoder { std::vector<Sym> syms; std::vector<uint32_t> out; const uint32_t* begin = nullptr; int64_t nbytes = 0; };
-struct Decoder { std::vector<uint32_t> words; size_t pos = 0; uint64_t state = 0; };
+struct Decoder { std::vector<uint32_t> words; size_t pos = 0; uint64_t state = 0; std::vector<int32_t> lut; };
 
 inline void enc_put(uint64_t& x, uint32_t*& ptr, uint32_t start, uint32_t freq, int scale_bits) {
   const uint64_t x_max = ((kRansL >> scale_bits) << 32) * freq;
@@ -156,15 +156,42 @@ int reslic_rans_decoder_decode(void* h, const int32_t* indexes, int64_t n, const
     return renorm();
   };
   const uint64_t mask = (1ull << kPrecision) - 1;
+  // Symbol lookup: a binary search over a 3000-entry row is a dozen dependent cache misses per symbol.
+  // For long runs a coarse table per row — the symbol that holds each multiple of 2^kLutShift — is built
+  // first (n_cdfs * 256 entries) and the search becomes one table read plus a short forward scan (the
+  // distributions are peaked: buckets that hold many symbols are the ones that are almost never hit).
+  constexpr int kLutShift = 8;
+  constexpr int kLutSize = 1 << (kPrecision - kLutShift);
+  const bool use_lut = n >= 8LL * kLutSize;
+  if (use_lut) {
+    d->lut.resize(static_cast<size_t>(n_cdfs) * kLutSize);
+    for (int32_t r = 0; r < n_cdfs; ++r) {
+      const int32_t* cdf = cdfs + static_cast<int64_t>(r) * cdf_stride;
+      const int32_t size = cdf_sizes[r];
+      int32_t sy = 0;
+      for (int k = 0; k < kLutSize; ++k) {
+        const int32_t v = k << kLutShift;
+        while (sy + 1 < size && cdf[sy + 1] <= v) ++sy;
+        d->lut[static_cast<size_t>(r) * kLutSize + k] = sy;
+      }
+    }
+  }
   for (int64_t i = 0; i < n; ++i) {
     const int32_t ci = indexes[i];
     if (ci < 0 || ci >= n_cdfs) return reslic::set_error(RESLIC_ERR_ARG, "rans_decoder_decode: cdf index out of range");
     const int32_t* cdf = cdfs + static_cast<int64_t>(ci) * cdf_stride;
     const int32_t size = cdf_sizes[ci], max_value = size - 2;
     const int32_t cum = static_cast<int32_t>(x & mask);
-    // first entry > cum, minus one  (cdf is strictly increasing on [0, size))
-    const int32_t* it = std::upper_bound(cdf, cdf + size, cum);
-    const int32_t s = static_cast<int32_t>(it - cdf) - 1;
+    int32_t s;
+    if (use_lut) {
+      s = d->lut[static_cast<size_t>(ci) * kLutSize + (cum >> kLutShift)];
+      while (s + 1 < size && cdf[s + 1] <= cum) ++s;
+      if (cdf[s] > cum) s = -1;             // cum below the row's first entry: corrupt
+    } else {
+      // first entry > cum, minus one  (cdf is strictly increasing on [0, size))
+      const int32_t* it = std::upper_bound(cdf, cdf + size, cum);
+      s = static_cast<int32_t>(it - cdf) - 1;
+    }
     if (s < 0 || s > max_value) return reslic::set_error(RESLIC_ERR_ARG, "rans_decoder_decode: corrupt stream");
     const uint64_t start = static_cast<uint64_t>(cdf[s]), freq = static_cast<uint64_t>(cdf[s + 1] - cdf[s]);
     x = freq * (x >> kPrecision) + (x & mask) - start;

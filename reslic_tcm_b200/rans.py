@@ -9,7 +9,9 @@ brought to the host with one copy instead of a per-element Python list.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Union
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional, Sequence, Union
 
 import torch
 from torch import Tensor
@@ -131,26 +133,41 @@ class RansDecoder:
 
 
 # ---- batched helpers used by EntropyModel.compress / decompress (one string per image)
-def encode_with_indexes_batch(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_length: Tensor, offset: Tensor
-                              ) -> List[bytes]:
+def _pool_map(fn, n: int, threads: Optional[int]):
+    """fn(0..n-1) on a thread pool: the coder calls are ctypes foreign calls (the GIL is released), and
+    every image has its own rANS state, so images code in parallel."""
+    workers = min(n, threads if threads else (os.cpu_count() or 1))
+    if workers <= 1:
+        return [fn(b) for b in range(n)]
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(fn, range(n)))
+
+
+def encode_with_indexes_batch(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_length: Tensor, offset: Tensor,
+                              threads: Optional[int] = None) -> List[bytes]:
+    """One rANS string per image (tcm.py:551-565 builds exactly these, image by image, from Python lists)."""
     t = _Tables(cdf, cdf_length.reshape(-1), offset.reshape(-1))
     s = symbols.detach().to(device="cpu", dtype=torch.int32)
     i = indexes.detach().to(device="cpu", dtype=torch.int32)
-    strings = []
-    for b in range(s.shape[0]):
+
+    def one(b):
         enc = BufferedRansEncoder()
         enc.encode_with_indexes(s[b], i[b], t, None, None)
-        strings.append(enc.flush())
-    return strings
+        return enc.flush()
+
+    return _pool_map(one, s.shape[0], threads)
 
 
 def decode_with_indexes_batch(strings: Sequence[bytes], indexes: Tensor, cdf: Tensor, cdf_length: Tensor,
-                              offset: Tensor) -> Tensor:
+                              offset: Tensor, threads: Optional[int] = None) -> Tensor:
     t = _Tables(cdf, cdf_length.reshape(-1), offset.reshape(-1))
     i = indexes.detach().to(device="cpu", dtype=torch.int32)
     out = torch.empty(i.shape, dtype=torch.int32)
-    dec = RansDecoder()
-    for b, sbytes in enumerate(strings):
-        dec.set_stream(sbytes)
+
+    def one(b):
+        dec = RansDecoder()
+        dec.set_stream(strings[b])
         out[b] = dec.decode_stream_tensor(i[b], t, None, None).reshape(i[b].shape)
+
+    _pool_map(one, len(strings), threads)
     return out.to(indexes.device)

@@ -100,3 +100,28 @@ def test_entropy_model_compress_decompress_cpu_buffers(tables):
     assert len(strings) == 3
     back = rans.decode_with_indexes_batch(strings, idx, cdf, length, offset)
     assert torch.equal(back, sym)
+
+
+def test_batch_helpers_thread_over_images_and_long_runs_use_the_symbol_table():
+    """encode/decode_with_indexes_batch: one stream per image, images coded on a thread pool (same bytes as
+    single-threaded), and the decoder's coarse symbol table (long runs) agrees with its binary search
+    (short runs) — incl. bypass-coded outliers."""
+    import torch
+    from oracle import compressai_ref as cr
+    from reslic_tcm_b200 import rans, synthetic
+
+    table = synthetic.scale_table()
+    cdf, off, cdf_len = cr.gc_update(table)
+    B, n = 5, 6000                                   # > 8 * 256 symbols per image: table path
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randint(0, 64, (B, n), generator=g, dtype=torch.int32)
+    sym = (torch.randn(B, n, generator=g) * table[idx.long()]).round().int()
+    sym[1, :40] = torch.tensor([70000, -70000] * 20, dtype=torch.int32)
+    one = rans.encode_with_indexes_batch(sym, idx, cdf, cdf_len, off, threads=1)
+    many = rans.encode_with_indexes_batch(sym, idx, cdf, cdf_len, off, threads=4)
+    assert one == many and len(one) == B
+    for th in (1, 4):
+        assert torch.equal(rans.decode_with_indexes_batch(one, idx, cdf, cdf_len, off, threads=th), sym)
+    # short prefix of image 1 through the binary-search path
+    short = rans.encode_with_indexes_batch(sym[1:2, :500], idx[1:2, :500], cdf, cdf_len, off)
+    assert torch.equal(rans.decode_with_indexes_batch(short, idx[1:2, :500], cdf, cdf_len, off), sym[1:2, :500])
