@@ -220,8 +220,8 @@ class EntropyModel(nn.Module):
             raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
 
     def compress(self, inputs, indexes, means=None):
-        """Symbols + indexes come from the fused kernel; the rANS coder itself is the
-        next-row component N3 and is not part of this path yet."""
+        """Symbols + indexes come from the fused kernel (one D2H copy each, no .tolist()); the strings
+        from the host rANS coder, one per image, images coded on a thread pool."""
         symbols = self.quantize(inputs, "symbols", means)
         if len(inputs.size()) < 2:
             raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
