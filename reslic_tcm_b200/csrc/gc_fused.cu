@@ -11,9 +11,10 @@
 //
 // The path is elementwise and HBM-bound (12 B read + 8..16 B written per element), so the
 // design rules are: 128-bit coalesced streaming loads/stores, scale table staged once per
-// CTA in shared memory, per-image rate reduced by warp shuffles + one fp64 partial per CTA,
-// and an instruction budget small enough (~100 issue slots/element) that FP32/MUFU issue
-// does not become the bound.  No tensor cores (nothing GEMM-shaped here).
+// CTA in shared memory, per-image rate reduced by warp shuffles + one 64-bit integer atomic
+// per warp and image, and an instruction budget (~73 issue slots per element in the loop)
+// small enough that FP32/MUFU issue stays under the HBM time.  No tensor cores (nothing
+// GEMM-shaped here).  DESIGN.md section 3.1 has the measurements behind each choice.
 #include "common.cuh"
 #include "gc_math.cuh"
 #include "reslic_internal.h"
