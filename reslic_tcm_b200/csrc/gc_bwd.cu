@@ -85,6 +85,85 @@ __global__ void __launch_bounds__(kThreads) gc_bwd_kernel(const GcBwdParams p) {
   }
 }
 
+// ------------------------------------------------------------------ 128-bit path
+// One element group (4 consecutive elements) per thread, one tile per CTA, image = blockIdx.y: this kernel
+// has no per-CTA state to amortise (no table, no rate), and for such kernels the plain non-persistent
+// shape at high occupancy is the one that reaches the copy bandwidth (scratch/copybench.cu).  Arithmetic per
+// element: one MUFU.RCP for 1/s, two MUFU.EX2 for the two pdf values; the likelihood itself is only needed
+// for the LowerBound rule "pass where L >= bound", and L >= 1.6e-8 whenever (v - 0.5)/s <= 3.5 and
+// s <= 1000 (the interval then holds a unit of pdf >= phi(4.5) wide 1/s >= 1e-3, or a whole unit step),
+// so only far-tail elements evaluate it.
+__device__ __forceinline__ void gc_bwd_elem_fast(const GcBwdParams& p, bool noise_mode, float y, float mu, float sg,
+                                                 float u, float gyh, float gst, float gl, float& gy, float& gmu,
+                                                 float& gsg) {
+  const float d = y - mu;
+  const float yhat = noise_mode ? y + u : rintf(d) + mu;
+  const float values = yhat - mu;
+  const float v = fabsf(values);
+  const float s = max_nan(sg, p.scale_bound);
+  float gv = 0.0f, gs = 0.0f;
+  if (p.g_lik) {
+    const float rs = rcp_approx(s);
+    const float a = (0.5f - v) * rs, b = (-0.5f - v) * rs;
+    bool pass_l = true;
+    if (p.lik_bound > 0.0f && !(gl < 0.0f)) {
+      const bool surely_above = (-a <= 3.5f) && (s <= 1000.0f) && (p.lik_bound <= 1e-8f);
+      if (!surely_above) {
+        const float L = gauss_interval_mass<true>(0.5f - min_nan(v, 1e30f), -0.5f - min_nan(v, 1e30f), s);
+        pass_l = L >= p.lik_bound;
+      }
+    }
+    const float g = pass_l ? gl : 0.0f;
+    const float k = 0.3989422804014327f;                      // 1/sqrt(2 pi)
+    const float c = -0.72134752044448170368f;                 // -log2(e) / 2
+    const float pa = k * ex2_approx(c * a * a), pb = k * ex2_approx(c * b * b);
+    const float dLdv = (pb - pa) * rs;
+    const float dLds = (b * pb - a * pa) * rs;
+    const float sgn = (values > 0.0f) ? 1.0f : ((values < 0.0f) ? -1.0f : 0.0f);   // torch.abs backward
+    gv = g * dLdv * sgn;
+    gs = g * dLds;
+    const bool pass_s = (sg >= p.scale_bound) || (gs < 0.0f);
+    gs = pass_s ? gs : 0.0f;
+  }
+  if (noise_mode) { gy = gyh + gst + gv; gmu = -gv; }
+  else { gy = gst; gmu = gyh; }
+  gsg = gs;
+}
+
+template <bool NOISE>
+__global__ void __launch_bounds__(kThreads) gc_bwd_vec_kernel(const GcBwdParams p) {
+  const int image = blockIdx.y;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (g >= (p.n >> 2)) return;
+  const int64_t e = g * 4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 y = ld_stream4(p.y + image * p.y_bs + e);
+  const float4 mu = p.mu ? ld_stream4(p.mu + image * p.mu_bs + e) : zero;
+  const float4 sg = p.sigma ? ld_stream4(p.sigma + image * p.sigma_bs + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 gyh = p.g_yhat ? ld_stream4(p.g_yhat + image * p.g_yhat_bs + e) : zero;
+  const float4 gst = p.g_ste ? ld_stream4(p.g_ste + image * p.g_ste_bs + e) : zero;
+  const float4 gl = p.g_lik ? ld_stream4(p.g_lik + image * p.g_lik_bs + e) : zero;
+  float4 u = zero;
+  if (NOISE) {
+    if (p.noise) u = ld_stream4(p.noise + image * p.noise_bs + e);
+    else {
+      const uint64_t gid = static_cast<uint64_t>(image) * static_cast<uint64_t>((p.n + 3) >> 2) + static_cast<uint64_t>(g);
+      const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                      p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+      u = make_float4(u32_to_centered_uniform(r.x), u32_to_centered_uniform(r.y),
+                      u32_to_centered_uniform(r.z), u32_to_centered_uniform(r.w));
+    }
+  }
+  float4 gy, gmu, gsg;
+  gc_bwd_elem_fast(p, NOISE, y.x, mu.x, sg.x, u.x, gyh.x, gst.x, gl.x, gy.x, gmu.x, gsg.x);
+  gc_bwd_elem_fast(p, NOISE, y.y, mu.y, sg.y, u.y, gyh.y, gst.y, gl.y, gy.y, gmu.y, gsg.y);
+  gc_bwd_elem_fast(p, NOISE, y.z, mu.z, sg.z, u.z, gyh.z, gst.z, gl.z, gy.z, gmu.z, gsg.z);
+  gc_bwd_elem_fast(p, NOISE, y.w, mu.w, sg.w, u.w, gyh.w, gst.w, gl.w, gy.w, gmu.w, gsg.w);
+  if (p.g_y) st_stream4(p.g_y + image * p.g_y_bs + e, gy);
+  if (p.g_mu) st_stream4(p.g_mu + image * p.g_mu_bs + e, gmu);
+  if (p.g_sigma) st_stream4(p.g_sigma + image * p.g_sigma_bs + e, gsg);
+}
+
 int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "gc_bwd: null descriptor");
   if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "gc_bwd: negative size");
@@ -106,10 +185,25 @@ int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st) {
   p.noise_mode = d->mode == RESLIC_Q_NOISE; p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
-  int64_t grid = p.tiles_per_image * p.B;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
-  if (grid > cap) grid = cap;
-  gc_bwd_kernel<<<static_cast<int>(grid), kThreads, 0, st>>>(p);
+  // 128-bit path: every tensor 16-byte aligned with batch strides and n multiples of 4, B within gridDim.y
+  bool vec = (d->n % 4 == 0) && d->B <= 65535;
+  auto chk = [&](const void* ptr, int64_t bs) {
+    if (ptr && ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (bs % 4) != 0)) vec = false;
+  };
+  chk(d->y, d->y_bs); chk(d->mu, d->mu_bs); chk(d->sigma, d->sigma_bs); chk(d->noise, d->noise_bs);
+  chk(d->g_yhat, d->g_yhat_bs); chk(d->g_ste, d->g_ste_bs); chk(d->g_lik, d->g_lik_bs);
+  chk(d->g_y, d->g_y_bs); chk(d->g_mu, d->g_mu_bs); chk(d->g_sigma, d->g_sigma_bs);
+  if (vec) {
+    const int64_t groups = d->n / 4;
+    const dim3 grid3(static_cast<unsigned>((groups + kThreads - 1) / kThreads), static_cast<unsigned>(d->B));
+    if (p.noise_mode) gc_bwd_vec_kernel<true><<<grid3, kThreads, 0, st>>>(p);
+    else gc_bwd_vec_kernel<false><<<grid3, kThreads, 0, st>>>(p);
+  } else {
+    int64_t grid = p.tiles_per_image * p.B;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+    if (grid > cap) grid = cap;
+    gc_bwd_kernel<<<static_cast<int>(grid), kThreads, 0, st>>>(p);
+  }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "gc_bwd launch");
   return RESLIC_OK;

@@ -26,10 +26,10 @@ def _ref_forward(y, sigma, mu, noise, training):
     return outputs, lik, ste
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 8, 8), (3, 5, 7, 3)])   # 128-bit kernel / scalar kernel (n % 4 != 0)
 @pytest.mark.parametrize("training", [True, False])
-def test_gc_backward_matches_autograd(training):
+def test_gc_backward_matches_autograd(training, shape):
     g = torch.Generator().manual_seed(17 + int(training))
-    shape = (2, 16, 8, 8)
     mu = torch.randn(shape, generator=g)
     sigma = torch.exp(torch.empty(shape).uniform_(-3.0, 3.0, generator=g))   # some below the 0.11 bound
     y = mu + sigma * torch.randn(shape, generator=g) * 1.5
@@ -38,8 +38,7 @@ def test_gc_backward_matches_autograd(training):
     wy, wl, ws = (torch.randn(shape, generator=g) for _ in range(3))
 
     leaves = [t.clone().requires_grad_(True) for t in (y, sigma, mu)]
-    out, lik, ste = _ref_forward(*leaves[:1], leaves[1], leaves[2], noise, training) if False else \
-        _ref_forward(leaves[0], leaves[1], leaves[2], noise, training)
+    out, lik, ste = _ref_forward(leaves[0], leaves[1], leaves[2], noise, training)
     loss = (out * wy).sum() + (torch.log(lik) * wl).sum() + (ste * ws).sum()
     loss.backward()
     ref = [t.grad for t in leaves]
