@@ -19,6 +19,8 @@
 #include "eb_math.cuh"
 #include "gc_math.cuh"
 #include "reslic_internal.h"
+#include "stanh_tables.cuh"
+#include <limits>
 
 namespace reslic {
 
@@ -180,31 +182,262 @@ __global__ void __launch_bounds__(kThreads) stanh_gc_fwd_kernel(const StanhParam
   }
 }
 
+// ------------------------------------------------------------------ 128-bit forward
+// Same outputs as stanh_gc_fwd_kernel for 16-byte aligned tensors with n % 4 == 0: four elements per
+// thread (LDG.128 / STG.128), persistent CTAs over contiguous tile ranges with a two-tile register
+// ping-pong (the launch structure of gc_fwd_kernel), table lookups through the cell grids of
+// stanh_tables.cuh, the soft terms as (1 - E) / (1 + E), E = 2^(2 beta log2e (b_k - x)) — one MUFU.EX2
+// and one MUFU.RCP per threshold of the window — and the likelihood two elements per packed f32x2 op.
+struct StanhVecParams {
+  StanhParams s;
+  unsigned int tpi, q_tiles, r_tiles;
+  float lik_floor;        // the bound, or -inf when disabled
+  float sat_r, c2;        // 9.1 / beta and 2 * beta * log2(e)
+  int rm;                 // quantize about the mean
+  int sym_same;           // the level index of the quantizer input is the requested symbol
+};
+
+template <bool FAST>
+__device__ __forceinline__ F2 stanh_mass2(F2 n1, F2 n2, F2 s) {
+  n1 = max_nan2(min_nan2(n1, 1e30f), -1e30f);
+  n2 = max_nan2(min_nan2(n2, 1e30f), -1e30f);
+  const F2 sc = min_nan2(s, 1e30f);
+  F2 a, b;
+  div2_rn(n1, n2, sc, a, b);
+  const F2 c = f2(-0.70710678118654752440f);
+  const F2 xa = mul2(c, a), xb = mul2(c, b);
+  if (FAST) {
+    F2 ea = erfc_pos_fast(min_nan2(abs2(xa), 12.0f));
+    F2 eb = erfc_pos_fast(min_nan2(abs2(xb), 12.0f));
+    ea.x = (xa.x < 0.0f) ? 2.0f - ea.x : ea.x;
+    ea.y = (xa.y < 0.0f) ? 2.0f - ea.y : ea.y;
+    eb.x = (xb.x < 0.0f) ? 2.0f - eb.x : eb.x;
+    eb.y = (xb.y < 0.0f) ? 2.0f - eb.y : eb.y;
+    return fma2(f2(0.5f), ea, mul2(f2(-0.5f), eb));
+  }
+  return make_float2(0.5f * erfcf(xa.x) - 0.5f * erfcf(xb.x), 0.5f * erfcf(xa.y) - 0.5f * erfcf(xb.y));
+}
+
+// soft quantizer value; beta > 0
+template <bool FAST>
+__device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r, float c2, const StanhSm& T) {
+  const int lo = stanh_count_ge_b(x - sat_r, T);         // k <  lo: tanh == +1
+  const float xr = x + sat_r;
+  float acc = 0.0f;
+  int k = lo;
+  for (;; ++k) {
+    const float2 e = T.bw[k];                            // (b_k, w_k / 2); NaN pad ends the loop
+    if (!(e.x < xr)) break;
+    if (FAST) {
+      const float E = ex2_approx(c2 * (e.x - x));        // exp(-2 beta (x - b_k))
+      acc = fmaf(e.y, (1.0f - E) * rcp_approx(1.0f + E), acc);
+    } else {
+      const float t = beta * (x - e.x);
+      const float sg = 1.0f / (1.0f + expf(-(2.0f * t)));
+      acc = fmaf(e.y, 2.0f * sg - 1.0f, acc);
+    }
+  }                                                      // k >= hi (= k now): tanh == -1
+  const float sat = 0.5f * ((T.cw[lo] - T.cw0) - (T.cwK - T.cw[k]));
+  return (x != x) ? x : sat + acc;
+}
+
+// hard level of x; c_out = #{k : x > b_k}
+__device__ __forceinline__ float stanh_hard_sm(float x, const StanhSm& T, bool symmetric, int& c_out) {
+  const int c = stanh_count_gt_b(x, T);
+  c_out = c;
+  float v = T.cw[c];
+  if (symmetric) {
+    int ce = c;
+    while (x == T.bw[ce].x) ++ce;                        // sign(0) = 0: mean of the two adjacent levels at a tie
+    v = (x != x) ? 0.0f : 0.5f * (v + T.cw[ce]);
+  }
+  return v;
+}
+
+// numerators (n1 >= n2) of the level cell that contains v; `guess` < 0: look the cell up, else start from it
+__device__ __forceinline__ void stanh_cell_bounds(float v, int guess, const StanhSm& T, float& n1, float& n2) {
+  int j;
+  if (guess < 0) j = stanh_count_gt_avg(v, T);
+  else {
+    j = guess;
+    while (j > 0 && !(v > T.avgp[j])) --j;
+    while (v > T.avgp[j + 1]) ++j;
+  }
+  const bool inside = (v > -1000.0f) && (v <= 1000.0f);    // the reference's +-1000 sentinels (:506,:511)
+  const float2 lu = T.lowup[j];
+  const float low = inside ? lu.x : 0.0f, up = inside ? lu.y : 0.0f;
+  if (v >= 0.0f) { n1 = low - v; n2 = -up - v; }
+  else { n1 = v + up; n2 = v - low; }                     // NaN v lands here and stays NaN
+}
+
+struct StanhIn { float4 y, m, s; };
+
+template <int MODE, bool FAST>      // MODE 0: hard levels, 1: soft form (beta > 0), 2: likelihood of the given values
+__global__ void __launch_bounds__(kThreads, 4) stanh_gc_vec_kernel(const StanhVecParams q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const StanhParams& p = q.s;
+  StanhSm T;
+  stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, smraw, T);
+  const bool need_lik = p.lik || p.bits;
+  const bool use_mu = p.mu != nullptr;
+  const bool rm = q.rm != 0;
+  const bool symmetric = p.symmetric != 0;
+  constexpr unsigned int kTileBytes = kThreads * 16;
+  const int groups = static_cast<int>(p.n >> 2);
+  const unsigned int cta = blockIdx.x;
+  unsigned int t = cta * q.q_tiles + min(cta, q.r_tiles);
+  const unsigned int t_end = t + q.q_tiles + (cta < q.r_tiles ? 1u : 0u);
+  const unsigned int tb = threadIdx.x * 16;
+
+  StanhIn a, b;
+  a.y = a.m = make_float4(0.f, 0.f, 0.f, 0.f); a.s = make_float4(1.f, 1.f, 1.f, 1.f);
+  b = a;
+  while (t < t_end) {
+    const int image = static_cast<int>(t / q.tpi);
+    const int chunk0 = static_cast<int>(t - image * q.tpi);
+    const unsigned int seg_end = (static_cast<unsigned int>(image) + 1u) * q.tpi;
+    const int ntiles = static_cast<int>(min(seg_end, t_end) - t);
+    t += ntiles;
+    const int64_t seg = static_cast<int64_t>(chunk0) * (kThreads * 4);
+    auto at_seg = [&](auto* base, int64_t bs) { return base + (static_cast<int64_t>(image) * bs + seg); };
+    const float* y = at_seg(p.y, p.y_bs);
+    const float* mu = use_mu ? at_seg(p.mu, p.mu_bs) : nullptr;
+    const float* sg = (need_lik && p.sigma) ? at_seg(p.sigma, p.sigma_bs) : nullptr;
+    float* o_yhat = p.yhat ? at_seg(p.yhat, p.yhat_bs) : nullptr;
+    float* o_lik = p.lik ? at_seg(p.lik, p.lik_bs) : nullptr;
+    int32_t* o_sym = p.sym ? at_seg(p.sym, p.sym_bs) : nullptr;
+    const int g = chunk0 * kThreads + threadIdx.x;
+
+    auto load = [&](StanhIn& r, int k) {
+      if (g + k * kThreads >= groups) return;
+      const unsigned int bo = tb + static_cast<unsigned int>(k) * kTileBytes;
+      auto at = [bo](const float* ptr) { return reinterpret_cast<const float*>(reinterpret_cast<const char*>(ptr) + bo); };
+      r.y = ld_stream4(at(y));
+      if (mu) r.m = ld_stream4(at(mu));
+      if (sg) r.s = ld_stream4(at(sg));
+    };
+    float acc = 0.0f;
+    auto compute = [&](const StanhIn& r, int k) {
+      if (g + k * kThreads >= groups) return;
+      const unsigned int bo = tb + static_cast<unsigned int>(k) * kTileBytes;
+      auto at = [bo](auto* ptr) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + bo); };
+      const float yy[4] = {r.y.x, r.y.y, r.y.z, r.y.w};
+      const float mm[4] = {r.m.x, r.m.y, r.m.z, r.m.w};
+      float yh[4], n1[4], n2[4];
+      int lv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = rm ? yy[i] - mm[i] : yy[i];
+        int c = -1;
+        lv[i] = 0;
+        if (MODE == 2) yh[i] = yy[i];
+        else {
+          const float qv = (MODE == 1) ? stanh_soft_sm<FAST>(x, p.beta, q.sat_r, q.c2, T) : stanh_hard_sm(x, T, symmetric, c);
+          yh[i] = rm ? qv + mm[i] : qv;
+          if (o_sym) {
+            if (MODE == 0 && q.sym_same) lv[i] = c;
+            else lv[i] = stanh_count_gt_b(yy[i] - mm[i], T);
+          }
+        }
+        if (need_lik) {
+          const float v = use_mu ? yh[i] - mm[i] : yh[i];             // :547-550
+          stanh_cell_bounds(v, (MODE == 0) ? c : -1, T, n1[i], n2[i]);
+        }
+      }
+      if (o_yhat) st_stream4(at(o_yhat), make_float4(yh[0], yh[1], yh[2], yh[3]));
+      if (o_sym) st_stream4(at(o_sym), make_int4(lv[0] + p.sym_offset, lv[1] + p.sym_offset, lv[2] + p.sym_offset, lv[3] + p.sym_offset));
+      if (need_lik) {
+        const F2 s0 = max_nan2(make_float2(r.s.x, r.s.y), p.scale_bound), s1 = max_nan2(make_float2(r.s.z, r.s.w), p.scale_bound);
+        const F2 L0 = max_nan2(stanh_mass2<FAST>(make_float2(n1[0], n1[1]), make_float2(n2[0], n2[1]), s0), q.lik_floor);
+        const F2 L1 = max_nan2(stanh_mass2<FAST>(make_float2(n1[2], n1[3]), make_float2(n2[2], n2[3]), s1), q.lik_floor);
+        if (o_lik) st_stream4(at(o_lik), make_float4(L0.x, L0.y, L1.x, L1.y));
+        if (FAST) {
+          // one MUFU.LG2 per group while the product of four bounded likelihoods stays normal
+          if (q.lik_floor >= 1e-9f) acc += lg2_approx((L0.x * L0.y) * (L1.x * L1.y));
+          else acc += (lg2_approx(L0.x) + lg2_approx(L0.y)) + (lg2_approx(L1.x) + lg2_approx(L1.y));
+        } else {
+          acc += (log2f(L0.x) + log2f(L0.y)) + (log2f(L1.x) + log2f(L1.y));
+        }
+      }
+    };
+
+    load(a, 0);
+    for (int k = 0; k < ntiles; k += 2) {
+      if (k + 1 < ntiles) load(b, k + 1);
+      compute(a, k);
+      if (k + 2 < ntiles) load(a, k + 2);
+      if (k + 1 < ntiles) compute(b, k + 1);
+    }
+    if (p.bits) {
+      auto owner = [&](unsigned int tau) -> unsigned int {
+        const unsigned int big = q.r_tiles * (q.q_tiles + 1u);
+        return tau < big ? tau / (q.q_tiles + 1u) : q.r_tiles + (tau - big) / q.q_tiles;
+      };
+      const unsigned int first = static_cast<unsigned int>(image) * q.tpi;
+      const unsigned int n_ctas = owner(first + q.tpi - 1u) - owner(first) + 1u;
+      rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate);
+    }
+  }
+}
+
 // Activation alone (module forward) and the two squared-error sums compute_gap needs, in one pass:
 // out_soft / out_hard nullable; gap[0] += sum (x - soft)^2, gap[1] += sum (x - hard)^2.
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p, float* out_soft, float* out_hard,
-                                                             double* partials, unsigned int* counter) {
-  extern __shared__ float sm[];
+                                                             double* partials, unsigned int* counter, int vec,
+                                                             float sat_r, float c2) {
+  extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double s_red[2][kThreads / 32];
   __shared__ bool s_last;
-  StanhTables T;
-  stage_tables(p, sm, T);
+  StanhSm T;
+  stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, smraw, T);
   const bool want_soft = out_soft || p.gap, want_hard = out_hard || p.gap;
+  const bool soft_is_hard = p.beta == -1.0f;
+  const bool symmetric = p.symmetric != 0;
   double se_soft = 0.0, se_hard = 0.0;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < p.n;
-       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+  // soft value of one element; a beta <= 0 other than -1 has no saturation window: all K thresholds
+  auto soft_of = [&](float x) {
+    int c;
+    if (soft_is_hard) return stanh_hard_sm(x, T, symmetric, c);
+    if (p.beta > 0.0f) return stanh_soft_sm<FAST>(x, p.beta, sat_r, c2, T);
+    float acc = 0.0f;
+    for (int k = 0; k < T.K; ++k) {
+      const float2 e = T.bw[k];
+      const float sg = 1.0f / (1.0f + expf(-(2.0f * (p.beta * (x - e.x)))));
+      acc = fmaf(e.y, 2.0f * sg - 1.0f, acc);
+    }
+    return (x != x) ? x : acc;
+  };
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const int64_t first = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
+  const int64_t n_vec = vec ? (p.n >> 2) : 0;
+  for (int64_t i = first; i < n_vec; i += stride) {
+    const float4 x4 = ld_stream4(p.y + 4 * i);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    float qs[4], qh[4], ds = 0.0f, dh = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c;
+      if (want_soft) { qs[j] = soft_of(xs[j]); const float d = xs[j] - qs[j]; ds = fmaf(d, d, ds); }
+      if (want_hard) { qh[j] = stanh_hard_sm(xs[j], T, symmetric, c); const float d = xs[j] - qh[j]; dh = fmaf(d, d, dh); }
+    }
+    if (out_soft) st_stream4(out_soft + 4 * i, make_float4(qs[0], qs[1], qs[2], qs[3]));
+    if (out_hard) st_stream4(out_hard + 4 * i, make_float4(qh[0], qh[1], qh[2], qh[3]));
+    se_soft += static_cast<double>(ds); se_hard += static_cast<double>(dh);
+  }
+  for (int64_t i = 4 * n_vec + first; i < p.n; i += stride) {     // everything (scalar launch) or the n % 4 tail
     const float x = p.y[i];
     int c;
     if (want_soft) {
-      const float q = (p.beta == -1.0f) ? stanh_hard(x, T, p.symmetric, c) : stanh_soft(x, p.beta, T);
-      if (out_soft) out_soft[i] = q;
-      const float d = x - q;
+      const float qv = soft_of(x);
+      if (out_soft) out_soft[i] = qv;
+      const float d = x - qv;
       se_soft += static_cast<double>(d * d);
     }
     if (want_hard) {
-      const float q = stanh_hard(x, T, p.symmetric, c);
-      if (out_hard) out_hard[i] = q;
-      const float d = x - q;
+      const float qv = stanh_hard_sm(x, T, symmetric, c);
+      if (out_hard) out_hard[i] = qv;
+      const float d = x - qv;
       se_hard += static_cast<double>(d * d);
     }
   }
@@ -349,13 +582,62 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
                               &p.bits, &p.bits_accumulate, &p.workspace);
     if (rc != RESLIC_OK) return rc;
   }
-  const int64_t total = p.tiles_per_image * p.B;
-  int64_t grid = static_cast<int64_t>(sm_count()) * 8;
-  if (grid > total) grid = total;
-  const size_t smem = tables_smem(p.K);
-  if (math_mode() == RESLIC_MATH_MIRROR) stanh_gc_fwd_kernel<false><<<static_cast<int>(grid), kThreads, smem, st>>>(p);
-  else stanh_gc_fwd_kernel<true><<<static_cast<int>(grid), kThreads, smem, st>>>(p);
-  cudaError_t err = cudaGetLastError();
+  const bool fast = math_mode() != RESLIC_MATH_MIRROR;
+  // 128-bit path: every tensor 16-byte aligned, batch strides and n multiples of 4, a soft form with beta > 0
+  const bool soft = d->training == 1 && p.beta != -1.0f;
+  bool vec = (d->n % 4 == 0) && !(soft && !(p.beta > 0.0f)) && (d->n / 4 + kThreads - 1) / kThreads * d->B < (1LL << 31);
+  auto chk = [&](const void* ptr, int64_t bs) {
+    if (ptr && ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (bs % 4) != 0)) vec = false;
+  };
+  chk(d->y, d->y_bs); chk(d->mu, d->mu_bs); if (need_lik) chk(d->sigma, d->sigma_bs);
+  chk(d->yhat, d->yhat_bs); chk(d->lik, d->lik_bs); chk(d->sym, d->sym_bs);
+  cudaError_t err = cudaSuccess;
+  if (vec) {
+    StanhVecParams q{};
+    q.s = p;
+    const int64_t tpi = (d->n / 4 + kThreads - 1) / kThreads;
+    const int64_t total = tpi * d->B;
+    const int mode = d->training == 2 ? 2 : (soft ? 1 : 0);
+    q.lik_floor = d->likelihood_bound > 0.0f ? d->likelihood_bound : -std::numeric_limits<float>::infinity();
+    q.sat_r = soft ? kSatT / p.beta : 0.0f;
+    q.c2 = soft ? 2.0f * p.beta * 1.44269504088896340736f : 0.0f;
+    q.rm = d->mu && (d->training == 1 ? d->removing_mean != 0 : true);
+    q.sym_same = q.rm || !d->mu;
+    const size_t smem = stanh_sm_bytes(p.K);
+    auto go = [&](auto kernel, int* occ) -> cudaError_t {
+      if (*occ == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, stanh_sm_bytes(kStanhMaxK)) != cudaSuccess || nb < 1) nb = 1;
+        *occ = nb;
+      }
+      int64_t grid = static_cast<int64_t>(*occ) * sm_count();
+      if (grid > total) grid = total;
+      q.tpi = static_cast<unsigned int>(tpi);
+      q.q_tiles = static_cast<unsigned int>(total / grid);
+      q.r_tiles = static_cast<unsigned int>(total % grid);
+      if (static_cast<int64_t>(q.q_tiles) + 1 >= (1LL << 32) / (kThreads * 16)) return cudaErrorInvalidValue;
+      kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(q);
+      return cudaGetLastError();
+    };
+    static int occ[6] = {0, 0, 0, 0, 0, 0};
+    if (fast) {
+      if (mode == 0) err = go(stanh_gc_vec_kernel<0, true>, &occ[0]);
+      else if (mode == 1) err = go(stanh_gc_vec_kernel<1, true>, &occ[1]);
+      else err = go(stanh_gc_vec_kernel<2, true>, &occ[2]);
+    } else {
+      if (mode == 0) err = go(stanh_gc_vec_kernel<0, false>, &occ[3]);
+      else if (mode == 1) err = go(stanh_gc_vec_kernel<1, false>, &occ[4]);
+      else err = go(stanh_gc_vec_kernel<2, false>, &occ[5]);
+    }
+  } else {
+    const int64_t total = p.tiles_per_image * p.B;
+    int64_t grid = static_cast<int64_t>(sm_count()) * 8;
+    if (grid > total) grid = total;
+    const size_t smem = tables_smem(p.K);
+    if (!fast) stanh_gc_fwd_kernel<false><<<static_cast<int>(grid), kThreads, smem, st>>>(p);
+    else stanh_gc_fwd_kernel<true><<<static_cast<int>(grid), kThreads, smem, st>>>(p);
+    err = cudaGetLastError();
+  }
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_gc_fwd launch");
   return RESLIC_OK;
 }
@@ -373,7 +655,7 @@ int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, fl
   StanhParams p{};
   p.y = x; p.n = n; p.gap = gap;
   fill_tables(p, t);
-  int64_t grid = (n + kThreads - 1) / kThreads;
+  int64_t grid = ((n + 3) / 4 + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (grid > cap) grid = cap;
   double* partials = nullptr; unsigned int* counter = nullptr;
@@ -384,7 +666,14 @@ int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, fl
     counter = static_cast<unsigned int*>(workspace);
     partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
   }
-  stanh_act_kernel<<<static_cast<int>(grid), kThreads, tables_smem(p.K), st>>>(p, out_soft, out_hard, partials, counter);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const int vec = (n >= 4 && al16(x) && al16(out_soft) && al16(out_hard)) ? 1 : 0;
+  const bool soft = p.beta > 0.0f;
+  const float sat_r = soft ? kSatT / p.beta : 0.0f, c2 = soft ? 2.0f * p.beta * 1.44269504088896340736f : 0.0f;
+  if (math_mode() == RESLIC_MATH_MIRROR)
+    stanh_act_kernel<false><<<static_cast<int>(grid), kThreads, stanh_sm_bytes(p.K), st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
+  else
+    stanh_act_kernel<true><<<static_cast<int>(grid), kThreads, stanh_sm_bytes(p.K), st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_act launch");
   return RESLIC_OK;
@@ -447,24 +736,6 @@ struct StanhBwdParams {
   double* g_par;       // optional [5K+2]: A[K+1] | Bq[K+1] | Ww[K] | Wb[K] | Hd[K] (see reslic_stanh_gc_bwd_desc)
 };
 
-__device__ __forceinline__ float stanh_soft_grad(float x, float beta, const StanhTables& T) {
-  int lo = 0, hi = T.K;
-  if (beta > 0.0f) {
-    const float r = kSatT / beta;
-    lo = count_ge(x - r, T.b, T.K, T.steps);
-    hi = count_gt(x + r, T.b, T.K, T.steps);
-    if (hi < lo) hi = lo;
-  }
-  float acc = 0.0f;
-  for (int k = lo; k < hi; ++k) {
-    const float t = beta * (x - T.b[k]);
-    const float sg = 1.0f / (1.0f + expf(-(2.0f * t)));
-    // d/dx [2 sigma(2t) - 1] = 4 beta sigma (1 - sigma)
-    acc = fmaf(T.w[k] * 0.5f, 4.0f * beta * sg * (1.0f - sg), acc);
-  }
-  return acc;
-}
-
 // Parameter-gradient accumulators of one CTA (doubles in shared memory, flushed with one global atomic per
 // entry at the end).  For an element with upstream gradient G on the soft quantizer output q and
 // saturation window [lo, hi):  dq/dw_k = +1/2 for k < lo, -1/2 for k >= hi — recorded as ONE add to A[lo]
@@ -473,107 +744,164 @@ __device__ __forceinline__ float stanh_soft_grad(float x, float beta, const Stan
 struct StanhParAcc {
   double* A; double* Bq; double* Ww; double* Wb; double* Hd;
 };
-__device__ __forceinline__ void stanh_soft_param_grad(float x, float beta, const StanhTables& T, float G,
-                                                      const StanhParAcc& acc) {
-  int lo = 0, hi = T.K;
-  if (beta > 0.0f) {
-    const float r = kSatT / beta;
-    lo = count_ge(x - r, T.b, T.K, T.steps);
-    hi = count_gt(x + r, T.b, T.K, T.steps);
-    if (hi < lo) hi = lo;
+
+// Soft quantizer value, its derivative and (PAR) the parameter-gradient sums of one element in ONE walk over
+// the window: tanh = (1 - E) / (1 + E), d tanh / dt = 1 - tanh^2.  beta <= 0 (other than -1) walks all K.
+template <bool PAR>
+__device__ __forceinline__ void stanh_soft_bwd(float x, float beta, float sat_r, float c2, const StanhSm& T, float G,
+                                               const StanhParAcc& acc, float& q, float& dq) {
+  int lo = 0;
+  float xr = __int_as_float(0x7f800000);
+  if (beta > 0.0f) { lo = stanh_count_ge_b(x - sat_r, T); xr = x + sat_r; }
+  float aq = 0.0f, ad = 0.0f;
+  int k = lo;
+  for (; k < T.K; ++k) {
+    const float2 e = T.bw[k];
+    if (!(e.x < xr)) break;
+    const float E = ex2_approx(c2 * (e.x - x));
+    const float th = (1.0f - E) * rcp_approx(1.0f + E);
+    const float sech2 = fmaf(-th, th, 1.0f);
+    aq = fmaf(e.y, th, aq);
+    ad = fmaf(e.y * beta, sech2, ad);
+    if (PAR) {
+      atomicAdd(&acc.Ww[k], static_cast<double>(G * 0.5f * th));
+      atomicAdd(&acc.Wb[k], static_cast<double>(-G * e.y * beta * sech2));
+    }
   }
-  atomicAdd(&acc.A[lo], static_cast<double>(G));
-  atomicAdd(&acc.Bq[hi], static_cast<double>(G));
-  for (int k = lo; k < hi; ++k) {
-    const float t = beta * (x - T.b[k]);
-    const float sg = 1.0f / (1.0f + expf(-(2.0f * t)));
-    atomicAdd(&acc.Ww[k], static_cast<double>(G * 0.5f * (2.0f * sg - 1.0f)));
-    atomicAdd(&acc.Wb[k], static_cast<double>(G * (T.w[k] * 0.5f) * (-4.0f * beta * sg * (1.0f - sg))));
+  if (PAR) {
+    atomicAdd(&acc.A[lo], static_cast<double>(G));
+    atomicAdd(&acc.Bq[k], static_cast<double>(G));
+  }
+  const float sat = 0.5f * ((T.cw[lo] - T.cw0) - (T.cwK - T.cw[k]));
+  q = (x != x) ? x : sat + aq;
+  dq = ad;
+}
+
+// One element of the backward.  Returns gy, gmu, gs.
+template <bool PAR>
+__device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const StanhSm& T, const StanhParAcc& acc,
+                                               float sat_r, float c2, float y, float mu, float sg_in, float gyh, float gl,
+                                               float& gy, float& gmu, float& gs_out) {
+  const bool use_mu = p.mu != nullptr;
+  const bool rm = use_mu && (p.training ? p.removing_mean != 0 : true);
+  const float x = rm ? y - mu : y;
+  const bool soft = p.training && p.st.beta != -1.0f;
+  const bool symmetric = p.st.symmetric != 0;
+  float qv, dq = 0.0f, gv = 0.0f, gs = 0.0f;
+  int lvl = -1;
+  // the soft walk needs the total upstream gradient on q for the parameter sums, which includes the
+  // likelihood's share gv: without PAR one walk suffices, with PAR the value comes first and the sums later
+  StanhParAcc none{};
+  if (soft) stanh_soft_bwd<false>(x, p.st.beta, sat_r, c2, T, 0.0f, none, qv, dq);
+  else qv = stanh_hard_sm(x, T, symmetric, lvl);
+  const float yhat = rm ? qv + mu : qv;
+  if (p.g_lik) {
+    const float s = max_nan(sg_in, p.scale_bound);
+    const float v = use_mu ? yhat - mu : yhat;
+    int j;
+    if (soft) j = stanh_count_gt_avg(v, T);
+    else { j = lvl; while (j > 0 && !(v > T.avgp[j])) --j; while (v > T.avgp[j + 1]) ++j; }
+    const bool inside = (v > -1000.0f) && (v <= 1000.0f);
+    const float2 lu = T.lowup[j];
+    const float low = inside ? lu.x : 0.0f, up = inside ? lu.y : 0.0f;
+    float n1, n2, dir;
+    if (v >= 0.0f) { n1 = low - v; n2 = -up - v; dir = -1.0f; }
+    else { n1 = v + up; n2 = v - low; dir = 1.0f; }
+    const float rs = rcp_approx(s);
+    const float a1 = n1 * rs, a2 = n2 * rs;
+    bool pass_l = true;
+    if (p.lik_bound > 0.0f && !(gl < 0.0f)) {
+      // L >= 1.6e-8 whenever the cell is at least 1e-3 sigma wide and starts within 3.5 sigma of the mean
+      const bool near = (a1 * a2 <= 0.0f) || (fminf(fabsf(a1), fabsf(a2)) <= 3.5f);
+      const bool surely_above = near && (a1 - a2 >= 1e-3f) && (p.lik_bound <= 1e-8f) && (s <= 1e30f);
+      if (!surely_above) {
+        const float L = gauss_interval_mass<true>(max_nan(min_nan(n1, 1e30f), -1e30f), max_nan(min_nan(n2, 1e30f), -1e30f), s);
+        pass_l = L >= p.lik_bound;
+      }
+    }
+    const float g = pass_l ? gl : 0.0f;
+    const float kk = 0.3989422804014327f, ch = -0.72134752044448170368f;     // 1/sqrt(2 pi), -log2(e)/2
+    const float p1 = kk * ex2_approx(ch * a1 * a1), p2 = kk * ex2_approx(ch * a2 * a2);
+    gv = g * (p1 - p2) * dir * rs;
+    gs = -g * (a1 * p1 - a2 * p2) * rs;
+    if (PAR && g != 0.0f) {
+      // L = Phi(a1) - Phi(a2): v >= 0: a1 = (low - v)/s, a2 = (-up - v)/s;  v < 0: a1 = (v + up)/s, a2 = (v - low)/s;
+      // low = dist[j-1], up = dist[j] (the half-widths depend on the weights)
+      const float dlow = (v >= 0.0f ? p1 : p2) * rs, dup = (v >= 0.0f ? p2 : p1) * rs;
+      if (inside && j > 0) atomicAdd(&acc.Hd[j - 1], static_cast<double>(g * dlow));
+      if (inside && j < T.K) atomicAdd(&acc.Hd[j], static_cast<double>(g * dup));
+    }
+    const bool pass_s = (sg_in >= p.scale_bound) || (gs < 0.0f);
+    gs = pass_s ? gs : 0.0f;
+  }
+  // v = yhat - mu:  dv/dy = dq,  dv/dmu = (rm ? 1 - dq : 0) - (mu given ? 1 : 0)
+  const float dyhat_dmu = rm ? 1.0f - dq : 0.0f;
+  gy = (gyh + gv) * dq;
+  gmu = gyh * dyhat_dmu + gv * (dyhat_dmu - (use_mu ? 1.0f : 0.0f));
+  gs_out = gs;
+  if (PAR && (gyh + gv) != 0.0f && x == x) {
+    if (soft) {
+      float q2, d2;
+      stanh_soft_bwd<true>(x, p.st.beta, sat_r, c2, T, gyh + gv, acc, q2, d2);
+    } else {
+      // hard form: the level is still linear in the weights — dq/dw_k = +1/2 where x > b_k, -1/2 where
+      // x < b_k; at an exact tie the non-symmetric form (relu(sign(0)) = 0) gives -1/2, the symmetric one 0
+      int c_ge = lvl;
+      if (symmetric) while (x == T.bw[c_ge].x) ++c_ge;
+      atomicAdd(&acc.A[lvl], static_cast<double>(gyh + gv));
+      atomicAdd(&acc.Bq[c_ge], static_cast<double>(gyh + gv));
+    }
   }
 }
 
-__global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdParams p) {
-  extern __shared__ float sm[];
-  StanhTables T;
-  stage_tables(p.st, sm, T);
+// W = 4: one 128-bit group per thread and tile (aligned tensors, n % 4 == 0); W = 1: any layout.
+template <int W, bool PAR>
+__global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdParams p, float sat_r, float c2) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  StanhSm T;
+  stage_stanh_sm(p.st.b, p.st.w, p.st.cum_w, p.st.avg, p.st.dist, p.st.K, smraw, T);
   StanhParAcc acc{};
   const int n_acc = 5 * p.st.K + 2;
-  if (p.g_par) {
-    // doubles behind the float tables (5K+1 floats, rounded up to an 8-byte boundary)
-    double* base = reinterpret_cast<double*>(sm + ((5 * p.st.K + 1 + 1) & ~1));
+  if (PAR) {
+    double* base = reinterpret_cast<double*>(smraw + ((stanh_sm_bytes(p.st.K) + 7) & ~size_t(7)));
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) base[i] = 0.0;
     acc.A = base; acc.Bq = acc.A + p.st.K + 1; acc.Ww = acc.Bq + p.st.K + 1; acc.Wb = acc.Ww + p.st.K; acc.Hd = acc.Wb + p.st.K;
     __syncthreads();
   }
   const int64_t total = p.tiles_per_image * p.B;
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
-    const int image = static_cast<int>(t / p.tiles_per_image);
-    const int64_t e = (t - image * p.tiles_per_image) * kThreads + threadIdx.x;
+    const int64_t image = t / p.tiles_per_image;
+    const int64_t e = ((t - image * p.tiles_per_image) * kThreads + threadIdx.x) * W;
     if (e >= p.n) continue;
-    const float y = p.y[image * p.y_bs + e];
-    const float mu = p.mu ? p.mu[image * p.mu_bs + e] : 0.0f;
-    const bool rm = p.mu && (p.training ? p.removing_mean != 0 : true);
-    const float x = rm ? y - mu : y;
-    const bool soft = p.training && p.st.beta != -1.0f;
-    int lvl;
-    const float q = soft ? stanh_soft(x, p.st.beta, T) : stanh_hard(x, T, p.st.symmetric, lvl);
-    const float dq = soft ? stanh_soft_grad(x, p.st.beta, T) : 0.0f;          // d q / d x
-    const float yhat = rm ? q + mu : q;
-    // d yhat/dy = dq ; d yhat/dmu = rm ? (1 - dq) : 0
-    const float gyh = p.g_yhat ? p.g_yhat[image * p.g_yhat_bs + e] : 0.0f;
-    float gv = 0.0f, gs = 0.0f;
-    if (p.g_lik) {
-      const float gl = p.g_lik[image * p.g_lik_bs + e];
-      const float sg_in = p.sigma[image * p.sigma_bs + e];
-      const float s = max_nan(sg_in, p.scale_bound);
-      const float v = p.mu ? yhat - mu : yhat;
-      const int j = count_gt(v, T.avg, T.K, T.steps);
-      const bool inside = (v > -1000.0f) && (v <= 1000.0f);
-      const float low = (inside && j > 0) ? T.dist[j - 1] : 0.0f;
-      const float up = (inside && j < T.K) ? T.dist[j] : 0.0f;
-      float n1, n2, dir;
-      if (v >= 0.0f) { n1 = low - v; n2 = -up - v; dir = -1.0f; }
-      else { n1 = v + up; n2 = v - low; dir = 1.0f; }
-      const float L = gauss_interval_mass<true>(max_nan(min_nan(n1, 1e30f), -1e30f), max_nan(min_nan(n2, 1e30f), -1e30f), s);
-      const bool pass_l = !(p.lik_bound > 0.0f) || (L >= p.lik_bound) || (gl < 0.0f);
-      const float g = pass_l ? gl : 0.0f;
-      const float rs = 1.0f / s;
-      const float a1 = n1 * rs, a2 = n2 * rs;
-      const float k = 0.3989422804014327f;
-      const float p1 = k * expf(-0.5f * a1 * a1), p2 = k * expf(-0.5f * a2 * a2);
-      gv = g * (p1 - p2) * dir * rs;
-      gs = -g * (a1 * p1 - a2 * p2) * rs;
-      if (p.g_par && g != 0.0f) {
-        // L = Phi(a1) - Phi(a2): v >= 0: a1 = (low - v)/s, a2 = (-up - v)/s;  v < 0: a1 = (v + up)/s, a2 = (v - low)/s;
-        // low = dist[j-1], up = dist[j] (the half-widths depend on the weights)
-        const float dlow = (v >= 0.0f ? p1 : p2) * rs, dup = (v >= 0.0f ? p2 : p1) * rs;
-        if (inside && j > 0) atomicAdd(&acc.Hd[j - 1], static_cast<double>(g * dlow));
-        if (inside && j < T.K) atomicAdd(&acc.Hd[j], static_cast<double>(g * dup));
-      }
-      const bool pass_s = (sg_in >= p.scale_bound) || (gs < 0.0f);
-      gs = pass_s ? gs : 0.0f;
+    if (W == 4) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 y = ld_stream4(p.y + image * p.y_bs + e);
+      const float4 mu = p.mu ? ld_stream4(p.mu + image * p.mu_bs + e) : zero;
+      const float4 sg = p.g_lik ? ld_stream4(p.sigma + image * p.sigma_bs + e) : zero;
+      const float4 gyh = p.g_yhat ? ld_stream4(p.g_yhat + image * p.g_yhat_bs + e) : zero;
+      const float4 gl = p.g_lik ? ld_stream4(p.g_lik + image * p.g_lik_bs + e) : zero;
+      float4 gy, gmu, gs;
+      stanh_bwd_elem<PAR>(p, T, acc, sat_r, c2, y.x, mu.x, sg.x, gyh.x, gl.x, gy.x, gmu.x, gs.x);
+      stanh_bwd_elem<PAR>(p, T, acc, sat_r, c2, y.y, mu.y, sg.y, gyh.y, gl.y, gy.y, gmu.y, gs.y);
+      stanh_bwd_elem<PAR>(p, T, acc, sat_r, c2, y.z, mu.z, sg.z, gyh.z, gl.z, gy.z, gmu.z, gs.z);
+      stanh_bwd_elem<PAR>(p, T, acc, sat_r, c2, y.w, mu.w, sg.w, gyh.w, gl.w, gy.w, gmu.w, gs.w);
+      if (p.g_y) st_stream4(p.g_y + image * p.g_y_bs + e, gy);
+      if (p.g_mu) st_stream4(p.g_mu + image * p.g_mu_bs + e, gmu);
+      if (p.g_sigma) st_stream4(p.g_sigma + image * p.g_sigma_bs + e, gs);
+    } else {
+      const float y = p.y[image * p.y_bs + e];
+      const float mu = p.mu ? p.mu[image * p.mu_bs + e] : 0.0f;
+      const float sg = p.g_lik ? p.sigma[image * p.sigma_bs + e] : 0.0f;
+      const float gyh = p.g_yhat ? p.g_yhat[image * p.g_yhat_bs + e] : 0.0f;
+      const float gl = p.g_lik ? p.g_lik[image * p.g_lik_bs + e] : 0.0f;
+      float gy, gmu, gs;
+      stanh_bwd_elem<PAR>(p, T, acc, sat_r, c2, y, mu, sg, gyh, gl, gy, gmu, gs);
+      if (p.g_y) p.g_y[image * p.g_y_bs + e] = gy;
+      if (p.g_mu) p.g_mu[image * p.g_mu_bs + e] = gmu;
+      if (p.g_sigma) p.g_sigma[image * p.g_sigma_bs + e] = gs;
     }
-    // v = yhat - mu:  dv/dy = dq,  dv/dmu = (rm ? 1 - dq : 0) - (mu given ? 1 : 0)
-    const float dyhat_dmu = rm ? 1.0f - dq : 0.0f;
-    const float gy = (gyh + gv) * dq;
-    const float gmu = gyh * dyhat_dmu + gv * (dyhat_dmu - (p.mu ? 1.0f : 0.0f));
-    if (p.g_par && (gyh + gv) != 0.0f && x == x) {
-      if (soft) {
-        stanh_soft_param_grad(x, p.st.beta, T, gyh + gv, acc);
-      } else {
-        // hard form: the level is still linear in the weights — dq/dw_k = +1/2 where x > b_k, -1/2 where
-        // x < b_k; at an exact tie the non-symmetric form (relu(sign(0)) = 0) gives -1/2, the symmetric one 0
-        const int c_gt = count_gt(x, T.b, T.K, T.steps);
-        const int c_ge = p.st.symmetric ? count_ge(x, T.b, T.K, T.steps) : c_gt;
-        atomicAdd(&acc.A[c_gt], static_cast<double>(gyh + gv));
-        atomicAdd(&acc.Bq[c_ge], static_cast<double>(gyh + gv));
-      }
-    }
-    if (p.g_y) p.g_y[image * p.g_y_bs + e] = gy;
-    if (p.g_mu) p.g_mu[image * p.g_mu_bs + e] = gmu;
-    if (p.g_sigma) p.g_sigma[image * p.g_sigma_bs + e] = gs;
   }
-  if (p.g_par) {
+  if (PAR) {
     __syncthreads();
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) {
       const double v = acc.A[i];
@@ -602,22 +930,44 @@ int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st) {
   p.y_bs = d->y_bs; p.mu_bs = d->mu_bs; p.sigma_bs = d->sigma_bs; p.g_yhat_bs = d->g_yhat_bs; p.g_lik_bs = d->g_lik_bs;
   p.g_y_bs = d->g_y_bs; p.g_mu_bs = d->g_mu_bs; p.g_sigma_bs = d->g_sigma_bs;
   fill_tables(p.st, &d->tables);
-  p.n = d->n; p.B = d->B; p.tiles_per_image = (d->n + kThreads - 1) / kThreads;
+  p.n = d->n; p.B = d->B;
   p.training = d->training; p.removing_mean = d->removing_mean;
   p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
+  bool vec = (d->n % 4 == 0);
+  auto chk = [&](const void* ptr, int64_t bs) {
+    if (ptr && ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (bs % 4) != 0)) vec = false;
+  };
+  chk(d->y, d->y_bs); chk(d->mu, d->mu_bs); if (d->g_lik) chk(d->sigma, d->sigma_bs);
+  chk(d->g_yhat, d->g_yhat_bs); chk(d->g_lik, d->g_lik_bs);
+  chk(d->g_y, d->g_y_bs); chk(d->g_mu, d->g_mu_bs); chk(d->g_sigma, d->g_sigma_bs);
+  const int64_t per_tile = static_cast<int64_t>(kThreads) * (vec ? 4 : 1);
+  p.tiles_per_image = (d->n + per_tile - 1) / per_tile;
   int64_t grid = p.tiles_per_image * p.B;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-  if (grid > cap) grid = cap;
   p.g_par = d->g_params;
-  size_t smem = tables_smem(p.st.K);
+  // without parameter sums there is no per-CTA state beyond the tables: many short CTAs (the shape that
+  // reaches the copy bandwidth); with them, few persistent CTAs so that the shared accumulators are flushed rarely
+  const int64_t cap = static_cast<int64_t>(sm_count()) * (p.g_par ? 16 : 64);
+  if (grid > cap) grid = cap;
+  size_t smem = stanh_sm_bytes(p.st.K);
   if (p.g_par) {
-    smem = static_cast<size_t>((5 * p.st.K + 2) & ~1) * sizeof(float) + static_cast<size_t>(5 * p.st.K + 2) * sizeof(double);
+    smem = ((smem + 7) & ~size_t(7)) + static_cast<size_t>(5 * p.st.K + 2) * sizeof(double);
     cudaError_t e = cudaMemsetAsync(p.g_par, 0, static_cast<size_t>(5 * p.st.K + 2) * sizeof(double), st);
-    if (e == cudaSuccess && smem > 48 * 1024)
-      e = cudaFuncSetAttribute(stanh_gc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess && smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(stanh_gc_bwd_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stanh_gc_bwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    }
     if (e != cudaSuccess) return set_cuda_error(e, "stanh_gc_bwd setup");
   }
-  stanh_gc_bwd_kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(p);
+  const bool soft = p.st.beta > 0.0f;
+  const float sat_r = soft ? kSatT / p.st.beta : 0.0f, c2 = 2.0f * p.st.beta * 1.44269504088896340736f;
+  if (vec) {
+    if (p.g_par) stanh_gc_bwd_kernel<4, true><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
+    else stanh_gc_bwd_kernel<4, false><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
+  } else {
+    if (p.g_par) stanh_gc_bwd_kernel<1, true><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
+    else stanh_gc_bwd_kernel<1, false><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
+  }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_gc_bwd launch");
   return RESLIC_OK;
