@@ -21,6 +21,7 @@
 #include "reslic_internal.h"
 #include "stanh_tables.cuh"
 #include <limits>
+#include <type_traits>
 
 namespace reslic {
 
@@ -219,14 +220,14 @@ __device__ __forceinline__ F2 stanh_mass2(F2 n1, F2 n2, F2 s) {
 }
 
 // soft quantizer value; beta > 0
-template <bool FAST>
-__device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r, float c2, const StanhSm& T) {
+template <bool FAST, int KMAX>
+__device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r, float c2, const StanhSm<KMAX>& T) {
   const int lo = stanh_count_ge_b(x - sat_r, T);         // k <  lo: tanh == +1
   const float xr = x + sat_r;
   float acc = 0.0f;
   int k = lo;
   for (;; ++k) {
-    const float2 e = T.bw[k];                            // (b_k, w_k / 2); NaN pad ends the loop
+    const float2 e = T.bw()[k];                            // (b_k, w_k / 2); NaN pad ends the loop
     if (!(e.x < xr)) break;
     if (FAST) {
       const float E = ex2_approx(c2 * (e.x - x));        // exp(-2 beta (x - b_k))
@@ -237,34 +238,36 @@ __device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r,
       acc = fmaf(e.y, 2.0f * sg - 1.0f, acc);
     }
   }                                                      // k >= hi (= k now): tanh == -1
-  const float sat = 0.5f * ((T.cw[lo] - T.cw0) - (T.cwK - T.cw[k]));
+  const float sat = 0.5f * ((T.cw()[lo] - T.cw0) - (T.cwK - T.cw()[k]));
   return (x != x) ? x : sat + acc;
 }
 
 // hard level of x; c_out = #{k : x > b_k}
-__device__ __forceinline__ float stanh_hard_sm(float x, const StanhSm& T, bool symmetric, int& c_out) {
+template <int KMAX>
+__device__ __forceinline__ float stanh_hard_sm(float x, const StanhSm<KMAX>& T, bool symmetric, int& c_out) {
   const int c = stanh_count_gt_b(x, T);
   c_out = c;
-  float v = T.cw[c];
+  float v = T.cw()[c];
   if (symmetric) {
     int ce = c;
-    while (x == T.bw[ce].x) ++ce;                        // sign(0) = 0: mean of the two adjacent levels at a tie
-    v = (x != x) ? 0.0f : 0.5f * (v + T.cw[ce]);
+    if (x == T.bw()[c].x) { do ++ce; while (x == T.bw()[ce].x); }   // sign(0) = 0: mean of the two adjacent levels at a tie
+    v = (x != x) ? 0.0f : 0.5f * (v + T.cw()[ce]);
   }
   return v;
 }
 
-// numerators (n1 >= n2) of the level cell that contains v; `guess` < 0: look the cell up, else start from it
-__device__ __forceinline__ void stanh_cell_bounds(float v, int guess, const StanhSm& T, float& n1, float& n2) {
+// numerators (n1 >= n2) of the level cell that contains v; `guess` < 0: look the cell up, else try it first
+template <int KMAX>
+__device__ __forceinline__ void stanh_cell_bounds(float v, int guess, const StanhSm<KMAX>& T, float& n1, float& n2) {
   int j;
   if (guess < 0) j = stanh_count_gt_avg(v, T);
   else {
-    j = guess;
-    while (j > 0 && !(v > T.avgp[j])) --j;
-    while (v > T.avgp[j + 1]) ++j;
+    j = guess;                                              // the level's own cell unless mu pushed v across a mid-point
+    const float a0 = T.avgp()[j], a1 = T.avgp()[j + 1];
+    if (!(v > a0) || (v > a1)) j = stanh_count_gt_avg(v, T);
   }
   const bool inside = (v > -1000.0f) && (v <= 1000.0f);    // the reference's +-1000 sentinels (:506,:511)
-  const float2 lu = T.lowup[j];
+  const float2 lu = T.lowup()[j];
   const float low = inside ? lu.x : 0.0f, up = inside ? lu.y : 0.0f;
   if (v >= 0.0f) { n1 = low - v; n2 = -up - v; }
   else { n1 = v + up; n2 = v - low; }                     // NaN v lands here and stays NaN
@@ -272,11 +275,11 @@ __device__ __forceinline__ void stanh_cell_bounds(float v, int guess, const Stan
 
 struct StanhIn { float4 y, m, s; };
 
-template <int MODE, bool FAST>      // MODE 0: hard levels, 1: soft form (beta > 0), 2: likelihood of the given values
+template <int MODE, bool FAST, int KMAX>      // MODE 0: hard levels, 1: soft form (beta > 0), 2: likelihood of the given values
 __global__ void __launch_bounds__(kThreads, 4) stanh_gc_vec_kernel(const StanhVecParams q) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const StanhParams& p = q.s;
-  StanhSm T;
+  StanhSm<KMAX> T;
   stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, smraw, T);
   const bool need_lik = p.lik || p.bits;
   const bool use_mu = p.mu != nullptr;
@@ -382,14 +385,14 @@ __global__ void __launch_bounds__(kThreads, 4) stanh_gc_vec_kernel(const StanhVe
 
 // Activation alone (module forward) and the two squared-error sums compute_gap needs, in one pass:
 // out_soft / out_hard nullable; gap[0] += sum (x - soft)^2, gap[1] += sum (x - hard)^2.
-template <bool FAST>
+template <bool FAST, int KMAX>
 __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p, float* out_soft, float* out_hard,
                                                              double* partials, unsigned int* counter, int vec,
                                                              float sat_r, float c2) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double s_red[2][kThreads / 32];
   __shared__ bool s_last;
-  StanhSm T;
+  StanhSm<KMAX> T;
   stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, smraw, T);
   const bool want_soft = out_soft || p.gap, want_hard = out_hard || p.gap;
   const bool soft_is_hard = p.beta == -1.0f;
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p
     if (p.beta > 0.0f) return stanh_soft_sm<FAST>(x, p.beta, sat_r, c2, T);
     float acc = 0.0f;
     for (int k = 0; k < T.K; ++k) {
-      const float2 e = T.bw[k];
+      const float2 e = T.bw()[k];
       const float sg = 1.0f / (1.0f + expf(-(2.0f * (p.beta * (x - e.x)))));
       acc = fmaf(e.y, 2.0f * sg - 1.0f, acc);
     }
@@ -459,13 +462,26 @@ __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p
     s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {
+    // the last CTA adds the per-CTA partials: thread i takes partials i, i + 256, ... in order, then the same
+    // fixed tree — the loads of a thread are independent, so this costs one L2 round trip, not gridDim.x
     __threadfence();
-    const volatile double* pp = partials;
     double a = 0.0, b = 0.0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) { a += pp[2 * i]; b += pp[2 * i + 1]; }
-    p.gap[0] = a; p.gap[1] = b;
-    *counter = 0u;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) { a += __ldcg(partials + 2 * i); b += __ldcg(partials + 2 * i + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[0][warp] = a; s_red[1][warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a = 0.0; b = 0.0;
+      for (int i = 0; i < kThreads / 32; ++i) { a += s_red[0][i]; b += s_red[1][i]; }
+      p.gap[0] = a; p.gap[1] = b;
+      *counter = 0u;
+    }
   }
 }
 
@@ -603,11 +619,10 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
     q.c2 = soft ? 2.0f * p.beta * 1.44269504088896340736f : 0.0f;
     q.rm = d->mu && (d->training == 1 ? d->removing_mean != 0 : true);
     q.sym_same = q.rm || !d->mu;
-    const size_t smem = stanh_sm_bytes(p.K);
-    auto go = [&](auto kernel, int* occ) -> cudaError_t {
+    auto go = [&](auto kernel, int* occ, size_t smem) -> cudaError_t {
       if (*occ == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, stanh_sm_bytes(kStanhMaxK)) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         *occ = nb;
       }
       int64_t grid = static_cast<int64_t>(*occ) * sm_count();
@@ -619,16 +634,21 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
       kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(q);
       return cudaGetLastError();
     };
-    static int occ[6] = {0, 0, 0, 0, 0, 0};
-    if (fast) {
-      if (mode == 0) err = go(stanh_gc_vec_kernel<0, true>, &occ[0]);
-      else if (mode == 1) err = go(stanh_gc_vec_kernel<1, true>, &occ[1]);
-      else err = go(stanh_gc_vec_kernel<2, true>, &occ[2]);
-    } else {
-      if (mode == 0) err = go(stanh_gc_vec_kernel<0, false>, &occ[3]);
-      else if (mode == 1) err = go(stanh_gc_vec_kernel<1, false>, &occ[4]);
-      else err = go(stanh_gc_vec_kernel<2, false>, &occ[5]);
-    }
+    static int occ[12] = {0};
+    auto pick = [&](auto kmax) -> cudaError_t {
+      constexpr int KM = decltype(kmax)::value;
+      constexpr size_t smem = StanhSm<KM>::kBytes;
+      int* o = occ + (KM == 256 ? 0 : 6);
+      if (fast) {
+        if (mode == 0) return go(stanh_gc_vec_kernel<0, true, KM>, o + 0, smem);
+        if (mode == 1) return go(stanh_gc_vec_kernel<1, true, KM>, o + 1, smem);
+        return go(stanh_gc_vec_kernel<2, true, KM>, o + 2, smem);
+      }
+      if (mode == 0) return go(stanh_gc_vec_kernel<0, false, KM>, o + 3, smem);
+      if (mode == 1) return go(stanh_gc_vec_kernel<1, false, KM>, o + 4, smem);
+      return go(stanh_gc_vec_kernel<2, false, KM>, o + 5, smem);
+    };
+    err = p.K <= 256 ? pick(std::integral_constant<int, 256>{}) : pick(std::integral_constant<int, 1024>{});
   } else {
     const int64_t total = p.tiles_per_image * p.B;
     int64_t grid = static_cast<int64_t>(sm_count()) * 8;
@@ -670,10 +690,15 @@ int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, fl
   const int vec = (n >= 4 && al16(x) && al16(out_soft) && al16(out_hard)) ? 1 : 0;
   const bool soft = p.beta > 0.0f;
   const float sat_r = soft ? kSatT / p.beta : 0.0f, c2 = soft ? 2.0f * p.beta * 1.44269504088896340736f : 0.0f;
-  if (math_mode() == RESLIC_MATH_MIRROR)
-    stanh_act_kernel<false><<<static_cast<int>(grid), kThreads, stanh_sm_bytes(p.K), st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
-  else
-    stanh_act_kernel<true><<<static_cast<int>(grid), kThreads, stanh_sm_bytes(p.K), st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
+  const bool mirror = math_mode() == RESLIC_MATH_MIRROR;
+  auto launch = [&](auto kernel, size_t smem) {
+    kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
+  };
+  if (p.K <= 256) {
+    if (mirror) launch(stanh_act_kernel<false, 256>, StanhSm<256>::kBytes); else launch(stanh_act_kernel<true, 256>, StanhSm<256>::kBytes);
+  } else {
+    if (mirror) launch(stanh_act_kernel<false, 1024>, StanhSm<1024>::kBytes); else launch(stanh_act_kernel<true, 1024>, StanhSm<1024>::kBytes);
+  }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_act launch");
   return RESLIC_OK;
@@ -747,8 +772,8 @@ struct StanhParAcc {
 
 // Soft quantizer value, its derivative and (PAR) the parameter-gradient sums of one element in ONE walk over
 // the window: tanh = (1 - E) / (1 + E), d tanh / dt = 1 - tanh^2.  beta <= 0 (other than -1) walks all K.
-template <bool PAR>
-__device__ __forceinline__ void stanh_soft_bwd(float x, float beta, float sat_r, float c2, const StanhSm& T, float G,
+template <bool PAR, int KMAX>
+__device__ __forceinline__ void stanh_soft_bwd(float x, float beta, float sat_r, float c2, const StanhSm<KMAX>& T, float G,
                                                const StanhParAcc& acc, float& q, float& dq) {
   int lo = 0;
   float xr = __int_as_float(0x7f800000);
@@ -756,7 +781,7 @@ __device__ __forceinline__ void stanh_soft_bwd(float x, float beta, float sat_r,
   float aq = 0.0f, ad = 0.0f;
   int k = lo;
   for (; k < T.K; ++k) {
-    const float2 e = T.bw[k];
+    const float2 e = T.bw()[k];
     if (!(e.x < xr)) break;
     const float E = ex2_approx(c2 * (e.x - x));
     const float th = (1.0f - E) * rcp_approx(1.0f + E);
@@ -772,14 +797,14 @@ __device__ __forceinline__ void stanh_soft_bwd(float x, float beta, float sat_r,
     atomicAdd(&acc.A[lo], static_cast<double>(G));
     atomicAdd(&acc.Bq[k], static_cast<double>(G));
   }
-  const float sat = 0.5f * ((T.cw[lo] - T.cw0) - (T.cwK - T.cw[k]));
+  const float sat = 0.5f * ((T.cw()[lo] - T.cw0) - (T.cwK - T.cw()[k]));
   q = (x != x) ? x : sat + aq;
   dq = ad;
 }
 
 // One element of the backward.  Returns gy, gmu, gs.
-template <bool PAR>
-__device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const StanhSm& T, const StanhParAcc& acc,
+template <bool PAR, int KMAX>
+__device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const StanhSm<KMAX>& T, const StanhParAcc& acc,
                                                float sat_r, float c2, float y, float mu, float sg_in, float gyh, float gl,
                                                float& gy, float& gmu, float& gs_out) {
   const bool use_mu = p.mu != nullptr;
@@ -800,9 +825,9 @@ __device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const St
     const float v = use_mu ? yhat - mu : yhat;
     int j;
     if (soft) j = stanh_count_gt_avg(v, T);
-    else { j = lvl; while (j > 0 && !(v > T.avgp[j])) --j; while (v > T.avgp[j + 1]) ++j; }
+    else { j = lvl; if (!(v > T.avgp()[j]) || (v > T.avgp()[j + 1])) j = stanh_count_gt_avg(v, T); }
     const bool inside = (v > -1000.0f) && (v <= 1000.0f);
-    const float2 lu = T.lowup[j];
+    const float2 lu = T.lowup()[j];
     const float low = inside ? lu.x : 0.0f, up = inside ? lu.y : 0.0f;
     float n1, n2, dir;
     if (v >= 0.0f) { n1 = low - v; n2 = -up - v; dir = -1.0f; }
@@ -847,7 +872,7 @@ __device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const St
       // hard form: the level is still linear in the weights — dq/dw_k = +1/2 where x > b_k, -1/2 where
       // x < b_k; at an exact tie the non-symmetric form (relu(sign(0)) = 0) gives -1/2, the symmetric one 0
       int c_ge = lvl;
-      if (symmetric) while (x == T.bw[c_ge].x) ++c_ge;
+      if (symmetric) while (x == T.bw()[c_ge].x) ++c_ge;
       atomicAdd(&acc.A[lvl], static_cast<double>(gyh + gv));
       atomicAdd(&acc.Bq[c_ge], static_cast<double>(gyh + gv));
     }
@@ -855,15 +880,15 @@ __device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const St
 }
 
 // W = 4: one 128-bit group per thread and tile (aligned tensors, n % 4 == 0); W = 1: any layout.
-template <int W, bool PAR>
+template <int W, bool PAR, int KMAX>
 __global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdParams p, float sat_r, float c2) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  StanhSm T;
+  StanhSm<KMAX> T;
   stage_stanh_sm(p.st.b, p.st.w, p.st.cum_w, p.st.avg, p.st.dist, p.st.K, smraw, T);
   StanhParAcc acc{};
   const int n_acc = 5 * p.st.K + 2;
   if (PAR) {
-    double* base = reinterpret_cast<double*>(smraw + ((stanh_sm_bytes(p.st.K) + 7) & ~size_t(7)));
+    double* base = reinterpret_cast<double*>(smraw + StanhSm<KMAX>::kBytes);
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) base[i] = 0.0;
     acc.A = base; acc.Bq = acc.A + p.st.K + 1; acc.Ww = acc.Bq + p.st.K + 1; acc.Wb = acc.Ww + p.st.K; acc.Hd = acc.Wb + p.st.K;
     __syncthreads();
@@ -948,25 +973,31 @@ int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st) {
   // reaches the copy bandwidth); with them, few persistent CTAs so that the shared accumulators are flushed rarely
   const int64_t cap = static_cast<int64_t>(sm_count()) * (p.g_par ? 16 : 64);
   if (grid > cap) grid = cap;
-  size_t smem = stanh_sm_bytes(p.st.K);
-  if (p.g_par) {
-    smem = ((smem + 7) & ~size_t(7)) + static_cast<size_t>(5 * p.st.K + 2) * sizeof(double);
-    cudaError_t e = cudaMemsetAsync(p.g_par, 0, static_cast<size_t>(5 * p.st.K + 2) * sizeof(double), st);
-    if (e == cudaSuccess && smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(stanh_gc_bwd_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stanh_gc_bwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    }
-    if (e != cudaSuccess) return set_cuda_error(e, "stanh_gc_bwd setup");
-  }
   const bool soft = p.st.beta > 0.0f;
   const float sat_r = soft ? kSatT / p.st.beta : 0.0f, c2 = 2.0f * p.st.beta * 1.44269504088896340736f;
-  if (vec) {
-    if (p.g_par) stanh_gc_bwd_kernel<4, true><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
-    else stanh_gc_bwd_kernel<4, false><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
-  } else {
-    if (p.g_par) stanh_gc_bwd_kernel<1, true><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
-    else stanh_gc_bwd_kernel<1, false><<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
+  if (p.g_par) {
+    cudaError_t e = cudaMemsetAsync(p.g_par, 0, static_cast<size_t>(5 * p.st.K + 2) * sizeof(double), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "stanh_gc_bwd setup");
+  }
+  auto launch = [&](auto kernel, size_t smem) -> cudaError_t {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(p, sat_r, c2);
+    return cudaSuccess;
+  };
+  auto pick = [&](auto kmax) -> cudaError_t {
+    constexpr int KM = decltype(kmax)::value;
+    const size_t par = static_cast<size_t>(5 * p.st.K + 2) * sizeof(double);
+    if (vec) return p.g_par ? launch(stanh_gc_bwd_kernel<4, true, KM>, StanhSm<KM>::kBytes + par)
+                            : launch(stanh_gc_bwd_kernel<4, false, KM>, StanhSm<KM>::kBytes);
+    return p.g_par ? launch(stanh_gc_bwd_kernel<1, true, KM>, StanhSm<KM>::kBytes + par)
+                   : launch(stanh_gc_bwd_kernel<1, false, KM>, StanhSm<KM>::kBytes);
+  };
+  {
+    const cudaError_t e = p.st.K <= 256 ? pick(std::integral_constant<int, 256>{}) : pick(std::integral_constant<int, 1024>{});
+    if (e != cudaSuccess) return set_cuda_error(e, "stanh_gc_bwd setup");
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_gc_bwd launch");

@@ -70,3 +70,19 @@ if which in ("all", "stanh"):
 if which in ("all", "eb"):
     eb_cases(256, 192, 4, 4)
     eb_cases(24, 192, 12, 8)
+if which == "once":
+    # one eager call of each op (for an ncu launch list)
+    B, C, h, w = 256, 64, 16, 16
+    g = torch.Generator(device=dev).manual_seed(1)
+    mu = torch.randn(B, C, h, w, device=dev, generator=g)
+    sigma = torch.exp(torch.empty(B, C, h, w, device=dev).uniform_(-3.0, 4.16, generator=g))
+    y = mu + sigma * torch.randn(B, C, h, w, device=dev, generator=g)
+    cfg = {"beta": 10.0, "num_sigmoids": 0, "extrema": 80, "symmetry": False, "trainable": False, "removing_mean": True}
+    m = GaussianConditionalStanh(None, channels=C, gaussian_configuration=cfg).to(dev)
+    m.stanh.update_state(torch.device(dev))
+    for _ in range(3):
+        m.forward_fused(y, sigma, training=True, means=mu, want=("yhat", "lik"))
+        m.forward_fused(y, sigma, training=False, means=mu, want=("yhat", "lik"))
+        m._stanh_backward(y, sigma, mu, True, y, sigma)
+        compute_gap(m.stanh, y)
+    torch.cuda.synchronize()
