@@ -321,6 +321,105 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
   if (p.bits) rate_commit(acc, image, static_cast<unsigned int>(p.bpi * (kThreads / 32)), p.B, p.workspace, p.bits, p.bits_accumulate);
 }
 
+// ------------------------------------------------------------------ noise / direct mode, fast math
+// One CTA per (group of `cpc` consecutive channels, split of the batch): the transformed parameters of the
+// group are staged ONCE per CTA and reused for every image of the split (eb_fwd_kernel re-stages them —
+// softplus and tanh included — for every 256-element tile).  The group's elements of one image are one
+// contiguous run of cpc*hw floats; the next image's values are loaded before the current ones are
+// evaluated.  Both cumulative logits of an element run as the two lanes of packed f32x2 operations
+// (eb_math.cuh).  The eight warps' rates meet in shared memory and one thread commits per (CTA, image).
+constexpr int kEbRunMax = 4;      // elements per thread and image: runs of up to 1024 floats
+__global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p, int cpc, int groups, int splits, float lik_floor) {
+  __shared__ float s_par[kEbMaxCh * kEbStride];
+  __shared__ float s_red[2][kEbWarps];
+  const int grp = blockIdx.x % groups;
+  const int split = blockIdx.x / groups;
+  const int c0 = grp * cpc;
+  const int nch = min(cpc, p.C - c0);
+  const int run = nch * p.hw;                       // <= kEbRunMax * kThreads (host)
+  const int64_t base = static_cast<int64_t>(c0) * p.hw;
+  const bool need_lik = p.lik || p.bits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float zv[kEbRunMax], nv[kEbRunMax];
+  auto load_image = [&](int64_t b) {
+    const float* __restrict__ z = p.z + b * p.z_bs + base;
+    const float* __restrict__ nz = (p.noise_mode && p.noise) ? p.noise + b * p.noise_bs + base : nullptr;
+#pragma unroll
+    for (int j = 0; j < kEbRunMax; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      zv[j] = (i < run) ? ld_stream1(z + i) : 0.0f;
+      nv[j] = (nz && i < run) ? ld_stream1(nz + i) : 0.0f;
+    }
+  };
+  int64_t b = split;
+  if (b < p.B) load_image(b);                       // in flight while the parameters are transformed
+  if (need_lik)
+    for (int i = threadIdx.x; i < nch * kEbStride; i += kThreads) {
+      const int cl = i / kEbStride, j = i - cl * kEbStride;
+      s_par[i] = eb_staged_param_fast(p, c0 + cl, j);
+    }
+  else
+    for (int i = threadIdx.x; i < nch; i += kThreads) s_par[i * kEbStride + oMed] = p.medians[c0 + i];
+  __syncthreads();
+  // channel of this thread's j-th element: fixed for the whole launch
+  int cl[kEbRunMax];
+#pragma unroll
+  for (int j = 0; j < kEbRunMax; ++j) cl[j] = min((threadIdx.x + j * kThreads) / p.hw, nch - 1);
+  int phase = 0;
+  for (; b < p.B; b += splits, phase ^= 1) {
+    float cz[kEbRunMax], cn[kEbRunMax];
+#pragma unroll
+    for (int j = 0; j < kEbRunMax; ++j) { cz[j] = zv[j]; cn[j] = nv[j]; }
+    if (b + splits < p.B) load_image(b + splits);
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kEbRunMax; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      if (i < run) {
+        const float* P = s_par + cl[j] * kEbStride;
+        const float med = P[oMed];
+        const float q = rintf(cz[j] - med);
+        const float s = q + med;                       // "dequantize" / ste_round(z - med) + med
+        float out = s;
+        if (p.noise_mode) {
+          float u = cn[j];
+          if (!p.noise) {
+            const uint64_t eid = static_cast<uint64_t>(b) * static_cast<uint64_t>(p.ne) + static_cast<uint64_t>(base + i);
+            const uint64_t gid = eid >> 2;
+            const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                            p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+            const int k = static_cast<int>(eid & 3);
+            u = u32_to_centered_uniform(k == 0 ? r.x : k == 1 ? r.y : k == 2 ? r.z : r.w);
+          }
+          out = cz[j] + u;                             // "noise": medians ignored
+        }
+        const int64_t e = base + i;
+        if (p.zhat) st_stream1(p.zhat + b * p.zhat_bs + e, out);
+        if (p.ste) st_stream1(p.ste + b * p.ste_bs + e, s);
+        if (p.sym) st_stream1(p.sym + b * p.sym_bs + e, __float2int_rn(q));
+        if (need_lik) {
+          const float L = eb_likelihood_fast(P, out, lik_floor);
+          if (p.lik) st_stream1(p.lik + b * p.lik_bs + e, L);
+          acc += lg2_approx(L);
+        }
+      }
+    }
+    if (p.bits) {
+      const float v = warp_sum_f32(acc);
+      if (lane == 0) s_red[phase][warp] = v;
+      __syncthreads();                                 // s_red[phase] is rewritten two images later, behind the next barrier
+      if (warp == 0) {
+        float total = 0.0f;
+        if (lane == 0) {
+#pragma unroll
+          for (int w = 0; w < kEbWarps; ++w) total += s_red[phase][w];   // fixed order: reproducible
+        }
+        rate_commit(total, static_cast<int>(b), static_cast<unsigned int>(groups), p.B, p.workspace, p.bits, p.bits_accumulate);
+      }
+    }
+  }
+}
+
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "eb_fwd: null descriptor");
   if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_fwd: negative size");
@@ -400,9 +499,25 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
     err = cudaLaunchKernelEx(&cfg, eb_lut_kernel, p);
   } else {
-    const int64_t grid64 = bpi * d->B;
-    if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
-    eb_fwd_kernel<<<static_cast<int>(grid64), kThreads, 0, st>>>(p);
+    // direct evaluation.  Fast math: channel groups of ~512 elements per image, parameters staged once per CTA
+    int64_t cpc = (2 * kThreads + d->hw - 1) / d->hw;
+    if (cpc > kEbMaxCh) cpc = kEbMaxCh;
+    if (cpc > d->C) cpc = d->C;
+    if (cpc < 1) cpc = 1;
+    const int64_t groups = (d->C + cpc - 1) / cpc;
+    const bool fast_ok = math_mode() != RESLIC_MATH_MIRROR && cpc * d->hw <= kEbRunMax * kThreads && groups <= 60000;
+    if (fast_ok) {
+      int64_t splits = (static_cast<int64_t>(sm_count()) * 4 + groups - 1) / groups;   // one resident wave
+      if (splits > d->B) splits = d->B;
+      if (splits < 1) splits = 1;
+      const float lik_floor = d->likelihood_bound > 0.0f ? d->likelihood_bound : -__builtin_huge_valf();
+      eb_fwd_fast_kernel<<<static_cast<int>(groups * splits), kThreads, 0, st>>>(p, static_cast<int>(cpc), static_cast<int>(groups),
+                                                                               static_cast<int>(splits), lik_floor);
+    } else {
+      const int64_t grid64 = bpi * d->B;
+      if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
+      eb_fwd_kernel<<<static_cast<int>(grid64), kThreads, 0, st>>>(p);
+    }
     err = cudaGetLastError();
   }
   if (err != cudaSuccess) return set_cuda_error(err, "eb_fwd launch");
