@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 11
+#define RESLIC_ABI_VERSION 12
 
 enum {
   RESLIC_OK = 0,
@@ -230,9 +230,15 @@ typedef struct reslic_eb_bwd_desc {
   float* g_matrix[5]; float* g_bias[5]; float* g_factor[4];   /* same shapes as the parameters, nullable as a set */
   float* g_medians;                        /* [C], nullable                                   */
   uint64_t philox_seed, philox_offset;
+  /* Optional scratch (device, zero-initialised once, left zeroed by every launch; one per stream): with it
+   * a channel's B*hw elements are cut over several CTAs, whose partial sums the channel's last CTA adds in
+   * a fixed order (bit-reproducible); without it one CTA serves a whole channel.  Size:
+   * reslic_eb_bwd_workspace_bytes(C). */
+  void* workspace; int64_t workspace_bytes;
 } reslic_eb_bwd_desc;
 
 int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream);
+int64_t reslic_eb_bwd_workspace_bytes(int64_t C);
 
 /* ----------------------------------------------------------------------------------
  * STanH ("sum of tanh") quantizer family.

@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
 EB_LUT_STRIDE = 130
@@ -106,6 +106,7 @@ class EbBwdDesc(C.Structure):
         ("g_matrix", C.c_void_p * 5), ("g_bias", C.c_void_p * 5), ("g_factor", C.c_void_p * 4),
         ("g_medians", C.c_void_p),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -189,6 +190,7 @@ EXPORTS = {
                                            C.c_void_p, C.c_void_p]),
     "reslic_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "reslic_eb_bwd_f32": (C.c_int, [C.POINTER(EbBwdDesc), C.c_void_p]),
+    "reslic_eb_bwd_workspace_bytes": (C.c_int64, [C.c_int64]),
     "reslic_eb_fwd_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p]),
     "reslic_eb_build_lut_f32": (C.c_int, [C.POINTER(EbDesc), C.c_void_p, C.c_void_p]),
     "reslic_stanh_gc_fwd_f32": (C.c_int, [C.POINTER(StanhGcDesc), C.c_void_p]),

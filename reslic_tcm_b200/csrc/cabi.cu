@@ -215,6 +215,7 @@ int reslic_stanh_act_f32(const float* x, int64_t n, const reslic_stanh_tables* t
 int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream) {
   return reslic::eb_bwd_launch(d, static_cast<cudaStream_t>(stream));
 }
+int64_t reslic_eb_bwd_workspace_bytes(int64_t C) { return C > 0 ? reslic::eb_bwd_workspace_bytes(C) : 0; }
 
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
   return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));

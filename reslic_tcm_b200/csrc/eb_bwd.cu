@@ -24,8 +24,13 @@ struct EbBwdParams {
   int64_t B; int hw, C, noise_mode;
   float lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  int splits;                    // CTAs per channel
+  unsigned int* counters;        // [C] arrival tickets (zero between launches)
+  float* partials;               // [C][splits][kPartStride]
 };
 
+constexpr int kPartStride = 64;
+constexpr int kEbBwdMaxSplits = 8;
 constexpr int kNP = 58;   // transformed parameters per channel (median excluded)
 
 // Forward with tape, then backward: adds g_out * d logits / d P[j] to gP[j], returns d logits / d x * g_out.
@@ -95,6 +100,83 @@ __device__ __forceinline__ float logits_backward(const float* __restrict__ P, fl
   return gx;
 }
 
+// Fast form (math mode != MIRROR): ONE taped forward of both cumulative logits (x - 1/2, x + 1/2) as the two
+// lanes of packed f32x2 operations (tanh3_pair of eb_math.cuh), then the backward of both lanes, packed where
+// the lanes stay apart and as two scalar FMAs where they meet in a parameter-gradient accumulator.  The
+// reference form above evaluates the forward four times per element (two for the value, one inside each
+// logits_backward) with library tanhf.  g = (d loss / d lower, d loss / d upper); returns d loss / d x.
+__device__ __forceinline__ float2 logits_pair_tape(const float* __restrict__ P, float2 x, float2 hin[4][3], float2 th[4][3]) {
+  float2 h[3], t[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) t[j] = __ffma2_rn(make_float2(P[oM0 + j], P[oM0 + j]), x, make_float2(P[oB0 + j], P[oB0 + j]));
+  tanh3_pair(t, th[0]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { h[j] = __ffma2_rn(make_float2(P[oF0 + j], P[oF0 + j]), th[0][j], t[j]); hin[0][j] = h[j]; }
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const float* M = P + oM1 + l * 15;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float2 a = __ffma2_rn(make_float2(M[3 * j], M[3 * j]), h[0], make_float2(M[9 + j], M[9 + j]));
+      a = __ffma2_rn(make_float2(M[3 * j + 1], M[3 * j + 1]), h[1], a);
+      t[j] = __ffma2_rn(make_float2(M[3 * j + 2], M[3 * j + 2]), h[2], a);
+    }
+    tanh3_pair(t, th[l + 1]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { h[j] = __ffma2_rn(make_float2(M[12 + j], M[12 + j]), th[l + 1][j], t[j]); hin[l + 1][j] = h[j]; }
+  }
+  float2 a = __ffma2_rn(make_float2(P[oM4], P[oM4]), h[0], make_float2(P[oB4], P[oB4]));
+  a = __ffma2_rn(make_float2(P[oM4 + 1], P[oM4 + 1]), h[1], a);
+  return __ffma2_rn(make_float2(P[oM4 + 2], P[oM4 + 2]), h[2], a);
+}
+
+__device__ __forceinline__ float logits_backward_pair(const float* __restrict__ P, float2 x, float2 g, const float2 hin[4][3],
+                                                      const float2 th[4][3], float* gP) {
+  auto dot2 = [](float2 a, float2 b, float acc) { return fmaf(a.x, b.x, fmaf(a.y, b.y, acc)); };
+  const float2 one = make_float2(1.0f, 1.0f);
+  float2 gh[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    gP[oM4 + k] = dot2(g, hin[3][k], gP[oM4 + k]);
+    gh[k] = __fmul2_rn(make_float2(P[oM4 + k], P[oM4 + k]), g);
+  }
+  gP[oB4] += g.x + g.y;
+#pragma unroll
+  for (int l = 2; l >= 0; --l) {
+    const float* M = P + oM1 + l * 15;
+    float* gM = gP + oM1 + l * 15;
+    float2 gt[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float2 tj = th[l + 1][j];
+      gM[12 + j] = dot2(gh[j], tj, gM[12 + j]);                                  // d/d a_j  (a = tanh(factor))
+      const float2 sech2 = __ffma2_rn(make_float2(-tj.x, -tj.y), tj, one);
+      gt[j] = __fmul2_rn(gh[j], __ffma2_rn(make_float2(M[12 + j], M[12 + j]), sech2, one));   // h = t + a*tanh(t)
+      gM[9 + j] += gt[j].x + gt[j].y;                                            // bias
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gM[3 * j + k] = dot2(gt[j], hin[l][k], gM[3 * j + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float2 a = __fmul2_rn(make_float2(M[k], M[k]), gt[0]);
+      a = __ffma2_rn(make_float2(M[3 + k], M[3 + k]), gt[1], a);
+      gh[k] = __ffma2_rn(make_float2(M[6 + k], M[6 + k]), gt[2], a);
+    }
+  }
+  float gx = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float2 tj = th[0][j];
+    gP[oF0 + j] = dot2(gh[j], tj, gP[oF0 + j]);
+    const float2 sech2 = __ffma2_rn(make_float2(-tj.x, -tj.y), tj, one);
+    const float2 gt = __fmul2_rn(gh[j], __ffma2_rn(make_float2(P[oF0 + j], P[oF0 + j]), sech2, one));
+    gP[oB0 + j] += gt.x + gt.y;
+    gP[oM0 + j] = dot2(gt, x, gP[oM0 + j]);
+    gx = fmaf(P[oM0 + j], gt.x + gt.y, gx);
+  }
+  return gx;
+}
+
 // d(transformed)/d(raw) of staged slot j: sigmoid(m) for matrices, 1 - tanh(f)^2 for factors, 1 for biases
 template <typename PP>
 __device__ __forceinline__ float eb_param_chain(const PP& p, int c, int j, float** dst) {
@@ -115,10 +197,13 @@ __device__ __forceinline__ float eb_param_chain(const PP& p, int c, int j, float
   return 1.0f;
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p) {
   __shared__ float s_par[kEbStride + 1];
   __shared__ float s_red[kThreads / 32][kNP + 1];
-  const int c = blockIdx.x;
+  __shared__ bool s_last;
+  const int c = blockIdx.x / p.splits;
+  const int split = blockIdx.x - c * p.splits;
   if (threadIdx.x < kEbStride) s_par[threadIdx.x] = eb_staged_param(p, c, threadIdx.x);
   __syncthreads();
   const float med = s_par[oMed];
@@ -128,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
   float gmed = 0.0f;
   const int64_t total = p.B * p.hw;
   const int64_t base_c = static_cast<int64_t>(c) * p.hw;
-  for (int64_t idx = threadIdx.x; idx < total; idx += kThreads) {
+  for (int64_t idx = static_cast<int64_t>(split) * kThreads + threadIdx.x; idx < total; idx += static_cast<int64_t>(p.splits) * kThreads) {
     const int64_t b = idx / p.hw;
     const int64_t e = base_c + (idx - b * p.hw);                  // offset inside image b
     const float zv = p.z[b * p.z_bs + e];
@@ -152,11 +237,18 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
     float gx = 0.0f;
     if (p.g_lik) {
       const float gl = p.g_lik[b * p.g_lik_bs + e];
-      const float lower = logits_cumulative(s_par, x - 0.5f);
-      const float upper = logits_cumulative(s_par, x + 0.5f);
+      float2 hin[4][3], th[4][3];
+      const float2 xx = make_float2(x - 0.5f, x + 0.5f);
+      float lower, upper;
+      if (FAST) { const float2 lu = logits_pair_tape(s_par, xx, hin, th); lower = lu.x; upper = lu.y; }
+      else { lower = logits_cumulative(s_par, xx.x); upper = logits_cumulative(s_par, xx.y); }
       const float sum = lower + upper;
       const float sg = (sum < 0.0f) ? 1.0f : ((sum > 0.0f) ? -1.0f : 0.0f);
-      const float su = sigmoid_ref(sg * upper), sl = sigmoid_ref(sg * lower);
+      float su, sl;
+      if (FAST) {
+        su = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * (sg * upper)));
+        sl = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * (sg * lower)));
+      } else { su = sigmoid_ref(sg * upper); sl = sigmoid_ref(sg * lower); }
       const float D = su - sl;
       const float L = fabsf(D);
       const bool pass = !(p.lik_bound > 0.0f) || (L >= p.lik_bound) || (gl < 0.0f);
@@ -165,8 +257,11 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
       const float du = g * sd * sg * su * (1.0f - su);
       const float dl = -g * sd * sg * sl * (1.0f - sl);
       if (du != 0.0f || dl != 0.0f) {
-        gx = logits_backward(s_par, x + 0.5f, du, gP);
-        gx += logits_backward(s_par, x - 0.5f, dl, gP);
+        if (FAST) gx = logits_backward_pair(s_par, xx, make_float2(dl, du), hin, th, gP);
+        else {
+          gx = logits_backward(s_par, x + 0.5f, du, gP);
+          gx += logits_backward(s_par, x - 0.5f, dl, gP);
+        }
       }
     }
     const float gzh = p.g_zhat ? p.g_zhat[b * p.g_zhat_bs + e] : 0.0f;
@@ -189,9 +284,27 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
     if (lane == 0) s_red[warp][kNP] = v;
   }
   __syncthreads();
-  if (threadIdx.x <= kNP) {
-    float v = 0.0f;
+  float v = 0.0f;
+  if (threadIdx.x <= kNP)
     for (int w = 0; w < kThreads / 32; ++w) v += s_red[w][threadIdx.x];
+  if (p.splits > 1) {
+    // the channel's CTAs leave their sums in the workspace; the one that arrives last adds them in split order
+    // (a fixed order whoever is last: bit-reproducible) and writes the gradients
+    float* part = p.partials + (static_cast<int64_t>(c) * p.splits) * kPartStride;
+    if (threadIdx.x <= kNP) part[split * kPartStride + threadIdx.x] = v;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.counters[c], 1u) == static_cast<unsigned int>(p.splits - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x <= kNP) {
+      v = 0.0f;
+      for (int sp = 0; sp < p.splits; ++sp) v += __ldcg(part + sp * kPartStride + threadIdx.x);
+    }
+    if (threadIdx.x == 0) p.counters[c] = 0u;
+  }
+  if (threadIdx.x <= kNP) {
     if (threadIdx.x < kNP) {
       if (p.g_matrix[0]) {
         float* dst;
@@ -202,6 +315,11 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
       p.g_medians[c] = v;
     }
   }
+}
+
+static int64_t eb_bwd_counter_bytes(int64_t C) { return ((C * 4 + 255) / 256) * 256; }
+int64_t eb_bwd_workspace_bytes(int64_t C) {
+  return eb_bwd_counter_bytes(C) + C * kEbBwdMaxSplits * kPartStride * static_cast<int64_t>(sizeof(float));
 }
 
 int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
@@ -233,7 +351,24 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   p.noise_mode = d->mode == RESLIC_Q_NOISE; p.lik_bound = d->likelihood_bound;
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
-  eb_bwd_kernel<<<static_cast<int>(d->C), kThreads, 0, st>>>(p);
+  // CTAs per channel: enough to fill the machine (one 256-thread CTA of this kernel per SM) about three times over
+  int64_t splits = 1;
+  if (d->workspace) {
+    if (d->workspace_bytes < eb_bwd_workspace_bytes(d->C) || (reinterpret_cast<uintptr_t>(d->workspace) & 15u))
+      return set_error(RESLIC_ERR_WORKSPACE, "eb_bwd: workspace misaligned or smaller than reslic_eb_bwd_workspace_bytes(C)");
+    splits = (3 * static_cast<int64_t>(sm_count()) + d->C - 1) / d->C;
+    const int64_t per_thread = (d->B * d->hw + kThreads - 1) / kThreads;     // elements per thread of an unsplit channel
+    if (splits > per_thread) splits = per_thread;
+    if (splits > kEbBwdMaxSplits) splits = kEbBwdMaxSplits;
+    if (splits < 1) splits = 1;
+    p.counters = static_cast<unsigned int*>(d->workspace);
+    p.partials = reinterpret_cast<float*>(static_cast<char*>(d->workspace) + eb_bwd_counter_bytes(d->C));
+  }
+  p.splits = static_cast<int>(splits);
+  if (d->C * splits > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_bwd: grid too large");
+  const int grid = static_cast<int>(d->C * splits);
+  if (math_mode() == RESLIC_MATH_MIRROR) eb_bwd_kernel<false><<<grid, kThreads, 0, st>>>(p);
+  else eb_bwd_kernel<true><<<grid, kThreads, 0, st>>>(p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "eb_bwd launch");
   return RESLIC_OK;

@@ -353,13 +353,37 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
   };
   int64_t b = split;
   if (b < p.B) load_image(b);                       // in flight while the parameters are transformed
-  if (need_lik)
-    for (int i = threadIdx.x; i < nch * kEbStride; i += kThreads) {
-      const int cl = i / kEbStride, j = i - cl * kEbStride;
-      s_par[i] = eb_staged_param_fast(p, c0 + cl, j);
+  if (need_lik) {
+    // thread -> (parameter slot j, channel quarter): the slot's source array, stride and transform are resolved
+    // once, the loop over the group's channels is then load / transform / store
+    const int j = threadIdx.x & 63, cq = threadIdx.x >> 6;
+    if (j < kEbStride) {
+      const float* src; int stride, kind;                 // kind 0: copy, 1: softplus, 2: tanh
+      if (j < oB0) { src = p.matrix[0] + j; stride = 3; kind = 1; }
+      else if (j < oF0) { src = p.bias[0] + (j - oB0); stride = 3; kind = 0; }
+      else if (j < oM1) { src = p.factor[0] + (j - oF0); stride = 3; kind = 2; }
+      else if (j < oM4) {
+        const int l = (j - oM1) / 15, r = (j - oM1) - l * 15;
+        if (r < 9) { src = p.matrix[1 + l] + r; stride = 9; kind = 1; }
+        else if (r < 12) { src = p.bias[1 + l] + (r - 9); stride = 3; kind = 0; }
+        else { src = p.factor[1 + l] + (r - 12); stride = 3; kind = 2; }
+      }
+      else if (j < oB4) { src = p.matrix[4] + (j - oM4); stride = 3; kind = 1; }
+      else if (j == oB4) { src = p.bias[4]; stride = 1; kind = 0; }
+      else { src = p.medians; stride = 1; kind = 0; }
+      for (int cl = cq; cl < nch; cl += kThreads / 64) {
+        float v = src[static_cast<int64_t>(c0 + cl) * stride];
+        if (kind == 1) v = v > 15.0f ? v : 0.6931471805599453f * lg2_approx(1.0f + ex2_approx(1.4426950408889634f * v));
+        else if (kind == 2) {
+          const float e = ex2_approx(-2.8853900817779268f * fabsf(v));
+          v = copysignf((1.0f - e) * rcp_approx(1.0f + e), v);
+        }
+        s_par[cl * kEbStride + j] = v;
+      }
     }
-  else
+  } else {
     for (int i = threadIdx.x; i < nch; i += kThreads) s_par[i * kEbStride + oMed] = p.medians[c0 + i];
+  }
   __syncthreads();
   // channel of this thread's j-th element: fixed for the whole launch
   int cl[kEbRunMax];
@@ -499,8 +523,8 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
     err = cudaLaunchKernelEx(&cfg, eb_lut_kernel, p);
   } else {
-    // direct evaluation.  Fast math: channel groups of ~512 elements per image, parameters staged once per CTA
-    int64_t cpc = (2 * kThreads + d->hw - 1) / d->hw;
+    // direct evaluation.  Fast math: channel groups of ~256 elements per image, parameters staged once per CTA
+    int64_t cpc = (kThreads + d->hw - 1) / d->hw;
     if (cpc > kEbMaxCh) cpc = kEbMaxCh;
     if (cpc > d->C) cpc = d->C;
     if (cpc < 1) cpc = 1;

@@ -123,29 +123,6 @@ __device__ __forceinline__ float eb_staged_param(const P& p, int c, int j) {
   return p.medians[c];
 }
 
-// the same with MUFU forms (absolute error <= 1e-7 per entry): the fast kernel transforms the parameters of
-// its channel group once per CTA, and with the library forms that prologue costs as much as an image
-template <typename P>
-__device__ __forceinline__ float eb_staged_param_fast(const P& p, int c, int j) {
-  auto softplus = [](float x) { return x > 15.0f ? x : 0.6931471805599453f * lg2_approx(1.0f + ex2_approx(1.4426950408889634f * x)); };
-  auto tanh_f = [](float x) {
-    const float e = ex2_approx(-2.8853900817779268f * fabsf(x));
-    return copysignf((1.0f - e) * rcp_approx(1.0f + e), x);
-  };
-  if (j < oB0) return softplus(p.matrix[0][c * 3 + j]);
-  if (j < oF0) return p.bias[0][c * 3 + (j - oB0)];
-  if (j < oM1) return tanh_f(p.factor[0][c * 3 + (j - oF0)]);
-  if (j < oM4) {
-    const int l = (j - oM1) / 15, r = (j - oM1) - l * 15;
-    if (r < 9) return softplus(p.matrix[1 + l][c * 9 + r]);
-    if (r < 12) return p.bias[1 + l][c * 3 + (r - 9)];
-    return tanh_f(p.factor[1 + l][c * 3 + (r - 12)]);
-  }
-  if (j < oB4) return softplus(p.matrix[4][c * 3 + (j - oM4)]);
-  if (j == oB4) return p.bias[4][c];
-  return p.medians[c];
-}
-
 // sign-trick likelihood from the two cumulative logits, adaptive_entropy_bottleneck.py:658-666
 __device__ __forceinline__ float eb_combine(float lower, float upper, float lik_bound) {
   const float sum = lower + upper;

@@ -24,6 +24,7 @@ int math_mode();                                          // RESLIC_MATH_*      
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st);
 int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st);
 int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st);
+int64_t eb_bwd_workspace_bytes(int64_t C);
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st);
 int eb_build_lut_launch(const reslic_eb_desc* d, float* lut, cudaStream_t st);
 int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st);

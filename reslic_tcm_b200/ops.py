@@ -445,6 +445,21 @@ def eb_forward(
     return res
 
 
+_eb_bwd_ws = {}
+
+
+def _eb_bwd_workspace(device: torch.device, channels: int) -> Tensor:
+    """Zero-initialised scratch of reslic_eb_bwd_f32, one per (device, stream) — launches on one stream are
+    ordered, and every launch leaves its arrival counters zeroed."""
+    need = int(_cabi.load().reslic_eb_bwd_workspace_bytes(channels))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _eb_bwd_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _eb_bwd_ws[key] = ws
+    return ws
+
+
 def eb_backward(
     z: Tensor,
     matrices: Sequence[Tensor],
@@ -508,6 +523,8 @@ def eb_backward(
         d.g_z, d.g_z_bs = g_z.data_ptr(), Cc * hw
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    ws = _eb_bwd_workspace(z.device, Cc)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     with torch.cuda.device(z.device):
         code = lib.reslic_eb_bwd_f32(C.byref(d), _cabi.current_stream_ptr(z.device))
     _cabi.check(code, "reslic_eb_bwd_f32")

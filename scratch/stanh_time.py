@@ -86,3 +86,14 @@ if which == "once":
         m._stanh_backward(y, sigma, mu, True, y, sigma)
         compute_gap(m.stanh, y)
     torch.cuda.synchronize()
+if which == "once_eb":
+    B, C, h, w = 256, 192, 4, 4
+    mod = EntropyBottleneck(C).to(dev).train()
+    synthetic.load_eb_parameters(mod, synthetic.eb_parameters())
+    m, b, f = mod._params(); med = mod._medians_flat()
+    z = torch.randn(B, C, h, w, device=dev) * 4
+    gz = torch.randn(B, C, h, w, device=dev)
+    for i in range(3):
+        ops.eb_forward(z, m, b, f, med, training=True, want=("zhat", "lik"), seed=1, offset=i)
+        ops.eb_backward(z, m, b, f, med, training=True, g_zhat=gz, g_lik=gz, seed=1, offset=i)
+    torch.cuda.synchronize()

@@ -74,10 +74,11 @@ def test_module_forward_is_differentiable_and_philox_backward_is_consistent():
 
 
 @pytest.mark.parametrize("training", [True, False])
-def test_eb_backward_matches_autograd(training):
+@pytest.mark.parametrize("shape", [(3, 6, 5, 4), (40, 6, 16, 16)])   # one CTA per channel / channels cut over 8 CTAs
+def test_eb_backward_matches_autograd(training, shape):
     from reslic_tcm_b200 import EntropyBottleneck, synthetic
 
-    C, shape = 6, (3, 6, 5, 4)
+    C = shape[1]
     params = synthetic.eb_parameters(C, trained_like=True, seed=99)
     g = torch.Generator().manual_seed(5)
     z = 2.5 * torch.randn(shape, generator=g)
@@ -123,6 +124,26 @@ def test_eb_backward_matches_autograd(training):
             check(f"d/d_factor{i}", getattr(mod, f"_factor{i}").grad, ref.factors[i].grad)
     if not training:
         check("d/dquantiles", mod.quantiles.grad, ref.quantiles.grad)
+
+
+def test_eb_backward_split_channels_are_bit_reproducible_and_leave_the_workspace_clean():
+    from reslic_tcm_b200 import EntropyBottleneck, ops, synthetic
+
+    C = 12
+    mod = EntropyBottleneck(C).to(DEV).train()
+    synthetic.load_eb_parameters(mod, synthetic.eb_parameters(C, trained_like=True, seed=3))
+    m, b, f = mod._params()
+    med = mod._medians_flat()
+    torch.manual_seed(4)
+    z = 3.0 * torch.randn(64, C, 8, 8, device=DEV)
+    gz, gl = torch.randn_like(z), torch.randn_like(z)
+    runs = [ops.eb_backward(z, m, b, f, med, training=True, g_zhat=gz, g_lik=gl, seed=9, offset=2) for _ in range(3)]
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0])
+        for a, c in zip(r[1] + r[2] + r[3], runs[0][1] + runs[0][2] + runs[0][3]):
+            assert torch.equal(a, c)
+    ws = ops._eb_bwd_workspace(z.device, C)
+    assert int(ws[: 4 * C].view(torch.int32).abs().sum()) == 0          # arrival counters back to zero
 
 
 @pytest.mark.parametrize("training,removing_mean,symmetry", [(True, True, False), (True, False, False),
