@@ -149,8 +149,9 @@ class HostPipeline:
     symbols, tcm.py:551-565) sees; when the latents are produced on the GPU use TcmEntropyPath."""
 
     def __init__(self, path: TcmEntropyPath, batch: int, y_hw, z_hw, *, with_indexes: bool, training: bool = False,
-                 chunks: int = 4, device=None, num_pixels: Optional[int] = None, depth: int = 2):
+                 chunks: int = 4, device=None, num_pixels: Optional[int] = None, depth: int = 2, seed: int = 0):
         self.path, self.with_indexes, self.training, self.num_pixels = path, with_indexes, training, num_pixels
+        self.seed = int(seed)          # Philox key of the noise modes (the counter is the element index inside a launch)
         dev = torch.device(device if device is not None else "cuda")
         self.dev = dev
         B = batch
@@ -221,7 +222,7 @@ class HostPipeline:
                     self.s_comp.wait_event(slot["ev_out"][c])          # ... and its outputs have left the device
                 res = slot["sub"][c].forward(d_in["y"][a:b], d_in["mu"][a:b], d_in["sigma"][a:b], d_in["z"][a:b],
                                              training=self.training, with_indexes=self.with_indexes,
-                                             num_pixels=self.num_pixels)
+                                             num_pixels=self.num_pixels, seed=self.seed)
                 slot["ev_comp"][c].record(self.s_comp)
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(slot["ev_comp"][c])

@@ -117,3 +117,21 @@ def test_host_pipeline_streams_batches_and_matches_the_device_pass():
         assert torch.equal(got[k]["symbols"], ref["symbols"].cpu()), k
         assert torch.equal(got[k]["indexes"], ref["indexes"].cpu()), k
         assert torch.allclose(got[k]["bits"], ref["bits"].cpu(), rtol=1e-6), k      # chunking regroups fp32 partials
+
+
+def test_host_pipeline_training_mode_uses_the_callers_philox_seed():
+    """Noise mode through HostPipeline: with one chunk the launches are those of the device-resident pass, so the
+    same seed must give the same per-image bits; another seed must not."""
+    B, y_hw, z_hw = 4, (16, 8), (4, 2)
+    _, path, _ = _setup(5, B, y_hw, z_hw)
+    host = synthetic.make_batch(5, range(B), y_hw=y_hw, z_hw=z_hw, pin=True)
+    ref = path.forward(host["y"].to(DEV), host["mu"].to(DEV), host["sigma"].to(DEV), host["z"].to(DEV),
+                       training=True, seed=77)["bits"].clone().cpu()
+    hp = HostPipeline(path, B, y_hw, z_hw, with_indexes=False, training=True, chunks=1, device=DEV, seed=77)
+    out = hp.run(host)
+    out["done"].synchronize()
+    assert torch.allclose(out["bits"], ref, rtol=1e-6)
+    hp2 = HostPipeline(path, B, y_hw, z_hw, with_indexes=False, training=True, chunks=1, device=DEV, seed=78)
+    out2 = hp2.run(host)
+    out2["done"].synchronize()
+    assert not torch.allclose(out2["bits"], ref, rtol=1e-6)
