@@ -277,10 +277,9 @@ struct StanhIn { float4 y, m, s; };
 
 template <int MODE, bool FAST, int KMAX>      // MODE 0: hard levels, 1: soft form (beta > 0), 2: likelihood of the given values
 __global__ void __launch_bounds__(kThreads, 4) stanh_gc_vec_kernel(const StanhVecParams q) {
-  extern __shared__ __align__(16) unsigned char smraw[];
   const StanhParams& p = q.s;
   StanhSm<KMAX> T;
-  stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, smraw, T);
+  stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, T);
   const bool need_lik = p.lik || p.bits;
   const bool use_mu = p.mu != nullptr;
   const bool rm = q.rm != 0;
@@ -325,25 +324,27 @@ __global__ void __launch_bounds__(kThreads, 4) stanh_gc_vec_kernel(const StanhVe
       const unsigned int bo = tb + static_cast<unsigned int>(k) * kTileBytes;
       auto at = [bo](auto* ptr) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + bo); };
       const float yy[4] = {r.y.x, r.y.y, r.y.z, r.y.w};
-      const float mm[4] = {r.m.x, r.m.y, r.m.z, r.m.w};
+      const float mm[4] = {r.m.x, r.m.y, r.m.z, r.m.w};                 // zeros without means
+      // the mean the quantizer works about: mu, or 0 (y - 0 and q + 0 are exact)
+      const float mq[4] = {rm ? mm[0] : 0.0f, rm ? mm[1] : 0.0f, rm ? mm[2] : 0.0f, rm ? mm[3] : 0.0f};
       float yh[4], n1[4], n2[4];
       int lv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float x = rm ? yy[i] - mm[i] : yy[i];
+        const float x = yy[i] - mq[i];
         int c = -1;
         lv[i] = 0;
         if (MODE == 2) yh[i] = yy[i];
         else {
           const float qv = (MODE == 1) ? stanh_soft_sm<FAST>(x, p.beta, q.sat_r, q.c2, T) : stanh_hard_sm(x, T, symmetric, c);
-          yh[i] = rm ? qv + mm[i] : qv;
+          yh[i] = qv + mq[i];
           if (o_sym) {
             if (MODE == 0 && q.sym_same) lv[i] = c;
             else lv[i] = stanh_count_gt_b(yy[i] - mm[i], T);
           }
         }
         if (need_lik) {
-          const float v = use_mu ? yh[i] - mm[i] : yh[i];             // :547-550
+          const float v = yh[i] - mm[i];                               // :547-550 (mm = 0 without means)
           stanh_cell_bounds(v, (MODE == 0) ? c : -1, T, n1[i], n2[i]);
         }
       }
@@ -389,11 +390,10 @@ template <bool FAST, int KMAX>
 __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p, float* out_soft, float* out_hard,
                                                              double* partials, unsigned int* counter, int vec,
                                                              float sat_r, float c2) {
-  extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double s_red[2][kThreads / 32];
   __shared__ bool s_last;
   StanhSm<KMAX> T;
-  stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, smraw, T);
+  stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, T);
   const bool want_soft = out_soft || p.gap, want_hard = out_hard || p.gap;
   const bool soft_is_hard = p.beta == -1.0f;
   const bool symmetric = p.symmetric != 0;
@@ -882,13 +882,12 @@ __device__ __forceinline__ void stanh_bwd_elem(const StanhBwdParams& p, const St
 // W = 4: one 128-bit group per thread and tile (aligned tensors, n % 4 == 0); W = 1: any layout.
 template <int W, bool PAR, int KMAX>
 __global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdParams p, float sat_r, float c2) {
-  extern __shared__ __align__(16) unsigned char smraw[];
   StanhSm<KMAX> T;
-  stage_stanh_sm(p.st.b, p.st.w, p.st.cum_w, p.st.avg, p.st.dist, p.st.K, smraw, T);
+  stage_stanh_sm(p.st.b, p.st.w, p.st.cum_w, p.st.avg, p.st.dist, p.st.K, T);
   StanhParAcc acc{};
   const int n_acc = 5 * p.st.K + 2;
   if (PAR) {
-    double* base = reinterpret_cast<double*>(smraw + StanhSm<KMAX>::kBytes);
+    double* base = reinterpret_cast<double*>(stanh_smem + StanhSm<KMAX>::kBytes);
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) base[i] = 0.0;
     acc.A = base; acc.Bq = acc.A + p.st.K + 1; acc.Ww = acc.Bq + p.st.K + 1; acc.Wb = acc.Ww + p.st.K; acc.Hd = acc.Wb + p.st.K;
     __syncthreads();

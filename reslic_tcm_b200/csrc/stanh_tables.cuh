@@ -19,6 +19,7 @@
 namespace reslic {
 
 constexpr int kStanhPad = 4;          // NaN entries behind each table: every ordered comparison with them is false
+extern __shared__ __align__(16) unsigned char stanh_smem[];
 
 template <int KMAX>
 struct StanhSm {
@@ -31,17 +32,18 @@ struct StanhSm {
   static constexpr int oSa = oSb + (kCells + 2) * 2;            // uint16 [kCells + 2]
   static constexpr int kBytes = (oSa + (kCells + 2) * 2 + 15) & ~15;
 
-  unsigned char* raw;
   float b_lo, b_inv, a_lo, a_inv, gmax;   // cell(x) = RN(clamp((x - lo) * inv, 0, gmax)), NaN -> 0
   float cw0, cwK;
   int K;
 
-  __device__ __forceinline__ const float2* bw() const { return reinterpret_cast<const float2*>(raw + oBw); }
-  __device__ __forceinline__ const float2* lowup() const { return reinterpret_cast<const float2*>(raw + oLowUp); }
-  __device__ __forceinline__ const float* cw() const { return reinterpret_cast<const float*>(raw + oCw); }
-  __device__ __forceinline__ const float* avgp() const { return reinterpret_cast<const float*>(raw + oAvg); }
-  __device__ __forceinline__ const uint16_t* sb() const { return reinterpret_cast<const uint16_t*>(raw + oSb); }
-  __device__ __forceinline__ const uint16_t* sa() const { return reinterpret_cast<const uint16_t*>(raw + oSa); }
+  // the tables sit at the start of the CTA's dynamic shared memory; naming the array (instead of carrying a
+  // pointer) lets every access be one LDS [index * size + constant]
+  __device__ __forceinline__ const float2* bw() const { return reinterpret_cast<const float2*>(stanh_smem + oBw); }
+  __device__ __forceinline__ const float2* lowup() const { return reinterpret_cast<const float2*>(stanh_smem + oLowUp); }
+  __device__ __forceinline__ const float* cw() const { return reinterpret_cast<const float*>(stanh_smem + oCw); }
+  __device__ __forceinline__ const float* avgp() const { return reinterpret_cast<const float*>(stanh_smem + oAvg); }
+  __device__ __forceinline__ const uint16_t* sb() const { return reinterpret_cast<const uint16_t*>(stanh_smem + oSb); }
+  __device__ __forceinline__ const uint16_t* sa() const { return reinterpret_cast<const uint16_t*>(stanh_smem + oSa); }
 };
 
 __device__ __forceinline__ int stanh_cell(float x, float lo, float inv, float gmax) {
@@ -87,8 +89,9 @@ __device__ __forceinline__ int stanh_count_gt_avg(float v, const StanhSm<KMAX>& 
 // All threads of the CTA must call; ends with a barrier.  K <= KMAX.
 template <int KMAX>
 __device__ __forceinline__ void stage_stanh_sm(const float* b, const float* w, const float* cum_w, const float* avg,
-                                               const float* dist, int K, unsigned char* raw, StanhSm<KMAX>& T) {
+                                               const float* dist, int K, StanhSm<KMAX>& T) {
   using S = StanhSm<KMAX>;
+  unsigned char* raw = stanh_smem;
   const int G = 4 * K;
   float2* bw = reinterpret_cast<float2*>(raw + S::oBw);
   float2* lowup = reinterpret_cast<float2*>(raw + S::oLowUp);
@@ -97,7 +100,7 @@ __device__ __forceinline__ void stage_stanh_sm(const float* b, const float* w, c
   uint16_t* sb = reinterpret_cast<uint16_t*>(raw + S::oSb);
   uint16_t* sa = reinterpret_cast<uint16_t*>(raw + S::oSa);
   const float nan = __int_as_float(0x7fc00000);
-  T.raw = raw; T.K = K; T.gmax = static_cast<float>(G);
+  T.K = K; T.gmax = static_cast<float>(G);
   auto inv_of = [&](float span) {
     float inv = (span > 0.0f) ? static_cast<float>(G) / span : 0.0f;
     return (inv <= 3.0e38f) ? inv : 0.0f;
