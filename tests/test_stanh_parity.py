@@ -245,3 +245,48 @@ def test_rate_modes_across_kernels_share_one_workspace():
     launches(lambda k: {"workspace": ws, "bits_deferred": True})
     assert torch.equal(ops.rate_finalize(ws, B), total)
     assert int(ws.view(torch.int64).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("extrema", [80, 200])         # K = 160 (KMAX 256 tables) / K = 400 (KMAX 1024 tables)
+@pytest.mark.parametrize("beta", [3.0, -1])
+def test_trained_like_nonuniform_tables_against_oracle(extrema, beta):
+    """The cell-grid lookups must be exact for ANY ascending table: weights and thresholds perturbed as a trained
+    module would have them, including two thresholds 1e-4 apart (several entries in one grid cell), inputs that sit
+    exactly on thresholds and far outside the table."""
+    cfg = dict(beta=beta, num_sigmoids=0, extrema=extrema, trainable=True, removing_mean=True, symmetry=False)
+    m = stanh.GaussianConditionalStanh(None, channels=8, gaussian_configuration=cfg).to(DEV)
+    gen = torch.Generator().manual_seed(11 + extrema)
+    K = 2 * extrema
+    with torch.no_grad():
+        w = 1.0 + 0.3 * (2 * torch.rand(K, generator=gen) - 1)
+        b = m.stanh.b.detach().cpu() + 0.3 * (2 * torch.rand(K, generator=gen) - 1)
+        b = torch.sort(b)[0]
+        b[K // 2 + 3] = b[K // 2 + 2] + 1e-4
+        b[K // 2 + 4] = b[K // 2 + 2] + 2e-4
+        b = torch.sort(b)[0]
+        m.stanh.w.copy_(w)
+        m.stanh.b.copy_(b)
+    m.stanh.update_state(torch.device(DEV))
+    cum_w = m.stanh.cum_w.detach().cpu()
+    shape = (2, 8, 16, 16)
+    mu = torch.randn(shape, generator=gen)
+    sigma = torch.exp(torch.empty(shape).uniform_(-3, 4, generator=gen))
+    y = mu + sigma * torch.randn(shape, generator=gen) * 2
+    y.view(-1)[:K] = b + mu.view(-1)[:K]                  # exactly ON the thresholds (up to the rounding of the sum)
+    mu.view(-1)[K:K + 6] = 0.0
+    y.view(-1)[K:K + 6] = torch.tensor([b[K // 2 + 2], b[K // 2 + 3], b[K // 2 + 4], 3.0 * extrema, -3.0 * extrema, float("nan")])
+    tol = max(2e-6, 6e-8 * float(w.sum())) * 4
+    for training in (False, True):
+        with torch.no_grad():
+            yh, lik = m(y.to(DEV), sigma.to(DEV), training=training, means=mu.to(DEV))
+        yh_ref = sr.quantize(y, "training" if training else "dequantize", mu, w, b, beta, False, True)
+        a = yh.cpu()
+        ok = ((a - yh_ref).abs() <= tol * yh_ref.abs().clamp_min(1.0)) | (torch.isnan(a) & torch.isnan(yh_ref))
+        bad = torch.nonzero(~ok.reshape(-1))[:5].reshape(-1).tolist()
+        assert not bad, [(i, y.reshape(-1)[i].item(), a.reshape(-1)[i].item(), yh_ref.reshape(-1)[i].item()) for i in bad]
+        avg, dist = sr.mid_and_half_gaps(cum_w)
+        assert_lik_close(lik, cr_bound(sr.likelihood(a, sigma, mu, avg, dist)), what=f"training={training}")
+    with torch.no_grad():
+        sym = m.quantize(y.to(DEV), "symbols", means=mu.to(DEV)).cpu()
+    finite = ~torch.isnan(y)
+    assert torch.equal(sym[finite], sr.symbols(y, mu, cum_w, w, b, False)[finite])
