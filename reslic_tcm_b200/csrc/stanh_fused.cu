@@ -276,7 +276,7 @@ __device__ __forceinline__ void stanh_cell_bounds(float v, int guess, const Stan
 struct StanhIn { float4 y, m, s; };
 
 template <int MODE, bool FAST, int KMAX>      // MODE 0: hard levels, 1: soft form (beta > 0), 2: likelihood of the given values
-__global__ void __launch_bounds__(kThreads, 4) stanh_gc_vec_kernel(const StanhVecParams q) {
+__global__ void __launch_bounds__(kThreads, 5) stanh_gc_vec_kernel(const StanhVecParams q) {
   const StanhParams& p = q.s;
   StanhSm<KMAX> T;
   stage_stanh_sm(p.b, p.w, p.cum_w, p.avg, p.dist, p.K, T);
