@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 12
+#define RESLIC_ABI_VERSION 13
 
 enum {
   RESLIC_OK = 0,
@@ -371,6 +371,24 @@ void reslic_rans_encoder_destroy(void* enc);
 int reslic_rans_encoder_push(void* enc, const int32_t* symbols, const int32_t* indexes, int64_t n,
                              const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
                              const int32_t* cdf_sizes, const int32_t* offsets);
+/* Device-side front end of reslic_rans_encoder_push: the per-symbol table lookup
+ *   value = symbol - offsets[index], clamped to the escape slot cdf_sizes[index] - 2;
+ *   slots[i] = cdf[value] << 16 | (cdf[value + 1] - cdf[value])
+ * for n symbols, on the GPU behind the kernel that produced symbols and indexes, so that ONE packed 32-bit
+ * slot per symbol crosses PCIe instead of two int32.  All pointers are DEVICE pointers; at most 1024 CDFs.
+ * Symbols outside their table take the escape slot and are listed, in no particular order, as
+ * (esc_pos[k], esc_raw[k]) = (position, bypass value) for k < min(status[0], esc_capacity).
+ * status (int32[2], written by the call): [0] number of escaped symbols — if it exceeds esc_capacity the
+ * list is incomplete and the caller must fall back to reslic_rans_encoder_push; [1] error bits
+ * (1: an index outside [0, n_cdfs), 2: an invalid cdf entry — zero/negative frequency or >= 2^16). */
+int reslic_rans_slots_u32(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                          int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                          uint32_t* slots, int32_t* esc_pos, int64_t* esc_raw, int64_t esc_capacity,
+                          int32_t* status, void* stream);
+/* HOST: push n symbols whose lookups reslic_rans_slots_u32 has done; the escapes that belong to these n
+ * symbols sorted by position (relative to slots[0]).  Produces the same stream as reslic_rans_encoder_push. */
+int reslic_rans_encoder_push_slots(void* enc, const uint32_t* slots, int64_t n, const int32_t* esc_pos,
+                                   const int64_t* esc_raw, int64_t n_esc);
 /* returns the byte count (or -1); *data stays owned by the encoder until its next call */
 int64_t reslic_rans_encoder_flush(void* enc, const uint8_t** data);
 void* reslic_rans_decoder_create(const uint8_t* data, int64_t nbytes);

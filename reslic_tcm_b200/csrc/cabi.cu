@@ -217,6 +217,14 @@ int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream) {
 }
 int64_t reslic_eb_bwd_workspace_bytes(int64_t C) { return C > 0 ? reslic::eb_bwd_workspace_bytes(C) : 0; }
 
+int reslic_rans_slots_u32(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                          int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                          uint32_t* slots, int32_t* esc_pos, int64_t* esc_raw, int64_t esc_capacity,
+                          int32_t* status, void* stream) {
+  return reslic::rans_slots_launch(symbols, indexes, n, cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets, slots, esc_pos,
+                                   esc_raw, esc_capacity, status, static_cast<cudaStream_t>(stream));
+}
+
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
   return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }

@@ -97,6 +97,42 @@ int reslic_rans_encoder_push(void* h, const int32_t* symbols, const int32_t* ind
   return RESLIC_OK;
 }
 
+// The same with the table lookups already done on the device (rans_slots.cu): slots[i] = start << 16 | range,
+// escapes (position ascending, raw bypass value) for the symbols that took their table's escape slot.
+int reslic_rans_encoder_push_slots(void* h, const uint32_t* slots, int64_t n, const int32_t* esc_pos,
+                                   const int64_t* esc_raw, int64_t n_esc) {
+  auto* e = static_cast<Encoder*>(h);
+  if (!e || n < 0 || n_esc < 0 || (n > 0 && !slots) || (n_esc > 0 && (!esc_pos || !esc_raw)))
+    return reslic::set_error(RESLIC_ERR_ARG, "rans_encoder_push_slots: bad argument");
+  e->syms.reserve(e->syms.size() + static_cast<size_t>(n) + static_cast<size_t>(n_esc) * 4);
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t s = slots[i];
+    const uint32_t range = s & 0xffffu;
+    if (range == 0) return reslic::set_error(RESLIC_ERR_ARG, "rans_encoder_push_slots: empty slot (zero frequency)");
+    e->syms.push_back({static_cast<uint16_t>(s >> 16), static_cast<uint16_t>(range), false});
+    if (k < n_esc && esc_pos[k] == i) {
+      if (esc_raw[k] < 0) return reslic::set_error(RESLIC_ERR_ARG, "rans_encoder_push_slots: negative bypass value");
+      const uint64_t raw = static_cast<uint64_t>(esc_raw[k]);
+      ++k;
+      int32_t n_bypass = 0;
+      while ((raw >> (n_bypass * kBypassPrecision)) != 0) ++n_bypass;
+      int32_t val = n_bypass;
+      while (val >= kMaxBypassVal) {
+        e->syms.push_back({static_cast<uint16_t>(kMaxBypassVal), static_cast<uint16_t>(kMaxBypassVal + 1), true});
+        val -= kMaxBypassVal;
+      }
+      e->syms.push_back({static_cast<uint16_t>(val), static_cast<uint16_t>(val + 1), true});
+      for (int32_t j = 0; j < n_bypass; ++j) {
+        const int32_t v = static_cast<int32_t>((raw >> (j * kBypassPrecision)) & kMaxBypassVal);
+        e->syms.push_back({static_cast<uint16_t>(v), static_cast<uint16_t>(v + 1), true});
+      }
+    }
+  }
+  if (k != n_esc) return reslic::set_error(RESLIC_ERR_ARG, "rans_encoder_push_slots: escape positions not ascending or out of range");
+  return RESLIC_OK;
+}
+
 // Encodes everything pushed so far (in reverse, as rANS requires) and returns the byte count;
 // the bytes stay owned by the encoder until the next push/flush/destroy.
 int64_t reslic_rans_encoder_flush(void* h, const uint8_t** data) {

@@ -230,6 +230,12 @@ class EntropyModel(nn.Module):
         self._check_cdf_size()
         self._check_cdf_length()
         self._check_offsets_size()
+        if symbols.is_cuda and indexes.is_cuda and indexes.dtype == torch.int32 and self._quantized_cdf.size(0) <= 1024:
+            # table lookups on the device, one packed slot per symbol over PCIe; same strings as the host lookup
+            out = ops.rans_slots(symbols, indexes, self._quantized_cdf, self._cdf_length, self._offset)
+            strings = _rans().encode_slots_batch(*out)
+            if strings is not None:
+                return strings
         return _rans().encode_with_indexes_batch(symbols, indexes, self._quantized_cdf, self._cdf_length,
                                                  self._offset)
 

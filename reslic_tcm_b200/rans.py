@@ -74,6 +74,20 @@ class BufferedRansEncoder:
         if code != 0:
             raise ValueError(self._lib.reslic_last_error().decode())
 
+    def encode_slots(self, slots: Tensor, esc_pos: Optional[Tensor] = None, esc_raw: Optional[Tensor] = None) -> None:
+        """Symbols whose table lookups ran on the device (ops.rans_slots): host int32 ``slots`` and the escapes
+        that belong to them, positions ascending and relative to ``slots[0]``."""
+        s = slots.detach().reshape(-1).to(device="cpu", dtype=torch.int32).contiguous()
+        n_esc = 0 if esc_pos is None else esc_pos.numel()
+        ep = er = None
+        if n_esc:
+            ep = esc_pos.detach().reshape(-1).to(device="cpu", dtype=torch.int32).contiguous()
+            er = esc_raw.detach().reshape(-1).to(device="cpu", dtype=torch.int64).contiguous()
+        code = self._lib.reslic_rans_encoder_push_slots(self._h, s.data_ptr(), s.numel(), ep.data_ptr() if n_esc else None,
+                                                        er.data_ptr() if n_esc else None, n_esc)
+        if code != 0:
+            raise ValueError(self._lib.reslic_last_error().decode())
+
     def flush(self) -> bytes:
         data = C.c_void_p()
         n = self._lib.reslic_rans_encoder_flush(self._h, C.byref(data))
@@ -156,6 +170,37 @@ def encode_with_indexes_batch(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf
         return enc.flush()
 
     return _pool_map(one, s.shape[0], threads)
+
+
+def encode_slots_batch(slots: Tensor, esc_pos: Tensor, esc_raw: Tensor, status: Tensor,
+                       threads: Optional[int] = None) -> Optional[List[bytes]]:
+    """One rANS string per image from the output of ops.rans_slots over a [B, ...] batch: one D2H copy of the packed
+    slots (4 bytes per symbol instead of 8), the escape list sorted and cut per image on the host.  Returns None
+    when the escape list overflowed its capacity (the caller then codes from symbols and indexes); raises on
+    invalid tables or indexes."""
+    st = status.detach().cpu()
+    n_esc, err = int(st[0]), int(st[1])
+    if err:
+        raise ValueError("rans_slots: " + ("cdf index out of range" if err & 1 else "invalid cdf (zero or negative frequency)"))
+    if n_esc > esc_pos.numel():
+        return None
+    s = slots.detach().to(device="cpu")
+    B = s.shape[0]
+    per = s[0].numel() if B else 0
+    pos = esc_pos[:n_esc].detach().cpu()
+    raw = esc_raw[:n_esc].detach().cpu()
+    if n_esc:
+        pos, order = torch.sort(pos)
+        raw = raw[order]
+    cuts = torch.searchsorted(pos.to(torch.int64), torch.arange(B + 1, dtype=torch.int64) * per).tolist()
+
+    def one(b):
+        enc = BufferedRansEncoder()
+        lo, hi = cuts[b], cuts[b + 1]
+        enc.encode_slots(s[b], (pos[lo:hi] - b * per) if hi > lo else None, raw[lo:hi] if hi > lo else None)
+        return enc.flush()
+
+    return _pool_map(one, B, threads)
 
 
 def decode_with_indexes_batch(strings: Sequence[bytes], indexes: Tensor, cdf: Tensor, cdf_length: Tensor,

@@ -77,3 +77,44 @@ def test_tcm_style_sliced_stream():
             assert torch.equal(y_hat, gc.quantize(y[:, sl], "dequantize", mu[:, sl]))
     bits_model = float(gc.forward_fused(y, sg, mu, want=("bits",)).bits.sum())
     assert len(stream) * 8 < 1.05 * bits_model + 256
+
+
+def test_device_side_slots_match_the_host_lookup_and_give_identical_strings():
+    """reslic_rans_slots_u32 against its host restatement (bit-exact slots, same escape set), the strings of
+    GaussianConditional.compress against the host-lookup path, and the fallback when the escape list overflows."""
+    from reslic_tcm_b200 import ops, rans
+    from tests.util import rans_slots_reference
+
+    gc = GaussianConditional(None).to(DEV)
+    gc.update_scale_table(cr.get_scale_table())
+    gen = torch.Generator().manual_seed(21)
+    shape = (3, 16, 12, 10)
+    sigma = torch.exp(torch.empty(shape).uniform_(-3, 4, generator=gen))
+    mu = torch.randn(shape, generator=gen)
+    y = mu + sigma * torch.randn(shape, generator=gen)
+    y.view(-1)[::501] += 5000.0                       # escapes
+    y.view(-1)[7::733] -= 9000.0
+    yd, md, sd = y.to(DEV), mu.to(DEV), sigma.to(DEV)
+    idx = gc.build_indexes(sd)
+    sym = gc.quantize(yd, "symbols", md)
+    slots, esc_pos, esc_raw, status = ops.rans_slots(sym, idx, gc._quantized_cdf, gc._cdf_length, gc._offset)
+    ref_slots, ref_pos, ref_raw = rans_slots_reference(sym.cpu(), idx.cpu(), gc._quantized_cdf.cpu(), gc._cdf_length.cpu(),
+                                                       gc._offset.cpu())
+    assert torch.equal(slots.cpu(), ref_slots)
+    n_esc = int(status[0])
+    assert int(status[1]) == 0 and n_esc == ref_pos.numel() > 10
+    pos, order = torch.sort(esc_pos[:n_esc].cpu())
+    assert torch.equal(pos, ref_pos) and torch.equal(esc_raw[:n_esc].cpu()[order], ref_raw)
+    strings = gc.compress(yd, idx, md)                 # device-side lookup
+    host = rans.encode_with_indexes_batch(sym, idx, gc._quantized_cdf, gc._cdf_length, gc._offset)
+    assert strings == host
+    back = gc.decompress(strings, idx, means=md)
+    assert torch.equal(back, gc.quantize(yd, "dequantize", md))
+    # overflowing escape list -> None (compress falls back to the host lookup)
+    small = ops.rans_slots(sym, idx, gc._quantized_cdf, gc._cdf_length, gc._offset, esc_capacity=4)
+    assert rans.encode_slots_batch(*small) is None
+    # an index outside the tables is reported, not read
+    bad = idx.clone()
+    bad.view(-1)[3] = 64
+    with pytest.raises(ValueError, match="index out of range"):
+        rans.encode_slots_batch(*ops.rans_slots(sym, bad, gc._quantized_cdf, gc._cdf_length, gc._offset))

@@ -125,3 +125,29 @@ def test_batch_helpers_thread_over_images_and_long_runs_use_the_symbol_table():
     # short prefix of image 1 through the binary-search path
     short = rans.encode_with_indexes_batch(sym[1:2, :500], idx[1:2, :500], cdf, cdf_len, off)
     assert torch.equal(rans.decode_with_indexes_batch(short, idx[1:2, :500], cdf, cdf_len, off), sym[1:2, :500])
+
+
+def test_push_slots_gives_the_same_stream_as_push(tables):
+    """reslic_rans_encoder_push_slots (lookups done elsewhere — on the GPU by reslic_rans_slots_u32) must produce the
+    byte-identical stream, escapes included."""
+    from tests.util import rans_slots_reference
+
+    cdf, length, offset = tables
+    sym, idx, _ = _draw(tables, 30000, 5)
+    sym[::997] = 40000                    # far outside every table: bypass escapes, also on the narrowest CDFs
+    sym[5::1499] = -70000
+    want = rans.RansEncoder().encode_with_indexes(sym, idx, cdf, length, offset)
+    slots, esc_pos, esc_raw = rans_slots_reference(sym, idx, cdf, length, offset)
+    assert esc_pos.numel() > 40
+    enc = rans.BufferedRansEncoder()
+    enc.encode_slots(slots, esc_pos, esc_raw)
+    assert enc.flush() == want
+    # two pushes, escapes given relative to each push
+    half = 15000
+    cut = int(torch.searchsorted(esc_pos.long(), torch.tensor([half]))[0])
+    enc.encode_slots(slots[:half], esc_pos[:cut], esc_raw[:cut])
+    enc.encode_slots(slots[half:], esc_pos[cut:] - half, esc_raw[cut:])
+    assert enc.flush() == want
+    with pytest.raises(ValueError, match="ascending"):
+        enc.encode_slots(slots[:10], torch.tensor([20], dtype=torch.int32), torch.tensor([3]))
+    enc.flush()

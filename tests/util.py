@@ -54,3 +54,20 @@ def assert_equal_exact(actual: torch.Tensor, ref: torch.Tensor, what="tensor"):
     if n:
         i = int(torch.nonzero(~same.reshape(-1))[0])
         raise AssertionError(f"{what}: {n} mismatches; first at flat {i}: got {a.reshape(-1)[i].item()} ref {r.reshape(-1)[i].item()}")
+
+
+def rans_slots_reference(sym, idx, cdf, length, offset):
+    """Host restatement of reslic_rans_slots_u32 (the lookup at the head of compressai.ans.encode_with_indexes,
+    SURVEY.md App. A.6): (slots int32, escape positions ascending, escape raw values)."""
+    s, i = sym.reshape(-1).long(), idx.reshape(-1).long()
+    max_value = (length.reshape(-1).long() - 2)[i]
+    value = s - offset.reshape(-1).long()[i]
+    neg, big = value < 0, value >= max_value
+    raw = torch.where(neg, -2 * value - 1, 2 * (value - max_value))
+    value = torch.where(neg | big, max_value, value)
+    c = cdf.long()
+    start, nxt = c[i, value], c[i, value + 1]
+    slots = (start << 16) | (nxt - start)
+    slots = torch.where(slots >= 2 ** 31, slots - 2 ** 32, slots).to(torch.int32)
+    esc = torch.nonzero(neg | big).reshape(-1)
+    return slots.reshape(sym.shape), esc.to(torch.int32), raw[esc]
