@@ -485,6 +485,14 @@ def run_ours(args):
     if world == 1 and not args.no_training_kernels:
         training_kernels = training_kernels_leg(dev, peak)
 
+    # ---- e2e with the rANS table lookup on the device: one packed (start, range) slot per symbol comes back instead
+    # of int32 symbols + int32 indexes (what the host coder consumes either way) — reported beside `e2e`
+    e2e_slots = None
+    if not args.no_e2e and c.with_indexes:
+        gcm = sets[0]["path"].gaussian_conditional
+        gcm.update()                                   # CDF tables of the scale table in place (setup, untimed)
+        e2e_slots = run_e2e(args, c, sets[0], host, dev, world, B, elems_rank, kw, packed_slots=True)
+
     sampler.stop()
     clocks = sampler.summary()
 
@@ -509,7 +517,7 @@ def run_ours(args):
                        "mode": f"per-slice launches (1 EB + 5 GC per step) replayed as CUDA graphs, steps chained in graphs of {group} (one packed rate all-reduce per graph when N > 1)",
                        "l2": f"{len(sets)} rotating buffer sets of {(bpe * y_elems + 12 * z_elems) / 1e6:.0f} MB each (> 126 MB L2)",
                        "bpp_mean_image0_set": float(bits.mean()) / c.num_pixels_per_image},
-            "roofline": roof, "whole_y": whole, "training_kernels": training_kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "whole_y": whole, "training_kernels": training_kernels, "cpu_baseline": cpu, "e2e": e2e, "e2e_slots": e2e_slots,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         sys.stdout.flush()
@@ -588,7 +596,7 @@ def training_kernels_leg(dev, peak):
     return {"shape": {"y_slice": [B, C, h, w], "z": [B, Cz, hz, hz]}, "kernels": out}
 
 
-def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw):
+def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw, packed_slots=False):
     """Same step through the public API with HOST buffers (reslic_tcm_b200.pipeline.HostPipeline):
     every step copies y, mu, sigma, z from pinned host memory, runs the pass, and reads symbols and
     indexes (the rANS coder's input, tcm.py:551-552) plus the per-image bits back to pinned host
@@ -598,7 +606,8 @@ def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw):
     from reslic_tcm_b200.pipeline import HostPipeline
 
     hp = HostPipeline(s["path"], B, c.y_hw, c.z_hw, with_indexes=c.with_indexes, training=c.training,
-                      chunks=args.e2e_chunks, device=dev, num_pixels=c.num_pixels_per_image, seed=kw.get("seed", 0))
+                      chunks=args.e2e_chunks, device=dev, num_pixels=c.num_pixels_per_image, seed=kw.get("seed", 0),
+                      packed_slots=packed_slots)
     steps = max(3, min(args.steps, 60))
     for _ in range(3):
         out = hp.run(host)
@@ -629,7 +638,7 @@ def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw):
         ms = float(t.item())
     return {"value": elems_rank * world / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
             "d2h_bytes_per_step": hp.d2h_bytes, "ms_per_step": ms / steps, "steps": steps,
-            "what": f"pinned host y/mu/sigma/z -> H2D -> 1+5 launches -> D2H {'/'.join(hp.out_names)}, "
+            "what": f"pinned host y/mu/sigma/z -> H2D -> 1+5{'+1' if packed_slots else ''} launches -> D2H {'/'.join(hp.out_names)}, "
                     f"{len(hp.ranges)} image chunks pipelined on 3 streams, batches double-buffered"}
 
 

@@ -306,12 +306,13 @@ def build_indexes(scales: Tensor, scale_table: Tensor, scale_bound: float = 0.11
 
 
 def rans_slots(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_length: Tensor, offset: Tensor,
-               esc_capacity: Optional[int] = None):
+               esc_capacity: Optional[int] = None, out: Optional[Tuple[Tensor, Tensor, Tensor, Tensor]] = None):
     """Device-side front end of the rANS coder (reslic_rans_slots_u32): the per-symbol table lookup of
     ``compressai.ans.encode_with_indexes`` (tcm.py:522,564-565) for int32 ``symbols`` / ``indexes`` of any shape.
     Returns ``(slots, esc_pos, esc_raw, status)`` — uint32-in-int32 slots shaped like ``symbols``
     (``start << 16 | range``), the unordered escape list and the int32[2] status (escape count, error bits), all on
-    the device; :func:`reslic_tcm_b200.rans.encode_slots_batch` turns them into strings."""
+    the device; :func:`reslic_tcm_b200.rans.encode_slots_batch` turns them into strings.  ``out``: preallocated
+    ``(slots, esc_pos, esc_raw, status)`` to write into (static buffers of a pipeline)."""
     lib = _cabi.load()
     for name, t in (("symbols", symbols), ("indexes", indexes)):
         _require_cuda(name, t, torch.int32)
@@ -325,11 +326,19 @@ def rans_slots(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_length: Tensor
     if c.dim() != 2 or sizes.numel() != c.shape[0] or offs.numel() != c.shape[0]:
         raise ValueError("cdf must be [n_cdfs, stride] with one length and one offset per row")
     n = s.numel()
-    cap = int(esc_capacity) if esc_capacity is not None else n // 64 + 4096
-    slots = torch.empty(s.shape, dtype=torch.int32, device=dev)
-    esc_pos = torch.empty(cap, dtype=torch.int32, device=dev)
-    esc_raw = torch.empty(cap, dtype=torch.int64, device=dev)
-    status = torch.empty(2, dtype=torch.int32, device=dev)
+    if out is not None:
+        slots, esc_pos, esc_raw, status = out
+        if (slots.numel() != n or slots.dtype != torch.int32 or not slots.is_contiguous() or esc_pos.dtype != torch.int32
+                or esc_raw.dtype != torch.int64 or esc_raw.numel() != esc_pos.numel() or status.numel() != 2
+                or status.dtype != torch.int32 or any(t.device != dev for t in out)):
+            raise ValueError("rans_slots: out buffers have the wrong shape, dtype or device")
+        cap = esc_pos.numel()
+    else:
+        cap = int(esc_capacity) if esc_capacity is not None else n // 64 + 4096
+        slots = torch.empty(s.shape, dtype=torch.int32, device=dev)
+        esc_pos = torch.empty(cap, dtype=torch.int32, device=dev)
+        esc_raw = torch.empty(cap, dtype=torch.int64, device=dev)
+        status = torch.empty(2, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         code = lib.reslic_rans_slots_u32(s.data_ptr(), i.data_ptr(), n, c.data_ptr(), c.shape[0], c.shape[1],
                                          sizes.data_ptr(), offs.data_ptr(), slots.data_ptr(), esc_pos.data_ptr(),

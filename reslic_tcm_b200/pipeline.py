@@ -149,7 +149,8 @@ class HostPipeline:
     symbols, tcm.py:551-565) sees; when the latents are produced on the GPU use TcmEntropyPath."""
 
     def __init__(self, path: TcmEntropyPath, batch: int, y_hw, z_hw, *, with_indexes: bool, training: bool = False,
-                 chunks: int = 4, device=None, num_pixels: Optional[int] = None, depth: int = 2, seed: int = 0):
+                 chunks: int = 4, device=None, num_pixels: Optional[int] = None, depth: int = 2, seed: int = 0,
+                 packed_slots: bool = False):
         self.path, self.with_indexes, self.training, self.num_pixels = path, with_indexes, training, num_pixels
         self.seed = int(seed)          # Philox key of the noise modes (the counter is the element index inside a launch)
         dev = torch.device(device if device is not None else "cuda")
@@ -166,7 +167,18 @@ class HostPipeline:
         self.depth = max(1, int(depth))
         C, Cz = synthetic.M_LATENT, synthetic.Z_CHANNELS
         f32 = dict(dtype=torch.float32, device=dev)
+        # packed_slots: the rANS table lookup runs on the device (ops.rans_slots) and ONE packed (start, range) word per
+        # symbol goes back instead of int32 symbols + int32 indexes — what rans.encode_slots_batch consumes
+        self.packed_slots = bool(packed_slots)
+        if self.packed_slots:
+            gc = path.gaussian_conditional
+            if not with_indexes or gc._quantized_cdf.numel() == 0:
+                raise ValueError("packed_slots needs with_indexes and the CDF tables (update_scale_table) of the Gaussian conditional")
+            self._tables = tuple(t.detach().to(device=dev, dtype=torch.int32).contiguous()
+                                 for t in (gc._quantized_cdf, gc._cdf_length.reshape(-1), gc._offset.reshape(-1)))
         self.out_names = ["bits"] + (["symbols", "indexes"] if with_indexes else [])
+        if self.packed_slots:
+            self.out_names = ["bits", "slots", "esc_pos", "esc_raw", "slot_status"]
         self.slots = []
         for _ in range(self.depth):
             d_in = {k: torch.empty(B, C, *y_hw, **f32) for k in ("y", "mu", "sigma")}
@@ -181,11 +193,23 @@ class HostPipeline:
                 p._bufs, p._key = None, None
                 sub.append(p)
             h_out = {"bits": torch.empty(B, dtype=torch.float64).pin_memory()}
-            if with_indexes:
+            d_slot = None
+            if self.packed_slots:
+                i32 = dict(dtype=torch.int32, device=dev)
+                nchunk = len(self.ranges)
+                caps = [(b - a) * C * y_hw[0] * y_hw[1] // 1024 + 1024 for a, b in self.ranges]   # escape-list capacity per chunk
+                cap = max(caps)
+                d_slot = [(torch.empty(b - a, C, *y_hw, **i32), torch.empty(cap, **i32),
+                           torch.empty(cap, dtype=torch.int64, device=dev), torch.empty(2, **i32)) for a, b in self.ranges]
+                h_out["slots"] = torch.empty(B, C, *y_hw, dtype=torch.int32).pin_memory()
+                h_out["esc_pos"] = torch.empty(nchunk, cap, dtype=torch.int32).pin_memory()
+                h_out["esc_raw"] = torch.empty(nchunk, cap, dtype=torch.int64).pin_memory()
+                h_out["slot_status"] = torch.empty(nchunk, 2, dtype=torch.int32).pin_memory()
+            elif with_indexes:
                 for k in ("symbols", "indexes"):
                     h_out[k] = torch.empty(B, C, *y_hw, dtype=torch.int32).pin_memory()
             self.slots.append({
-                "d_in": d_in, "sub": sub, "h_out": h_out, "used": False,
+                "d_in": d_in, "sub": sub, "h_out": h_out, "used": False, "d_slot": d_slot,
                 "ev_in": [torch.cuda.Event() for _r in self.ranges],      # chunk uploaded
                 "ev_comp": [torch.cuda.Event() for _r in self.ranges],    # chunk computed (inputs free, outputs ready)
                 "ev_out": [torch.cuda.Event() for _r in self.ranges],     # chunk downloaded (device outputs free)
@@ -223,17 +247,41 @@ class HostPipeline:
                 res = slot["sub"][c].forward(d_in["y"][a:b], d_in["mu"][a:b], d_in["sigma"][a:b], d_in["z"][a:b],
                                              training=self.training, with_indexes=self.with_indexes,
                                              num_pixels=self.num_pixels, seed=self.seed)
+                if self.packed_slots:
+                    ops.rans_slots(res["symbols"], res["indexes"], *self._tables, out=slot["d_slot"][c])
                 slot["ev_comp"][c].record(self.s_comp)
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(slot["ev_comp"][c])
-                for k in self.out_names:
-                    h_out[k][a:b].copy_(res[k], non_blocking=True)
+                if self.packed_slots:
+                    d_sl, d_ep, d_er, d_st = slot["d_slot"][c]
+                    h_out["bits"][a:b].copy_(res["bits"], non_blocking=True)
+                    h_out["slots"][a:b].copy_(d_sl, non_blocking=True)
+                    h_out["esc_pos"][c].copy_(d_ep, non_blocking=True)
+                    h_out["esc_raw"][c].copy_(d_er, non_blocking=True)
+                    h_out["slot_status"][c].copy_(d_st, non_blocking=True)
+                else:
+                    for k in self.out_names:
+                        h_out[k][a:b].copy_(res[k], non_blocking=True)
                 slot["ev_out"][c].record(self.s_d2h)
         slot["done"].record(self.s_d2h)
         slot["used"] = True
         out = dict(h_out)
         out["done"] = slot["done"]
         return out
+
+    def strings(self, out: Dict[str, Tensor], threads: Optional[int] = None):
+        """rANS strings (one per image) of a ``packed_slots`` batch whose ``done`` event has been synchronised: the
+        host coder's state update over the downloaded slots.  None if a chunk's escape list overflowed."""
+        from . import rans
+
+        res = []
+        for c, (a, b) in enumerate(self.ranges):
+            part = rans.encode_slots_batch(out["slots"][a:b], out["esc_pos"][c], out["esc_raw"][c], out["slot_status"][c],
+                                           threads=threads)
+            if part is None:
+                return None
+            res += part
+        return res
 
     def synchronize(self) -> None:
         """Wait until every enqueued batch is on the host."""

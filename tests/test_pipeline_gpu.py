@@ -135,3 +135,27 @@ def test_host_pipeline_training_mode_uses_the_callers_philox_seed():
     out2 = hp2.run(host)
     out2["done"].synchronize()
     assert not torch.allclose(out2["bits"], ref, rtol=1e-6)
+
+
+def test_host_pipeline_packed_slots_give_the_strings_of_the_symbol_index_path():
+    """packed_slots: the rANS lookup runs on the device and one 32-bit slot per symbol is downloaded; the strings coded
+    from them must be byte-identical to those coded from the downloaded symbols and indexes."""
+    from reslic_tcm_b200 import rans
+
+    B, y_hw, z_hw = 5, (16, 8), (4, 2)
+    _, path, _ = _setup(2, B, y_hw, z_hw)
+    gc = path.gaussian_conditional
+    gc.update()
+    host = synthetic.make_batch(2, range(B), y_hw=y_hw, z_hw=z_hw, pin=True)
+    host["y"].view(-1)[::4099] += 30000.0                                  # a few escapes, spread over the chunks
+    plain = HostPipeline(path, B, y_hw, z_hw, with_indexes=True, chunks=2, device=DEV)
+    packed = HostPipeline(path, B, y_hw, z_hw, with_indexes=True, chunks=2, device=DEV, packed_slots=True)
+    assert packed.d2h_bytes < 0.6 * plain.d2h_bytes
+    a = plain.run(host)
+    b = packed.run(host)
+    a["done"].synchronize()
+    b["done"].synchronize()
+    want = rans.encode_with_indexes_batch(a["symbols"], a["indexes"], gc._quantized_cdf, gc._cdf_length, gc._offset)
+    got = packed.strings(b)
+    assert int(b["slot_status"][:, 0].sum()) > 0 and got == want
+    assert torch.equal(a["bits"], b["bits"])
