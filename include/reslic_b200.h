@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 13
+#define RESLIC_ABI_VERSION 14
 
 enum {
   RESLIC_OK = 0,
@@ -82,6 +82,13 @@ int64_t reslic_workspace_bytes(int64_t B);
  * launches that accumulated.  Stream-ordered after them. */
 int reslic_rate_finalize_f64(void* workspace, int64_t workspace_bytes, int64_t B, double* bits,
                              int32_t accumulate, void* stream);
+
+/* Per-image rate of a likelihood tensor that already exists: bits[b] (mode as above) -sum log2 lik[b, 0..n),
+ * image b at lik + b * lik_bs.  Replaces `torch.log(likelihoods).sum() / -math.log(2)` of the reference's
+ * RateDistortionLoss (src/training/loss.py:22-25; src/eval.py:27-31) — one read pass instead of a log tensor
+ * and a reduction over it; same deterministic commit and workspace as the *_fwd kernels. */
+int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B, int64_t n, double* bits,
+                                    int32_t bits_accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------------
  * Gaussian conditional, fused forward.

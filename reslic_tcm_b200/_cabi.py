@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
 EB_LUT_STRIDE = 130
@@ -204,6 +204,8 @@ EXPORTS = {
     "reslic_rans_encoder_destroy": (None, [C.c_void_p]),
     "reslic_rans_encoder_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                            C.c_int32, C.c_void_p, C.c_void_p]),
+    "reslic_rate_from_likelihood_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
+                                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "reslic_rans_slots_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "reslic_rans_encoder_push_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),

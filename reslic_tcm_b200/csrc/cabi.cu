@@ -225,6 +225,12 @@ int reslic_rans_slots_u32(const int32_t* symbols, const int32_t* indexes, int64_
                                    esc_raw, esc_capacity, status, static_cast<cudaStream_t>(stream));
 }
 
+int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B, int64_t n, double* bits,
+                                    int32_t bits_accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+  return reslic::rate_from_lik_launch(lik, lik_bs, B, n, bits, bits_accumulate, workspace, workspace_bytes,
+                                      static_cast<cudaStream_t>(stream));
+}
+
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream) {
   return reslic::eb_fwd_launch(d, static_cast<cudaStream_t>(stream));
 }

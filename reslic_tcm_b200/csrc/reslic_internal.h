@@ -36,6 +36,8 @@ int lrp_tail_launch(float* y_hat, int64_t y_bs, const float* lrp, int64_t l_bs, 
 int rans_slots_launch(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs, int32_t n_cdfs,
                       int32_t cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, uint32_t* slots,
                       int32_t* esc_pos, int64_t* esc_raw, int64_t esc_capacity, int32_t* status, cudaStream_t st);
+int rate_from_lik_launch(const float* lik, int64_t lik_bs, int64_t B, int64_t n, double* bits, int32_t bits_accumulate,
+                         void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int dequantize_launch(const int32_t* sym, const float* mu, int64_t n, float* out, cudaStream_t st);
 
 }  // namespace reslic

@@ -118,6 +118,30 @@ def rate_finalize(workspace: Tensor, B: int, bits: Optional[Tensor] = None, accu
     return bits
 
 
+def rate_from_likelihood(likelihoods: Tensor, out: Optional[dict] = None) -> Optional[Tensor]:
+    """bits[b] = -sum log2 likelihoods[b] (float64 [B]) of an existing likelihood tensor [B, ...] in one read pass
+    (reslic_rate_from_likelihood_f32; the reference: torch.log(L).sum() / -ln 2, training/loss.py:22-25).
+    ``out``: the rate keys of :func:`gc_forward` (bits, bits_accumulate, bits_deferred, bits_collect, workspace)."""
+    lib = _cabi.load()
+    _require_cuda("likelihoods", likelihoods)
+    t, bs, n = image_major(likelihoods)
+    B = likelihoods.shape[0] if likelihoods.dim() > 0 else 1
+
+    class _D:      # the rate fields _rate_outputs fills
+        bits = None
+        bits_accumulate = 0
+        workspace = None
+        workspace_bytes = 0
+
+    d, keep = _D(), [t]
+    bits = _rate_outputs(d, dict(out or {}), B, likelihoods.device, keep)
+    with torch.cuda.device(likelihoods.device):
+        code = lib.reslic_rate_from_likelihood_f32(t.data_ptr(), bs, B, n, d.bits, d.bits_accumulate, d.workspace,
+                                                   d.workspace_bytes, _cabi.current_stream_ptr(likelihoods.device))
+    _cabi.check(code, "reslic_rate_from_likelihood_f32")
+    return bits
+
+
 def gc_forward(
     y: Tensor,
     scales: Optional[Tensor] = None,
