@@ -29,6 +29,7 @@ __device__ __forceinline__ uint32_t slot_of(const SlotParams& p, const int32_t* 
   if (ci < 0 || ci >= p.n_cdfs) { err |= 1; return 0u; }
   const int32_t* __restrict__ cdf = p.cdfs + static_cast<int64_t>(ci) * p.stride;
   const int32_t max_value = s_sizes[ci] - 2;
+  if (max_value < 1 || max_value + 2 > p.stride) { err |= 2; return 0u; }      // cdf length outside 3..stride: never read
   long long value = static_cast<long long>(sy) - s_offsets[ci];
   long long raw = -1;
   if (value < 0) { raw = -2 * value - 1; value = max_value; }
