@@ -132,12 +132,17 @@ def run_reference(args):
                                 num_pixels=n_img * c.num_pixels_per_image,
                                 noise_y=batch.get("noise_y"), noise_z=batch.get("noise_z"))
 
-    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    for _ in range(warm):
+    # K steps as asked, W warm-up steps, but bounded in time (a slow host must not turn the arm into a long job):
+    # at most ~20 s of warm-up and ~120 s of timed steps; `steps` / `warmup` in the line are what actually ran
+    want_steps, want_warm = max(1, args.steps), max(1, args.warmup)
+    warm, t0 = 0, time.perf_counter()
+    while warm < want_warm and (warm == 0 or time.perf_counter() - t0 < 20.0):
         step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+        warm += 1
+    steps, t0 = 0, time.perf_counter()
+    while steps < want_steps and (steps == 0 or time.perf_counter() - t0 < 120.0):
         step()
+        steps += 1
     dt = time.perf_counter() - t0
     val = elems * steps / dt / 1e6
     sample = f"{n_img} of {c.batch} images of config {c.cfg} per step ({elems} latent elements), {steps} steps"
