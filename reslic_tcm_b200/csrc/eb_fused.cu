@@ -9,10 +9,12 @@
 // (training/loss.py:24-27) — ~75 launches and 3 HBM round trips in the reference.
 //
 // z stays in its native [B, C, h, w] layout: channel c of image b is a contiguous run of
-// hw floats, so the "permute" is just index arithmetic.  Each CTA walks 256-element tiles
-// of one image; the (softplus / tanh transformed) parameters of the few channels a tile
-// touches are staged in shared memory once per tile.  The kernel is FP32/MUFU-issue bound
-// (24 tanh + 2 sigmoid per element), not HBM bound; z is 3.75 % of y's elements.
+// hw floats, so the "permute" is just index arithmetic.  Eval mode is a per-channel table of the
+// 65 likelihoods about the median (eb_lut8_kernel / eb_lut_kernel); noise mode evaluates the MLP per
+// element — eb_fwd_fast_kernel: one CTA per (channel group, batch split), parameters staged once per
+// CTA, both cumulative logits as packed f32x2 lanes; eb_fwd_kernel (per-tile staging, library tanhf)
+// is the RESLIC_MATH_MIRROR form.  Noise mode is FP32/MUFU-issue bound (24 tanh + 2 sigmoid per
+// element), not HBM bound; z is 3.75 % of y's elements.  DESIGN.md section 3.2.
 #include "common.cuh"
 #include "eb_math.cuh"
 #include "reslic_internal.h"

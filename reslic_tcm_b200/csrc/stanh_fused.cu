@@ -7,14 +7,20 @@
 // The reference evaluates the quantizer as a dense [1, K, N] broadcast (K = 2*extrema = 160
 // thresholds per element: O(K*N) flops AND memory) and finds the likelihood bin with two
 // [N, K+1] one-hot matrices.  Here every element does
-//   * hard form (beta = -1): one binary search over the sorted thresholds in shared memory
+//   * hard form (beta = -1): one count "how many sorted thresholds lie below x"
 //     (value = level[#{k : x > b_k}]);
 //   * soft form (finite beta): tanh(beta*(x-b_k)) is exactly +-1 in fp32 once |beta*(x-b_k)| > 9.1
 //     (SURVEY.md §7.4 H1), so only the thresholds inside that window are evaluated and the
 //     saturated rest comes from the prefix sums the module already keeps (cum_w);
-//   * likelihood bin: one more binary search over the level mid-points (average_points), then the
+//   * likelihood bin: one more count over the level mid-points (average_points), then the
 //     same exact-division + erfc arithmetic as the plain Gaussian-conditional kernel.
-// O(log K + window) per element, 12 B read + 8 B written, no intermediate tensors.
+// 12 B read + 8 B written per element, no intermediate tensors.
+//
+// Two generations of kernels live here.  The 128-bit ones (stanh_gc_vec_kernel, stanh_act_kernel,
+// stanh_gc_bwd_kernel) answer the counts through the cell grids of stanh_tables.cuh (one LDS.U16 + two
+// compares) and are what aligned tensors take; the scalar ones (stanh_gc_fwd_kernel, eb_stanh_fwd_kernel:
+// binary searches, one element per thread) serve unaligned tensors, n % 4 != 0, a beta <= 0 other than
+// -1, and the factorized STanH bottleneck.  DESIGN.md section 3.3 has the measurements.
 #include "common.cuh"
 #include "eb_math.cuh"
 #include "gc_math.cuh"

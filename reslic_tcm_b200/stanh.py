@@ -396,9 +396,16 @@ class HypeEntropyModelSoS(EntropyModel):
         res = {}
         for name, dtype in (("yhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32)):
             if name in want:
-                t = torch.empty(inputs.shape, dtype=dtype, device=inputs.device)
+                t = (out or {}).get(name)          # caller's buffer (static buffers of a captured graph), else a fresh one
+                if t is None:
+                    t = torch.empty(inputs.shape, dtype=dtype, device=inputs.device)
+                elif t.shape != inputs.shape or t.dtype != dtype or t.device != inputs.device:
+                    raise ValueError(f"out['{name}'] must be a {dtype} tensor shaped like the inputs on their device")
+                tv, bs, _ = ops.image_major(t)
+                if tv.data_ptr() != t.data_ptr():
+                    raise ValueError(f"out['{name}'] must be image-major (contiguous per image)")
                 setattr(d, name, t.data_ptr())
-                setattr(d, name + "_bs", t.stride(0) if (B > 1) else n)
+                setattr(d, name + "_bs", bs)
                 res[name] = t
         if "bits" in want:      # out: the rate keys of ops.gc_forward (bits, bits_accumulate, bits_deferred, bits_collect, workspace)
             res["bits"] = ops._rate_outputs(d, dict(out or {}), B, inputs.device, keep)

@@ -68,3 +68,59 @@ def test_eb_outputs_stay_inside_their_buffers(shape, training):
     torch.cuda.synchronize()
     for name, (buf, view, pad, n) in bufs.items():
         assert _intact(buf, pad, n), f"{name}: guard band overwritten"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16), (3, 5, 7, 3), (1, 1, 1, 1), (2, 3, 4, 4), (5, 8, 1, 4)])
+@pytest.mark.parametrize("beta,training", [(10.0, True), (-1, True), (10.0, False)])
+def test_stanh_outputs_stay_inside_their_buffers(shape, beta, training):
+    """The 128-bit STanH forward (aligned shapes) and the scalar one (odd shapes): outputs in guarded buffers."""
+    from reslic_tcm_b200.stanh import GaussianConditionalStanh
+
+    cfg = dict(beta=beta, num_sigmoids=0, extrema=20, trainable=False, removing_mean=True, symmetry=False)
+    m = GaussianConditionalStanh(None, channels=shape[1], gaussian_configuration=cfg).to(DEV)
+    m.stanh.update_state(torch.device(DEV))
+    g = torch.Generator().manual_seed(sum(shape) + 2)
+    y = (8.0 * torch.randn(shape, generator=g)).to(DEV)
+    mu = torch.randn(shape, generator=g).to(DEV)
+    sg = (torch.rand(shape, generator=g) * 3 + 0.05).to(DEV)
+    outs, bufs = {}, {}
+    for name, dt in (("yhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32)):
+        bufs[name] = _guarded(shape, dt)
+        outs[name] = bufs[name][1]
+    bbuf, bits, bpad, bn = _guarded((shape[0],), torch.float64)
+    outs["bits"] = bits
+    m.forward_fused(y, sg, training=training, means=mu, want=("yhat", "lik", "sym", "bits"), out=outs)
+    torch.cuda.synchronize()
+    for name, (buf, view, pad, n) in bufs.items():
+        assert _intact(buf, pad, n), f"{name}: guard band overwritten"
+        assert bool((view != (CANARY if view.dtype.is_floating_point else -77)).any()), f"{name}: nothing written"
+    assert _intact(bbuf, bpad, bn) and torch.isfinite(bits).all()
+    # same values as the kernel's own allocation path
+    r = m.forward_fused(y, sg, training=training, means=mu, want=("yhat", "lik", "sym"))
+    assert torch.equal(r["yhat"], outs["yhat"]) and torch.equal(r["sym"], outs["sym"])
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096, 4099])
+def test_rans_slots_and_rate_outputs_stay_inside_their_buffers(n):
+    from oracle import compressai_ref as cr
+
+    cdf, offset, length = cr.gc_update(cr.get_scale_table())
+    g = torch.Generator().manual_seed(n)
+    sym = torch.randint(-40, 40, (n,), generator=g, dtype=torch.int32).to(DEV)
+    idx = torch.randint(0, 64, (n,), generator=g, dtype=torch.int32).to(DEV)
+    sbuf, slots, spad, sn = _guarded((n,), torch.int32)
+    cap = 16
+    pbuf, epos, ppad, pn = _guarded((cap,), torch.int32)
+    rbuf, eraw, rpad, rn = _guarded((cap,), torch.int64)
+    tbuf, status, tpad, tn = _guarded((2,), torch.int32)
+    ops.rans_slots(sym, idx, cdf.to(DEV), length.to(DEV), offset.to(DEV), out=(slots, epos, eraw, status))
+    torch.cuda.synchronize()
+    for buf, pad, nn_ in ((sbuf, spad, sn), (pbuf, ppad, pn), (rbuf, rpad, rn), (tbuf, tpad, tn)):
+        assert _intact(buf, pad, nn_)
+    assert int(status[1]) == 0
+    lik = (torch.rand(3, n, generator=g) * 0.9 + 1e-6).to(DEV)
+    bbuf, bits, bpad, bn = _guarded((3,), torch.float64)
+    ops.rate_from_likelihood(lik, out={"bits": bits})
+    torch.cuda.synchronize()
+    assert _intact(bbuf, bpad, bn)
+    assert torch.allclose(bits, -(torch.log2(lik.double()).sum(1)), rtol=2e-6)
