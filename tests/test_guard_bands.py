@@ -123,4 +123,4 @@ def test_rans_slots_and_rate_outputs_stay_inside_their_buffers(n):
     ops.rate_from_likelihood(lik, out={"bits": bits})
     torch.cuda.synchronize()
     assert _intact(bbuf, bpad, bn)
-    assert torch.allclose(bits, -(torch.log2(lik.double()).sum(1)), rtol=2e-6)
+    assert torch.allclose(bits, -(torch.log2(lik.double()).sum(1)), rtol=2e-6, atol=2e-5)    # 48.16 fixed point: 2^-16 bit
