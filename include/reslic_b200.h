@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 14
+#define RESLIC_ABI_VERSION 15
 
 enum {
   RESLIC_OK = 0,
@@ -128,6 +128,11 @@ typedef struct reslic_gc_desc {
                                            /* RESLIC_RATE_DEFERRED: see above             */
   void* workspace; int64_t workspace_bytes;/* required iff a rate output is requested     */
   uint64_t philox_seed, philox_offset;
+  /* Optional hint: the y (same B, n) that the NEXT launch on this stream will read — TCM's next channel slice of
+   * the same latent (tcm.py:438-457).  CTAs that finish early prefetch it into L2 (cp.async.bulk.prefetch.L2), which
+   * moves a third of the next launch's reads into this launch's under-used tail.  Never dereferenced by the math;
+   * NULL or a misaligned pointer = no prefetch. */
+  const float* next_y;  int64_t next_y_bs;
 } reslic_gc_desc;
 
 int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream);
@@ -205,6 +210,10 @@ typedef struct reslic_eb_desc {
   uint64_t philox_seed, philox_offset;
   const float* lut;                        /* optional, DEQUANTIZE mode: [C, RESLIC_EB_LUT_STRIDE] table  */
                                            /* from reslic_eb_build_lut_f32 for THESE parameters and bound */
+  /* Optional hint as reslic_gc_desc.next_y: next_y_n floats per image (image b at next_y + b * next_y_bs) that the
+   * NEXT launch will read — the first channel slice of y, which exists before z does (tcm.py:427-443).  Prefetched
+   * into L2 by the table-mode launch, whose own traffic leaves HBM idle. */
+  const float* next_y;  int64_t next_y_bs, next_y_n;
 } reslic_eb_desc;
 
 int reslic_eb_fwd_f32(const reslic_eb_desc* d, void* stream);

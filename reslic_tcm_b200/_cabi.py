@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
 EB_LUT_STRIDE = 130
@@ -46,6 +46,7 @@ class GcDesc(C.Structure):
         ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("next_y", C.c_void_p), ("next_y_bs", C.c_int64),
     ]
 
 
@@ -87,6 +88,7 @@ class EbDesc(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
         ("lut", C.c_void_p),
+        ("next_y", C.c_void_p), ("next_y_bs", C.c_int64), ("next_y_n", C.c_int64),
     ]
 
 

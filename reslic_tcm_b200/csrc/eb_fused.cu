@@ -31,6 +31,7 @@ struct EbParams {
   int hw, C, tile, bpi, noise_mode, splits;
   float lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  const float* next_y; int64_t next_y_bs, next_y_n;   // optional L2 prefetch hint (table mode)
   const float* lut;     // optional prebuilt [C, 2*kLutN] table (eval mode)
   float* lut_out;       // eb_build_lut_kernel's destination
 };
@@ -185,6 +186,18 @@ __global__ void __launch_bounds__(kThreads) eb_lut8_kernel(const EbParams p) {
   const int image = blockIdx.x / octets;
   const int c = (blockIdx.x - image * octets) * kEbWarps + warp;
   const bool need_lik = p.lik || p.bits;
+  if (p.next_y != nullptr && threadIdx.x == 0) {
+    // this CTA's share of the image's next_y bytes, one bulk L2 prefetch (this launch moves 12 bytes per z element:
+    // HBM is idle, and the slice launch that follows is short enough to feel a third of its reads arriving early)
+    const unsigned int total = static_cast<unsigned int>(p.next_y_n) * 4u;
+    const unsigned int share = ((total + octets - 1) / octets + 15u) & ~15u;
+    const unsigned int off = static_cast<unsigned int>(blockIdx.x - image * octets) * share;
+    if (off < total) {
+      const unsigned int bytes = min(share, total - off);
+      const char* addr = reinterpret_cast<const char*>(p.next_y + static_cast<int64_t>(image) * p.next_y_bs) + off;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+    }
+  }
   float acc = 0.0f;
   if (c < p.C) {
     const int64_t base_c = static_cast<int64_t>(c) * p.hw;
@@ -472,6 +485,13 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   p.ne = d->C * d->hw; p.hw = static_cast<int>(d->hw); p.C = static_cast<int>(d->C);
   p.noise_mode = d->mode == RESLIC_Q_NOISE; p.lik_bound = d->likelihood_bound;
   p.lut = p.noise_mode ? nullptr : d->lut;
+  // prefetch hint: 16-byte aligned images of a multiple of 4 floats, < 4 GB each; anything else is dropped
+  // (and only up to 12 MB: beyond that the launch that follows is long enough to have no idle HBM time to fill,
+  // see gc_fused.cu)
+  if (d->next_y && d->next_y_n > 0 && d->next_y_n < (1LL << 30) && (d->next_y_n % 4) == 0 && (d->next_y_bs % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(d->next_y) & 15u) == 0 && d->next_y_n * d->B * 4 <= (12LL << 20)) {
+    p.next_y = d->next_y; p.next_y_bs = d->next_y_bs; p.next_y_n = d->next_y_n;
+  }
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
   // a tile may touch at most kEbMaxCh channels: tile <= (kEbMaxCh - 1) * hw

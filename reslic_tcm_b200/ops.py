@@ -156,6 +156,7 @@ def gc_forward(
     out: Optional[dict] = None,
     seed: int = 0,
     offset: int = 0,
+    next_y: Optional[Tensor] = None,
 ) -> GcOutputs:
     """One fused pass over a Gaussian-conditional slice.
 
@@ -244,6 +245,13 @@ def gc_forward(
         res.bits = _rate_outputs(d, out, B, y.device, keep)
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    if next_y is not None and next_y.is_cuda and next_y.dtype == torch.float32 and next_y.shape == y.shape:
+        # hint only (L2 prefetch of the next launch's y, e.g. TCM's next channel slice): a view that is not
+        # image-major is simply not prefetched
+        tv, bs_n, _ = image_major(next_y)
+        if tv.data_ptr() == next_y.data_ptr():
+            d.next_y, d.next_y_bs = next_y.data_ptr(), bs_n
+            keep.append(next_y)
     with torch.cuda.device(y.device):
         code = lib.reslic_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(y.device))
     _cabi.check(code, "reslic_gc_fwd_f32")
@@ -447,6 +455,7 @@ def eb_forward(
     seed: int = 0,
     offset: int = 0,
     lut: Optional[Tensor] = None,
+    next_y: Optional[Tensor] = None,
 ) -> EbOutputs:
     """One fused pass of the factorized bottleneck over z [B, C, *spatial] (tcm.py:429-433).
     ``lut``: the table from :func:`eb_build_lut` for these very parameters (eval mode only; ignored
@@ -505,6 +514,11 @@ def eb_forward(
         res.bits = _rate_outputs(d, out, B, z.device, keep)
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    if next_y is not None and next_y.is_cuda and next_y.dtype == torch.float32 and next_y.dim() > 0 and next_y.shape[0] == B:
+        tv, bs_n, n_n = image_major(next_y)        # hint only: the first y slice the following launch reads
+        if tv.data_ptr() == next_y.data_ptr():
+            d.next_y, d.next_y_bs, d.next_y_n = next_y.data_ptr(), bs_n, n_n
+            keep.append(next_y)
     with torch.cuda.device(z.device):
         code = lib.reslic_eb_fwd_f32(C.byref(d), _cabi.current_stream_ptr(z.device))
     _cabi.check(code, "reslic_eb_fwd_f32")

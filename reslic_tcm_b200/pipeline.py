@@ -19,6 +19,7 @@ capturable (``capture()``), which removes the Python/launch overhead from steady
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -30,6 +31,10 @@ from .entropy_models import EntropyBottleneck, GaussianConditional
 
 
 class TcmEntropyPath(nn.Module):
+    # each slice launch prefetches the NEXT slice's y into L2 from the CTAs that finish early (reslic_gc_desc.next_y);
+    # RESLIC_PREFETCH_NEXT=0 switches the hint off (A/B measurements)
+    prefetch_next_slice = os.environ.get("RESLIC_PREFETCH_NEXT", "1") != "0"
+
     def __init__(self, z_channels: int = synthetic.Z_CHANNELS, num_slices: int = synthetic.NUM_SLICES):
         super().__init__()
         self.num_slices = int(num_slices)
@@ -93,7 +98,9 @@ class TcmEntropyPath(nn.Module):
                            likelihood_bound=eb._likelihood_bound if eb.use_likelihood_bound else 0.0,
                            want=("ste", "lik", "bits"),
                            out={"ste": b["z_hat"], "lik": b["z_lik"], "bits_deferred": True, "workspace": b["workspace"]},
-                           seed=seed, offset=offset, lut=None if training else eb._eval_lut())
+                           seed=seed, offset=offset, lut=None if training else eb._eval_lut(),
+                           next_y=y[:, :y.shape[1] // (1 if fuse_slices else self.num_slices)]
+                           if (self.prefetch_next_slice and not fuse_slices) else None)
         want = ["ste", "lik", "bits"] + (["sym", "idx"] if with_indexes else []) + (["yhat"] if training else [])
         for k in range(n_launch):
             sl = slice(cs * k, cs * (k + 1))
@@ -110,7 +117,8 @@ class TcmEntropyPath(nn.Module):
                            noise=None if noise_y is None else noise_y[:, sl],
                            scale_table=gc.scale_table if with_indexes else None, scale_bound=gc._scale_bound,
                            likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
-                           offset=offset + 1 + k)
+                           offset=offset + 1 + k,
+                           next_y=y[:, cs * (k + 1):cs * (k + 2)] if (k + 1 < n_launch and self.prefetch_next_slice) else None)
         res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
                "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
         if with_indexes:

@@ -21,7 +21,7 @@ __global__ void fill(float* y, float* mu, float* sg, size_t n, unsigned seed) {
 int main(int argc, char** argv) {
   int B = argc > 1 ? atoi(argv[1]) : 24; long n = argc > 2 ? atol(argv[2]) : 64 * 48 * 32;
   int with_idx = argc > 3 ? atoi(argv[3]) : 1; int noise = argc > 4 ? atoi(argv[4]) : 0;
-  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50; int deferred = argc > 6 ? atoi(argv[6]) : 0; int smul = argc > 7 ? atoi(argv[7]) : 1;  // smul: batch stride = smul * n (a channel slice of a wider tensor)
+  int nset = 3, reps = argc > 5 ? atoi(argv[5]) : 50; int deferred = argc > 6 ? atoi(argv[6]) : 0; int smul = argc > 7 ? atoi(argv[7]) : 1; int prefetch = argc > 8 ? atoi(argv[8]) : 0;  // smul: batch stride = smul * n (a channel slice of a wider tensor)
   size_t N = (size_t)B * n; size_t NA = N * smul; long bs = n * smul;
   std::vector<float*> y(nset), mu(nset), sg(nset), yh(nset), lk(nset), nz(nset); std::vector<int*> sym(nset), idx(nset);
   float tabh[64]; for (int i = 0; i < 64; ++i) tabh[i] = expf(logf(0.11f) + i * (logf(256.f) - logf(0.11f)) / 63.f);
@@ -45,6 +45,10 @@ int main(int argc, char** argv) {
     d.ste = yh[s] + so; d.ste_bs = bs; d.lik = lk[s] + so; d.lik_bs = bs;
     if (noise) { d.yhat = nz[s] + so; d.yhat_bs = bs; }
     if (with_idx) { d.scale_table = tab; d.table_len = 64; d.sym = sym[s] + so; d.sym_bs = bs; d.idx = idx[s] + so; d.idx_bs = bs; }
+    if (prefetch) {   // the y the next launch of this sequence reads
+      const long so_next = (long)(smul > 1 ? (slice_ctr % smul) : 0) * n;
+      d.next_y = y[(s + 1) % nset] + so_next; d.next_y_bs = bs;
+    }
     d.bits = deferred ? nullptr : bits; d.bits_accumulate = deferred ? RESLIC_RATE_DEFERRED : 0; d.workspace = ws; d.workspace_bytes = wsb; d.philox_seed = 1;
     int rc = reslic_gc_fwd_f32(&d, st);
     if (rc) { printf("launch failed %d %s\n", rc, reslic_last_error()); exit(1); }

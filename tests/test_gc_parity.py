@@ -366,3 +366,24 @@ def test_full_size_properties(gc, cfg):
     assert_equal_exact(r.ste[:1], yhat_ref)
     assert_lik_close(r.lik[:1], lik_ref)
     assert torch.allclose(r.bits[:1].cpu(), cr.per_image_bits(lik_ref), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_next_slice_prefetch_hint_changes_no_result():
+    """reslic_gc_desc.next_y / reslic_eb_desc.next_y are L2 prefetch hints: any value (the next channel slice, a
+    misaligned view, a tensor of another shape) leaves every output bit-identical."""
+    import torch
+    from reslic_tcm_b200 import ops, synthetic
+
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(12)
+    y = torch.randn(6, 128, 16, 8, generator=g).to(dev) * 3
+    mu = torch.randn(6, 128, 16, 8, generator=g).to(dev)
+    sg = (torch.rand(6, 128, 16, 8, generator=g) * 4 + 0.05).to(dev)
+    tab = synthetic.scale_table(dev)
+    want = ("ste", "lik", "sym", "idx", "bits")
+    base = ops.gc_forward(y[:, :64], sg[:, :64], mu[:, :64], want=want, scale_table=tab)
+    for hint in (y[:, 64:], y[:, 64:].reshape(-1)[1:], y[:, :3], None):
+        r = ops.gc_forward(y[:, :64], sg[:, :64], mu[:, :64], want=want, scale_table=tab, next_y=hint)
+        for name in ("ste", "lik", "sym", "idx", "bits"):
+            assert torch.equal(getattr(r, name), getattr(base, name)), name
