@@ -396,7 +396,7 @@ static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
   // the next-launch L2 prefetch pays on short launches only (measured: 24 x 98304, 3.1 tiles per CTA, 14.1 -> 13.2 us;
   // 256 x 16384 at 5.5 tiles per CTA 21.9 -> 22.0; 64 x 98304 24.2 -> 24.5; whole y 58.2 -> 60.4: a long launch
   // has no idle HBM time to fill and the prefetch only competes with its own streams)
-  if (total > 4 * grid) p.next_y = nullptr;
+  if (total > 4 * grid) p.next_y = nullptr;     // (issuing it before the CTA's last tile pair instead of after its range: 14.0 vs 13.7 us)
   p.tpi = static_cast<unsigned int>(p.tiles_per_image);
   p.total_tiles = static_cast<unsigned int>(total);
   p.q_tiles = static_cast<unsigned int>(total / grid);
