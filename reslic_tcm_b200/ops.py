@@ -7,6 +7,7 @@ fallback implementation.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -116,6 +117,38 @@ def rate_finalize(workspace: Tensor, B: int, bits: Optional[Tensor] = None, accu
                                             1 if accumulate else 0, _cabi.current_stream_ptr(workspace.device))
     _cabi.check(code, "reslic_rate_finalize_f64")
     return bits
+
+
+_PREFETCH_NEXT = os.environ.get("RESLIC_PREFETCH_NEXT", "1") != "0"
+
+
+def next_channel_slice(y: Tensor) -> Optional[Tensor]:
+    """If ``y`` is a channel-slice view [B, C, ...] of a wider contiguous tensor that still has room for another C
+    channels behind it (``y.chunk(5, 1)[k]`` with k < 4, tcm.py:438-443), the view of those next C channels — the
+    L2 prefetch hint of :func:`gc_forward`; else None.  Only ever describes memory inside ``y``'s own storage."""
+    if y.dim() < 2 or not y.is_cuda or y.dtype != torch.float32:
+        return None
+    B, C = y.shape[0], y.shape[1]
+    inner = 1
+    for s_ in y.shape[2:]:
+        inner *= s_
+    if inner == 0 or C == 0 or y.stride(1) != inner:
+        return None
+    expect = 1
+    for size, stride in zip(reversed(y.shape[2:]), reversed(y.stride()[2:])):
+        if size != 1 and stride != expect:
+            return None
+        expect *= size
+    row = y.stride(0)                      # elements per image of the wider tensor (kept by chunk / slicing even for B = 1)
+    if row < 2 * C * inner or row % inner:
+        return None
+    off = y.storage_offset() % row         # position inside the image, assuming the wider tensor starts on a row boundary
+    if off % inner or off + 2 * C * inner > row:
+        return None
+    start = y.storage_offset() + C * inner
+    if (start + (B - 1) * row + C * inner) * y.element_size() > y.untyped_storage().nbytes():
+        return None
+    return y.detach().as_strided(y.shape, y.stride(), start)
 
 
 def rate_from_likelihood(likelihoods: Tensor, out: Optional[dict] = None) -> Optional[Tensor]:
@@ -245,6 +278,8 @@ def gc_forward(
         res.bits = _rate_outputs(d, out, B, y.device, keep)
     d.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    if next_y is None and _PREFETCH_NEXT:
+        next_y = next_channel_slice(y)      # TCM's slice loop through the module API: the next chunk of the same latent
     if next_y is not None and next_y.is_cuda and next_y.dtype == torch.float32 and next_y.shape == y.shape:
         # hint only (L2 prefetch of the next launch's y, e.g. TCM's next channel slice): a view that is not
         # image-major is simply not prefetched

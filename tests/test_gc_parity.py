@@ -387,3 +387,27 @@ def test_next_slice_prefetch_hint_changes_no_result():
         r = ops.gc_forward(y[:, :64], sg[:, :64], mu[:, :64], want=want, scale_table=tab, next_y=hint)
         for name in ("ste", "lik", "sym", "idx", "bits"):
             assert torch.equal(getattr(r, name), getattr(base, name)), name
+
+
+@pytest.mark.gpu
+def test_next_channel_slice_inference():
+    """ops.next_channel_slice: the module-API path (GaussianConditional.forward on y.chunk(5, 1)[k]) finds the next
+    chunk of the same latent for the L2 prefetch hint, and only ever memory inside the same storage."""
+    dev = "cuda:0"
+    y = torch.randn(2, 320, 4, 3, device=dev)
+    chunks = y.chunk(5, 1)
+    for k in range(4):
+        nxt = ops.next_channel_slice(chunks[k])
+        assert nxt is not None and nxt.data_ptr() == chunks[k + 1].data_ptr() and torch.equal(nxt, chunks[k + 1])
+    assert ops.next_channel_slice(chunks[4]) is None                      # last slice: nothing behind it
+    assert ops.next_channel_slice(y) is None                              # not a slice
+    assert ops.next_channel_slice(y[:, :, :2]) is None                    # spatial slicing: not image-major
+    assert ops.next_channel_slice(y[:1].chunk(5, 1)[1]) is not None       # B = 1 keeps the row stride
+    assert ops.next_channel_slice(torch.randn(2, 64, 4, 3, device=dev)) is None
+    # the module path with the inferred hint gives the results of the explicit-slice path
+    gc = GaussianConditional(None).to(dev).eval()
+    sg = torch.rand_like(y) * 3 + 0.05
+    mu = torch.randn_like(y)
+    a = gc(chunks[1], sg.chunk(5, 1)[1], means=mu.chunk(5, 1)[1])
+    b = gc(chunks[1].contiguous(), sg.chunk(5, 1)[1].contiguous(), means=mu.chunk(5, 1)[1].contiguous())
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
