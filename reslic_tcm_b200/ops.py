@@ -126,7 +126,7 @@ def next_channel_slice(y: Tensor) -> Optional[Tensor]:
     """If ``y`` is a channel-slice view [B, C, ...] of a wider contiguous tensor that still has room for another C
     channels behind it (``y.chunk(5, 1)[k]`` with k < 4, tcm.py:438-443), the view of those next C channels — the
     L2 prefetch hint of :func:`gc_forward`; else None.  Only ever describes memory inside ``y``'s own storage."""
-    if y.dim() < 2 or not y.is_cuda or y.dtype != torch.float32:
+    if y.dim() < 2 or y.dtype != torch.float32:
         return None
     B, C = y.shape[0], y.shape[1]
     inner = 1

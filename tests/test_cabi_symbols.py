@@ -106,3 +106,23 @@ def test_entropy_bottleneck_state_dict_names_and_update(lib):
     cdf, off, ln = ref.update()
     assert torch.equal(eb.quantized_cdf, cdf) and torch.equal(eb.offset, off) and torch.equal(eb.cdf_length, ln)
     assert float(eb.loss().detach()) == pytest.approx(float(ref.loss()), rel=1e-6)
+
+
+def test_next_channel_slice_is_pure_view_logic():
+    """ops.next_channel_slice (the inferred L2 prefetch hint of the module path) on CPU tensors: it finds
+    y.chunk(5, 1)[k + 1] behind y.chunk(5, 1)[k] and never describes memory outside the storage."""
+    from reslic_tcm_b200 import ops
+
+    y = torch.randn(3, 320, 4, 3)
+    ch = y.chunk(5, 1)
+    for k in range(4):
+        nxt = ops.next_channel_slice(ch[k])
+        assert nxt is not None and nxt.data_ptr() == ch[k + 1].data_ptr() and torch.equal(nxt, ch[k + 1])
+    assert ops.next_channel_slice(ch[4]) is None and ops.next_channel_slice(y) is None
+    assert ops.next_channel_slice(y[:, :64, :2]) is None
+    assert ops.next_channel_slice(y[:, 10:74]) is not None and ops.next_channel_slice(y[:, 200:264]) is None   # 264 + 64 > 320
+    # a slice of a tensor that sits at the END of a larger storage: the bound is the storage, not the shape
+    flat = torch.randn(2 * 128 * 6 + 5)
+    t = flat[5:].view(2, 128, 6)
+    assert ops.next_channel_slice(t[:, :64]) is None or ops.next_channel_slice(t[:, :64]).data_ptr() == t[:, 64:].data_ptr()
+    assert ops.next_channel_slice(y.double()[:, :64]) is None
