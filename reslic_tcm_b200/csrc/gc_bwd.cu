@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) gc_bwd_kernel(const GcBwdParams p) {
 // ------------------------------------------------------------------ 128-bit path
 // One element group (4 consecutive elements) per thread, one tile per CTA, image = blockIdx.y: this kernel
 // has no per-CTA state to amortise (no table, no rate), and for such kernels the plain non-persistent
-// shape at high occupancy is the one that reaches the copy bandwidth (scratch/copybench.cu).  Arithmetic per
+// shape at high occupancy is the one that reaches the copy bandwidth (tools/dev/copybench.cu).  Arithmetic per
 // element: one MUFU.RCP for 1/s, two MUFU.EX2 for the two pdf values; the likelihood itself is only needed
 // for the LowerBound rule "pass where L >= bound", and L >= 1.6e-8 whenever (v - 0.5)/s <= 3.5 and
 // s <= 1000 (the interval then holds a unit of pdf >= phi(4.5) wide 1/s >= 1e-3, or a whole unit step),
