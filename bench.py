@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py — entropy-model hot path throughput (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 3] [--scaling strong|weak] [--impl ours|reference]
 
-A "step" is one pass of the hot path over one batch of synthetic latents of the named
-config (default: BASELINE.json configs[1] = TCM N=64, Kodak-shaped 768x512, batch 24,
-eval-mode round quantization + build_indexes): 1 EntropyBottleneck launch on z + 5
-Gaussian-conditional launches (one per channel slice, as TCM drives them) + the per-image
-rate sum.  Prints ONE JSON line (rank 0).
+A "step" is one pass of the hot path over one GLOBAL batch of synthetic latents of the named config.  Default
+workload: BASELINE.json configs[2] = TCM N=128, Kodak-shaped 768x512, batch 64, likelihood + bpp — the config the
+metric names "at 1/2/4/8 GPUs".  Per step and rank: 1 EntropyBottleneck launch on z + 5 Gaussian-conditional
+launches (one per channel slice, each waiting for its predecessor, as TCM drives them) + the per-image rate sum.
+Prints ONE JSON line (rank 0).
 
-* value      — latent elements (y + z) of ALL ranks / second, inputs resident in HBM,
-               steps replayed as CUDA graphs, CUDA-event timed, max over ranks.
-* e2e        — same metric through the public API with HOST (pinned) buffers: H2D of
-               y/mu/sigma/z and D2H of symbols/indexes/bits inside the timed region.
-* roofline   — the Gaussian-conditional kernel alone: algorithmic bytes / its average
-               launch duration (graph of the 5 slice launches replayed back to back).
-* cpu_baseline / --impl reference — the oracle restatement of the reference's own CPU op
-               chain (oracle/compressai_ref.py) on the host cores, bounded sample.
-Multi-GPU: weak scaling — every rank processes its own config-shaped batch of distinct
-images; the only collective is one packed-scalar all-reduce per step.
+* scaling    — "strong" (default): the config's batch is cut across the ranks (dist.shard_range: 64 -> 8 per GPU at
+               N = 8; the north star's T1 / (N * TN)); "weak": every rank runs a full config-shaped batch.
+* value      — latent elements (y + z) of the global batch / second, inputs resident in HBM, steps replayed as
+               CUDA graphs, CUDA-event timed, max over ranks.  `--chains` independent batches are in flight at
+               once (graph branches over different buffer sets; every batch is still a dependent launch chain).
+* e2e        — same metric through the public API with HOST (pinned) buffers: H2D of y/mu/sigma/z and D2H of the
+               step's results inside the timed region.
+* roofline   — the Gaussian-conditional kernel alone: algorithmic bytes / its average launch duration (one
+               dependent chain of slice launches replayed back to back); `per_config` repeats it for the other
+               BASELINE configs (N = 1), `legs` carries config 5 sharded the same way (N > 1).
+* cpu_baseline / --impl reference — the oracle restatement of the reference's own CPU op chain
+               (oracle/compressai_ref.py) on the host cores, bounded sample.
+Multi-GPU: the only exchange is the packed scalar rate row of each step.
 """
 from __future__ import annotations
 
@@ -39,32 +42,48 @@ from reslic_tcm_b200 import ops, synthetic  # noqa: E402
 
 METRIC = "entropy_model_latent_melem_per_s"
 UNIT = "Melem/s"
+DEFAULT_CONFIG = 3
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--config", type=int, default=2, choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--config", type=int, default=DEFAULT_CONFIG, choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nbuf", type=int, default=3, help="rotating buffer sets (L2-cold inputs)")
+    ap.add_argument("--chains", type=int, default=3,
+                    help="independent batches in flight at once (graph branches; buffer set s always runs on chain s %% chains)")
+    ap.add_argument("--steps-per-graph", type=int, default=12, help="consecutive steps captured in one CUDA graph")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--legs", default="auto", help="extra configs measured beside the main one: 'auto' (N=1: 2,4,5; N>1: 5), 'none', or a list '2,5'")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="rate exchange at N > 1: peer = fused NVLink stores from the collecting launch; nccl = packed all-reduce")
+    ap.add_argument("--shard-of", type=int, default=0,
+                    help="development aid: run rank 0's shard of a G-rank strong-scaling job on ONE GPU (no exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-whole-y", action="store_true")
     ap.add_argument("--no-training-kernels", action="store_true")
-    ap.add_argument("--rotations-per-graph", type=int, default=2,
-                    help="consecutive steps chained in one CUDA graph = this many rotations of the buffer sets (0: one graph per step)")
     ap.add_argument("--e2e-chunks", type=int, default=1,
-                    help="image chunks per batch in the host pipeline (batches are double-buffered, so 1 streams best; more chunks cut per-batch latency)")
-    return ap.parse_args()
+                    help="image chunks per batch in the host pipeline (batches are double-buffered, so 1 streams best)")
+    return ap.parse_args(argv)
 
 
 def bytes_per_y_elem(c: synthetic.Config) -> int:
     """Algorithmic HBM bytes per y element of one GC launch: read y, mu,
     sigma (12) + write y_hat, L (8) [+ symbols, indexes (8)] [+ noisy y (4) in training]."""
     return 12 + 8 + (8 if c.with_indexes else 0) + (4 if c.training else 0)
+
+
+def workload_config(c: synthetic.Config, world: int, scaling: str) -> dict:
+    """The `config` object of the JSON line — identical for both arms (the reference arm steps over a bounded
+    sample of the same workload and says so in `cpu_baseline.sample`)."""
+    return {"workload": c.name, "cfg": c.cfg, "global_batch": c.batch * (world if scaling == "weak" else 1),
+            "y_shape_per_image": [synthetic.M_LATENT, *c.y_hw], "z_shape_per_image": [synthetic.Z_CHANNELS, *c.z_hw],
+            "mode": "training (noise)" if c.training else ("eval round + symbols + indexes" if c.with_indexes else "eval round, likelihood + bpp")}
 
 
 def ref_eb(params):
@@ -145,13 +164,15 @@ def run_reference(args):
         steps += 1
     dt = time.perf_counter() - t0
     val = elems * steps / dt / 1e6
-    sample = f"{n_img} of {c.batch} images of config {c.cfg} per step ({elems} latent elements), {steps} steps"
+    sample = (f"each step = {n_img} of the {c.batch} images of config {c.cfg} ({elems} latent elements; throughput is per element, "
+              f"so the sample size does not enter the ratio), {steps} steps")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": c.name, "cfg": c.cfg, "images_per_step": n_img, "cpu": cpu_model()},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(c, max(world, args.gpus, 1), args.scaling),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,31 +250,370 @@ class ClockSampler(threading.Thread):
         return out
 
 
-# --------------------------------------------------------------------------- GPU arm
-def bind_to_gpu_numa(dev) -> None:
-    """Multi-rank runs: pin this process to the CPUs local to its GPU (sysfs local_cpulist) so that its
-    pinned host buffers are allocated on that NUMA node and the e2e copies do not cross sockets."""
+# --------------------------------------------------------------------------- host placement
+def _parse_cpulist(txt: str) -> set:
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(dev) -> tuple:
+    """(cpu set, source) of the CPUs local to `dev`: NVML's ideal affinity first (what `nvidia-smi topo -m`
+    prints — it knows the real topology even where the container's sysfs reports node 0 for every GPU), the
+    PCI device's sysfs local_cpulist second."""
+    p = torch.cuda.get_device_properties(dev)
     try:
-        p = torch.cuda.get_device_properties(dev)
-        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
-        cpus = set()
-        for part in txt.split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
+        import pynvml as nv
+
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(p.uuid))
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(p.uuid)).encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
         if cpus:
-            os.sched_setaffinity(0, cpus)
-            print(f"[bench] rank on {bdf}: bound to {len(cpus)} local CPUs ({txt})", file=sys.stderr)
+            return cpus, "nvml"
+    except Exception:
+        pass
+    bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    return _parse_cpulist(open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read()), "sysfs"
+
+
+def bind_to_gpu_numa(dev) -> dict:
+    """Multi-rank runs: pin this process to the CPUs local to its GPU so that its pinned host buffers are
+    first-touched on that NUMA node and the e2e copies do not cross sockets.  Returns what was done."""
+    info = {"bound": False}
+    try:
+        cpus, src = gpu_local_cpus(dev)
+        allowed = os.sched_getaffinity(0)
+        info.update(source=src, local_cpus=len(cpus), allowed_cpus=len(allowed))
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+        info["cpus_used"] = len(use or allowed)
+        nodes = set()
+        for n in os.listdir("/sys/devices/system/node"):
+            if n.startswith("node") and _parse_cpulist(open(f"/sys/devices/system/node/{n}/cpulist").read()) & (use or allowed):
+                nodes.add(int(n[4:]))
+        info["numa_nodes"] = sorted(nodes)
     except Exception as e:      # topology not exposed in this container: run unbound
-        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+        info["error"] = repr(e)
+    print(f"[bench] host placement: {info}", file=sys.stderr)
+    return info
+
+
+# --------------------------------------------------------------------------- GPU arm
+class Workload:
+    """One rank's share of one BASELINE config on the device: `nbuf` rotating buffer sets (each its own
+    TcmEntropyPath = static outputs + rate workspace), graphs of consecutive steps, the kernel-only leg."""
+
+    def __init__(self, c: synthetic.Config, images: range, dev, nbuf: int, params, pin_host: bool = False):
+        from reslic_tcm_b200.pipeline import TcmEntropyPath
+
+        self.c, self.dev, self.B = c, dev, len(images)
+        self.host = synthetic.make_batch(c.cfg, images, with_noise=False, pin=pin_host)
+        self.kw = dict(training=c.training, with_indexes=c.with_indexes, num_pixels=c.num_pixels_per_image, seed=1234)
+        self.sets = []
+        for _ in range(max(1, nbuf)):
+            path = TcmEntropyPath().to(dev).eval()
+            synthetic.load_eb_parameters(path.entropy_bottleneck, params)
+            path.gaussian_conditional.scale_table = synthetic.scale_table(dev)
+            inp = {k: self.host[k].to(dev, non_blocking=True) for k in ("y", "mu", "sigma", "z")}
+            torch.cuda.synchronize()
+            res = path.forward(inp["y"], inp["mu"], inp["sigma"], inp["z"], **self.kw)   # warm-up: lazy init, LUT, allocator
+            self.sets.append({"path": path, "inp": inp, "res": res})
+        torch.cuda.synchronize()
+        self.y_elems, self.z_elems = self.B * c.y_elems_per_image, self.B * c.z_elems_per_image
+        self.bpe = bytes_per_y_elem(c)
+        self._side = []
+
+    def set_bytes(self) -> int:
+        return self.bpe * self.y_elems + 12 * self.z_elems
+
+    def step(self, i: int, **over):
+        s = self.sets[i % len(self.sets)]
+        kw = dict(self.kw, **over)
+        return s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kw)
+
+    def capture(self, n_steps: int, chains: int = 1, first: int = 0, after_step=None, **over):
+        """ONE graph of steps first .. first+n_steps-1.  Consecutive launches of a step are PDL edges; with
+        chains > 1 the steps are dealt onto that many forked capture streams — buffer set s always on chain
+        s % chains, so two steps over the same buffers stay ordered — i.e. `chains` independent batches are in
+        flight at once, each still a dependent chain.  `after_step(j, set)` is captured behind step j."""
+        chains = max(1, min(chains, len(self.sets)))
+        while len(self._side) < chains - 1:
+            self._side.append(torch.cuda.Stream(device=self.dev))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(self.dev)
+            lanes = [cur] + self._side[:chains - 1]
+            for s in lanes[1:]:
+                s.wait_stream(cur)
+            for j in range(first, first + n_steps):
+                si = j % len(self.sets)
+                with torch.cuda.stream(lanes[si % chains]):
+                    self.step(j, **over)
+                    if after_step is not None:
+                        after_step(j - first, self.sets[si])
+            for s in lanes[1:]:
+                cur.wait_stream(s)
+        return g
+
+    def drain_deferred(self):
+        for s in self.sets:
+            b = s["path"].buffers(s["inp"]["y"], s["inp"]["z"], self.c.with_indexes, self.c.training)
+            ops.rate_finalize(b["workspace"], self.B, bits=b["bits"])
+
+    def gc_only_us(self, fuse: bool, min_reps: int = 50):
+        """Only the GC launches of a step (5 per-slice, or 1 over the whole y) over the rotating buffer sets as ONE
+        dependent chain, captured as one graph of >= 60 launches so that the launch duration is not diluted by
+        graph-replay boundaries; the rate stays deferred in the workspace and is drained after the timed region.
+        Returns (us per launch, launches per step)."""
+        n_launch = 1 if fuse else synthetic.NUM_SLICES
+        over = dict(skip_z=True, fuse_slices=fuse, defer_rate=True)
+        n_steps = max(len(self.sets), -(-60 // n_launch))
+        n_steps += (-n_steps) % len(self.sets)
+        for i in range(len(self.sets)):
+            self.step(i, **over)
+        self.drain_deferred()
+        torch.cuda.synchronize()
+        g = self.capture(n_steps, chains=1, **over)
+        per_graph = n_steps * n_launch
+        reps = max(3, -(-min_reps * n_launch // per_graph))
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(reps):
+            g.replay()
+        r1.record()
+        self.drain_deferred()            # outside the timed region: this leg times the kernel alone
+        torch.cuda.synchronize()
+        return r0.elapsed_time(r1) * 1e3 / (reps * per_graph), n_launch
+
+
+def load_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return peak, src
+
+
+def load_traffic():
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            db = json.load(open(os.path.join(ROOT, "profiles", name))).get("gc_fwd_kernel", [])
+            return (db if isinstance(db, list) else [db]), name
+        except Exception:
+            continue
+    return [], None
+
+
+def roof_obj(w: Workload, us: float, n_launch: int, peak: float, peak_src: str, traffic_db, what: str) -> dict:
+    elems = w.y_elems // n_launch
+    achieved = w.bpe * elems / (us * 1e-6) / 1e9
+    traffic = None      # dram read+write bytes per launch from the committed ncu --set full captures
+    for t in traffic_db:
+        if t.get("config") == w.c.cfg and t.get("elems_per_launch") == elems:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": "gc_fwd_kernel", "bytes_per_elem": w.bpe, "elems_per_launch": elems,
+            "us_per_launch": us, "peak_source": peak_src, "gc_melem_per_s": elems / us, "launch": what}
+
+
+SLICE_WHAT = "one 64-channel slice of y per launch, dependent chain (TCM's call pattern, tcm.py:443-457)"
+WHOLE_WHAT = "all 320 channels of y in one launch (models whose mu/sigma exist for every channel at once)"
+
+
+class Timer:
+    """Timed loop over graphs of `group` steps (+ one partial graph for the tail), max over ranks."""
+
+    def __init__(self, w: Workload, group: int, chains: int, world: int, exchange=None, **over):
+        self.w, self.group, self.chains, self.world, self.ex = w, max(1, group), chains, world, exchange
+        self.over = dict(over, **(exchange.step_kwargs() if exchange is not None else {}))
+        self.graphs = {}
+
+    def graph(self, n: int):
+        if n not in self.graphs:
+            hook = self.ex.after_step if self.ex is not None else None
+            self.graphs[n] = self.w.capture(n, self.chains, after_step=hook, **self.over)
+        return self.graphs[n]
+
+    def run(self, n_steps: int):
+        """Enqueue n_steps steps.  Every graph starts at buffer set 0, so a partial graph is just a shorter one."""
+        left = n_steps
+        while left > 0:
+            n = min(left, self.group)
+            if self.ex is not None:
+                self.ex.before_graph(n)
+            self.graph(n).replay()
+            if self.ex is not None:
+                self.ex.after_graph(n)
+            left -= n
+
+    def timed(self, steps: int, warmup: int, barrier, sampler=None):
+        import torch.distributed as dist
+
+        self.graph(self.group)
+        if steps % self.group:
+            self.graph(steps % self.group)
+        self.run(max(warmup, 3))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.active.set()
+        e0.record()
+        self.run(steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.w.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if sampler is not None:
+            # the timed region may be shorter than an NVML sample: keep the identical loop running (untimed) until the
+            # sampler has seen >= 1 s of it — the same number of graphs on every rank (ms is the max over ranks), so the
+            # exchange stays in step
+            extra = int(max(0.0, 1000.0 - ms) / max(ms / steps * self.group, 1e-6)) + 1
+            for k in range(extra):
+                self.run(self.group)
+                if k % 64 == 63:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            sampler.active.clear()
+        return ms / steps
+
+
+class NcclExchange:
+    """Rate exchange by NCCL (the checked fallback): the steps of one graph share ONE packed all-reduce of a
+    [group, 4] float64 matrix (bits, sq_err, pixels, images), packed by tiny kernels inside the graph."""
+
+    name = "nccl all-reduce of one packed [steps, 4] float64 matrix per graph"
+
+    def __init__(self, w: Workload, group: int):
+        from reslic_tcm_b200 import dist as rdist
+
+        self.red = rdist.RateReducer(w.dev, slots=group)
+        self.red.set_static(0.0, w.B * w.c.num_pixels_per_image, w.B)
+        self.work = None
+
+    def step_kwargs(self):
+        return {}
+
+    def after_step(self, j, s):
+        self.red.pack_bits(s["res"]["bits"], slot=j)
+
+    def before_graph(self, n):
+        if self.work is not None:         # stream-level wait: the previous collective has read the matrix
+            self.work.wait()
+            self.work = None
+
+    def after_graph(self, n):
+        self.work = self.red.all_reduce(async_op=True)
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+        torch.cuda.synchronize()
+        return self.red.result(0)
+
+    def close(self):
+        pass
+
+
+class PeerExchange:
+    """Rate exchange fused into the collecting launch (reslic_tcm_b200.dist.PeerRateExchange): the last slice launch
+    of every step stores the step's packed row into every rank's buffer over NVLink; no collective kernel exists.
+    One tiny read kernel per graph adds the rows of the PREVIOUS graph's steps (one graph behind, so it never waits
+    in steady state) — it is also what keeps a rank from running a ring ahead of the others."""
+
+    name = "packed rate row stored to every rank over NVLink by the collecting launch itself (no collective kernel); one read kernel per graph, one graph behind"
+
+    def __init__(self, w: Workload, group: int):
+        from reslic_tcm_b200 import dist as rdist
+
+        self.ex = rdist.PeerRateExchange(w.dev, ring=max(256, 8 * group))
+        self.ex.set_static(w.B * w.c.num_pixels_per_image, w.B)
+        self.pending, self.last = [], None
+        self.rows = torch.zeros(self.ex.ring, 4, dtype=torch.float64, device=w.dev)
+
+    def step_kwargs(self):
+        return {"exchange": self.ex}
+
+    after_step = None
+
+    def before_graph(self, n):
+        pass
+
+    def after_graph(self, n):
+        self.pending.append(n)
+        if len(self.pending) > 1:
+            m = self.pending.pop(0)
+            self.last = self.ex.read(m, out=self.rows[:m])
+
+    def result(self):
+        while self.pending:
+            m = self.pending.pop(0)
+            self.last = self.ex.read(m, out=self.rows[:m])
+        torch.cuda.synchronize()
+        self.ex.check()
+        return self.ex.result(self.last[0].tolist())
+
+    def close(self):
+        self.ex.close()
+
+
+def measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
+                   sampler=None, exchange_factory=None, steps=None, pin_host=False, light=False):
+    """value / ms_per_step / roofline (+ whole-y) of one config for this rank's `images`."""
+    w = Workload(c, images, dev, args.nbuf, params, pin_host=pin_host)
+    steps = steps or args.steps
+    ex = exchange_factory(w) if exchange_factory is not None else None
+    tm = Timer(w, args.steps_per_graph, args.chains, world, ex)
+    ms_step = tm.timed(steps, args.warmup, barrier, sampler)
+    out = {"workload": c.name, "cfg": c.cfg, "images_per_gpu": w.B, "value": global_elems / (ms_step * 1e-3) / 1e6, "unit": UNIT,
+           "ms_per_step": ms_step, "steps": steps, "launches_per_step": 1 + synthetic.NUM_SLICES}
+    if ex is not None:
+        # the exchanged global row against the checked fallback: an NCCL all-reduce of the same step's local row
+        import torch.distributed as dist
+
+        got = ex.result()
+        local = torch.tensor([float(w.sets[0]["res"]["bits"].double().sum()), 0.0, float(w.B * c.num_pixels_per_image), float(w.B)],
+                             dtype=torch.float64, device=dev)
+        dist.all_reduce(local)
+        want = local.tolist()
+        out["exchange_check"] = {"exchange": got, "nccl_all_reduce": {"bits": want[0], "pixels": want[2], "images": want[3]},
+                                 "match": bool(abs(got["bits"] - want[0]) <= 1e-9 * abs(want[0]) and got["pixels"] == want[2] and got["images"] == want[3])}
+        out["exchange_name"] = ex.name
+        ex.close()
+    us, n = w.gc_only_us(False)
+    out["roofline"] = roof_obj(w, us, n, peak, peak_src, traffic_db, SLICE_WHAT)
+    if not args.no_whole_y:
+        tw = Timer(w, args.steps_per_graph, args.chains, world, None, fuse_slices=True)
+        wms = tw.timed(min(steps, 100) if light else steps, min(args.warmup, 6), barrier)
+        usw, n1 = w.gc_only_us(True)
+        out["whole_y"] = {"value": global_elems / (wms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wms, "launches_per_step": 2,
+                          "roofline": roof_obj(w, usw, n1, peak, peak_src, traffic_db, WHOLE_WHAT)}
+    return w, out
 
 
 def run_ours(args):
     import torch.distributed as dist
 
     from reslic_tcm_b200 import _cabi, dist as rdist
-    from reslic_tcm_b200.pipeline import TcmEntropyPath
 
     _cabi.load()  # no extension -> loud failure, never a fallback
     # stdout carries exactly ONE JSON line: libraries that write banners to fd 1 (NCCL prints its version
@@ -267,77 +627,21 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        bind_to_gpu_numa(dev)      # before any pinned allocation: first touch puts the pages on the GPU's node
-    c = synthetic.CONFIGS[args.config]
-    B = c.batch                                   # weak scaling: every rank gets a full batch
-    images = range(rank * B, (rank + 1) * B)      # of distinct images
-    host = synthetic.make_batch(c.cfg, images, with_noise=False, pin=True)
+    placement = bind_to_gpu_numa(dev) if world > 1 else None     # before any pinned allocation (first touch)
     params = synthetic.eb_parameters()
-    kw = dict(training=c.training, with_indexes=c.with_indexes, num_pixels=c.num_pixels_per_image, seed=1234)
+    peak, peak_src = load_peak()
+    traffic_db, traffic_src = load_traffic()
+    sim = args.shard_of if (args.shard_of > 1 and world == 1) else 0
+    eff_world = sim or world
 
-    sets = []
-    for i in range(max(1, args.nbuf)):
-        path = TcmEntropyPath().to(dev).eval()
-        synthetic.load_eb_parameters(path.entropy_bottleneck, params)
-        path.gaussian_conditional.scale_table = synthetic.scale_table(dev)
-        inp = {k: host[k].to(dev, non_blocking=True) for k in ("y", "mu", "sigma", "z")}
-        torch.cuda.synchronize()
-        graph, res = path.capture(inp["y"], inp["mu"], inp["sigma"], inp["z"], **kw)
-        sets.append({"path": path, "inp": inp, "graph": graph, "res": res})
-    # rate exchange: steps that are enqueued together (one graph of `group` steps) share ONE packed
-    # all-reduce of a [group, 4] float64 matrix; two reducers alternate so that group g+1 never waits
-    # on group g's collective
-    group = len(sets) * max(1, args.rotations_per_graph)
-    reducers = [rdist.RateReducer(dev, slots=group) for _ in range(2)]
-    single = rdist.RateReducer(dev)
-    for r_ in reducers + [single]:
-        r_.set_static(0.0, B * c.num_pixels_per_image, B)
-    y_elems, z_elems = B * c.y_elems_per_image, B * c.z_elems_per_image
-    elems_rank = y_elems + z_elems
-    launches_per_step = 1 + synthetic.NUM_SLICES
-
-    # One graph per step (one batch), plus graphs of `group` consecutive steps — one per buffer set — so
-    # that back-to-back batches are chained by programmatic (PDL) edges instead of graph-replay boundaries;
-    # the group graphs (one per reducer) end with the `group` tiny kernels that pack sum(bits) of each step.
-    super_graphs = []
-    if group > 1 and args.rotations_per_graph > 0:
-        for red in reducers:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for j in range(group):
-                    s = sets[j % len(sets)]
-                    s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kw)
-                    if world > 1:
-                        red.pack_bits(s["res"]["bits"], slot=j)
-            super_graphs.append(g)
-
-    works = [None, None, None]
-
-    def step(i, collective=True):
-        sets[i % len(sets)]["graph"].replay()
-        if world > 1 and collective:  # the path's only exchange: one packed-scalar all-reduce
-            if works[2] is not None:
-                works[2].wait()
-            single.pack_bits(sets[i % len(sets)]["res"]["bits"])
-            works[2] = single.all_reduce(async_op=True)
-
-    def run_steps(i0, n, collective=True):
-        """Steps i0 .. i0+n-1, in groups of `group` where they line up with the buffer rotation."""
-        i, end = i0, i0 + n
-        while i < end:
-            if super_graphs and i % group == 0 and i + group <= end:
-                k = (i // group) % 2
-                if works[k] is not None:       # stream-level wait: this reducer's previous collective has read its matrix
-                    works[k].wait()
-                    works[k] = None
-                super_graphs[k].replay()
-                if world > 1 and collective:
-                    works[k] = reducers[k].all_reduce(async_op=True)
-                i += group
-            else:
-                step(i, collective)
-                i += 1
+    def shard(c):
+        """(this rank's images, latent elements of the global batch)."""
+        per_image = c.y_elems_per_image + c.z_elems_per_image
+        if args.scaling == "weak":
+            return range(rank * c.batch, (rank + 1) * c.batch), c.batch * per_image * eff_world
+        if c.batch < eff_world:
+            raise SystemExit(f"config {c.cfg} has {c.batch} image(s): it does not shard over {eff_world} ranks (replicas only)")
+        return rdist.shard_range(c.batch, rank, eff_world), c.batch * per_image
 
     def barrier():
         if world > 1:
@@ -350,153 +654,52 @@ def run_ours(args):
         uuid = None
     sampler = ClockSampler(local, uuid)
     sampler.start()
-    warm = max(args.warmup, 3)
-    run_steps(0, warm + (-warm) % group)        # warm-up ends on a rotation boundary
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.active.set()
-    e0.record()
-    run_steps(0, args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # the timed region may be shorter than an NVML sample: keep the identical loop running
-    # (untimed) until the sampler has seen >= 1 s of it
-    t_end = time.perf_counter() + max(0.0, 1.0 - ms / 1e3)
-    i = args.steps
-    i += (-i) % group
-    while time.perf_counter() < t_end:
-        run_steps(i, group, collective=False)   # time-bounded loop: ranks run different counts, so no collectives here
-        i += group
-        if i % (64 * group) < group:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
-    sampler.active.clear()
+
+    exchange_name, exchange_factory = None, None
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = elems_rank * world / (ms_per_step * 1e-3) / 1e6
+        def exchange_factory(w):
+            return make_exchange(args, w, rank, world)
 
-    # ---- roofline leg: the GC kernel alone, 5 slice launches per graph, replayed back to back
-    bpe = bytes_per_y_elem(c)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # ---- main leg
+    c = synthetic.CONFIGS[args.config]
+    images, global_elems = shard(c)
+    w, main = measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
+                             sampler=sampler, exchange_factory=exchange_factory, pin_host=not args.no_e2e)
+    if world > 1:
+        exchange_name = main.pop("exchange_name", None)
 
-    def gc_only_leg(fuse):
-        """Only the GC launches of a step (5 per-slice, or 1 over the whole y) over the rotating buffer
-        sets, captured as ONE graph of >= 60 launches so that the kernel's launch duration is not diluted
-        by graph-replay boundaries (inside a graph consecutive launches are PDL edges); the rate stays deferred
-        in the workspace and is drained after the timed region.  Returns us per launch."""
-        n_launch = 1 if fuse else synthetic.NUM_SLICES
-        kk = dict(kw, skip_z=True, fuse_slices=fuse, defer_rate=True)   # the kernel alone: rate finalised once per graph
-        passes = max(1, -(-60 // (n_launch * len(sets))))
-
-        def run_all():
-            for _ in range(passes):
-                for s in sets:
-                    s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
-
-        def drain():   # the deferred sums (48.16 fixed point in 64 bits: no overflow over any run length) -> bits
-            for s in sets:
-                b = s["path"].buffers(s["inp"]["y"], s["inp"]["z"], kw.get("with_indexes", False), kw.get("training", False))
-                ops.rate_finalize(b["workspace"], s["inp"]["y"].shape[0], bits=b["bits"])
-
-        run_all()
-        drain()
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            run_all()
-        per_graph = passes * len(sets) * n_launch
-        reps = max(3, -(-max(args.steps, 50) * n_launch // per_graph))
-        for i in range(2):
-            g.replay()
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for i in range(reps):
-            g.replay()
-        r1.record()
-        drain()                # outside the timed region: this leg times the kernel alone
-        torch.cuda.synchronize()
-        return r0.elapsed_time(r1) * 1e3 / (reps * per_graph), n_launch
-
-    traffic_db = {}
-    try:
-        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("gc_fwd_kernel", {})
-    except Exception:
-        pass
-
-    def roof_obj(us, n_launch):
-        elems = y_elems // n_launch
-        achieved = bpe * elems / (us * 1e-6) / 1e9
-        traffic = None      # dram read+write bytes per launch from the committed ncu --set full captures
-        for t in (traffic_db if isinstance(traffic_db, list) else [traffic_db]):
-            if t.get("config") == c.cfg and t.get("elems_per_launch") == elems:
-                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "gc_fwd_kernel", "bytes_per_elem": bpe, "elems_per_launch": elems,
-                "us_per_launch": us, "peak_source": peak_src, "gc_melem_per_s": elems / us}
-
-    us_slice, n5 = gc_only_leg(False)
-    roof = roof_obj(us_slice, n5)
-    roof["launch"] = "one 64-channel slice of y per launch (TCM's call pattern, tcm.py:443-457)"
-
-    # ---- whole-y mode: all 320 channels in ONE GC launch (models whose mu/sigma exist for all
-    # channels at once, e.g. the reference's ScaleHyperprior); reported beside the per-slice mode
-    whole = None
-    if not args.no_whole_y:
-        wgraphs = []
-        for s in sets:
-            kk = dict(kw, fuse_slices=True)
-            s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kk)
-            wgraphs.append(g)
-        for i in range(5):
-            wgraphs[i % len(wgraphs)].replay()
-        barrier()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        for i in range(args.steps):
-            wgraphs[i % len(wgraphs)].replay()
-        w1.record()
-        barrier()
-        wms = w0.elapsed_time(w1)
-        if world > 1:
-            tt = torch.tensor([wms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            wms = float(tt.item())
-        us_whole, n1 = gc_only_leg(True)
-        whole = {"value": elems_rank * world / (wms / args.steps * 1e-3) / 1e6, "unit": UNIT,
-                 "ms_per_step": wms / args.steps, "launches_per_step": 2, "roofline": roof_obj(us_whole, n1)}
-
-    # ---- e2e leg: public API with host buffers (H2D inputs, D2H symbols/indexes/bits)
+    # ---- e2e leg: public API with host buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, c, sets[0], host, dev, world, B, elems_rank, kw)
+        e2e = run_e2e(args, c, w, dev, world, global_elems, packed_slots=c.with_indexes)
+    bits0 = w.sets[0]["res"]["bits"].double().cpu()
 
     # ---- training-path kernels on a config-5 slice (single-GPU runs): backward, noise-mode bottleneck, STanH
     training_kernels = None
-    if world == 1 and not args.no_training_kernels:
+    if world == 1 and not sim and not args.no_training_kernels:
         training_kernels = training_kernels_leg(dev, peak)
+    del w
+    torch.cuda.empty_cache()
 
-    # ---- e2e with the rANS table lookup on the device: one packed (start, range) slot per symbol comes back instead
-    # of int32 symbols + int32 indexes (what the host coder consumes either way) — reported beside `e2e`
-    e2e_slots = None
-    if not args.no_e2e and c.with_indexes:
-        gcm = sets[0]["path"].gaussian_conditional
-        gcm.update()                                   # CDF tables of the scale table in place (setup, untimed)
-        e2e_slots = run_e2e(args, c, sets[0], host, dev, world, B, elems_rank, kw, packed_slots=True)
+    # ---- the other BASELINE configs: per-config roofline objects (N = 1) / config 5 sharded the same way (N > 1)
+    if args.legs == "auto":
+        leg_cfgs = [k for k in ((2, 4, 5) if eff_world == 1 else (5,)) if k != c.cfg]
+    elif args.legs == "none":
+        leg_cfgs = []
+    else:
+        leg_cfgs = [int(k) for k in args.legs.split(",") if k.strip() and int(k) != c.cfg]
+    legs = {}
+    for k in leg_cfgs:
+        ck = synthetic.CONFIGS[k]
+        imgs, gel = shard(ck)
+        wk, legs[str(k)] = measure_config(ck, imgs, dev, args, params, world, gel, peak, peak_src, traffic_db, barrier,
+                                          exchange_factory=exchange_factory, steps=min(args.steps, 100), light=True,
+                                          pin_host=(k == 2 and not args.no_e2e))
+        legs[str(k)].pop("exchange_name", None)
+        if k == 2 and not args.no_e2e:      # the compress-path config: host round trip with the packed rANS slots
+            legs[str(k)]["e2e"] = run_e2e(args, ck, wk, dev, world, gel, packed_slots=True)
+        del wk
+        torch.cuda.empty_cache()
 
     sampler.stop()
     clocks = sampler.summary()
@@ -512,19 +715,35 @@ def run_ours(args):
                "cpu": cpu_model()}
 
     if rank == 0:
-        bits = sets[0]["res"]["bits"].double().cpu()
+        cfg = workload_config(c, world, args.scaling)
+        cfg.update({
+            "images_per_gpu": main["images_per_gpu"], "launches_per_step": main["launches_per_step"],
+            "step": f"1 EB + 5 GC launches per step (each GC launch waits for its predecessor), {args.steps_per_graph} steps per CUDA graph, "
+                    f"{min(args.chains, args.nbuf)} independent batches in flight (graph branches over different buffer sets)",
+            "l2": f"{args.nbuf} rotating buffer sets of {(bytes_per_y_elem(c) * main['images_per_gpu'] * c.y_elems_per_image + 12 * main['images_per_gpu'] * c.z_elems_per_image) / 1e6:.0f} MB each "
+                  f"per GPU; inputs + outputs of one step exceed the 126 MB L2 only while a rank holds >= 13 images of this config — "
+                  f"smaller shards are L2-assisted, which is what a real 8-GPU run sees too",
+            "bpp_mean_rank0": float(bits0.mean()) / c.num_pixels_per_image,
+        })
+        if exchange_name:
+            cfg["exchange"] = exchange_name
+        if sim:
+            cfg["simulated_shard_of"] = sim
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": c.name, "cfg": c.cfg, "images_per_gpu": B, "y_shape": [B, 320, *c.y_hw],
-                       "z_shape": [B, 192, *c.z_hw], "launches_per_step": launches_per_step,
-                       "mode": f"per-slice launches (1 EB + 5 GC per step) replayed as CUDA graphs, steps chained in graphs of {group} (one packed rate all-reduce per graph when N > 1)",
-                       "l2": f"{len(sets)} rotating buffer sets of {(bpe * y_elems + 12 * z_elems) / 1e6:.0f} MB each (> 126 MB L2)",
-                       "bpp_mean_image0_set": float(bits.mean()) / c.num_pixels_per_image},
-            "roofline": roof, "whole_y": whole, "training_kernels": training_kernels, "cpu_baseline": cpu, "e2e": e2e, "e2e_slots": e2e_slots,
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "roofline": main["roofline"], "whole_y": main.get("whole_y"),
+            "per_config": {str(c.cfg): {k: main[k] for k in ("workload", "value", "ms_per_step", "roofline", "whole_y") if k in main}, **legs},
+            "legs": {k: {"workload": v["workload"], "value": v["value"], "ms_per_step": v["ms_per_step"], "images_per_gpu": v["images_per_gpu"],
+                         "scaling": args.scaling} for k, v in legs.items()},
+            "training_kernels": training_kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": main["launches_per_step"] * args.steps, "clocks": clocks, "traffic_source": traffic_src,
         }
+        if placement is not None:
+            line["host_placement"] = placement
+        if main.get("exchange_check") is not None:
+            line["exchange_check"] = main["exchange_check"]
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -532,6 +751,29 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def make_exchange(args, w, rank, world):
+    """The rate exchange of an N > 1 run: peer stores fused into the collecting launch; the NCCL all-reduce is the
+    fallback (--exchange nccl, or when the peer buffers cannot be mapped — then every rank must fall back together)."""
+    import torch.distributed as dist
+
+    if args.exchange in ("auto", "peer"):
+        ok, ex = 1, None
+        try:
+            ex = PeerExchange(w, args.steps_per_graph)
+        except Exception as e:      # CUDA IPC not permitted in this container, no peer access, ...
+            if args.exchange == "peer":
+                raise
+            print(f"[bench] peer exchange unavailable ({e!r}); falling back to NCCL", file=sys.stderr)
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=w.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 1:
+            return ex
+        if ex is not None:
+            ex.close()
+    return NcclExchange(w, args.steps_per_graph)
 
 
 def training_kernels_leg(dev, peak):
@@ -601,30 +843,32 @@ def training_kernels_leg(dev, peak):
     return {"shape": {"y_slice": [B, C, h, w], "z": [B, Cz, hz, hz]}, "kernels": out}
 
 
-def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw, packed_slots=False):
+def run_e2e(args, c, w: Workload, dev, world, global_elems, packed_slots=False):
     """Same step through the public API with HOST buffers (reslic_tcm_b200.pipeline.HostPipeline):
-    every step copies y, mu, sigma, z from pinned host memory, runs the pass, and reads symbols and
-    indexes (the rANS coder's input, tcm.py:551-552) plus the per-image bits back to pinned host
-    memory.  Chunked over images so that H2D, kernels and D2H overlap."""
+    every step copies this rank's y, mu, sigma, z from pinned host memory, runs the pass, and reads the
+    step's results back to pinned host memory — the per-image bits, and for the compress-path configs the
+    rANS coder's input (tcm.py:551-552) as ONE packed (start, range) slot per symbol."""
     import torch.distributed as dist
 
     from reslic_tcm_b200.pipeline import HostPipeline
 
-    hp = HostPipeline(s["path"], B, c.y_hw, c.z_hw, with_indexes=c.with_indexes, training=c.training,
-                      chunks=args.e2e_chunks, device=dev, num_pixels=c.num_pixels_per_image, seed=kw.get("seed", 0),
+    s = w.sets[0]
+    if packed_slots:
+        s["path"].gaussian_conditional.update()       # CDF tables of the scale table in place (setup, untimed)
+    hp = HostPipeline(s["path"], w.B, c.y_hw, c.z_hw, with_indexes=c.with_indexes, training=c.training,
+                      chunks=args.e2e_chunks, device=dev, num_pixels=c.num_pixels_per_image, seed=w.kw.get("seed", 0),
                       packed_slots=packed_slots)
-    steps = max(3, min(args.steps, 60))
+    host = w.host
+    steps = max(3, min(args.steps, 40))
     for _ in range(3):
         out = hp.run(host)
     torch.cuda.synchronize()
     out = {k: v.clone() for k, v in out.items() if k != "done"}
-    # correctness of the host round trip: same bits as the device-resident graph
-    s["graph"].replay()
+    # correctness of the host round trip: same bits as the device-resident pass
+    ref_bits = w.step(0)["bits"].double().cpu()
     torch.cuda.synchronize()
-    ref_bits = s["res"]["bits"].double().cpu()
-    # (chunked launches group the fp32 partials differently; chunked NOISE launches also draw different noise —
-    # the Philox counter is the element index inside a launch — so that case is not comparable)
-    comparable = not (c.training and len(hp.ranges) > 1)
+    # (chunked launches group the fp32 partials differently; NOISE launches draw fresh noise per run)
+    comparable = not c.training
     if comparable and not torch.allclose(out["bits"], ref_bits, rtol=1e-6):
         raise RuntimeError("e2e pipeline disagrees with the device-resident pass")
     if world > 1:
@@ -641,8 +885,8 @@ def run_e2e(args, c, s, host, dev, world, B, elems_rank, kw, packed_slots=False)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"value": elems_rank * world / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
-            "d2h_bytes_per_step": hp.d2h_bytes, "ms_per_step": ms / steps, "steps": steps,
+    return {"value": global_elems / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
+            "d2h_bytes_per_step": hp.d2h_bytes, "ms_per_step": ms / steps, "steps": steps, "bytes_are": "per rank",
             "what": f"pinned host y/mu/sigma/z -> H2D -> 1+5{'+1' if packed_slots else ''} launches -> D2H {'/'.join(hp.out_names)}, "
                     f"{len(hp.ranges)} image chunks pipelined on 3 streams, batches double-buffered"}
 

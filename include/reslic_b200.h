@@ -20,6 +20,11 @@
  *    This lets a channel slice of y[B,320,h,w] (tcm.py:438 `y.chunk`) be passed without a
  *    copy.  16-byte aligned bases and strides%4==0 and n%4==0 take the 128-bit path; any
  *    other layout takes a scalar CUDA path (never a CPU fallback).
+ *  - every descriptor struct starts with `struct_size`, which the caller sets to sizeof(the struct) as ITS
+ *    header declares it; a call whose struct_size differs from the library's sizeof is rejected with
+ *    RESLIC_ERR_ARG before any field is read (a binding built against another ABI revision cannot make the
+ *    library read past its struct).  reslic_sizeof_*() export the library's sizes for bindings that cannot
+ *    include this header (ctypes, cgo, JNI).
  *  - `workspace`: device scratch of at least reslic_workspace_bytes() bytes, zero-filled
  *    ONCE by the caller before first use (kernels leave it zeroed); one workspace per
  *    stream in flight.
@@ -33,7 +38,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 15
+#define RESLIC_ABI_VERSION 16
 
 enum {
   RESLIC_OK = 0,
@@ -62,8 +67,18 @@ int reslic_abi_version(void);
 const char* reslic_last_error(void);
 /* Number of SMs of the current device (grid sizing is done inside the library). */
 int reslic_device_sm_count(void);
-/* Scratch bytes needed by any *_fwd call with a rate output for B images. */
+/* Scratch bytes needed by any *_fwd call with a rate output for B images (4 words per image + 4). */
 int64_t reslic_workspace_bytes(int64_t B);
+/* sizeof of every struct of this header as the LIBRARY was compiled (see `struct_size` above). */
+int64_t reslic_sizeof_gc_desc(void);
+int64_t reslic_sizeof_gc_bwd_desc(void);
+int64_t reslic_sizeof_eb_desc(void);
+int64_t reslic_sizeof_eb_bwd_desc(void);
+int64_t reslic_sizeof_stanh_tables(void);
+int64_t reslic_sizeof_stanh_gc_desc(void);
+int64_t reslic_sizeof_stanh_gc_bwd_desc(void);
+int64_t reslic_sizeof_eb_stanh_desc(void);
+int64_t reslic_sizeof_rate_exchange(void);
 
 /* Rate output modes (the `bits_accumulate` field of every *_fwd descriptor):
  *   0  bits[b]  = -sum log2 L of this launch       (written by the launch's last-arriving warp)
@@ -91,6 +106,51 @@ int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B,
                                     int32_t bits_accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------------
+ * Multi-GPU rate exchange without a collective kernel.
+ * The path shards by images; the only coupling between ranks is the scalar rate (and distortion) sum that
+ * the reference gets by gathering whole likelihood tensors to GPU 0 (nn.DataParallel: src/utils/helper.py:106-113,
+ * src/train.py:168-169) before src/training/loss.py:24-27 reduces them.  Here the launch that COLLECTS a batch's
+ * rate also publishes it: the warp that completes the batch stores one packed row
+ *     { sum_b bits[b], extra[0] (e.g. the squared-error sum), pixels, images }      (4 doubles)
+ * straight into every rank's exchange buffer over NVLink (peer stores) and then sets that row's flag — no
+ * separate kernel, no NCCL call on the step.  reslic_rate_exchange_read_f64 later adds the `world` rows of a
+ * step in rank order (bit-identical on every rank).
+ *
+ * Exchange buffer (one per rank, zero-filled once; `peer_base[r]` is rank r's buffer as mapped in THIS process —
+ * reslic_peer_buffer_* below, or any other peer-accessible allocation):
+ *     rows  double  [ring][world][4]       row (slot, r) is written by rank r only
+ *     flags uint64  [ring][world]          = step + 1 once row (step % ring, r) is complete
+ * `cursor` is a zero-initialised DEVICE word local to this rank: the number of steps it has published; the
+ * collecting launch advances it, so CUDA-graph replays publish consecutive steps.  A rank may run at most
+ * `ring` steps ahead of the slowest reader.  */
+typedef struct reslic_rate_exchange {
+  uint64_t struct_size;                    /* = sizeof(reslic_rate_exchange)                                  */
+  int32_t world, rank;                     /* 1 <= world <= 64                                                */
+  int32_t ring;                            /* slots per buffer                                                */
+  int32_t reserved;
+  void* const* peer_base;                  /* DEVICE array [world] of buffer bases (entry `rank` = own buffer) */
+  unsigned long long* cursor;              /* DEVICE word, see above                                          */
+  const double* extra;                     /* DEVICE, nullable: value published as the row's second field,    */
+                                           /* read when the batch completes                                   */
+  double pixels, images;                   /* the row's third and fourth field                                */
+} reslic_rate_exchange;
+int64_t reslic_rate_exchange_bytes(int32_t world, int32_t ring);
+/* out[s][0..3] = sum over ranks (in rank order) of the rows of steps first_step + s, s < n_steps, read from THIS
+ * rank's buffer `own_base`; waits (bounded: about 2 s, then the step's row is NaN and status[0] |= 1) until every
+ * rank's flag for the step has arrived.  status: DEVICE int32[1], zeroed by the caller. */
+int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t ring, int64_t first_step,
+                                  int32_t n_steps, double* out, int32_t* status, void* stream);
+
+/* Peer-accessible device memory for the exchange buffers (CUDA IPC): `create` allocates `bytes` zero-filled bytes on
+ * the current device and fills the 64-byte handle that another PROCESS on the same node passes to `open` (which
+ * maps the buffer, enabling peer access) — torch.distributed moves the handles.  `close` unmaps, `destroy` frees. */
+#define RESLIC_PEER_HANDLE_BYTES 64
+int reslic_peer_buffer_create(int64_t bytes, void** dptr, uint8_t* handle);
+int reslic_peer_buffer_open(const uint8_t* handle, void** dptr);
+int reslic_peer_buffer_close(void* dptr);
+int reslic_peer_buffer_destroy(void* dptr);
+
+/* ----------------------------------------------------------------------------------
  * Gaussian conditional, fused forward.
  * Replaces, in ONE pass over a slice (any subset of outputs):
  *   compressai GaussianConditional.forward            (call site tcm.py:455)
@@ -102,6 +162,7 @@ int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B,
  *   sum log(L) / -ln2  per image                       (training/loss.py:24-27; eval.py:27-31)
  * -------------------------------------------------------------------------------- */
 typedef struct reslic_gc_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_gc_desc); checked by the library           */
   /* inputs */
   const float* y;       int64_t y_bs;      /* latent slice                                */
   const float* mu;      int64_t mu_bs;     /* means; NULL = no means (values = inputs)    */
@@ -133,6 +194,9 @@ typedef struct reslic_gc_desc {
    * moves a third of the next launch's reads into this launch's under-used tail.  Never dereferenced by the math;
    * NULL or a misaligned pointer = no prefetch. */
   const float* next_y;  int64_t next_y_bs;
+  /* Optional (HOST pointer, read during the call): publish the batch's rate to every rank, see reslic_rate_exchange.
+   * Only with bits_accumulate 0 or RESLIC_RATE_COLLECT — the modes in which this launch completes bits[]. */
+  const reslic_rate_exchange* exchange;
 } reslic_gc_desc;
 
 int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream);
@@ -149,6 +213,7 @@ int reslic_gc_fwd_f32(const reslic_gc_desc* d, void* stream);
  *   mode DEQUANTIZE : g_y = g_ste,                g_mu = g_yhat,       g_sigma = gs*pass
  *   with gv = gL*pass_L * dL/dv * sign(yhat - mu), gs = gL*pass_L * dL/ds. */
 typedef struct reslic_gc_bwd_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_gc_bwd_desc); checked by the library           */
   const float* y;       int64_t y_bs;
   const float* mu;      int64_t mu_bs;     /* NULL = no means                              */
   const float* sigma;   int64_t sigma_bs;
@@ -191,6 +256,7 @@ int reslic_dequantize_f32(const int32_t* sym, const float* mu, int64_t n, float*
  * z is [B, C, hw] with batch stride z_bs; parameters are the module's raw tensors.
  * -------------------------------------------------------------------------------- */
 typedef struct reslic_eb_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_eb_desc); checked by the library           */
   const float* z;      int64_t z_bs;
   const float* noise;  int64_t noise_bs;   /* as in reslic_gc_desc                        */
   int64_t B, C, hw;
@@ -234,6 +300,7 @@ int reslic_eb_build_lut_f32(const reslic_eb_desc* d, float* lut, void* stream);
  * all B*hw elements of the channel; they are OVERWRITTEN (raw-parameter space: softplus' / tanh'
  * already applied).  g_medians is non-zero only in DEQUANTIZE mode (z_hat = round(z-med)+med). */
 typedef struct reslic_eb_bwd_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_eb_bwd_desc); checked by the library           */
   const float* z;      int64_t z_bs;
   const float* noise;  int64_t noise_bs;   /* NULL = Philox(seed, offset) as in the forward   */
   int64_t B, C, hw;
@@ -285,6 +352,7 @@ typedef struct reslic_stanh_tables {
  *         i.e. stanh.map_sos_cdf without the per-element Python loop (:144-157)
  * Layout conventions as reslic_gc_desc. */
 typedef struct reslic_stanh_gc_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_stanh_gc_desc); checked by the library           */
   const float* y;      int64_t y_bs;
   const float* mu;     int64_t mu_bs;      /* NULL = no means                              */
   const float* sigma;  int64_t sigma_bs;
@@ -318,6 +386,7 @@ int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream);
  * thresholds), dLoss/db_k = Wb[k], dLoss/d distance_points[m] = Hd[m]; mapping those to the module's raw
  * w / b (mirroring of the symmetric form, distance_points = diff(cum_w)/2) is K-sized host work. */
 typedef struct reslic_stanh_gc_bwd_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_stanh_gc_bwd_desc); checked by the library           */
   const float* y;      int64_t y_bs;
   const float* mu;     int64_t mu_bs;
   const float* sigma;  int64_t sigma_bs;
@@ -340,6 +409,7 @@ int reslic_stanh_gc_bwd_f32(const reslic_stanh_gc_bwd_desc* d, void* stream);
  * z without medians (training != 0: soft, beta; == 0: hard), variable-bin sign-trick likelihood
  * (:551-603, :643-666), level index, per-image rate.  z is [B, C, hw]; filters (3,3,3,3). */
 typedef struct reslic_eb_stanh_desc {
+  uint64_t struct_size;                    /* = sizeof(reslic_eb_stanh_desc); checked by the library           */
   const float* z;  int64_t z_bs;
   int64_t B, C, hw;
   int32_t training;

@@ -14,6 +14,9 @@ against outputs of the reference itself:
   (default STanH parameters, medians 0): pins _logits_cumulative, the sign trick and the
   permute wrapper.
 
+* ``stanh_update_golden.npz`` — the reference's unmodified ``GaussianConditionalStanh.update`` and
+  ``EntropyBottleneckStanh.update`` (pmf / cdf / _offset / _cdf_length over the STanH levels): SURVEY.md §8f N2.
+
 Third-party pieces that are NOT in the reference tree (compressai's quantize-about-medians,
 GaussianConditional.update, pmf_to_quantized_cdf) have no runnable reference here; those
 parts of the oracle are restated from the published algorithm and remain "unpinned".
@@ -217,6 +220,69 @@ def gen_eb_stanh():
     return out
 
 
+def gen_stanh_update():
+    """N2 pin: the reference's OWN ``update()`` methods, unmodified, on CPU —
+    ``GaussianConditionalStanh.update`` (src/entropy_models/adaptive_gaussian_conditional.py:397-454) and
+    ``EntropyBottleneckStanh.update`` (src/entropy_models/adaptive_entropy_bottleneck.py:481-514): the per-scale /
+    per-channel pmf over the STanH levels, the float cdf, ``_offset``, ``_cdf_length`` and ``_quantized_cdf``.
+    ``_quantized_cdf`` passes through ``compressai._CXX.pmf_to_quantized_cdf``, a third-party C++ op that is NOT in the
+    reference tree (the shim substitutes the oracle's restatement of the published algorithm), so that one array pins
+    the reference's row assembly (``_pmf_to_cdf``, :197-205: pmf row + tail mass, padding) but not the op itself."""
+    import contextlib
+    import io
+
+    em, _ = shim.load_stanh_modules()
+    cpu = torch.device("cpu")
+    out = {}
+    cases = {
+        "A": dict(symmetry=False, extrema=8, beta=10, perturb=False, table=[0.11, 0.5, 1.0, 4.0, 32.0]),
+        "B": dict(symmetry=False, extrema=5, beta=3, perturb=True, table=[0.2, 0.9, 2.5, 11.0]),
+        "C": dict(symmetry=True, extrema=6, beta=5, perturb=True, table=[0.11, 0.7, 3.0, 19.0, 64.0, 256.0]),
+    }
+    for tag, c in cases.items():
+        g = torch.Generator().manual_seed(1700 + ord(tag))
+        cfg = dict(beta=c["beta"], num_sigmoids=0, extrema=c["extrema"], trainable=True, removing_mean=True, symmetry=c["symmetry"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            gcs = em.GaussianConditionalStanh(None, channels=4, gaussian_configuration=cfg)
+            if c["perturb"]:
+                with torch.no_grad():
+                    gcs.stanh.w.mul_(1.0 + 0.2 * torch.rand(gcs.stanh.w.shape, generator=g))
+            gcs.scale_table = torch.tensor(c["table"])
+            gcs.update(cpu)
+        st = gcs.stanh
+        d = dict(scale_table=gcs.scale_table, w_param=st.w.detach(), b_param=st.b.detach(), cum_w=st.cum_w, pmf=gcs.pmf, cdf=gcs.cdf,
+                 offset=torch.as_tensor(gcs._offset).reshape(-1), cdf_length=gcs._cdf_length.reshape(-1), quantized_cdf=gcs._quantized_cdf,
+                 meta=torch.tensor([float(c["symmetry"]), c["extrema"], c["beta"]]))
+        for k, v in d.items():
+            out[f"gc{tag}_{k}"] = v.detach()
+    for tag, sym in (("N", False), ("S", True)):
+        torch.manual_seed(41 + int(sym))
+        g = torch.Generator().manual_seed(42 + int(sym))
+        cfg = dict(beta=4, num_sigmoids=0, extrema=6, trainable=True, symmetry=sym)
+        C = 5
+        with contextlib.redirect_stdout(io.StringIO()):
+            eb = em.EntropyBottleneckStanh(C, factorized_configuration=cfg)
+            with torch.no_grad():
+                eb.stanh.w.mul_(1.0 + 0.2 * torch.rand(eb.stanh.w.shape, generator=g))
+                for i in range(5):
+                    m = getattr(eb, f"_matrix{i}")
+                    m.add_(0.3 * torch.randn(m.shape, generator=g))
+                    if i < 4:
+                        f = getattr(eb, f"_factor{i}")
+                        f.copy_(0.5 * torch.randn(f.shape, generator=g))
+            eb.update(cpu)
+        d = dict(w_param=eb.stanh.w.detach(), b_param=eb.stanh.b.detach(), cum_w=eb.stanh.cum_w, pmf=eb.pmf.detach(), cdf=eb.cdf.detach())
+        for i in range(5):
+            d[f"_matrix{i}"] = getattr(eb, f"_matrix{i}").detach()
+            d[f"_bias{i}"] = getattr(eb, f"_bias{i}").detach()
+            if i < 4:
+                d[f"_factor{i}"] = getattr(eb, f"_factor{i}").detach()
+        for k, v in d.items():
+            out[f"eb{tag}_{k}"] = v.detach()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "stanh_update_golden.npz"), **{k: v.numpy() for k, v in out.items()})
+    return out
+
+
 if __name__ == "__main__":
     if not shim.available():
         raise SystemExit("reference not available: golden vectors can only be generated in the build container")
@@ -224,5 +290,6 @@ if __name__ == "__main__":
     b = gen_eb()
     c = gen_stanh()
     gen_eb_stanh()
-    print("stanh:", len(c), "arrays")
+    u = gen_stanh_update()
+    print("stanh:", len(c), "arrays; stanh update:", len(u), "arrays")
     print("wrote", GOLDEN_DIR, {k: tuple(v.shape) for k, v in a.items()}, {k: tuple(v.shape) for k, v in b.items()})

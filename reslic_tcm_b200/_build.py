@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libreslic_b200.so")
-CUDA_SOURCES = ["cabi.cu", "gc_fused.cu", "gc_bwd.cu", "eb_fused.cu", "eb_bwd.cu", "stanh_fused.cu", "rans_slots.cu", "rate_reduce.cu", "cdf_tables.cpp", "rans.cpp"]
+CUDA_SOURCES = ["cabi.cu", "gc_fused.cu", "gc_bwd.cu", "eb_fused.cu", "eb_bwd.cu", "stanh_fused.cu", "rans_slots.cu", "rate_reduce.cu", "rate_exchange.cu", "cdf_tables.cpp", "rans.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

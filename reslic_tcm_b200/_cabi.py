@@ -16,7 +16,8 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 15
+ABI_VERSION = 16
+PEER_HANDLE_BYTES = 64
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
 EB_LUT_STRIDE = 130
@@ -27,10 +28,29 @@ c_f32p = C.c_void_p
 c_i32p = C.c_void_p
 
 
+def new(cls):
+    """A zeroed descriptor with ``struct_size`` filled in — the only way descriptors are made here."""
+    d = cls()
+    d.struct_size = C.sizeof(cls)
+    return d
+
+
+class RateExchangeDesc(C.Structure):
+    """struct reslic_rate_exchange."""
+
+    _fields_ = [
+        ("struct_size", C.c_uint64),
+        ("world", C.c_int32), ("rank", C.c_int32), ("ring", C.c_int32), ("reserved", C.c_int32),
+        ("peer_base", C.c_void_p), ("cursor", C.c_void_p), ("extra", C.c_void_p),
+        ("pixels", C.c_double), ("images", C.c_double),
+    ]
+
+
 class GcDesc(C.Structure):
     """struct reslic_gc_desc (field order must match the header)."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("y", C.c_void_p), ("y_bs", C.c_int64),
         ("mu", C.c_void_p), ("mu_bs", C.c_int64),
         ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
@@ -47,6 +67,7 @@ class GcDesc(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
         ("next_y", C.c_void_p), ("next_y_bs", C.c_int64),
+        ("exchange", C.POINTER(RateExchangeDesc)),
     ]
 
 
@@ -54,6 +75,7 @@ class GcBwdDesc(C.Structure):
     """struct reslic_gc_bwd_desc."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("y", C.c_void_p), ("y_bs", C.c_int64),
         ("mu", C.c_void_p), ("mu_bs", C.c_int64),
         ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
@@ -74,6 +96,7 @@ class EbDesc(C.Structure):
     """struct reslic_eb_desc."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("z", C.c_void_p), ("z_bs", C.c_int64),
         ("noise", C.c_void_p), ("noise_bs", C.c_int64),
         ("B", C.c_int64), ("C", C.c_int64), ("hw", C.c_int64),
@@ -96,6 +119,7 @@ class EbBwdDesc(C.Structure):
     """struct reslic_eb_bwd_desc."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("z", C.c_void_p), ("z_bs", C.c_int64),
         ("noise", C.c_void_p), ("noise_bs", C.c_int64),
         ("B", C.c_int64), ("C", C.c_int64), ("hw", C.c_int64),
@@ -125,6 +149,7 @@ class StanhGcDesc(C.Structure):
     """struct reslic_stanh_gc_desc."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("y", C.c_void_p), ("y_bs", C.c_int64),
         ("mu", C.c_void_p), ("mu_bs", C.c_int64),
         ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
@@ -144,6 +169,7 @@ class StanhGcBwdDesc(C.Structure):
     """struct reslic_stanh_gc_bwd_desc."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("y", C.c_void_p), ("y_bs", C.c_int64),
         ("mu", C.c_void_p), ("mu_bs", C.c_int64),
         ("sigma", C.c_void_p), ("sigma_bs", C.c_int64),
@@ -164,6 +190,7 @@ class EbStanhDesc(C.Structure):
     """struct reslic_eb_stanh_desc."""
 
     _fields_ = [
+        ("struct_size", C.c_uint64),
         ("z", C.c_void_p), ("z_bs", C.c_int64),
         ("B", C.c_int64), ("C", C.c_int64), ("hw", C.c_int64),
         ("training", C.c_int32), ("likelihood_bound", C.c_float),
@@ -185,6 +212,22 @@ EXPORTS = {
     "reslic_set_math_mode": (C.c_int, [C.c_int]),
     "reslic_get_math_mode": (C.c_int, []),
     "reslic_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "reslic_sizeof_gc_desc": (C.c_int64, []),
+    "reslic_sizeof_gc_bwd_desc": (C.c_int64, []),
+    "reslic_sizeof_eb_desc": (C.c_int64, []),
+    "reslic_sizeof_eb_bwd_desc": (C.c_int64, []),
+    "reslic_sizeof_stanh_tables": (C.c_int64, []),
+    "reslic_sizeof_stanh_gc_desc": (C.c_int64, []),
+    "reslic_sizeof_stanh_gc_bwd_desc": (C.c_int64, []),
+    "reslic_sizeof_eb_stanh_desc": (C.c_int64, []),
+    "reslic_sizeof_rate_exchange": (C.c_int64, []),
+    "reslic_rate_exchange_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "reslic_rate_exchange_read_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
+    "reslic_peer_buffer_create": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "reslic_peer_buffer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "reslic_peer_buffer_close": (C.c_int, [C.c_void_p]),
+    "reslic_peer_buffer_destroy": (C.c_int, [C.c_void_p]),
     "reslic_rate_finalize_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "reslic_gc_fwd_f32": (C.c_int, [C.POINTER(GcDesc), C.c_void_p]),
     "reslic_gc_bwd_f32": (C.c_int, [C.POINTER(GcBwdDesc), C.c_void_p]),
@@ -217,6 +260,15 @@ EXPORTS = {
     "reslic_rans_decoder_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "reslic_pmf_to_quantized_cdf": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+# struct of this binding -> the library function that reports its sizeof (checked at load: a stale binding fails
+# loudly here instead of making the library read past a short struct)
+STRUCT_SIZES = {
+    GcDesc: "reslic_sizeof_gc_desc", GcBwdDesc: "reslic_sizeof_gc_bwd_desc", EbDesc: "reslic_sizeof_eb_desc",
+    EbBwdDesc: "reslic_sizeof_eb_bwd_desc", StanhTables: "reslic_sizeof_stanh_tables",
+    StanhGcDesc: "reslic_sizeof_stanh_gc_desc", StanhGcBwdDesc: "reslic_sizeof_stanh_gc_bwd_desc",
+    EbStanhDesc: "reslic_sizeof_eb_stanh_desc", RateExchangeDesc: "reslic_sizeof_rate_exchange",
 }
 
 _lib = None
@@ -252,6 +304,9 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.reslic_abi_version() != ABI_VERSION:
             raise ReslicError(f"ABI mismatch: library {lib.reslic_abi_version()} != binding {ABI_VERSION}")
+        for cls, fn in STRUCT_SIZES.items():
+            if C.sizeof(cls) != getattr(lib, fn)():
+                raise ReslicError(f"struct layout mismatch: {cls.__name__} is {C.sizeof(cls)} bytes here, {getattr(lib, fn)()} in the library")
         mode = os.environ.get("RESLIC_MATH_MODE")
         if mode:
             check_code = lib.reslic_set_math_mode({"fast": MATH_FAST, "mirror": MATH_MIRROR}[mode.lower()])

@@ -12,9 +12,10 @@ static int g_math_mode = RESLIC_MATH_FAST;
 int math_mode() { return g_math_mode; }
 const GcTuning& gc_tuning() {
   static GcTuning t = [] {
-    GcTuning v{-1, 1, 0};
+    GcTuning v{-1, 1, 0, 1};
     if (const char* e = std::getenv("RESLIC_GC_CTAS_PER_SM")) v.ctas_per_sm = std::atoi(e);
     if (const char* e = std::getenv("RESLIC_PDL")) v.pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RESLIC_GC_BALANCE")) v.balance = std::atoi(e);
     if (const char* e = std::getenv("RESLIC_GC_MIN_CTAS")) v.min_ctas = std::atoi(e);   // 4 / 5: force one build; 0: by launch size
     return v;
   }();
@@ -159,9 +160,18 @@ int reslic_set_math_mode(int mode) {
   return RESLIC_OK;
 }
 int reslic_get_math_mode(void) { return reslic::g_math_mode; }
+int64_t reslic_sizeof_gc_desc(void) { return sizeof(reslic_gc_desc); }
+int64_t reslic_sizeof_gc_bwd_desc(void) { return sizeof(reslic_gc_bwd_desc); }
+int64_t reslic_sizeof_eb_desc(void) { return sizeof(reslic_eb_desc); }
+int64_t reslic_sizeof_eb_bwd_desc(void) { return sizeof(reslic_eb_bwd_desc); }
+int64_t reslic_sizeof_stanh_tables(void) { return sizeof(reslic_stanh_tables); }
+int64_t reslic_sizeof_stanh_gc_desc(void) { return sizeof(reslic_stanh_gc_desc); }
+int64_t reslic_sizeof_stanh_gc_bwd_desc(void) { return sizeof(reslic_stanh_gc_bwd_desc); }
+int64_t reslic_sizeof_eb_stanh_desc(void) { return sizeof(reslic_eb_stanh_desc); }
+int64_t reslic_sizeof_rate_exchange(void) { return sizeof(reslic_rate_exchange); }
 int64_t reslic_workspace_bytes(int64_t B) {
   if (B <= 0) return 0;
-  return 4 * B * static_cast<int64_t>(sizeof(unsigned long long));
+  return (4 * B + 4) * static_cast<int64_t>(sizeof(unsigned long long));   // + batch total / count / flags / spare (rate_publish)
 }
 int reslic_rate_finalize_f64(void* workspace, int64_t workspace_bytes, int64_t B, double* bits, int32_t accumulate,
                              void* stream) {
@@ -180,6 +190,7 @@ int reslic_build_indexes_f32(const float* sigma, int64_t n, float scale_bound, c
                              int32_t table_len, int32_t* idx, void* stream) {
   reslic_gc_desc d;
   std::memset(&d, 0, sizeof(d));
+  d.struct_size = sizeof(d);
   d.sigma = sigma; d.sigma_bs = n; d.B = 1; d.n = n; d.mode = RESLIC_Q_DEQUANTIZE;
   d.scale_bound = scale_bound; d.scale_table = scale_table; d.table_len = table_len;
   d.idx = idx; d.idx_bs = n;

@@ -117,9 +117,59 @@ __device__ __forceinline__ unsigned long long rate_commit_issue(float acc, int i
   return now;
 }
 
+// ---- multi-GPU rate exchange (reslic_rate_exchange): kernel-side copy of the descriptor; world == 0 = none
+struct RateEx {
+  void* const* peer;              // DEVICE array [world] of exchange-buffer bases as mapped in this process
+  unsigned long long* cursor;     // DEVICE word: steps this rank has published
+  const double* extra;            // nullable
+  double pixels, images;
+  int world, rank, ring;
+};
+__device__ __forceinline__ double rate_fixed_to_bits(long long sum, unsigned long long flag) {
+  double bits = static_cast<double>(sum) * (1.0 / 65536.0);
+  if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
+  else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
+  return bits;
+}
+// Called by the ONE lane that completed image `image` (fixed-point rate `sum`, non-finite `flag`).  The lane that
+// completes the LAST image of the batch owns the batch total — workspace words [4B] sum, [4B+1] images done,
+// [4B+2] flags, integer adds again, so the total is bit-reproducible — and publishes the packed row
+// {bits, extra, pixels, images} into slot (cursor % ring, rank) of EVERY rank's exchange buffer with plain peer
+// stores over NVLink, then releases the row's flag (= step + 1) behind a system-scope fence.  No other thread of
+// the grid waits for any of this.
+static __device__ __noinline__ void rate_publish(long long sum, unsigned long long flag, int64_t B, unsigned long long* ws,
+                                                 const RateEx ex) {
+  unsigned long long* bw = ws + 4 * B;
+  atomicAdd(&bw[0], static_cast<unsigned long long>(sum));
+  if (flag) atomicOr(&bw[2], flag);
+  __threadfence();
+  if (atomicAdd(&bw[1], 1ull) + 1ull != static_cast<unsigned long long>(B)) return;
+  __threadfence();
+  const long long total = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&bw[0]));
+  const unsigned long long f = *reinterpret_cast<volatile unsigned long long*>(&bw[2]);
+  bw[0] = 0ull; bw[1] = 0ull;
+  if (f) bw[2] = 0ull;
+  const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(ex.cursor);
+  *reinterpret_cast<volatile unsigned long long*>(ex.cursor) = step + 1ull;
+  const size_t cell = static_cast<size_t>(step % static_cast<unsigned long long>(ex.ring)) * ex.world + ex.rank;
+  const double2 r01 = make_double2(rate_fixed_to_bits(total, f), ex.extra ? *ex.extra : 0.0);
+  const double2 r23 = make_double2(ex.pixels, ex.images);
+  for (int p = 0; p < ex.world; ++p) {
+    double2* row = reinterpret_cast<double2*>(static_cast<double*>(ex.peer[p]) + cell * 4);
+    row[0] = r01; row[1] = r23;
+  }
+  __threadfence_system();
+  const size_t flags_at = static_cast<size_t>(ex.ring) * ex.world * 4;       // in doubles = 64-bit words
+  for (int p = 0; p < ex.world; ++p) {
+    volatile unsigned long long* fl = reinterpret_cast<volatile unsigned long long*>(static_cast<double*>(ex.peer[p]) + flags_at) + cell;
+    *fl = step + 1ull;
+  }
+}
+
+// (kernels without an exchange pass RateEx{} — world 0 folds the publish branch away)
 __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int image, unsigned int expected,
                                                    int64_t B, unsigned long long* ws, double* bits_out,
-                                                   bool accumulate, bool collect = false) {
+                                                   bool accumulate, bool collect, const RateEx& ex) {
   if ((threadIdx.x & 31) == 0 && (now >> 48) == expected) {
     __threadfence();
     long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
@@ -131,12 +181,11 @@ __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int i
       if (dflag) ws[3 * B + image] = 0ull;
       flag |= dflag;
     }
-    double bits = static_cast<double>(sum) * (1.0 / 65536.0);
-    if (flag & 1ull) bits = __longlong_as_double(0x7ff8000000000000LL);
-    else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
+    const double bits = rate_fixed_to_bits(sum, flag);
     bits_out[image] = accumulate ? bits_out[image] + bits : bits;   // single writer per image
     ws[image] = 0ull;
     if (flag) ws[B + image] = 0ull;
+    if (ex.world > 0) rate_publish(sum, flag, B, ws, ex);
   }
 }
 
@@ -146,7 +195,8 @@ __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int i
 // reslic_rate_finalize_f64 later turns the words into bits and re-zeroes them.  Integer addition
 // commutes, so the result is still bit-reproducible and may accumulate over any number of launches.
 // Workspace layout (64-bit words): [0,B) immediate sum/arrival, [B,2B) immediate flags,
-// [2B,3B) deferred sums (signed fixed point, bits * 2^16), [3B,4B) deferred flags.
+// [2B,3B) deferred sums (signed fixed point, bits * 2^16), [3B,4B) deferred flags,
+// [4B,4B+4) batch total / images done / batch flags / spare (rate_publish).
 __device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsigned long long* ws) {
   const float v = warp_sum_f32(acc);
   if ((threadIdx.x & 31) == 0) {
@@ -159,10 +209,16 @@ __device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsi
 // `expected` = number of warps (over the whole grid) that commit to `image`;
 // mode = the descriptor's bits_accumulate (0 write, 1 accumulate, 2 deferred, 3 write + collect deferred).
 __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
-                                            unsigned long long* ws, double* bits_out, int mode) {
+                                            unsigned long long* ws, double* bits_out, int mode,
+                                            const RateEx& ex) {
   if (mode == 2) { rate_defer(acc, image, B, ws); return; }
   const unsigned long long now = rate_commit_issue(acc, image, B, ws);
-  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3);
+  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3, ex);
+}
+
+__device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
+                                            unsigned long long* ws, double* bits_out, int mode) {
+  rate_commit(acc, image, expected, B, ws, bits_out, mode, RateEx{nullptr, nullptr, nullptr, 0.0, 0.0, 0, 0, 0});
 }
 
 }  // namespace reslic

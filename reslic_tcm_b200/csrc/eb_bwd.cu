@@ -339,6 +339,8 @@ int64_t eb_bwd_workspace_bytes(int64_t C) {
 
 int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "eb_bwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_eb_bwd_desc))
+    return set_error(RESLIC_ERR_ARG, "eb_bwd: struct_size != sizeof(reslic_eb_bwd_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_bwd: negative size");
   if (d->C == 0) return RESLIC_OK;
   if (d->C > (1 << 20) || d->hw > (1LL << 30)) return set_error(RESLIC_ERR_ARG, "eb_bwd: size too large");

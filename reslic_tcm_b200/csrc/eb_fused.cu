@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
 
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "eb_fwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_eb_desc))
+    return set_error(RESLIC_ERR_ARG, "eb_fwd: struct_size != sizeof(reslic_eb_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_fwd: negative size");
   if (d->B == 0 || d->C == 0 || d->hw == 0) return RESLIC_OK;
   if (d->B > (1 << 24) || d->C > (1 << 20) || d->hw > (1LL << 30))
@@ -572,6 +574,8 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
 
 int eb_build_lut_launch(const reslic_eb_desc* d, float* lut, cudaStream_t st) {
   if (!d || !lut) return set_error(RESLIC_ERR_ARG, "eb_build_lut: null descriptor or table");
+  if (d->struct_size != sizeof(reslic_eb_desc))
+    return set_error(RESLIC_ERR_ARG, "eb_build_lut: struct_size != sizeof(reslic_eb_desc) (binding built against another ABI revision)");
   if (d->C < 0 || d->C > (1 << 20)) return set_error(RESLIC_ERR_ARG, "eb_build_lut: C out of range");
   if (d->C == 0) return RESLIC_OK;
   if (!d->medians) return set_error(RESLIC_ERR_ARG, "eb_build_lut: medians is null");

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(kThreads) gc_bwd_vec_kernel(const GcBwdParams 
 
 int gc_bwd_launch(const reslic_gc_bwd_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "gc_bwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_gc_bwd_desc))
+    return set_error(RESLIC_ERR_ARG, "gc_bwd: struct_size != sizeof(reslic_gc_bwd_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "gc_bwd: negative size");
   if (d->B == 0 || d->n == 0) return RESLIC_OK;
   if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE)

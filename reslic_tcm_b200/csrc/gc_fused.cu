@@ -38,7 +38,19 @@ struct GcParams {
   float d_limit;      // groups with max(|y-mu|, sigma) < d_limit take the clamp-free path; 0 sends every group to the general one
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
   const float* next_y; uint32_t next_y_bs;   // optional: the y the NEXT launch will read (same shape), prefetched into L2
+  RateEx ex;                                 // multi-GPU rate exchange of the collecting launch; world == 0: none
+#ifdef RESLIC_TRACE
+  unsigned long long* trace;                 // development builds (tools/dev): per-CTA %globaltimer stamps
+#endif
 };
+#ifdef RESLIC_TRACE
+static unsigned long long* g_trace_next = nullptr;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int smid() { unsigned int r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#define TRACE(j) do { if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 6 + (j)] = gtime(); } while (0)
+#else
+#define TRACE(j) do {} while (0)
+#endif
 
 // build_indexes: idx = #{ j < len-1 : !(s <= table[j]) } = (len-1) - sum_j [s <= table[j]].
 // Shared-memory layout: pad2[g] = (lo_g, hi_g) with lo_0 = -inf, lo_g = table[g-1], hi_g = lo_{g+1}
@@ -199,11 +211,13 @@ gc_fwd_kernel(const GcParams p) {
   __shared__ float2 pad2[NEED_IDX ? kPadLen : 1];
   __shared__ float s_guess[2];
   float g_scale = 0.0f, g_off = 0.0f;
+  TRACE(0);
   // Programmatic dependent launch: this grid may have been scheduled while its predecessor
   // in the stream was still draining.  Nothing is read from global memory before the wait;
   // dependents are released at once so that THEIR launch overlaps this grid's execution.
   griddep_wait();
   griddep_launch_dependents();
+  TRACE(1);
   bool table_staged = !NEED_IDX;
   auto stage_table = [&]() {
     const float inf = __int_as_float(0x7f800000);
@@ -324,6 +338,7 @@ gc_fwd_kernel(const GcParams p) {
     for (int k = 0; k < ntiles; k += 2) {
       if (k + 1 < ntiles) load(b, k + 1);
       compute(a, k);
+      if (k == 0) TRACE(2);
       if (k + 2 < ntiles) load(a, k + 2);
       if (k + 1 < ntiles) compute(b, k + 1);
     }
@@ -339,7 +354,7 @@ gc_fwd_kernel(const GcParams p) {
         };
         const unsigned int first = static_cast<unsigned int>(image) * p.tpi;
         const unsigned int n_ctas = owner(first + p.tpi - 1u) - owner(first) + 1u;
-        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate);
+        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate, p.ex);
       }
     }
   }
@@ -347,6 +362,10 @@ gc_fwd_kernel(const GcParams p) {
   // tensor, tcm.py:438-457: the next slice's y exists long before its mu / sigma do).  A slice launch is short —
   // about 3 tiles per CTA — so its first and last microsecond leave HBM under-used; CTAs that are done early pull
   // the next launch's first third of reads into that gap with one bulk instruction per image segment.
+  TRACE(3);
+#ifdef RESLIC_TRACE
+  if (p.trace && threadIdx.x == 0) { p.trace[blockIdx.x * 6 + 4] = smid(); p.trace[blockIdx.x * 6 + 5] = t_end - (cta * p.q_tiles + min(cta, p.r_tiles)); }
+#endif
   if (VEC && p.next_y != nullptr && threadIdx.x == 0) {
     unsigned int t2 = cta * p.q_tiles + min(cta, p.r_tiles);
     const unsigned int image_bytes = static_cast<unsigned int>(p.n) * 4u;
@@ -391,6 +410,14 @@ static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
     // (measured: 61.5 -> 57.3 us on 24 x 491520; shorter launches lose more to the second prologue)
     grid = static_cast<int64_t>(resident_ctas(kernel, &occ)) * sm_count();
     if (total >= 16 * grid) grid *= 2;
+    else if (total > grid && total <= 2 * grid && gc_tuning().balance) {
+      // a little more than one wave of tiles (an 8-GPU shard of a slice: 768 tiles on 740 slots): the fewest CTAs that
+      // keep the longest range at two tiles, so that EVERY CTA has both of its tiles in flight together, instead of a full
+      // wave of one-tile CTAs plus a few stragglers that run a second tile alone — and the CTA slots left free host the
+      // next launch of an overlapping chain (measured, three chains in flight, 8 x 98304: 19.1 -> 16.0 us per 5 launches;
+      // mid-size launches lose: 24 x 98304 at 576 x 4 tiles 71 -> 80 us single chain, so the rule stops at two tiles)
+      grid = (total + 1) / 2;
+    }
   }
   if (grid > total) grid = total;
   // the next-launch L2 prefetch pays on short launches only (measured: 24 x 98304, 3.1 tiles per CTA, 14.1 -> 13.2 us;
@@ -413,6 +440,9 @@ static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
+#ifdef RESLIC_TRACE
+  p.trace = g_trace_next;
+#endif
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
@@ -437,6 +467,8 @@ static cudaError_t launch_noise(GcParams& p, bool vec, bool noise, bool fast, cu
 
 int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "gc_fwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_gc_desc))
+    return set_error(RESLIC_ERR_ARG, "gc_fwd: struct_size != sizeof(reslic_gc_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "gc_fwd: negative size");
   if (d->B == 0 || d->n == 0) return RESLIC_OK;  // empty input: nothing to do
   if (d->B > (1 << 24)) return set_error(RESLIC_ERR_ARG, "gc_fwd: B too large");
@@ -492,6 +524,17 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
                               &p.bits, &p.bits_accumulate, &p.workspace);
     if (rc != RESLIC_OK) return rc;
   }
+  if (d->exchange) {
+    const reslic_rate_exchange* x = d->exchange;
+    if (x->struct_size != sizeof(reslic_rate_exchange))
+      return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange->struct_size != sizeof(reslic_rate_exchange) (ABI mismatch)");
+    if (!want_rate || (d->bits_accumulate != 0 && d->bits_accumulate != RESLIC_RATE_COLLECT))
+      return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange needs a rate output in mode 0 or RESLIC_RATE_COLLECT");
+    if (x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->ring < 1 || !x->peer_base || !x->cursor)
+      return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange: bad world/rank/ring or null peer_base/cursor");
+    p.ex.peer = x->peer_base; p.ex.cursor = x->cursor; p.ex.extra = x->extra; p.ex.pixels = x->pixels; p.ex.images = x->images;
+    p.ex.world = x->world; p.ex.rank = x->rank; p.ex.ring = x->ring;
+  }
   const bool noise = d->mode == RESLIC_Q_NOISE;
   const bool fast = math_mode() != RESLIC_MATH_MIRROR;
   // The clamp-free path needs (2^22 + 1) / scale_bound far from overflow and, in FAST mode, a bound
@@ -508,3 +551,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
 }
 
 }  // namespace reslic
+
+#ifdef RESLIC_TRACE
+extern "C" void reslic_debug_set_trace(unsigned long long* ptr) { reslic::g_trace_next = ptr; }
+#endif

@@ -9,7 +9,7 @@ namespace reslic {
 int set_error(int code, const char* msg);                 // returns code
 int set_cuda_error(cudaError_t err, const char* where);   // returns (int)err
 int sm_count();
-struct GcTuning { int ctas_per_sm; int pdl; int min_ctas; };
+struct GcTuning { int ctas_per_sm; int pdl; int min_ctas; int balance; };
 const GcTuning& gc_tuning();                              // launch-shape knobs (env overridable)
 // Rate outputs of a *_fwd descriptor: requested when `bits` is given or the mode is RESLIC_RATE_DEFERRED.
 inline bool rate_requested(const double* bits, int32_t mode) { return bits != nullptr || mode == 2; }

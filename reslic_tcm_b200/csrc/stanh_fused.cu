@@ -583,6 +583,8 @@ static size_t tables_smem(int K) { return static_cast<size_t>(5 * K + 1) * sizeo
 
 int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_stanh_gc_desc))
+    return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: struct_size != sizeof(reslic_stanh_gc_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: negative size");
   if (d->B == 0 || d->n == 0) return RESLIC_OK;
   if (int rc = check_tables(&d->tables, "stanh_gc_fwd")) return rc;
@@ -712,6 +714,8 @@ int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, fl
 
 int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_eb_stanh_desc))
+    return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: struct_size != sizeof(reslic_eb_stanh_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: negative size");
   if (d->B == 0 || d->C == 0 || d->hw == 0) return RESLIC_OK;
   if (int rc = check_tables(&d->tables, "eb_stanh_fwd")) return rc;
@@ -942,6 +946,8 @@ __global__ void __launch_bounds__(kThreads) stanh_gc_bwd_kernel(const StanhBwdPa
 
 int stanh_gc_bwd_launch(const reslic_stanh_gc_bwd_desc* d, cudaStream_t st) {
   if (!d) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: null descriptor");
+  if (d->struct_size != sizeof(reslic_stanh_gc_bwd_desc))
+    return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: struct_size != sizeof(reslic_stanh_gc_bwd_desc) (binding built against another ABI revision)");
   if (d->B < 0 || d->n < 0) return set_error(RESLIC_ERR_ARG, "stanh_gc_bwd: negative size");
   if (d->B == 0 || d->n == 0) return RESLIC_OK;
   if (int rc = check_tables(&d->tables, "stanh_gc_bwd")) return rc;

@@ -190,6 +190,7 @@ def gc_forward(
     seed: int = 0,
     offset: int = 0,
     next_y: Optional[Tensor] = None,
+    exchange=None,
 ) -> GcOutputs:
     """One fused pass over a Gaussian-conditional slice.
 
@@ -197,6 +198,8 @@ def gc_forward(
     to a preallocated tensor (e.g. a channel slice of a full ``y_hat``) to write into.
     Mirrors GaussianConditional.forward + ste_round + build_indexes + quantize("symbols")
     + the log2-rate sum (tcm.py:455,457,544,548; loss.py:24-27).
+    ``exchange``: a :class:`reslic_tcm_b200.dist.PeerRateExchange` — the launch that completes ``bits`` (rate mode 0 or
+    collect) also publishes the batch's packed rate row to every rank (no collective kernel).
     """
     lib = _cabi.load()
     _require_cuda("inputs", y)
@@ -230,7 +233,7 @@ def gc_forward(
     out = dict(out or {})
     shape = y.shape
     B = shape[0] if y.dim() > 0 else 1
-    d = _cabi.GcDesc()
+    d = _cabi.new(_cabi.GcDesc)
     keep = []  # keep temporaries alive until the launch is enqueued
 
     def bind_in(name, t):
@@ -287,6 +290,10 @@ def gc_forward(
         if tv.data_ptr() == next_y.data_ptr():
             d.next_y, d.next_y_bs = next_y.data_ptr(), bs_n
             keep.append(next_y)
+    if exchange is not None:
+        if exchange.device != y.device:
+            raise ValueError("exchange lives on another device")
+        d.exchange = C.pointer(exchange.desc)
     with torch.cuda.device(y.device):
         code = lib.reslic_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(y.device))
     _cabi.check(code, "reslic_gc_fwd_f32")
@@ -315,7 +322,7 @@ def gc_backward(
     output, the ste_round output and the bounded likelihood (each may be None = zero)."""
     lib = _cabi.load()
     _require_cuda("inputs", y)
-    d = _cabi.GcBwdDesc()
+    d = _cabi.new(_cabi.GcBwdDesc)
     keep = []
 
     def bind(name, t):
@@ -462,7 +469,7 @@ def eb_build_lut(matrices: Sequence[Tensor], biases: Sequence[Tensor], factors: 
     if len(matrices) != 5 or len(biases) != 5 or len(factors) != 4:
         raise _cabi.ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
     Cc = matrices[0].shape[0]
-    d = _cabi.EbDesc()
+    d = _cabi.new(_cabi.EbDesc)
     keep: list = []
     _eb_fill_params(d, matrices, biases, factors, medians, Cc, keep)
     d.C = Cc
@@ -514,7 +521,7 @@ def eb_forward(
     hw = 1
     for s in z.shape[2:]:
         hw *= s
-    d = _cabi.EbDesc()
+    d = _cabi.new(_cabi.EbDesc)
     keep = [zc]
     d.z, d.z_bs = zc.data_ptr(), Cc * hw
     if noise is not None:
@@ -600,7 +607,7 @@ def eb_backward(
     for s_ in z.shape[2:]:
         hw *= s_
     zc = z.contiguous()
-    d = _cabi.EbBwdDesc()
+    d = _cabi.new(_cabi.EbBwdDesc)
     keep = [zc]
     d.z, d.z_bs = zc.data_ptr(), Cc * hw
     for name, t in (("noise", noise), ("g_zhat", g_zhat), ("g_lik", g_lik)):

@@ -70,7 +70,7 @@ class TcmEntropyPath(nn.Module):
     def forward(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, *, training: bool = False,
                 with_indexes: bool = False, num_pixels: Optional[int] = None, seed: int = 0,
                 offset: int = 0, noise_y: Optional[Tensor] = None, noise_z: Optional[Tensor] = None,
-                fuse_slices: bool = False, skip_z: bool = False, defer_rate: bool = False) -> Dict[str, Tensor]:
+                fuse_slices: bool = False, skip_z: bool = False, defer_rate: bool = False, exchange=None) -> Dict[str, Tensor]:
         """All tensors on the GPU, NCHW fp32: y/mu/sigma [B, 320, h, w], z [B, 192, h/4, w/4].
         Returns views of static buffers (valid until the next call).
 
@@ -79,7 +79,9 @@ class TcmEntropyPath(nn.Module):
         src/models/Balle2018.py: one gaussian_conditional call on the whole y); TCM itself needs
         the per-slice mode because slice k's parameters depend on y_hat of slices < k.
         ``defer_rate`` leaves the pass's rate in the workspace (no launch collects; ``bits`` is not
-        written): the caller sums several passes and calls ``ops.rate_finalize`` once."""
+        written): the caller sums several passes and calls ``ops.rate_finalize`` once.
+        ``exchange`` (a :class:`reslic_tcm_b200.dist.PeerRateExchange`): multi-GPU runs — the launch that collects the
+        batch's rate also publishes it to every rank over NVLink; no collective kernel runs."""
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         b = self.buffers(y, z, with_indexes, training)
         C = y.shape[1]
@@ -118,7 +120,8 @@ class TcmEntropyPath(nn.Module):
                            scale_table=gc.scale_table if with_indexes else None, scale_bound=gc._scale_bound,
                            likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
                            offset=offset + 1 + k,
-                           next_y=y[:, cs * (k + 1):cs * (k + 2)] if (k + 1 < n_launch and self.prefetch_next_slice) else None)
+                           next_y=y[:, cs * (k + 1):cs * (k + 2)] if (k + 1 < n_launch and self.prefetch_next_slice) else None,
+                           exchange=exchange if (k + 1 == n_launch and not defer_rate) else None)
         res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
                "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
         if with_indexes:

@@ -364,7 +364,7 @@ class HypeEntropyModelSoS(EntropyModel):
         ops._require_cuda("inputs", inputs)
         _no_grad_path(inputs, scales, means, self.stanh.w, self.stanh.b)
         want = set(want)
-        d = _cabi.StanhGcDesc()
+        d = _cabi.new(_cabi.StanhGcDesc)
         keep = []
 
         def bind(name, t):
@@ -416,7 +416,7 @@ class HypeEntropyModelSoS(EntropyModel):
 
     def _stanh_backward(self, inputs, scales, means, training, g_yhat, g_lik, want_params: bool = False):
         lib = _cabi.load()
-        d = _cabi.StanhGcBwdDesc()
+        d = _cabi.new(_cabi.StanhGcBwdDesc)
         keep = []
 
         def bind(name, t):
@@ -737,7 +737,7 @@ class EntropyBottleneckStanh(EntropyModel):
         hw = 1
         for s_ in xc.shape[2:]:
             hw *= s_
-        d = _cabi.EbStanhDesc()
+        d = _cabi.new(_cabi.EbStanhDesc)
         keep = [xc]
         d.z, d.z_bs = xc.data_ptr(), Cc * hw
         d.B, d.C, d.hw = B, Cc, hw

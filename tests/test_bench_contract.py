@@ -30,7 +30,11 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("tcm64_kodak768x512_b24")
+    assert d["config"]["workload"] == "tcm128_kodak768x512_b64_likelihood_bpp" and d["scaling"] == "strong"
+    # the reference arm steps over a bounded sample but names the SAME workload object as our arm
+    import bench
+
+    assert d["config"] == bench.workload_config(bench.synthetic.CONFIGS[3], 1, "strong")
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -39,14 +43,29 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_default_arm_line_on_gpu():
-    lines = _run(["--steps", "12", "--warmup", "3", "--cpu-images", "1", "--no-whole-y", "--no-training-kernels"])
+    lines = _run(["--steps", "24", "--warmup", "3", "--cpu-images", "1", "--no-training-kernels", "--legs", "2"])
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert BASE_KEYS <= set(d) and d["n_gpus"] == 1 and d["gpu_launches"] == 6 * 12
+    assert BASE_KEYS <= set(d) and d["n_gpus"] == 1 and d["gpu_launches"] == 6 * 24 and d["scaling"] == "strong"
+    assert d["config"]["workload"] == "tcm128_kodak768x512_b64_likelihood_bpp" and d["config"]["images_per_gpu"] == 64
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.2 < r["frac"] < 1.0 and r["kernel"] == "gc_fwd_kernel"
-    assert abs(r["achieved"] / r["peak"] - r["frac"]) < 1e-9
+    assert abs(r["achieved"] / r["peak"] - r["frac"]) < 1e-9 and r["bytes_per_elem"] == 20 and r["elems_per_launch"] == 64 * 98304
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] == 143327232 and d["e2e"]["d2h_bytes_per_step"] == 94372032
-    assert d["e2e_slots"]["d2h_bytes_per_step"] < 0.6 * d["e2e"]["d2h_bytes_per_step"]
+    # config 3 reads back the per-image bits only; its inputs are 64 images of y / mu / sigma / z
+    assert d["e2e"]["h2d_bytes_per_step"] == 64 * (3 * 491520 + 18432) * 4 and d["e2e"]["d2h_bytes_per_step"] == 64 * 8
     assert d["e2e"]["value"] < d["value"] and d["clocks"]["sm_max_mhz"]
+    # the other BASELINE configs carry their own roofline objects; config 2 is the compress-path one (packed slots home)
+    leg = d["per_config"]["2"]
+    assert leg["roofline"]["bytes_per_elem"] == 28 and leg["roofline"]["elems_per_launch"] == 24 * 98304
+    assert 0.2 < leg["whole_y"]["roofline"]["frac"] < 1.0
+    assert leg["e2e"]["h2d_bytes_per_step"] == 143327232 and leg["e2e"]["d2h_bytes_per_step"] < 0.6 * 94372032
+    assert d["per_config"]["3"]["roofline"] == d["roofline"] and d["legs"]["2"]["scaling"] == "strong"
+
+
+@pytest.mark.gpu
+def test_simulated_shard_line_on_gpu():
+    """--shard-of 8: rank 0's share of the 8-GPU strong-scaling job on one GPU (development aid)."""
+    lines = _run(["--steps", "24", "--warmup", "3", "--shard-of", "8", "--no-e2e", "--no-whole-y", "--no-cpu-baseline", "--legs", "none"])
+    d = json.loads(lines[0])
+    assert d["config"]["images_per_gpu"] == 8 and d["config"]["simulated_shard_of"] == 8 and d["value"] > 0

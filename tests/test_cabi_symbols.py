@@ -42,11 +42,43 @@ def test_abi_version_and_workspace(lib):
     assert lib.reslic_workspace_bytes(-3) == 0
 
 
-def test_struct_sizes_match_header_layout():
-    # 64-bit ABI: computed by hand from the header's field order
+def test_struct_sizes_match_header_layout(lib):
+    # 64-bit ABI: computed by hand from the header's field order (struct_size is the first member of every descriptor)
     assert ctypes.sizeof(_cabi.GcDesc) % 8 == 0
-    assert _cabi.GcDesc.B.offset == 64 and _cabi.GcDesc.mode.offset == 80
-    assert _cabi.EbDesc.matrix.offset == 64 and _cabi.EbDesc.medians.offset == 64 + 14 * 8
+    assert _cabi.GcDesc.struct_size.offset == 0 and _cabi.GcDesc.B.offset == 72 and _cabi.GcDesc.mode.offset == 88
+    assert _cabi.EbDesc.matrix.offset == 72 and _cabi.EbDesc.medians.offset == 72 + 14 * 8
+    # ... and every ctypes struct is exactly as large as the library's own sizeof
+    for cls, fn in _cabi.STRUCT_SIZES.items():
+        assert ctypes.sizeof(cls) == getattr(lib, fn)(), cls.__name__
+    for cls in _cabi.STRUCT_SIZES:
+        if cls is not _cabi.StanhTables:
+            assert cls._fields_[0][0] == "struct_size" and _cabi.new(cls).struct_size == ctypes.sizeof(cls)
+
+
+def test_short_or_stale_descriptor_is_rejected_before_any_field_is_read(lib):
+    """A binding built against another ABI revision (the pre-next_y struct of INTEGRATION.md) must get
+    RESLIC_ERR_ARG, not a library that reads past its struct.  No GPU needed: the check precedes everything."""
+    calls = [(_cabi.GcDesc, lib.reslic_gc_fwd_f32), (_cabi.GcBwdDesc, lib.reslic_gc_bwd_f32),
+             (_cabi.EbDesc, lib.reslic_eb_fwd_f32), (_cabi.EbBwdDesc, lib.reslic_eb_bwd_f32),
+             (_cabi.StanhGcDesc, lib.reslic_stanh_gc_fwd_f32), (_cabi.StanhGcBwdDesc, lib.reslic_stanh_gc_bwd_f32),
+             (_cabi.EbStanhDesc, lib.reslic_eb_stanh_fwd_f32)]
+    for cls, fn in calls:
+        for bad in (0, ctypes.sizeof(cls) - 16, ctypes.sizeof(cls) + 8):
+            d = cls()
+            d.struct_size = bad
+            assert fn(ctypes.byref(d), None) == -1, (cls.__name__, bad)
+            assert b"struct_size" in lib.reslic_last_error()
+    d = _cabi.new(_cabi.GcDesc)
+    assert lib.reslic_gc_fwd_f32(ctypes.byref(d), None) == 0      # correctly sized, B = 0: empty input, nothing to do
+    d = _cabi.new(_cabi.EbDesc)
+    d.struct_size -= 8
+    assert lib.reslic_eb_build_lut_f32(ctypes.byref(d), ctypes.c_void_p(8), None) == -1
+
+
+def test_rate_exchange_layout(lib):
+    assert lib.reslic_rate_exchange_bytes(8, 256) == 256 * 8 * (4 * 8 + 8)
+    assert lib.reslic_rate_exchange_bytes(0, 4) == 0 and lib.reslic_rate_exchange_bytes(2, 0) == 0
+    assert lib.reslic_workspace_bytes(24) == (4 * 24 + 4) * 8
 
 
 def test_missing_library_fails_loudly(monkeypatch):

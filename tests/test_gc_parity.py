@@ -227,7 +227,7 @@ def test_empty_and_errors(gc):
         GaussianConditional(None).to(DEV).build_indexes(x)
     with pytest.raises(TypeError):
         ops.gc_forward(x.double(), x.double(), x.double())
-    d = _cabi.GcDesc()
+    d = _cabi.new(_cabi.GcDesc)
     assert _cabi.load().reslic_gc_fwd_f32(d, None) == 0          # B = 0: empty, ok
     d.B, d.n = 1, 4
     assert _cabi.load().reslic_gc_fwd_f32(d, None) == -1         # no pointers: argument error
