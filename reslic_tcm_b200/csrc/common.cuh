@@ -131,19 +131,22 @@ __device__ __forceinline__ double rate_fixed_to_bits(long long sum, unsigned lon
   else if (flag & 2ull) bits = __longlong_as_double(0x7ff0000000000000LL);
   return bits;
 }
-// Called by the ONE lane that completed image `image` (fixed-point rate `sum`, non-finite `flag`).  The lane that
-// completes the LAST image of the batch owns the batch total — workspace words [4B] sum, [4B+1] images done,
-// [4B+2] flags, integer adds again, so the total is bit-reproducible — and publishes the packed row
-// {bits, extra, pixels, images} into slot (cursor % ring, rank) of EVERY rank's exchange buffer with plain peer
-// stores over NVLink, then releases the row's flag (= step + 1) behind a system-scope fence.  No other thread of
-// the grid waits for any of this.
-static __device__ __noinline__ void rate_publish(long long sum, unsigned long long flag, int64_t B, unsigned long long* ws,
-                                                 const RateEx ex) {
+// What one lane has won so far: the fixed-point rates of the images whose LAST arriver it was.  Kept in registers across
+// the kernel's tile loop and handed to rate_publish once, after the loop, where nothing else is live (with the publish
+// inside the loop the 48-register build of the Gaussian-conditional kernel spills three times as much).
+struct RateWin { long long sum; unsigned long long flag; unsigned int count; };
+
+// Called after the tile loop by every lane that completed at least one image.  The lane that completes the LAST image
+// of the batch owns the batch total — workspace words [4B] sum, [4B+1] images done, [4B+2] flags; integer adds again,
+// so the total is bit-reproducible — and publishes the packed row {bits, extra, pixels, images} into slot
+// (cursor % ring, rank) of EVERY rank's exchange buffer with plain peer stores over NVLink, then releases the row's
+// flag (= step + 1) behind a system-scope fence.  No other thread of the grid waits for any of this.
+static __device__ __noinline__ void rate_publish(const RateWin win, int64_t B, unsigned long long* ws, const RateEx ex) {
   unsigned long long* bw = ws + 4 * B;
-  atomicAdd(&bw[0], static_cast<unsigned long long>(sum));
-  if (flag) atomicOr(&bw[2], flag);
+  atomicAdd(&bw[0], static_cast<unsigned long long>(win.sum));
+  if (win.flag) atomicOr(&bw[2], win.flag);
   __threadfence();
-  if (atomicAdd(&bw[1], 1ull) + 1ull != static_cast<unsigned long long>(B)) return;
+  if (atomicAdd(&bw[1], static_cast<unsigned long long>(win.count)) + win.count != static_cast<unsigned long long>(B)) return;
   __threadfence();
   const long long total = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&bw[0]));
   const unsigned long long f = *reinterpret_cast<volatile unsigned long long*>(&bw[2]);
@@ -166,10 +169,10 @@ static __device__ __noinline__ void rate_publish(long long sum, unsigned long lo
   }
 }
 
-// (kernels without an exchange pass RateEx{} — world 0 folds the publish branch away)
+// (`win`: where the winning lane notes what it completed, for rate_publish after the loop; nullptr = no exchange)
 __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int image, unsigned int expected,
                                                    int64_t B, unsigned long long* ws, double* bits_out,
-                                                   bool accumulate, bool collect, const RateEx& ex) {
+                                                   bool accumulate, bool collect = false, RateWin* win = nullptr) {
   if ((threadIdx.x & 31) == 0 && (now >> 48) == expected) {
     __threadfence();
     long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
@@ -185,7 +188,7 @@ __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int i
     bits_out[image] = accumulate ? bits_out[image] + bits : bits;   // single writer per image
     ws[image] = 0ull;
     if (flag) ws[B + image] = 0ull;
-    if (ex.world > 0) rate_publish(sum, flag, B, ws, ex);
+    if (win != nullptr) { win->sum += sum; win->flag |= flag; win->count += 1u; }
   }
 }
 
@@ -210,15 +213,10 @@ __device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsi
 // mode = the descriptor's bits_accumulate (0 write, 1 accumulate, 2 deferred, 3 write + collect deferred).
 __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
                                             unsigned long long* ws, double* bits_out, int mode,
-                                            const RateEx& ex) {
+                                            RateWin* win = nullptr) {
   if (mode == 2) { rate_defer(acc, image, B, ws); return; }
   const unsigned long long now = rate_commit_issue(acc, image, B, ws);
-  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3, ex);
-}
-
-__device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
-                                            unsigned long long* ws, double* bits_out, int mode) {
-  rate_commit(acc, image, expected, B, ws, bits_out, mode, RateEx{nullptr, nullptr, nullptr, 0.0, 0.0, 0, 0, 0});
+  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3, win);
 }
 
 }  // namespace reslic

@@ -205,7 +205,11 @@ __device__ __forceinline__ void gc_group_vec(const GcParams& p, const float2* pa
 // the faster build for long launches; 5 (48 registers, a few spilled scalars, 25 % more warps to hide
 // the first-tile latency) wins on short ones (a TCM slice: < 4 tiles per CTA) — measured 14.1 vs 14.5 us
 // on 24 x 98304 and 66.8 vs 57.3 us on 24 x 491520, so the host picks by launch size.
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST, int MINB>
+// EXCH: the launch also publishes the batch's rate to every rank (reslic_rate_exchange).  A template flag, not a
+// run-time test: with the publish path merely PRESENT in the kernel the 48-register build spills three times as much
+// (117 LDL against 39 in the loop), which costs every launch 30 % — so only the collecting launch of a multi-GPU
+// step runs the instantiation that contains it.
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST, int MINB, bool EXCH>
 __global__ void __launch_bounds__(kThreads, MINB)
 gc_fwd_kernel(const GcParams p) {
   __shared__ float2 pad2[NEED_IDX ? kPadLen : 1];
@@ -257,6 +261,7 @@ gc_fwd_kernel(const GcParams p) {
   const unsigned int t_end = t + p.q_tiles + (cta < p.r_tiles ? 1u : 0u);
   const unsigned int tb = threadIdx.x * (W * 4);
 
+  RateWin win{0ll, 0ull, 0u};                // images this lane completed (EXCH only; published after the loop)
   GcIn a, b;
   a.y = a.m = a.u = make_float4(0.f, 0.f, 0.f, 0.f); a.s = make_float4(1.f, 1.f, 1.f, 1.f);
   b = a;                                     // absent inputs keep these defaults for the whole launch
@@ -354,7 +359,7 @@ gc_fwd_kernel(const GcParams p) {
         };
         const unsigned int first = static_cast<unsigned int>(image) * p.tpi;
         const unsigned int n_ctas = owner(first + p.tpi - 1u) - owner(first) + 1u;
-        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate, p.ex);
+        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate, EXCH ? &win : nullptr);
       }
     }
   }
@@ -362,6 +367,7 @@ gc_fwd_kernel(const GcParams p) {
   // tensor, tcm.py:438-457: the next slice's y exists long before its mu / sigma do).  A slice launch is short —
   // about 3 tiles per CTA — so its first and last microsecond leave HBM under-used; CTAs that are done early pull
   // the next launch's first third of reads into that gap with one bulk instruction per image segment.
+  if (EXCH && win.count != 0u) rate_publish(win, p.B, p.workspace, p.ex);
   TRACE(3);
 #ifdef RESLIC_TRACE
   if (p.trace && threadIdx.x == 0) { p.trace[blockIdx.x * 6 + 4] = smid(); p.trace[blockIdx.x * 6 + 5] = t_end - (cta * p.q_tiles + min(cta, p.r_tiles)); }
@@ -396,10 +402,10 @@ static int resident_ctas(K kernel, int* cache) {
   return *cache;
 }
 
-template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST, int MINB>
+template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC, bool FAST, int MINB, bool EXCH = false>
 static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
   static int occ = 0;
-  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, FAST, MINB>;
+  auto kernel = gc_fwd_kernel<NEED_LIK, NEED_IDX, NOISE, VEC, FAST, MINB, EXCH>;
   const int64_t total = p.tiles_per_image * p.B;
   const int waves = gc_tuning().ctas_per_sm;   // 0: one tile per CTA; k>0: k CTAs per SM; <0: resident count
   int64_t grid = total;
@@ -447,6 +453,13 @@ static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
 }
 template <bool NEED_LIK, bool NEED_IDX, bool NOISE, bool VEC>
 static cudaError_t launch_math(GcParams& p, bool fast, cudaStream_t st) {
+  if (p.ex.world > 0) {   // the collecting launch of a multi-GPU step (host checked: NEED_LIK and the 128-bit path)
+    constexpr bool kEx = NEED_LIK && VEC;
+    if (!fast) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, false, 4, kEx>(p, st);
+    const bool short_ex = p.tiles_per_image * p.B <= 8LL * 4 * sm_count() && gc_tuning().min_ctas != 4;
+    if (short_ex || gc_tuning().min_ctas == 5) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, true, VEC ? 5 : 4, kEx>(p, st);
+    return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, true, 4, kEx>(p, st);
+  }
   // the math policy only matters when a likelihood is computed
   if (NEED_LIK && !fast) return launch_one<NEED_LIK, NEED_IDX, NOISE, VEC, false, 4>(p, st);
   // short launches (at most 8 tiles per CTA slot of the 4-per-SM build) take the 5-per-SM build
@@ -535,6 +548,8 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
     p.ex.peer = x->peer_base; p.ex.cursor = x->cursor; p.ex.extra = x->extra; p.ex.pixels = x->pixels; p.ex.images = x->images;
     p.ex.world = x->world; p.ex.rank = x->rank; p.ex.ring = x->ring;
   }
+  if (p.ex.world > 0 && !vec)
+    return set_error(RESLIC_ERR_UNSUPPORTED, "gc_fwd: exchange needs the 128-bit path (16-byte aligned tensors, strides and n multiples of 4)");
   const bool noise = d->mode == RESLIC_Q_NOISE;
   const bool fast = math_mode() != RESLIC_MATH_MIRROR;
   // The clamp-free path needs (2^22 + 1) / scale_bound far from overflow and, in FAST mode, a bound

@@ -68,13 +68,35 @@ class LowerBound(nn.Module):
 
 
 def _no_grad_path(*tensors):
-    """Forward kernels are not differentiable yet (backward = SURVEY §8f N1): refuse
-    rather than silently cut the graph."""
+    """Guard of the few entry points that have no backward kernel (the fused multi-output ``forward_fused`` forms
+    and ``EntropyBottleneckStanh.forward``): refuse rather than silently cut the graph.  The module ``forward``s, the
+    ``quantize`` entry points and the STanH activation record autograd nodes (backward kernels: gc_bwd.cu, eb_bwd.cu,
+    stanh_fused.cu)."""
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise ReslicError(
-            "reslic_tcm_b200 forward kernels do not record an autograd graph yet; "
-            "call under torch.no_grad() (backward kernels: SURVEY.md §8f N1)"
+            "this reslic_tcm_b200 entry point has no backward kernel: call it under torch.no_grad() "
+            "(differentiable forms: the modules' forward() / quantize())"
         )
+
+
+class _QuantizeFn(torch.autograd.Function):
+    """``EntropyModel.quantize`` with the gradient autograd gives the reference:
+    "noise": out = inputs + U(-1/2, 1/2) -> identity to inputs (means ignored); "dequantize":
+    out = round(inputs - means) + means -> zero to inputs (torch.round), identity to means."""
+
+    @staticmethod
+    def forward(ctx, inputs, means, mode, seed, offset):
+        ctx.mode, ctx.has_means = mode, means is not None
+        if mode == "noise":
+            return ops.gc_forward(inputs, None, None, training=True, want=("yhat",), seed=seed, offset=offset).yhat
+        return ops.gc_forward(inputs, None, means, want=("ste",)).ste
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.mode == "noise":
+            return g, None, None, None, None
+        g_in = torch.zeros_like(g) if ctx.needs_input_grad[0] else None
+        return g_in, (g if ctx.has_means and ctx.needs_input_grad[1] else None), None, None, None
 
 
 class _GaussianConditionalFn(torch.autograd.Function):
@@ -170,14 +192,13 @@ class EntropyModel(nn.Module):
         """modes "noise" | "dequantize" | "symbols" (SURVEY.md App. A.1)."""
         if mode not in ("noise", "dequantize", "symbols"):
             raise ValueError(f'Invalid quantization mode: "{mode}"')
-        _no_grad_path(inputs, means)
-        if mode == "noise":
-            seed, offset = _philox_state(inputs.numel())
-            return ops.gc_forward(inputs, None, None, training=True, want=("yhat",), seed=seed,
-                                  offset=offset).yhat
-        if mode == "dequantize":
-            return ops.gc_forward(inputs, None, means, want=("ste",)).ste
-        return ops.gc_forward(inputs, None, means, want=("sym",)).sym
+        if mode == "symbols":       # integers: nothing to differentiate
+            return ops.gc_forward(inputs.detach(), None, None if means is None else means.detach(), want=("sym",)).sym
+        seed, offset = _philox_state(inputs.numel()) if mode == "noise" else (0, 0)
+        if means is not None and means.shape != inputs.shape:
+            means = means.expand_as(inputs)
+        # the reference calls this with grad enabled (GainBalle2018: quantize(y, "noise") inside the training forward)
+        return _QuantizeFn.apply(inputs, None if mode == "noise" else means, mode, seed, offset)
 
     @staticmethod
     def dequantize(inputs: Tensor, means: Optional[Tensor] = None, dtype: torch.dtype = torch.float) -> Tensor:
@@ -262,14 +283,10 @@ class EntropyModel(nn.Module):
 
 
 def _rans():
-    """The entropy coder is the next-row component N3: the symbols and CDF
-    indexes it consumes are produced on the GPU by this package, the coder itself is not part of
-    the path yet."""
-    try:
-        from . import rans
-    except ImportError as exc:  # pragma: no cover
-        raise ReslicError("rANS coder not built yet (SURVEY.md §8f N3): compress()/decompress() stop at the "
-                          "coder; use quantize(..., 'symbols') + build_indexes() for its inputs") from exc
+    """The host rANS coder (csrc/rans.cpp behind reslic_tcm_b200.rans — compressai.ans' API); its
+    inputs, the symbols and CDF indexes (or packed slots), are produced on the GPU by this package."""
+    from . import rans
+
     return rans
 
 

@@ -38,7 +38,7 @@ class _StanHBase(nn.Module):
     def _tables(self, beta: float):
         """(struct reslic_stanh_tables, keepalive tensors) for the current state."""
         dev = self.w.device
-        key = (self.w._version, self.b._version, id(self.cum_w), dev)
+        key = (id(self.w), id(self.b), self.w._version, self.b._version, self.w.data_ptr(), self.b.data_ptr(), id(self.cum_w), dev)
         cached = getattr(self, "_tables_cache", None)
         if cached is not None and cached[0] == key:
             b_sorted, w, cw, avg, dist = cached[1]
@@ -74,7 +74,9 @@ class _StanHBase(nn.Module):
         """activation.py:135-150 / 294-304: hard levels for beta == -1, else sum of tanh."""
         if beta is None:
             beta = self.beta
-        _no_grad_path(x, self.w, self.b)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, self.w, self.b)):
+            # the reference evaluates this under grad (update_state / quantize("training"), tcm_stanh.py:399,448)
+            return _StanhQuantizeFn.apply(self, x, None, float(beta) != -1.0, False, float(beta), self.w, self.b)
         return stanh_activation(self, x, beta)
 
     def gap_sums(self, x: Tensor, beta=None) -> Tensor:
