@@ -339,7 +339,7 @@ class Workload:
 
     def step(self, i: int, **over):
         s = self.sets[i % len(self.sets)]
-        kw = dict(self.kw, **over)
+        kw = dict(self.kw, offset=8 * i, **over)          # noise mode: every captured step draws its own Philox field
         return s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kw)
 
     def capture(self, n_steps: int, chains: int = 1, first: int = 0, after_step=None, **over):
@@ -371,11 +371,11 @@ class Workload:
             b = s["path"].buffers(s["inp"]["y"], s["inp"]["z"], self.c.with_indexes, self.c.training)
             ops.rate_finalize(b["workspace"], self.B, bits=b["bits"])
 
-    def gc_only_us(self, fuse: bool, min_reps: int = 50):
-        """Only the GC launches of a step (5 per-slice, or 1 over the whole y) over the rotating buffer sets as ONE
-        dependent chain, captured as one graph of >= 60 launches so that the launch duration is not diluted by
-        graph-replay boundaries; the rate stays deferred in the workspace and is drained after the timed region.
-        Returns (us per launch, launches per step)."""
+    def gc_only_us(self, fuse: bool, chains: int = 1, min_reps: int = 50):
+        """Only the GC launches of a step (5 per-slice, or 1 over the whole y) over the rotating buffer sets, captured as
+        one graph of >= 60 launches so that the launch duration is not diluted by graph-replay boundaries; `chains` as in
+        the timed region (1 = ONE dependent chain, the kernel in isolation).  The rate stays deferred in the workspace and
+        is drained after the timed region.  Returns (us per launch = elapsed / launches, launches per step)."""
         n_launch = 1 if fuse else synthetic.NUM_SLICES
         over = dict(skip_z=True, fuse_slices=fuse, defer_rate=True)
         n_steps = max(len(self.sets), -(-60 // n_launch))
@@ -384,7 +384,7 @@ class Workload:
             self.step(i, **over)
         self.drain_deferred()
         torch.cuda.synchronize()
-        g = self.capture(n_steps, chains=1, **over)
+        g = self.capture(n_steps, chains=chains, **over)
         per_graph = n_steps * n_launch
         reps = max(3, -(-min_reps * n_launch // per_graph))
         for _ in range(2):
@@ -433,8 +433,24 @@ def roof_obj(w: Workload, us: float, n_launch: int, peak: float, peak_src: str, 
             "us_per_launch": us, "peak_source": peak_src, "gc_melem_per_s": elems / us, "launch": what}
 
 
-SLICE_WHAT = "one 64-channel slice of y per launch, dependent chain (TCM's call pattern, tcm.py:443-457)"
+SLICE_WHAT = "one 64-channel slice of y per launch, each launch waiting for its predecessor (TCM's call pattern, tcm.py:443-457)"
 WHOLE_WHAT = "all 320 channels of y in one launch (models whose mu/sigma exist for every channel at once)"
+
+
+def roof_pair(w: Workload, fuse: bool, chains: int, peak, peak_src, traffic_db, what: str) -> dict:
+    """The roofline object of the GC kernel as the timed region runs it (`chains` independent batches in flight:
+    us_per_launch = elapsed / launches, i.e. the HBM rate the path sustains) with the kernel in isolation — ONE dependent
+    chain, nothing else on the GPU — beside it as `single_chain`."""
+    chains = max(1, min(chains, len(w.sets)))
+    us1, n = w.gc_only_us(fuse, 1)
+    single = roof_obj(w, us1, n, peak, peak_src, traffic_db, what + "; one dependent chain alone on the GPU")
+    if chains == 1:
+        return single
+    usc, n = w.gc_only_us(fuse, chains)
+    r = roof_obj(w, usc, n, peak, peak_src, traffic_db,
+                 what + f"; {chains} independent batches in flight as in the timed region (us_per_launch = elapsed / launches)")
+    r["single_chain"] = {k: single[k] for k in ("us_per_launch", "achieved", "frac", "gc_melem_per_s")}
+    return r
 
 
 class Timer:
@@ -599,14 +615,12 @@ def measure_config(c, images, dev, args, params, world, global_elems, peak, peak
                                  "match": bool(abs(got["bits"] - want[0]) <= 1e-9 * abs(want[0]) and got["pixels"] == want[2] and got["images"] == want[3])}
         out["exchange_name"] = ex.name
         ex.close()
-    us, n = w.gc_only_us(False)
-    out["roofline"] = roof_obj(w, us, n, peak, peak_src, traffic_db, SLICE_WHAT)
+    out["roofline"] = roof_pair(w, False, args.chains, peak, peak_src, traffic_db, SLICE_WHAT)
     if not args.no_whole_y:
         tw = Timer(w, args.steps_per_graph, args.chains, world, None, fuse_slices=True)
         wms = tw.timed(min(steps, 100) if light else steps, min(args.warmup, 6), barrier)
-        usw, n1 = w.gc_only_us(True)
         out["whole_y"] = {"value": global_elems / (wms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wms, "launches_per_step": 2,
-                          "roofline": roof_obj(w, usw, n1, peak, peak_src, traffic_db, WHOLE_WHAT)}
+                          "roofline": roof_pair(w, True, args.chains, peak, peak_src, traffic_db, WHOLE_WHAT)}
     return w, out
 
 

@@ -5,7 +5,9 @@ Boundary row a4 of SURVEY.md §8: the schedules stay scalar Python; the kernels 
 ``StanhAnnealings`` (src/annealings/functions.py:7-141: constructor arguments, ``beta``,
 ``step(gap, epoch, lss, plat=False)``) so that the trainer's hook (src/training/step.py:46-54) works
 unchanged.  Reference defects not replicated: the ``dec_epoc`` attribute typo (:88) and the
-unreachable "triangle" branch (:135-139).
+unreachable "triangle" branch (:135-139).  Not mirrored (host-side schedules the trainer does not instantiate for
+the TCM path, src/annealings/functions.py:144-346): ``RandomAnnealings``, ``Annealing_triangle``,
+``AugmentBetaOnPlateau``; this class is plain Python, not an ``nn.Module`` (it holds no tensors).
 """
 from __future__ import annotations
 
@@ -36,7 +38,9 @@ class StanhAnnealings:
         self.counter = 0
         self.beta_list = [self.beta]
         self.beta_max = self.beta
-        self._rng = rng or random.Random()
+        # the stochastic schedules draw from torch's global generator, as the reference does (random.uniform over torch
+        # ops in functions.py:103-113), so torch.manual_seed makes beta reproducible; `rng` overrides (tests)
+        self._rng = rng
         self._rules: Dict[str, Callable] = {
             "linear": self._linear, "linear_stoc": self._linear_stoc, "gap": self._gap, "gap_stoc": self._gap_stoc,
             "loss": self._loss, "AugmentBetaOnPlateau": self._plateau, "constant": lambda *a: None,
@@ -59,6 +63,13 @@ class StanhAnnealings:
         eps = 1.0 - self.threshold
         return a < best * eps if self.mode == "min" else a > best * eps
 
+    def _uniform(self, lo: float, hi: float) -> float:
+        if self._rng is not None:
+            return self._rng.uniform(lo, hi)
+        import torch
+
+        return float(torch.empty(1).uniform_(float(lo), float(max(hi, lo))).item())
+
     # ---- the schedules
     def _linear(self, gap, epoch, lss, plat):
         if self.beta >= 50000:
@@ -70,7 +81,7 @@ class StanhAnnealings:
 
     def _linear_stoc(self, gap, epoch, lss, plat):
         self.max_beta += self.factor / self.iteration
-        self.beta = self._rng.uniform(1, self.beta_max)
+        self.beta = self._uniform(1, self.beta_max)
 
     def _gap(self, gap, epoch, lss, plat):
         self.update_gap(gap)
@@ -79,7 +90,7 @@ class StanhAnnealings:
     def _gap_stoc(self, gap, epoch, lss, plat):
         self.update_gap(gap)
         self.beta_max = self.beta_max + self.factor * self.gap
-        self.beta = self._rng.uniform(1, min(self.beta_max, self.max_beta))
+        self.beta = self._uniform(1, min(self.beta_max, self.max_beta))
 
     def _loss(self, gap, epoch, lss, plat):
         self.update_loss(lss)

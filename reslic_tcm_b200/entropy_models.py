@@ -466,7 +466,7 @@ class EntropyBottleneck(EntropyModel):
         """Contiguous [C] copy of the medians for the kernel, refreshed only when `quantiles`
         changes (keeps a strided-copy kernel out of every forward / CUDA graph)."""
         q = self.quantiles
-        key = (q._version, q.data_ptr(), q.device)
+        key = (id(q), q._version, q.data_ptr(), q.device)
         if getattr(self, "_med_key", None) != key:
             self._med_flat = q.detach()[:, 0, 1].contiguous()
             self._med_key = key
@@ -478,7 +478,7 @@ class EntropyBottleneck(EntropyModel):
         compress loops then launch the bottleneck without its 5-layer table construction."""
         m, b, f = self._params()
         bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
-        key = tuple((t._version, t.data_ptr()) for t in (*m, *b, *f, self.quantiles)) + (bound,)
+        key = tuple((id(t), t._version, t.data_ptr()) for t in (*m, *b, *f, self.quantiles)) + (bound,)
         if getattr(self, "_lut_key", None) != key:
             self._lut = ops.eb_build_lut(m, b, f, self._medians_flat(), likelihood_bound=bound)
             self._lut_key = key

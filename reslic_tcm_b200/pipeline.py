@@ -134,7 +134,11 @@ class TcmEntropyPath(nn.Module):
     # ------------------------------------------------------------------ CUDA graph
     def capture(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, **kw):
         """Capture one pass over the given (static) input tensors into a CUDA graph.
-        Returns (graph, result dict); refill the inputs in place and ``graph.replay()``."""
+        Returns (graph, result dict); refill the inputs in place and ``graph.replay()``.
+        Training mode: kernel arguments are frozen at capture, so every replay of ONE graph draws the same Philox
+        noise field (seed, offset are arguments).  A training loop that replays graphs captures a few of them with
+        different ``offset=`` values and rotates (bench.py does: one per buffer set), or passes explicit
+        ``noise_y`` / ``noise_z`` tensors that it refills; eager calls take ``offset`` per call."""
         self.buffers(y, z, kw.get("with_indexes", False), kw.get("training", False))
         side = torch.cuda.Stream(device=y.device)
         side.wait_stream(torch.cuda.current_stream(y.device))
@@ -237,7 +241,8 @@ class HostPipeline:
         """host: pinned CPU tensors y, mu, sigma, z (full batch).  Enqueues the batch and returns its
         pinned host outputs plus ``"done"``, the event to synchronise before reading them; the buffers
         are reused ``depth`` calls later.  ``host`` must stay unchanged until the upload has run."""
-        slot = self.slots[self._turn % self.depth]
+        turn = self._turn
+        slot = self.slots[turn % self.depth]
         self._turn += 1
         if not slot["used"]:      # first use: order after whatever the caller has enqueued so far
             cur = torch.cuda.current_stream(self.dev)
@@ -255,9 +260,12 @@ class HostPipeline:
                 self.s_comp.wait_event(slot["ev_in"][c])
                 if slot["used"]:
                     self.s_comp.wait_event(slot["ev_out"][c])          # ... and its outputs have left the device
+                # Philox counter = (element index inside a launch, offset, seed): every launch of every chunk of every
+                # run gets its own offset (forward() uses offset .. offset + 5), so no two draws share a noise field
                 res = slot["sub"][c].forward(d_in["y"][a:b], d_in["mu"][a:b], d_in["sigma"][a:b], d_in["z"][a:b],
                                              training=self.training, with_indexes=self.with_indexes,
-                                             num_pixels=self.num_pixels, seed=self.seed)
+                                             num_pixels=self.num_pixels, seed=self.seed,
+                                             offset=(turn * len(self.ranges) + c) * 8)
                 if self.packed_slots:
                     ops.rans_slots(res["symbols"], res["indexes"], *self._tables, out=slot["d_slot"][c])
                 slot["ev_comp"][c].record(self.s_comp)

@@ -180,7 +180,7 @@ class NonSymStanH(_StanHBase):
         do not depend on the device's scan order (a GPU cumsum differs from the CPU one in the last
         bit); skipped when w has not changed since the last call."""
         device = self.w.device if device is None else device
-        key = (self.w._version, str(device))
+        key = (id(self.w), self.w.data_ptr(), self.w._version, str(device))       # id / data_ptr: a replaced Parameter restarts _version at 0
         if getattr(self, "_cum_key", None) == key:
             return
         with torch.no_grad():
@@ -261,7 +261,7 @@ class SymStanH(_StanHBase):
 
     def update_state(self, device=None):
         device = self.w.device if device is None else device
-        key = (self.w._version, self.b._version, str(device))
+        key = (id(self.w), id(self.b), self.w.data_ptr(), self.b.data_ptr(), self.w._version, self.b._version, str(device))
         if getattr(self, "_cum_key", None) == key and hasattr(self, "average_points"):
             return                       # nothing changed: the reference calls this every forward
         self._cum_key = key
@@ -314,6 +314,135 @@ def compute_gap(stanh: _StanHBase, inputs: Tensor, beta=None) -> Tensor:
     return torch.abs(sums[0] / n - sums[1] / n).to(torch.float32)
 
 
+def _stanh_bwd(stanh, inputs, scales, means, training, removing_mean, scale_bound, lik_bound, beta, g_yhat, g_lik,
+               want_params: bool = False):
+    """reslic_stanh_gc_bwd_f32: (g_y, g_mu, g_sigma, parameter-gradient sums or None).  ``scales`` / ``g_lik`` may be
+    None together (quantizer alone)."""
+    lib = _cabi.load()
+    d = _cabi.new(_cabi.StanhGcBwdDesc)
+    keep = []
+
+    def bind(name, t):
+        if t is None:
+            return
+        if t.shape != inputs.shape:
+            t = t.expand_as(inputs)
+        t, bs, _ = ops.image_major(t.contiguous() if not t.is_contiguous() and name.startswith("g_") else t)
+        keep.append(t)
+        setattr(d, name, t.data_ptr())
+        setattr(d, name + "_bs", bs)
+
+    _, _, n = ops.image_major(inputs)
+    bind("y", inputs); bind("mu", means); bind("sigma", scales); bind("g_yhat", g_yhat); bind("g_lik", g_lik)
+    B = inputs.shape[0] if inputs.dim() > 0 else 1
+    d.B, d.n = B, n
+    d.training, d.removing_mean = (1 if training else 0), (1 if removing_mean else 0)
+    d.scale_bound = float(scale_bound)
+    d.likelihood_bound = float(lik_bound)
+    d.tables, tk = stanh._tables(beta)
+    keep.append(tk)
+    outs = []
+    for name in ("g_y", "g_mu", "g_sigma"):
+        t = torch.empty(inputs.shape, dtype=torch.float32, device=inputs.device)
+        setattr(d, name, t.data_ptr())
+        setattr(d, name + "_bs", n)
+        outs.append(t)
+    g_par = None
+    if want_params:
+        g_par = torch.empty(5 * int(d.tables.K) + 2, dtype=torch.float64, device=inputs.device)
+        d.g_params, d.g_params_len = g_par.data_ptr(), g_par.numel()
+    with torch.cuda.device(inputs.device):
+        code = lib.reslic_stanh_gc_bwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
+    _cabi.check(code, "reslic_stanh_gc_bwd_f32")
+    return (*outs, g_par)
+
+
+def _stanh_param_grads(stanh, g_par: Tensor, w: Tensor, b: Tensor):
+    """Kernel sums (A | Bq | Ww | Wb | Hd, see reslic_stanh_gc_bwd_desc) -> gradients of the raw w / b."""
+    K = (g_par.numel() - 2) // 5
+    A, Bq, Ww, Wb, Hd = torch.split(g_par, [K + 1, K + 1, K, K, K])
+    # dLoss/dw_eff[k] = (sum_{m>k} A[m] - sum_{m<=k} Bq[m]) / 2 + Ww[k]
+    g_weff = 0.5 * ((A.sum() - torch.cumsum(A, 0)[:K]) - torch.cumsum(Bq, 0)[:K]) + Ww
+    with torch.enable_grad():
+        wl = w.detach().double().requires_grad_(True)
+        bl = b.detach().double().requires_grad_(True)
+        w_eff, b_eff, dist = stanh._effective(wl, bl)
+        g_w, g_b = torch.autograd.grad([w_eff, b_eff, dist], [wl, bl], [g_weff, Wb, Hd], allow_unused=True)
+    g_w = torch.zeros_like(w) if g_w is None else g_w.to(w.dtype)
+    g_b = torch.zeros_like(b) if g_b is None else g_b.to(b.dtype)
+    return g_w, g_b
+
+
+class _StanhQuantizeFn(torch.autograd.Function):
+    """The STanH quantizer ALONE as an autograd node: ``stanh_beta(x - mu*[removing_mean]) + mu*[removing_mean]``
+    (soft, ``training``) or ``stanh_hard(x - mu) + mu`` — the value of ``quantize(x, "training" | "dequantize", mu)``
+    and of the bare activation.  The reference runs these with grad enabled (``quantize(y, mode="training")`` in
+    src/models/stanh/tcm_stanh.py:448, wacnn_stanh.py:319; the activation inside update_state); backward is the
+    quantizer part of reslic_stanh_gc_bwd_f32 (no likelihood: sigma and g_lik absent), incl. the gradients of the
+    trainable STanH parameters."""
+
+    @staticmethod
+    def forward(ctx, stanh, inputs, means, training, removing_mean, beta, w, b):
+        with torch.no_grad():
+            x = inputs.detach()
+            m = None if means is None else means.detach()
+            if m is not None and m.shape != x.shape:
+                m = m.expand_as(x)
+            r = _stanh_quantize_launch(stanh, x, m, training, removing_mean, beta)
+        ctx.stanh, ctx.cfg = stanh, (bool(training), bool(removing_mean), float(beta))
+        ctx.save_for_backward(inputs, means, w, b)
+        return r
+
+    @staticmethod
+    def backward(ctx, g):
+        inputs, means, w, b = ctx.saved_tensors
+        training, removing_mean, beta = ctx.cfg
+        want_par = ctx.needs_input_grad[6] or ctx.needs_input_grad[7]
+        m = means
+        if m is not None and m.shape != inputs.shape:
+            m = m.expand_as(inputs)
+        g_y, g_mu, _, g_par = _stanh_bwd(ctx.stanh, inputs.detach(), None, None if m is None else m.detach(), training,
+                                         removing_mean, 0.11, 0.0, beta, g.contiguous(), None, want_params=want_par)
+        g_w = g_b = None
+        if want_par:
+            g_w, g_b = _stanh_param_grads(ctx.stanh, g_par, w, b)
+        if means is not None and g_mu.shape != means.shape:       # broadcast means: reduce the gradient back
+            g_mu = g_mu.sum_to_size(means.shape)
+        return (None, g_y if ctx.needs_input_grad[1] else None, g_mu if (means is not None and ctx.needs_input_grad[2]) else None,
+                None, None, None, g_w if ctx.needs_input_grad[6] else None, g_b if ctx.needs_input_grad[7] else None)
+
+
+def _stanh_quantize_launch(stanh, x: Tensor, means: Optional[Tensor], training: bool, removing_mean: bool, beta: float) -> Tensor:
+    """reslic_stanh_gc_fwd_f32 with the quantizer output only (no scales, no likelihood)."""
+    lib = _cabi.load()
+    ops._require_cuda("inputs", x)
+    d = _cabi.new(_cabi.StanhGcDesc)
+    keep = []
+
+    def bind(name, t):
+        t, bs, n = ops.image_major(t)
+        keep.append(t)
+        setattr(d, name, t.data_ptr())
+        setattr(d, name + "_bs", bs)
+        return n
+
+    n = bind("y", x)
+    if means is not None:
+        ops._require_cuda("means", means)
+        bind("mu", means)
+    d.B, d.n = (x.shape[0] if x.dim() > 0 else 1), n
+    d.training, d.removing_mean = (1 if training else 0), (1 if removing_mean else 0)
+    d.scale_bound, d.likelihood_bound = 0.11, 0.0
+    d.tables, tk = stanh._tables(beta)
+    keep.append(tk)
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    d.yhat, d.yhat_bs = out.data_ptr(), n
+    with torch.cuda.device(x.device):
+        code = lib.reslic_stanh_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(x.device))
+    _cabi.check(code, "reslic_stanh_gc_fwd_f32")
+    return out
+
+
 # ----------------------------------------------------------------------------- entropy model
 class _StanhGcFn(torch.autograd.Function):
     """Autograd node around the fused STanH forward / backward kernels.  ``w`` and ``b`` are the module's
@@ -361,7 +490,7 @@ class HypeEntropyModelSoS(EntropyModel):
         return perm, inv_perm
 
     def _stanh_fused(self, inputs: Tensor, scales: Optional[Tensor], means: Optional[Tensor], training: bool,
-                     want, beta=None, out: Optional[dict] = None):
+                     want, beta=None, out: Optional[dict] = None, likelihood_bound: Optional[float] = None):
         lib = _cabi.load()
         ops._require_cuda("inputs", inputs)
         _no_grad_path(inputs, scales, means, self.stanh.w, self.stanh.b)
@@ -392,7 +521,9 @@ class HypeEntropyModelSoS(EntropyModel):
         d.training = int(training) if training in (0, 1, 2) else (1 if training else 0)
         d.removing_mean = 1 if self.removing_mean else 0
         d.scale_bound = float(getattr(self, "_scale_bound", 0.11))
-        d.likelihood_bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
+        if likelihood_bound is None:
+            likelihood_bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
+        d.likelihood_bound = float(likelihood_bound)
         d.tables, tk = self.stanh._tables(self.stanh.beta if beta is None else beta)
         keep.append(tk)
         res = {}
@@ -417,68 +548,27 @@ class HypeEntropyModelSoS(EntropyModel):
         return res
 
     def _stanh_backward(self, inputs, scales, means, training, g_yhat, g_lik, want_params: bool = False):
-        lib = _cabi.load()
-        d = _cabi.new(_cabi.StanhGcBwdDesc)
-        keep = []
-
-        def bind(name, t):
-            if t is None:
-                return
-            if t.shape != inputs.shape:
-                t = t.expand_as(inputs)
-            t, bs, _ = ops.image_major(t.contiguous() if not t.is_contiguous() and name.startswith("g_") else t)
-            keep.append(t)
-            setattr(d, name, t.data_ptr())
-            setattr(d, name + "_bs", bs)
-
-        _, _, n = ops.image_major(inputs)
-        bind("y", inputs); bind("mu", means); bind("sigma", scales); bind("g_yhat", g_yhat); bind("g_lik", g_lik)
-        B = inputs.shape[0] if inputs.dim() > 0 else 1
-        d.B, d.n = B, n
-        d.training, d.removing_mean = (1 if training else 0), (1 if self.removing_mean else 0)
-        d.scale_bound = float(getattr(self, "_scale_bound", 0.11))
-        d.likelihood_bound = self._likelihood_bound if self.use_likelihood_bound else 0.0
-        d.tables, tk = self.stanh._tables(self.stanh.beta)
-        keep.append(tk)
-        outs = []
-        for name in ("g_y", "g_mu", "g_sigma"):
-            t = torch.empty(inputs.shape, dtype=torch.float32, device=inputs.device)
-            setattr(d, name, t.data_ptr())
-            setattr(d, name + "_bs", n)
-            outs.append(t)
-        g_par = None
-        if want_params:
-            g_par = torch.empty(5 * int(d.tables.K) + 2, dtype=torch.float64, device=inputs.device)
-            d.g_params, d.g_params_len = g_par.data_ptr(), g_par.numel()
-        with torch.cuda.device(inputs.device):
-            code = lib.reslic_stanh_gc_bwd_f32(C.byref(d), _cabi.current_stream_ptr(inputs.device))
-        _cabi.check(code, "reslic_stanh_gc_bwd_f32")
-        return (*outs, g_par)
+        return _stanh_bwd(self.stanh, inputs, scales, means, training, bool(self.removing_mean),
+                          float(getattr(self, "_scale_bound", 0.11)),
+                          self._likelihood_bound if self.use_likelihood_bound else 0.0, self.stanh.beta, g_yhat, g_lik,
+                          want_params)
 
     def _stanh_param_grads(self, g_par: Tensor, w: Tensor, b: Tensor):
-        """Kernel sums (A | Bq | Ww | Wb | Hd, see reslic_stanh_gc_bwd_desc) -> gradients of the raw w / b."""
-        K = (g_par.numel() - 2) // 5
-        A, Bq, Ww, Wb, Hd = torch.split(g_par, [K + 1, K + 1, K, K, K])
-        # dLoss/dw_eff[k] = (sum_{m>k} A[m] - sum_{m<=k} Bq[m]) / 2 + Ww[k]
-        g_weff = 0.5 * ((A.sum() - torch.cumsum(A, 0)[:K]) - torch.cumsum(Bq, 0)[:K]) + Ww
-        with torch.enable_grad():
-            wl = w.detach().double().requires_grad_(True)
-            bl = b.detach().double().requires_grad_(True)
-            w_eff, b_eff, dist = self.stanh._effective(wl, bl)
-            g_w, g_b = torch.autograd.grad([w_eff, b_eff, dist], [wl, bl], [g_weff, Wb, Hd], allow_unused=True)
-        g_w = torch.zeros_like(w) if g_w is None else g_w.to(w.dtype)
-        g_b = torch.zeros_like(b) if g_b is None else g_b.to(b.dtype)
-        return g_w, g_b
+        return _stanh_param_grads(self.stanh, g_par, w, b)
 
     def quantize(self, inputs, mode, means=None, perms=None):
         """modes "training" | "dequantize" | "symbols" (:95-157).  ``perms`` is accepted for API
         compatibility; the op is elementwise so no permutation is needed."""
-        if mode == "training":
-            return self._stanh_fused(inputs, None, means, True, ("yhat",))["yhat"]
-        if mode == "dequantize":
-            return self._stanh_fused(inputs, None, means, False, ("yhat",))["yhat"]
+        if mode in ("training", "dequantize"):
+            training = mode == "training"
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (inputs, means, self.stanh.w, self.stanh.b)):
+                # the reference runs this with grad enabled (tcm_stanh.py:448, wacnn_stanh.py:319)
+                return _StanhQuantizeFn.apply(self.stanh, inputs, means, training, bool(self.removing_mean),
+                                              float(self.stanh.beta), self.stanh.w, self.stanh.b)
+            return self._stanh_fused(inputs, None, means, training, ("yhat",))["yhat"]
         assert mode == "symbols", mode
-        return self._stanh_fused(inputs, None, means, False, ("sym",))["sym"]
+        with torch.no_grad():           # integers: nothing to differentiate
+            return self._stanh_fused(inputs.detach(), None, None if means is None else means.detach(), False, ("sym",))["sym"]
 
     def dequantize(self, inputs, means=None, dtype=torch.float):
         """Level index -> level value (+ means) (:174-193), as one gather instead of a Python loop."""
@@ -603,12 +693,7 @@ class GaussianConditionalStanh(HypeEntropyModelSoS):
     def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None):
         """Unbounded variable-bin likelihood of already-quantised ``inputs`` (:541-580): the fused
         pass with the quantizer switched off (y_hat = inputs)."""
-        saved = self.use_likelihood_bound
-        self.use_likelihood_bound = False
-        try:
-            return self._stanh_fused(inputs, scales, means, 2, ("lik",))["lik"]
-        finally:
-            self.use_likelihood_bound = saved
+        return self._stanh_fused(inputs, scales, means, 2, ("lik",), likelihood_bound=0.0)["lik"]
 
     def forward(self, values, scales, training=True, means=None):
         """:588-603 — note the reference's argument order and default ``training=True``."""
@@ -733,7 +818,11 @@ class EntropyBottleneckStanh(EntropyModel):
         if self.filters != (3, 3, 3, 3):
             raise _cabi.ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
         m, b, f = self._params()
-        _no_grad_path(x, *m, *b, *f, self.stanh.w, self.stanh.b)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, *m, *b, *f, self.stanh.w, self.stanh.b)):
+            raise _cabi.ReslicError(
+                "EntropyBottleneckStanh.forward is evaluation-only in this build: its likelihood has no backward kernel "
+                "yet, so it cannot sit inside a training step (src/models/stanh/wacnn_stanh.py:160, balle18_stanh.py:26 "
+                "call it there).  Call it under torch.no_grad(); quantize() is differentiable.")
         xc = x.contiguous()
         B, Cc = xc.shape[0], xc.shape[1]
         hw = 1
@@ -772,14 +861,23 @@ class EntropyBottleneckStanh(EntropyModel):
     def quantize(self, inputs, mode, means=None, perms=None):
         """EntropyModelSoS.quantize (:113-177): "training" (soft STanH, means ignored as in the
         reference), "dequantize" (hard levels about the means), "symbols" (level index)."""
+        grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (inputs, means, self.stanh.w, self.stanh.b))
         if mode == "training":
-            return self._fused(inputs, True, ("zhat",))["zhat"]
-        x = inputs - means if means is not None else inputs
+            if grad:    # the quantizer alone: differentiable through the STanH backward kernel
+                return _StanhQuantizeFn.apply(self.stanh, inputs, None, True, False, float(self.stanh.beta), self.stanh.w, self.stanh.b)
+            with torch.no_grad():
+                return self._fused(inputs, True, ("zhat",))["zhat"]
         if mode == "dequantize":
-            out = self._fused(x, False, ("zhat",))["zhat"]
-            return out + means if means is not None else out
+            if grad:
+                return _StanhQuantizeFn.apply(self.stanh, inputs, means, False, True, float(self.stanh.beta), self.stanh.w, self.stanh.b)
+            with torch.no_grad():
+                x = inputs - means if means is not None else inputs
+                out = self._fused(x, False, ("zhat",))["zhat"]
+                return out + means if means is not None else out
         assert mode == "symbols", mode
-        return self._fused(x, False, ("sym",))["sym"]
+        with torch.no_grad():
+            x = inputs.detach() - means.detach() if means is not None else inputs.detach()
+            return self._fused(x, False, ("sym",))["sym"]
 
     def forward(self, x: Tensor, training: bool = True):
         """:679-708 — note the reference default ``training=True``."""

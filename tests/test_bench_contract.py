@@ -51,6 +51,9 @@ def test_default_arm_line_on_gpu():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.2 < r["frac"] < 1.0 and r["kernel"] == "gc_fwd_kernel"
     assert abs(r["achieved"] / r["peak"] - r["frac"]) < 1e-9 and r["bytes_per_elem"] == 20 and r["elems_per_launch"] == 64 * 98304
+    # the kernel alone (one dependent chain) is reported beside the pattern of the timed region (3 batches in flight)
+    assert 0.2 < r["single_chain"]["frac"] <= r["frac"] * 1.05 and "in flight" in r["launch"]
+    assert 5 * r["us_per_launch"] * 1e-3 <= d["ms_per_step"] * 1.02          # the GC launches fit inside the step
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     # config 3 reads back the per-image bits only; its inputs are 64 images of y / mu / sigma / z
     assert d["e2e"]["h2d_bytes_per_step"] == 64 * (3 * 491520 + 18432) * 4 and d["e2e"]["d2h_bytes_per_step"] == 64 * 8
