@@ -794,9 +794,10 @@ def training_kernels_leg(dev, peak):
     """Per-launch times of the training-path kernels on one config-5 slice (256 patches of 256x256: y slice
     [256, 64, 16, 16], z [256, 192, 4, 4]) — the Gaussian-conditional backward, the noise-mode bottleneck
     forward / backward and the STanH family (soft beta = 10, hard, backward, compute_gap).  Each op is
-    captured as a graph of 12 launches over 3 rotating input sets (403 MB > L2 for the y-shaped ops) and
-    replayed 10 times; `frac` is algorithmic bytes / time against the same measured HBM peak (these kernels
-    are issue- or MUFU-bound, the fraction says how far from the copy roofline that leaves them)."""
+    captured as a graph of 12 launches over 3 rotating input sets (403 MB > L2 for the y-shaped ops), each launch
+    writing its own output tensors (12 distinct sets, so stores reach HBM), and replayed 10 times; `frac` is algorithmic
+    bytes / time against the same measured HBM peak (these kernels are issue- or MUFU-bound, the fraction says how far
+    from the copy roofline that leaves them)."""
     from reslic_tcm_b200 import EntropyBottleneck
     from reslic_tcm_b200.stanh import GaussianConditionalStanh, compute_gap
 
@@ -816,9 +817,10 @@ def training_kernels_leg(dev, peak):
             fn(i)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
+        keep = []          # every captured launch keeps its OWN outputs alive: the graph's allocator would otherwise hand
+        with torch.cuda.graph(gr):      # all 12 launches the same block, whose stores then never leave L2
             for i in range(launches):
-                fn(i)
+                keep.append(fn(i))
         gr.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -899,8 +901,41 @@ def run_e2e(args, c, w: Workload, dev, world, global_elems, packed_slots=False):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # the same bytes with no kernels at all, both directions at once on the pipeline's own streams and buffers, all ranks
+    # together: the ceiling the host links / host memory set for this step (what e2e can reach at most)
+    slot = hp.slots[0]
+    if world > 1:
+        dist.barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
+    hp.s_h2d.wait_stream(cur)
+    hp.s_d2h.wait_stream(cur)
+    c0.record()
+    hp.s_h2d.wait_event(c0)
+    hp.s_d2h.wait_event(c0)
+    dev_out = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in slot["h_out"].items()}
+    for _ in range(steps):
+        with torch.cuda.stream(hp.s_h2d):
+            for k in ("y", "mu", "sigma", "z"):
+                slot["d_in"][k].copy_(host[k], non_blocking=True)
+        with torch.cuda.stream(hp.s_d2h):
+            for k, v in slot["h_out"].items():
+                v.copy_(dev_out[k], non_blocking=True)
+    cur.wait_stream(hp.s_h2d)
+    cur.wait_stream(hp.s_d2h)
+    c1.record()
+    torch.cuda.synchronize()
+    cms = c0.elapsed_time(c1)
+    if world > 1:
+        t = torch.tensor([cms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cms = float(t.item())
+    ceiling = {"ms_per_step": cms / steps, "value": global_elems / (cms / steps * 1e-3) / 1e6,
+               "h2d_gb_per_s_per_rank": hp.h2d_bytes / (cms / steps * 1e-3) / 1e9,
+               "what": "the step's H2D and D2H copies alone (no kernels), all ranks at once, max over ranks"}
     return {"value": global_elems / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
             "d2h_bytes_per_step": hp.d2h_bytes, "ms_per_step": ms / steps, "steps": steps, "bytes_are": "per rank",
+            "copy_ceiling": ceiling,
             "what": f"pinned host y/mu/sigma/z -> H2D -> 1+5{'+1' if packed_slots else ''} launches -> D2H {'/'.join(hp.out_names)}, "
                     f"{len(hp.ranges)} image chunks pipelined on 3 streams, batches double-buffered"}
 

@@ -158,3 +158,23 @@ def test_next_channel_slice_is_pure_view_logic():
     t = flat[5:].view(2, 128, 6)
     assert ops.next_channel_slice(t[:, :64]) is None or ops.next_channel_slice(t[:, :64]).data_ptr() == t[:, 64:].data_ptr()
     assert ops.next_channel_slice(y.double()[:, :64]) is None
+
+
+def test_integration_doc_stub_is_generated_from_the_binding():
+    """INTEGRATION.md §3 shows the ctypes struct a maintainer would write; it is generated from _cabi.GcDesc
+    (tools/gen_integration_stub.py) so that it cannot lag an ABI revision behind again."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_integration_stub", os.path.join(root, "tools", "gen_integration_stub.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert mod.render(text) == text, "INTEGRATION.md is stale: run python tools/gen_integration_stub.py"
+    # and the stub as printed really is a correctly sized descriptor for this library
+    ns = {}
+    code = text[text.index(mod.BEGIN):text.index(mod.END)].split("```python\n", 1)[1].rsplit("```", 1)[0]
+    code = code.replace('C.CDLL("reslic_tcm_b200/lib/libreslic_b200.so")', "C.CDLL(LIB)")
+    exec(compile(code, "INTEGRATION.md", "exec"), {"LIB": _cabi.lib_path()}, ns)
+    assert ctypes.sizeof(ns["GcDesc"]) == ctypes.sizeof(_cabi.GcDesc)
