@@ -173,8 +173,8 @@ def test_integration_doc_stub_is_generated_from_the_binding():
     text = open(os.path.join(root, "INTEGRATION.md")).read()
     assert mod.render(text) == text, "INTEGRATION.md is stale: run python tools/gen_integration_stub.py"
     # and the stub as printed really is a correctly sized descriptor for this library
-    ns = {}
     code = text[text.index(mod.BEGIN):text.index(mod.END)].split("```python\n", 1)[1].rsplit("```", 1)[0]
     code = code.replace('C.CDLL("reslic_tcm_b200/lib/libreslic_b200.so")', "C.CDLL(LIB)")
-    exec(compile(code, "INTEGRATION.md", "exec"), {"LIB": _cabi.lib_path()}, ns)
+    ns = {"LIB": _cabi.lib_path()}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
     assert ctypes.sizeof(ns["GcDesc"]) == ctypes.sizeof(_cabi.GcDesc)
