@@ -356,14 +356,20 @@ class Workload:
             lanes = [cur] + self._side[:chains - 1]
             for s in lanes[1:]:
                 s.wait_stream(cur)
+            ex = over.get("exchange")
             for j in range(first, first + n_steps):
                 si = j % len(self.sets)
                 with torch.cuda.stream(lanes[si % chains]):
-                    self.step(j, **over)
+                    if ex is not None:      # the batch's number inside this graph: its exchange slot does not depend on
+                        self.step(j, **dict(over, exchange_step=j - first, exchange_advance=False))   # which chain finishes first
+                    else:
+                        self.step(j, **over)
                     if after_step is not None:
                         after_step(j - first, self.sets[si])
             for s in lanes[1:]:
                 cur.wait_stream(s)
+            if ex is not None:
+                ex.advance(n_steps)         # behind the join: every replay publishes the next n_steps steps
         return g
 
     def drain_deferred(self):
@@ -487,6 +493,9 @@ class Timer:
             self.graph(steps % self.group)
         self.run(max(warmup, 3))
         barrier()
+        if self.ex is not None:
+            self.ex.verify()          # a broken exchange fails here, after the warm-up, not after minutes of timed-out reads
+            barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler is not None:
             sampler.active.set()
@@ -540,6 +549,9 @@ class NcclExchange:
     def after_graph(self, n):
         self.work = self.red.all_reduce(async_op=True)
 
+    def verify(self):
+        pass
+
     def result(self):
         if self.work is not None:
             self.work.wait()
@@ -580,12 +592,16 @@ class PeerExchange:
             m = self.pending.pop(0)
             self.last = self.ex.read(m, out=self.rows[:m])
 
-    def result(self):
+    def verify(self):
+        """Drain the pending reads and raise if a row timed out or was overwritten."""
         while self.pending:
             m = self.pending.pop(0)
             self.last = self.ex.read(m, out=self.rows[:m])
         torch.cuda.synchronize()
         self.ex.check()
+
+    def result(self):
+        self.verify()
         return self.ex.result(self.last[0].tolist())
 
     def close(self):

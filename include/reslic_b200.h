@@ -120,16 +120,20 @@ int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B,
  * reslic_peer_buffer_* below, or any other peer-accessible allocation):
  *     rows  double  [ring][world][4]       row (slot, r) is written by rank r only
  *     flags uint64  [ring][world]          = step + 1 once row (step % ring, r) is complete
- * `cursor` is a zero-initialised DEVICE word local to this rank: the number of steps it has published; the
- * collecting launch advances it, so CUDA-graph replays publish consecutive steps.  A rank may run at most
- * `ring` steps ahead of the slowest reader.  */
+ * A launch publishes step number `*cursor + step`: `step` is the caller's number of the batch relative to `cursor`, a
+ * zero-initialised DEVICE word local to this rank that the CALLER advances (stream-ordered) — after every batch in
+ * eager use, or once per CUDA-graph replay by the number of batches the graph holds, whose launches then carry
+ * step = 0, 1, 2, ... as constants.  The slot of a batch is therefore fixed by WHICH batch it is, never by the order
+ * in which concurrently running batches (several streams, graph branches) happen to finish, and every rank files the
+ * same batch under the same step.  A rank may run at most `ring` steps ahead of the slowest reader.  */
 typedef struct reslic_rate_exchange {
   uint64_t struct_size;                    /* = sizeof(reslic_rate_exchange)                                  */
   int32_t world, rank;                     /* 1 <= world <= 64                                                */
   int32_t ring;                            /* slots per buffer                                                */
   int32_t reserved;
+  int64_t step;                            /* this batch's number relative to *cursor (>= 0)                  */
   void* const* peer_base;                  /* DEVICE array [world] of buffer bases (entry `rank` = own buffer) */
-  unsigned long long* cursor;              /* DEVICE word, see above                                          */
+  const unsigned long long* cursor;        /* DEVICE word, see above; NULL = 0                                */
   const double* extra;                     /* DEVICE, nullable: value published as the row's second field,    */
                                            /* read when the batch completes                                   */
   double pixels, images;                   /* the row's third and fourth field                                */

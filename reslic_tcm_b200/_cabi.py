@@ -41,6 +41,7 @@ class RateExchangeDesc(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint64),
         ("world", C.c_int32), ("rank", C.c_int32), ("ring", C.c_int32), ("reserved", C.c_int32),
+        ("step", C.c_int64),
         ("peer_base", C.c_void_p), ("cursor", C.c_void_p), ("extra", C.c_void_p),
         ("pixels", C.c_double), ("images", C.c_double),
     ]

@@ -120,7 +120,8 @@ __device__ __forceinline__ unsigned long long rate_commit_issue(float acc, int i
 // ---- multi-GPU rate exchange (reslic_rate_exchange): kernel-side copy of the descriptor; world == 0 = none
 struct RateEx {
   void* const* peer;              // DEVICE array [world] of exchange-buffer bases as mapped in this process
-  unsigned long long* cursor;     // DEVICE word: steps this rank has published
+  const unsigned long long* cursor;   // DEVICE word (nullable): base of the step numbers, advanced by the caller
+  long long step_rel;             // this batch's number relative to *cursor
   const double* extra;            // nullable
   double pixels, images;
   int world, rank, ring;
@@ -152,8 +153,8 @@ static __device__ __noinline__ void rate_publish(const RateWin win, int64_t B, u
   const unsigned long long f = *reinterpret_cast<volatile unsigned long long*>(&bw[2]);
   bw[0] = 0ull; bw[1] = 0ull;
   if (f) bw[2] = 0ull;
-  const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(ex.cursor);
-  *reinterpret_cast<volatile unsigned long long*>(ex.cursor) = step + 1ull;
+  const unsigned long long step = static_cast<unsigned long long>(ex.step_rel) +
+                                  (ex.cursor ? *reinterpret_cast<const volatile unsigned long long*>(ex.cursor) : 0ull);
   const size_t cell = static_cast<size_t>(step % static_cast<unsigned long long>(ex.ring)) * ex.world + ex.rank;
   const double2 r01 = make_double2(rate_fixed_to_bits(total, f), ex.extra ? *ex.extra : 0.0);
   const double2 r23 = make_double2(ex.pixels, ex.images);

@@ -543,9 +543,9 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
       return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange->struct_size != sizeof(reslic_rate_exchange) (ABI mismatch)");
     if (!want_rate || (d->bits_accumulate != 0 && d->bits_accumulate != RESLIC_RATE_COLLECT))
       return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange needs a rate output in mode 0 or RESLIC_RATE_COLLECT");
-    if (x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->ring < 1 || !x->peer_base || !x->cursor)
-      return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange: bad world/rank/ring or null peer_base/cursor");
-    p.ex.peer = x->peer_base; p.ex.cursor = x->cursor; p.ex.extra = x->extra; p.ex.pixels = x->pixels; p.ex.images = x->images;
+    if (x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->ring < 1 || !x->peer_base || x->step < 0)
+      return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange: bad world/rank/ring/step or null peer_base");
+    p.ex.peer = x->peer_base; p.ex.cursor = x->cursor; p.ex.step_rel = x->step; p.ex.extra = x->extra; p.ex.pixels = x->pixels; p.ex.images = x->images;
     p.ex.world = x->world; p.ex.rank = x->rank; p.ex.ring = x->ring;
   }
   if (p.ex.world > 0 && !vec)

@@ -110,6 +110,14 @@ class PeerRateExchange:
     src/train.py:168-169).  ``read(n)`` adds the ``world`` rows of the next n steps in rank order on the device (a
     tiny kernel that waits on LOCAL memory only) — identical bits on every rank.
 
+    Step numbers: a batch is published as step ``cursor + step`` — ``cursor`` a device word this object owns,
+    ``step`` the batch's number relative to it, given per call (``TcmEntropyPath.forward(exchange=..., exchange_step=j)``).
+    In eager use ``forward`` publishes step 0 and then advances the cursor by one (a tiny stream-ordered add).  A CUDA
+    graph that holds n batches captures them with ``exchange_step=0..n-1, exchange_advance=False`` and ONE
+    ``advance(n)`` behind them, so every replay publishes the next n steps; batches that run concurrently (graph
+    branches, several streams) therefore land in the slot that belongs to WHICH batch they are, not to whichever
+    finished first, and all ranks file the same batch under the same step.
+
     Discipline: every rank publishes the same sequence of steps; a rank may run at most ``ring`` steps ahead of the
     slowest reader (reads act as the back-pressure, so read at least every ``ring // 4`` steps).
 
@@ -193,6 +201,11 @@ class PeerRateExchange:
 
     def slot_of(self, step: int) -> int:
         return int(step) % self.ring
+
+    def advance(self, n: int = 1) -> None:
+        """cursor += n on the current stream (capturable): call once behind the launches that published steps
+        cursor .. cursor + n - 1."""
+        self.cursor.add_(int(n))
 
     # ------------------------------------------------------------------ reading
     def read(self, n_steps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

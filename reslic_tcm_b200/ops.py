@@ -191,6 +191,7 @@ def gc_forward(
     offset: int = 0,
     next_y: Optional[Tensor] = None,
     exchange=None,
+    exchange_step: int = 0,
 ) -> GcOutputs:
     """One fused pass over a Gaussian-conditional slice.
 
@@ -199,7 +200,8 @@ def gc_forward(
     Mirrors GaussianConditional.forward + ste_round + build_indexes + quantize("symbols")
     + the log2-rate sum (tcm.py:455,457,544,548; loss.py:24-27).
     ``exchange``: a :class:`reslic_tcm_b200.dist.PeerRateExchange` — the launch that completes ``bits`` (rate mode 0 or
-    collect) also publishes the batch's packed rate row to every rank (no collective kernel).
+    collect) also publishes the batch's packed rate row to every rank (no collective kernel) as step
+    ``exchange.cursor + exchange_step``; the caller advances the cursor (``exchange.advance``).
     """
     lib = _cabi.load()
     _require_cuda("inputs", y)
@@ -293,6 +295,7 @@ def gc_forward(
     if exchange is not None:
         if exchange.device != y.device:
             raise ValueError("exchange lives on another device")
+        exchange.desc.step = int(exchange_step)      # read by the library during the call below
         d.exchange = C.pointer(exchange.desc)
     with torch.cuda.device(y.device):
         code = lib.reslic_gc_fwd_f32(C.byref(d), _cabi.current_stream_ptr(y.device))

@@ -70,7 +70,8 @@ class TcmEntropyPath(nn.Module):
     def forward(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, *, training: bool = False,
                 with_indexes: bool = False, num_pixels: Optional[int] = None, seed: int = 0,
                 offset: int = 0, noise_y: Optional[Tensor] = None, noise_z: Optional[Tensor] = None,
-                fuse_slices: bool = False, skip_z: bool = False, defer_rate: bool = False, exchange=None) -> Dict[str, Tensor]:
+                fuse_slices: bool = False, skip_z: bool = False, defer_rate: bool = False, exchange=None,
+                exchange_step: int = 0, exchange_advance: bool = True) -> Dict[str, Tensor]:
         """All tensors on the GPU, NCHW fp32: y/mu/sigma [B, 320, h, w], z [B, 192, h/4, w/4].
         Returns views of static buffers (valid until the next call).
 
@@ -81,7 +82,10 @@ class TcmEntropyPath(nn.Module):
         ``defer_rate`` leaves the pass's rate in the workspace (no launch collects; ``bits`` is not
         written): the caller sums several passes and calls ``ops.rate_finalize`` once.
         ``exchange`` (a :class:`reslic_tcm_b200.dist.PeerRateExchange`): multi-GPU runs — the launch that collects the
-        batch's rate also publishes it to every rank over NVLink; no collective kernel runs."""
+        batch's rate also publishes it to every rank over NVLink; no collective kernel runs.  The batch
+        is step ``exchange.cursor + exchange_step``; with ``exchange_advance`` the cursor moves on by one behind it (eager
+        use) — a CUDA graph of n batches passes ``exchange_step=0..n-1, exchange_advance=False`` and calls
+        ``exchange.advance(n)`` once."""
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         b = self.buffers(y, z, with_indexes, training)
         C = y.shape[1]
@@ -121,7 +125,10 @@ class TcmEntropyPath(nn.Module):
                            likelihood_bound=gc._likelihood_bound, want=want, out=out, seed=seed,
                            offset=offset + 1 + k,
                            next_y=y[:, cs * (k + 1):cs * (k + 2)] if (k + 1 < n_launch and self.prefetch_next_slice) else None,
-                           exchange=exchange if (k + 1 == n_launch and not defer_rate) else None)
+                           exchange=exchange if (k + 1 == n_launch and not defer_rate) else None,
+                           exchange_step=exchange_step)
+        if exchange is not None and exchange_advance and not defer_rate:
+            exchange.advance(1)
         res = {"y_hat": b["y_hat"], "z_hat": b["z_hat"], "bits": b["bits"],
                "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}}
         if with_indexes:

@@ -60,7 +60,7 @@ def test_exchange_descriptor_is_validated_without_a_gpu():
     d.scale_bound = 0.11
     d.bits, d.workspace, d.workspace_bytes = 64, 64, 1 << 20
     x = _cabi.new(_cabi.RateExchangeDesc)
-    x.world, x.rank, x.ring, x.peer_base, x.cursor = 2, 0, 8, 64, 64
+    x.world, x.rank, x.ring, x.peer_base, x.cursor, x.step = 2, 0, 8, 64, 64, 0
     d.exchange = C.pointer(x)
     d.bits_accumulate = 1                 # "+=" mode: this launch does not complete bits[]
     assert lib.reslic_gc_fwd_f32(C.byref(d), None) == -1 and b"exchange needs a rate output" in lib.reslic_last_error()
@@ -70,7 +70,7 @@ def test_exchange_descriptor_is_validated_without_a_gpu():
     x.struct_size -= 8
     assert lib.reslic_gc_fwd_f32(C.byref(d), None) == -1 and b"reslic_rate_exchange" in lib.reslic_last_error()
     x.struct_size += 8
-    for field, bad in (("world", 0), ("world", 65), ("rank", 2), ("ring", 0), ("peer_base", None), ("cursor", None)):
+    for field, bad in (("world", 0), ("world", 65), ("rank", 2), ("ring", 0), ("peer_base", None), ("step", -1)):
         keep = getattr(x, field)
         setattr(x, field, bad)
         assert lib.reslic_gc_fwd_f32(C.byref(d), None) == -1, field
@@ -118,6 +118,38 @@ def test_world1_publish_and_read_over_ring_wraparound_and_graph_replays():
     torch.cuda.synchronize()
     ex.check()
     assert rows[:, 0].tolist() == [want] * 3 and int(ex.cursor.item()) == 13
+    # a graph of several batches on CONCURRENT branches: explicit step numbers, one advance behind the join — the slot
+    # of a batch must not depend on which branch finishes first (bench.py's launch pattern)
+    paths = [_path(dev) for _ in range(3)]
+    inps = [_inputs(dev, range(1 + k, 4 + 2 * k)) for k in range(3)]          # 3, 4, 5 images: three different rates
+    for p_, i_ in zip(paths, inps):
+        p_.forward(i_["y"], i_["mu"], i_["sigma"], i_["z"])
+    torch.cuda.synchronize()
+    wants = [float(p_.forward(i_["y"], i_["mu"], i_["sigma"], i_["z"])["bits"].double().sum()) for p_, i_ in zip(paths, inps)]
+    side = [torch.cuda.Stream(dev) for _ in range(2)]
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        cur = torch.cuda.current_stream(dev)
+        lanes = [cur] + side
+        for s_ in side:
+            s_.wait_stream(cur)
+        for j in range(6):
+            with torch.cuda.stream(lanes[j % 3]):
+                i_ = inps[j % 3]
+                ex.set_static(pixels=1, images=i_["y"].shape[0])
+                paths[j % 3].forward(i_["y"], i_["mu"], i_["sigma"], i_["z"], exchange=ex, exchange_step=j, exchange_advance=False)
+        for s_ in side:
+            cur.wait_stream(s_)
+        ex.advance(6)
+    for _ in range(2):
+        g2.replay()
+        rows = ex.read(6)
+        torch.cuda.synchronize()
+        ex.check()
+        assert rows[:, 0].tolist() == [wants[j % 3] for j in range(6)]
+        assert rows[:, 3].tolist() == [float(inps[j % 3]["y"].shape[0]) for j in range(6)]
+    assert int(ex.cursor.item()) == 25
+    ex.set_static(pixels=5 * 128 * 128, images=5, extra=2.5)
     # whole-y (one launch) collects and publishes as well
     path.forward(inp["y"], inp["mu"], inp["sigma"], inp["z"], exchange=ex, fuse_slices=True)
     assert ex.read(1)[0, 0].item() == pytest.approx(want, rel=1e-6)
