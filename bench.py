@@ -357,6 +357,16 @@ class Workload:
             for s in lanes[1:]:
                 s.wait_stream(cur)
             ex = over.get("exchange")
+            if ex is not None:              # open with a read of what the PREVIOUS graph published, on a branch of its own:
+                while len(self._side) < chains:     # it costs the steps nothing and keeps the ranks within a ring of each other
+                    self._side.append(torch.cuda.Stream(device=self.dev))
+                rd = self._side[chains - 1]
+                rd.wait_stream(cur)
+                with torch.cuda.stream(rd):
+                    ex.read_behind(n_steps, out=self._behind(ex, n_steps))
+                lanes_join = lanes[1:] + [rd]
+            else:
+                lanes_join = lanes[1:]
             for j in range(first, first + n_steps):
                 si = j % len(self.sets)
                 with torch.cuda.stream(lanes[si % chains]):
@@ -366,11 +376,16 @@ class Workload:
                         self.step(j, **over)
                     if after_step is not None:
                         after_step(j - first, self.sets[si])
-            for s in lanes[1:]:
+            for s in lanes_join:
                 cur.wait_stream(s)
             if ex is not None:
                 ex.advance(n_steps)         # behind the join: every replay publishes the next n_steps steps
         return g
+
+    def _behind(self, ex, n):
+        if getattr(self, "_behind_buf", None) is None or self._behind_buf.shape[0] < n:
+            self._behind_buf = torch.zeros(max(n, 64), 4, dtype=torch.float64, device=self.dev)
+        return self._behind_buf[:n]
 
     def drain_deferred(self):
         for s in self.sets:
@@ -565,18 +580,18 @@ class NcclExchange:
 class PeerExchange:
     """Rate exchange fused into the collecting launch (reslic_tcm_b200.dist.PeerRateExchange): the last slice launch
     of every step stores the step's packed row into every rank's buffer over NVLink; no collective kernel exists.
-    One tiny read kernel per graph adds the rows of the PREVIOUS graph's steps (one graph behind, so it never waits
-    in steady state) — it is also what keeps a rank from running a ring ahead of the others."""
+    Every graph opens, on a branch of its own, with one tiny read kernel over the rows the PREVIOUS graph published
+    (captured: Workload.capture) — off the steps' critical path, and what keeps a rank from running a ring ahead."""
 
-    name = "packed rate row stored to every rank over NVLink by the collecting launch itself (no collective kernel); one read kernel per graph, one graph behind"
+    name = ("packed rate row stored to every rank over NVLink by the collecting launch itself (no collective kernel); "
+            "one read kernel per graph on a side branch, one graph behind")
 
     def __init__(self, w: Workload, group: int):
         from reslic_tcm_b200 import dist as rdist
 
         self.ex = rdist.PeerRateExchange(w.dev, ring=max(256, 8 * group))
         self.ex.set_static(w.B * w.c.num_pixels_per_image, w.B)
-        self.pending, self.last = [], None
-        self.rows = torch.zeros(self.ex.ring, 4, dtype=torch.float64, device=w.dev)
+        self.published = 0
 
     def step_kwargs(self):
         return {"exchange": self.ex}
@@ -587,22 +602,17 @@ class PeerExchange:
         pass
 
     def after_graph(self, n):
-        self.pending.append(n)
-        if len(self.pending) > 1:
-            m = self.pending.pop(0)
-            self.last = self.ex.read(m, out=self.rows[:m])
+        self.published += n
 
     def verify(self):
-        """Drain the pending reads and raise if a row timed out or was overwritten."""
-        while self.pending:
-            m = self.pending.pop(0)
-            self.last = self.ex.read(m, out=self.rows[:m])
         torch.cuda.synchronize()
         self.ex.check()
 
     def result(self):
+        self.ex.read_step = max(self.published - 1, 0)        # the last step, by its absolute number
+        row = self.ex.read(1)[0]
         self.verify()
-        return self.ex.result(self.last[0].tolist())
+        return self.ex.result(row.tolist())
 
     def close(self):
         self.ex.close()
@@ -625,7 +635,8 @@ def measure_config(c, images, dev, args, params, world, global_elems, peak, peak
         got = ex.result()
         local = torch.tensor([float(w.sets[0]["res"]["bits"].double().sum()), 0.0, float(w.B * c.num_pixels_per_image), float(w.B)],
                              dtype=torch.float64, device=dev)
-        dist.all_reduce(local)
+        if world > 1:
+            dist.all_reduce(local)
         want = local.tolist()
         out["exchange_check"] = {"exchange": got, "nccl_all_reduce": {"bits": want[0], "pixels": want[2], "images": want[3]},
                                  "match": bool(abs(got["bits"] - want[0]) <= 1e-9 * abs(want[0]) and got["pixels"] == want[2] and got["images"] == want[3])}
@@ -686,7 +697,7 @@ def run_ours(args):
     sampler.start()
 
     exchange_name, exchange_factory = None, None
-    if world > 1:
+    if world > 1 or args.exchange == "peer":          # (--exchange peer on one GPU: the whole exchange path with world = 1)
         def exchange_factory(w):
             return make_exchange(args, w, rank, world)
 
@@ -695,8 +706,7 @@ def run_ours(args):
     images, global_elems = shard(c)
     w, main = measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
                              sampler=sampler, exchange_factory=exchange_factory, pin_host=not args.no_e2e)
-    if world > 1:
-        exchange_name = main.pop("exchange_name", None)
+    exchange_name = main.pop("exchange_name", None)
 
     # ---- e2e leg: public API with host buffers
     e2e = None
@@ -788,6 +798,8 @@ def make_exchange(args, w, rank, world):
     fallback (--exchange nccl, or when the peer buffers cannot be mapped — then every rank must fall back together)."""
     import torch.distributed as dist
 
+    if world == 1:
+        return PeerExchange(w, args.steps_per_graph)
     if args.exchange in ("auto", "peer"):
         ok, ex = 1, None
         try:

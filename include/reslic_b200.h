@@ -116,10 +116,11 @@ int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B,
  * separate kernel, no NCCL call on the step.  reslic_rate_exchange_read_f64 later adds the `world` rows of a
  * step in rank order (bit-identical on every rank).
  *
- * Exchange buffer (one per rank, zero-filled once; `peer_base[r]` is rank r's buffer as mapped in THIS process —
- * reslic_peer_buffer_* below, or any other peer-accessible allocation):
- *     rows  double  [ring][world][4]       row (slot, r) is written by rank r only
- *     flags uint64  [ring][world]          = step + 1 once row (step % ring, r) is complete
+ * Exchange buffer (one per rank, zero-filled once, 16-byte aligned; `peer_base[r]` is rank r's buffer as mapped in THIS
+ * process — reslic_peer_buffer_* below, or any other peer-accessible allocation):
+ *     cells  {double value; uint64 tag}  [ring][world][4]       row (slot, r) is written by rank r only
+ * tag = step + 1 once the value of row (step % ring, r) is there: every cell is ONE 16-byte store, so value and tag
+ * arrive together and the writer needs no fence.
  * A launch publishes step number `*cursor + step`: `step` is the caller's number of the batch relative to `cursor`, a
  * zero-initialised DEVICE word local to this rank that the CALLER advances (stream-ordered) — after every batch in
  * eager use, or once per CUDA-graph replay by the number of batches the graph holds, whose launches then carry
@@ -139,11 +140,14 @@ typedef struct reslic_rate_exchange {
   double pixels, images;                   /* the row's third and fourth field                                */
 } reslic_rate_exchange;
 int64_t reslic_rate_exchange_bytes(int32_t world, int32_t ring);
-/* out[s][0..3] = sum over ranks (in rank order) of the rows of steps first_step + s, s < n_steps, read from THIS
- * rank's buffer `own_base`; waits (bounded: about 2 s, then the step's row is NaN and status[0] |= 1) until every
- * rank's flag for the step has arrived.  status: DEVICE int32[1], zeroed by the caller. */
-int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t ring, int64_t first_step,
-                                  int32_t n_steps, double* out, int32_t* status, void* stream);
+/* out[s][0..3] = sum over ranks (in rank order) of the rows of steps base + first_step + s, s < n_steps, read from THIS
+ * rank's buffer `own_base`; base = *cursor (the DEVICE word of reslic_rate_exchange) or 0 when cursor is NULL.  With
+ * the cursor a read is relative to "now" — first_step = -n reads the n steps published last — so it can be captured
+ * in the same CUDA graph as the launches that publish; steps before 0 give a zero row.  Waits (bounded: about 2 s, then
+ * the step's row is NaN and status[0] |= 1) until every rank's row for the step has arrived; status[0] |= 2 if a row
+ * was overwritten (a rank ran `ring` steps ahead).  status: DEVICE int32[1], zeroed by the caller. */
+int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t ring, const unsigned long long* cursor,
+                                  int64_t first_step, int32_t n_steps, double* out, int32_t* status, void* stream);
 
 /* Peer-accessible device memory for the exchange buffers (CUDA IPC): `create` allocates `bytes` zero-filled bytes on
  * the current device and fills the 64-byte handle that another PROCESS on the same node passes to `open` (which

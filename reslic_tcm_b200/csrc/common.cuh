@@ -137,43 +137,50 @@ __device__ __forceinline__ double rate_fixed_to_bits(long long sum, unsigned lon
 // inside the loop the 48-register build of the Gaussian-conditional kernel spills three times as much).
 struct RateWin { long long sum; unsigned long long flag; unsigned int count; };
 
-// Called after the tile loop by every lane that completed at least one image.  The lane that completes the LAST image
-// of the batch owns the batch total — workspace words [4B] sum, [4B+1] images done, [4B+2] flags; integer adds again,
-// so the total is bit-reproducible — and publishes the packed row {bits, extra, pixels, images} into slot
-// (cursor % ring, rank) of EVERY rank's exchange buffer with plain peer stores over NVLink, then releases the row's
-// flag (= step + 1) behind a system-scope fence.  No other thread of the grid waits for any of this.
-static __device__ __noinline__ void rate_publish(const RateWin win, int64_t B, unsigned long long* ws, const RateEx ex) {
+// Called after the tile loop by every lane that completed at least one image.  One 64-bit atomicAdd per such lane on
+// workspace word [4B] — [63:48] images done, [47:0] sum of (image rate + 2^20) in 48.16 fixed point, so the lane whose
+// add completes the count holds the whole batch total in the atomic's return value (no fence, no second atomic; integer
+// adds, so the total is bit-reproducible); non-finite images go through the flag word [4B+2] (rare, fenced).  That lane
+// publishes the row {bits, extra, pixels, images} into slot ((*cursor + step) % ring, rank) of EVERY rank's exchange
+// buffer as four self-validating 16-byte cells {value, step + 1}: a 16-byte store is one transaction, so a reader that
+// sees the tag sees the value — no fence, no flag word, nothing to wait for: the lane issues 4 * world peer stores over
+// NVLink and retires.  Everything the publisher needs from memory (cursor, extra, flags) is loaded BEFORE the atomic, so
+// the launch ends one L2 round trip after its last image completes.  (B < 65536 is checked on the host; 2^20 per image
+// keeps a rounding-negative rate from borrowing out of the sum field.)
+constexpr unsigned long long kBatchBias = 1ull << 20;
+__device__ __forceinline__ void st_cell(void* p, double v, unsigned long long tag) {
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ void rate_publish(const RateWin win, int64_t B, unsigned long long* ws, const RateEx& ex) {
   unsigned long long* bw = ws + 4 * B;
-  atomicAdd(&bw[0], static_cast<unsigned long long>(win.sum));
-  if (win.flag) atomicOr(&bw[2], win.flag);
-  __threadfence();
-  if (atomicAdd(&bw[1], static_cast<unsigned long long>(win.count)) + win.count != static_cast<unsigned long long>(B)) return;
-  __threadfence();
-  const long long total = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&bw[0]));
+  if (win.flag) { atomicOr(&bw[2], win.flag); __threadfence(); }
+  const unsigned long long base = ex.cursor ? *reinterpret_cast<const volatile unsigned long long*>(ex.cursor) : 0ull;
+  const double extra = ex.extra ? *reinterpret_cast<const volatile double*>(ex.extra) : 0.0;
+  const unsigned long long add = (static_cast<unsigned long long>(win.count) << 48) +
+                                 static_cast<unsigned long long>(win.sum + static_cast<long long>(win.count * kBatchBias));
+  const unsigned long long now = atomicAdd(&bw[0], add) + add;
+  if ((now >> 48) != static_cast<unsigned long long>(B)) return;
+  const long long total = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(B) * static_cast<long long>(kBatchBias);
+  // (a flagged image fenced its atomicOr before its own add, and this lane's add came last: the flags are complete)
   const unsigned long long f = *reinterpret_cast<volatile unsigned long long*>(&bw[2]);
-  bw[0] = 0ull; bw[1] = 0ull;
+  bw[0] = 0ull;
   if (f) bw[2] = 0ull;
-  const unsigned long long step = static_cast<unsigned long long>(ex.step_rel) +
-                                  (ex.cursor ? *reinterpret_cast<const volatile unsigned long long*>(ex.cursor) : 0ull);
-  const size_t cell = static_cast<size_t>(step % static_cast<unsigned long long>(ex.ring)) * ex.world + ex.rank;
-  const double2 r01 = make_double2(rate_fixed_to_bits(total, f), ex.extra ? *ex.extra : 0.0);
-  const double2 r23 = make_double2(ex.pixels, ex.images);
+  const unsigned long long step = static_cast<unsigned long long>(ex.step_rel) + base;
+  const size_t cell = (static_cast<size_t>(step % static_cast<unsigned long long>(ex.ring)) * ex.world + ex.rank) * 64;   // bytes
+  const double bits = rate_fixed_to_bits(total, f);
   for (int p = 0; p < ex.world; ++p) {
-    double2* row = reinterpret_cast<double2*>(static_cast<double*>(ex.peer[p]) + cell * 4);
-    row[0] = r01; row[1] = r23;
-  }
-  __threadfence_system();
-  const size_t flags_at = static_cast<size_t>(ex.ring) * ex.world * 4;       // in doubles = 64-bit words
-  for (int p = 0; p < ex.world; ++p) {
-    volatile unsigned long long* fl = reinterpret_cast<volatile unsigned long long*>(static_cast<double*>(ex.peer[p]) + flags_at) + cell;
-    *fl = step + 1ull;
+    char* row = static_cast<char*>(ex.peer[p]) + cell;
+    st_cell(row, bits, step + 1ull);
+    st_cell(row + 16, extra, step + 1ull);
+    st_cell(row + 32, ex.pixels, step + 1ull);
+    st_cell(row + 48, ex.images, step + 1ull);
   }
 }
 
 // (`win`: where the winning lane notes what it completed, for rate_publish after the loop; nullptr = no exchange)
 __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int image, unsigned int expected,
                                                    int64_t B, unsigned long long* ws, double* bits_out,
-                                                   bool accumulate, bool collect = false, RateWin* win = nullptr) {
+                                                   bool accumulate, bool collect = false, const RateEx* ex = nullptr) {
   if ((threadIdx.x & 31) == 0 && (now >> 48) == expected) {
     __threadfence();
     long long sum = static_cast<long long>(now & (kArrOne - 1ull)) - static_cast<long long>(expected) * kRateBias;
@@ -189,7 +196,7 @@ __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int i
     bits_out[image] = accumulate ? bits_out[image] + bits : bits;   // single writer per image
     ws[image] = 0ull;
     if (flag) ws[B + image] = 0ull;
-    if (win != nullptr) { win->sum += sum; win->flag |= flag; win->count += 1u; }
+    if (ex != nullptr) rate_publish(RateWin{sum, flag, 1u}, B, ws, *ex);
   }
 }
 
@@ -200,7 +207,7 @@ __device__ __forceinline__ void rate_commit_finish(unsigned long long now, int i
 // commutes, so the result is still bit-reproducible and may accumulate over any number of launches.
 // Workspace layout (64-bit words): [0,B) immediate sum/arrival, [B,2B) immediate flags,
 // [2B,3B) deferred sums (signed fixed point, bits * 2^16), [3B,4B) deferred flags,
-// [4B,4B+4) batch total / images done / batch flags / spare (rate_publish).
+// [4B,4B+4) batch total + images done / spare / batch flags / spare (rate_publish).
 __device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsigned long long* ws) {
   const float v = warp_sum_f32(acc);
   if ((threadIdx.x & 31) == 0) {
@@ -214,10 +221,10 @@ __device__ __forceinline__ void rate_defer(float acc, int image, int64_t B, unsi
 // mode = the descriptor's bits_accumulate (0 write, 1 accumulate, 2 deferred, 3 write + collect deferred).
 __device__ __forceinline__ void rate_commit(float acc, int image, unsigned int expected, int64_t B,
                                             unsigned long long* ws, double* bits_out, int mode,
-                                            RateWin* win = nullptr) {
+                                            const RateEx* ex = nullptr) {
   if (mode == 2) { rate_defer(acc, image, B, ws); return; }
   const unsigned long long now = rate_commit_issue(acc, image, B, ws);
-  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3, win);
+  rate_commit_finish(now, image, expected, B, ws, bits_out, mode == 1, mode == 3, ex);
 }
 
 }  // namespace reslic

@@ -261,7 +261,6 @@ gc_fwd_kernel(const GcParams p) {
   const unsigned int t_end = t + p.q_tiles + (cta < p.r_tiles ? 1u : 0u);
   const unsigned int tb = threadIdx.x * (W * 4);
 
-  RateWin win{0ll, 0ull, 0u};                // images this lane completed (EXCH only; published after the loop)
   GcIn a, b;
   a.y = a.m = a.u = make_float4(0.f, 0.f, 0.f, 0.f); a.s = make_float4(1.f, 1.f, 1.f, 1.f);
   b = a;                                     // absent inputs keep these defaults for the whole launch
@@ -359,7 +358,7 @@ gc_fwd_kernel(const GcParams p) {
         };
         const unsigned int first = static_cast<unsigned int>(image) * p.tpi;
         const unsigned int n_ctas = owner(first + p.tpi - 1u) - owner(first) + 1u;
-        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate, EXCH ? &win : nullptr);
+        rate_commit(acc, image, n_ctas * (kThreads / 32), p.B, p.workspace, p.bits, p.bits_accumulate, EXCH ? &p.ex : nullptr);
       }
     }
   }
@@ -367,7 +366,6 @@ gc_fwd_kernel(const GcParams p) {
   // tensor, tcm.py:438-457: the next slice's y exists long before its mu / sigma do).  A slice launch is short —
   // about 3 tiles per CTA — so its first and last microsecond leave HBM under-used; CTAs that are done early pull
   // the next launch's first third of reads into that gap with one bulk instruction per image segment.
-  if (EXCH && win.count != 0u) rate_publish(win, p.B, p.workspace, p.ex);
   TRACE(3);
 #ifdef RESLIC_TRACE
   if (p.trace && threadIdx.x == 0) { p.trace[blockIdx.x * 6 + 4] = smid(); p.trace[blockIdx.x * 6 + 5] = t_end - (cta * p.q_tiles + min(cta, p.r_tiles)); }
@@ -543,6 +541,7 @@ int gc_fwd_launch(const reslic_gc_desc* d, cudaStream_t st) {
       return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange->struct_size != sizeof(reslic_rate_exchange) (ABI mismatch)");
     if (!want_rate || (d->bits_accumulate != 0 && d->bits_accumulate != RESLIC_RATE_COLLECT))
       return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange needs a rate output in mode 0 or RESLIC_RATE_COLLECT");
+    if (d->B >= 65536) return set_error(RESLIC_ERR_UNSUPPORTED, "gc_fwd: exchange supports fewer than 65536 images per launch");
     if (x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->ring < 1 || !x->peer_base || x->step < 0)
       return set_error(RESLIC_ERR_ARG, "gc_fwd: exchange: bad world/rank/ring/step or null peer_base");
     p.ex.peer = x->peer_base; p.ex.cursor = x->cursor; p.ex.step_rel = x->step; p.ex.extra = x->extra; p.ex.pixels = x->pixels; p.ex.images = x->images;

@@ -2,7 +2,7 @@
 //
 // The WRITER is not a kernel of its own: the launch that collects a batch's rate publishes the packed row into every
 // rank's buffer (rate_publish, common.cuh).  Here: the tiny kernel that adds the `world` rows of a step in rank order
-// once their flags have arrived, and the CUDA-IPC plumbing that maps the ranks' buffers into each other's processes.
+// once their tagged cells have arrived, and the CUDA-IPC plumbing that maps the ranks' buffers into each other's processes.
 // Replaces the gather of whole likelihood tensors to GPU 0 that the reference's nn.DataParallel performs before its
 // loss reduces them (src/utils/helper.py:106-113, src/train.py:168-169, src/training/loss.py:24-27).
 #include <cstring>
@@ -11,6 +11,12 @@
 
 namespace reslic {
 
+// one 16-byte cell {value, tag}, read in one transaction
+__device__ __forceinline__ void ld_cell(const void* p, double& v, unsigned long long& tag) {
+  long long a;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(tag) : "l"(p) : "memory");
+  v = __longlong_as_double(a);
+}
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -18,33 +24,36 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 
 // one thread per step; the waits are on LOCAL memory (the peers store into this rank's buffer)
-__global__ void rate_exchange_read_kernel(const double* base, int world, int ring, long long first_step, int n_steps,
-                                          double* out, int* status) {
+__global__ void rate_exchange_read_kernel(const char* base, int world, int ring, const unsigned long long* cursor,
+                                          long long first_step, int n_steps, double* out, int* status) {
   griddep_wait();
   griddep_launch_dependents();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_steps) return;
-  const unsigned long long step = static_cast<unsigned long long>(first_step + s);
-  const size_t cell0 = static_cast<size_t>(step % static_cast<unsigned long long>(ring)) * world;
-  const volatile unsigned long long* flags =
-      reinterpret_cast<const volatile unsigned long long*>(base + static_cast<size_t>(ring) * world * 4) + cell0;
+  const long long abs_step = first_step + s + (cursor ? static_cast<long long>(*cursor) : 0ll);
+  if (abs_step < 0) {                                   // before the first step (first replay of a graph that reads behind)
+    for (int j = 0; j < 4; ++j) out[static_cast<size_t>(s) * 4 + j] = 0.0;
+    return;
+  }
+  const unsigned long long step = static_cast<unsigned long long>(abs_step);
+  const char* slot = base + static_cast<size_t>(step % static_cast<unsigned long long>(ring)) * world * 64;
   const unsigned long long t0 = gtimer_ns();
   int err = 0;
-  for (int r = 0; r < world && !err; ++r) {
-    unsigned long long f;
-    while ((f = flags[r]) < step + 1ull) {
-      if (gtimer_ns() - t0 > 2000000000ull) { err = 1; break; }      // a rank never published: report, do not hang
-      __nanosleep(200);
-    }
-    if (!err && f != step + 1ull) err = 2;                            // overwritten: a rank ran >= ring steps ahead
-  }
-  __threadfence_system();
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  if (!err) {
-    const volatile double* rows = reinterpret_cast<const volatile double*>(base) + cell0 * 4;
-    for (int r = 0; r < world; ++r)
-      for (int j = 0; j < 4; ++j) acc[j] += rows[r * 4 + j];
-  } else {
+  for (int r = 0; r < world && !err; ++r) {            // rank order: every rank adds in the same order
+    for (int j = 0; j < 4 && !err; ++j) {
+      double v; unsigned long long tag;
+      for (;;) {
+        ld_cell(slot + r * 64 + j * 16, v, tag);
+        if (tag >= step + 1ull) break;
+        if (gtimer_ns() - t0 > 2000000000ull) { err = 1; break; }      // a rank never published: report, do not hang
+        __nanosleep(200);
+      }
+      if (!err && tag != step + 1ull) err = 2;                         // overwritten: a rank ran >= ring steps ahead
+      acc[j] += v;
+    }
+  }
+  if (err) {
     atomicOr(status, err);
     for (int j = 0; j < 4; ++j) acc[j] = __longlong_as_double(0x7ff8000000000000LL);
   }
@@ -57,19 +66,19 @@ extern "C" {
 
 int64_t reslic_rate_exchange_bytes(int32_t world, int32_t ring) {
   if (world < 1 || ring < 1) return 0;
-  return static_cast<int64_t>(ring) * world * (4 * sizeof(double) + sizeof(unsigned long long));
+  return static_cast<int64_t>(ring) * world * 64;      // four 16-byte cells {value, step + 1} per (slot, rank)
 }
 
-int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t ring, int64_t first_step, int32_t n_steps,
-                                  double* out, int32_t* status, void* stream) {
+int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t ring, const unsigned long long* cursor,
+                                  int64_t first_step, int32_t n_steps, double* out, int32_t* status, void* stream) {
   using namespace reslic;
-  if (n_steps < 0 || first_step < 0) return set_error(RESLIC_ERR_ARG, "rate_exchange_read: negative step count");
+  if (n_steps < 0 || (first_step < 0 && !cursor)) return set_error(RESLIC_ERR_ARG, "rate_exchange_read: negative step");
   if (n_steps == 0) return RESLIC_OK;
   if (!own_base || !out || !status) return set_error(RESLIC_ERR_ARG, "rate_exchange_read: null pointer");
   if (world < 1 || world > 64 || ring < 1 || n_steps > ring)
     return set_error(RESLIC_ERR_ARG, "rate_exchange_read: world outside 1..64, ring < 1 or more steps than ring slots");
   rate_exchange_read_kernel<<<(n_steps + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const double*>(own_base), world, ring, first_step, n_steps, out, status);
+      static_cast<const char*>(own_base), world, ring, cursor, first_step, n_steps, out, status);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "rate_exchange_read launch");
   return RESLIC_OK;

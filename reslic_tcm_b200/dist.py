@@ -208,9 +208,7 @@ class PeerRateExchange:
         self.cursor.add_(int(n))
 
     # ------------------------------------------------------------------ reading
-    def read(self, n_steps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[n_steps, 4] float64 on the device: the sums over ranks of the next ``n_steps`` published steps (enqueued on
-        the current stream; waits — bounded — for rows that have not arrived yet)."""
+    def _read(self, cursor_ptr, first: int, n_steps: int, out: Optional[torch.Tensor]) -> torch.Tensor:
         n_steps = int(n_steps)
         if not 0 <= n_steps <= self.ring:
             raise ValueError("read(): between 0 and `ring` steps per call")
@@ -220,12 +218,25 @@ class PeerRateExchange:
             raise ValueError("read(): out must be a contiguous float64 [n_steps, 4] tensor on the exchange's device")
         lib = _cabi.load()
         with torch.cuda.device(self.device):
-            code = lib.reslic_rate_exchange_read_f64(self.bases[self.rank], self.world, self.ring, self.read_step, n_steps,
+            code = lib.reslic_rate_exchange_read_f64(self.bases[self.rank], self.world, self.ring, cursor_ptr, int(first), n_steps,
                                                      out.data_ptr(), self.status.data_ptr(),
                                                      _cabi.current_stream_ptr(self.device))
         _cabi.check(code, "reslic_rate_exchange_read_f64")
-        self.read_step += n_steps
         return out
+
+    def read(self, n_steps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[n_steps, 4] float64 on the device: the sums over ranks of the next ``n_steps`` published steps (enqueued on
+        the current stream; waits — bounded — for rows that have not arrived yet).  Step numbers are absolute and kept
+        on the host, so this is the eager form; inside a CUDA graph use :meth:`read_behind`."""
+        out = self._read(None, self.read_step, n_steps, out)
+        self.read_step += int(n_steps)
+        return out
+
+    def read_behind(self, n_steps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The ``n_steps`` steps published LAST (cursor - n .. cursor - 1, read from the device cursor at execution
+        time): capturable, so a graph can open with a read of what its predecessor published — on a side branch it
+        costs the step nothing and still keeps the ranks within a ring of each other.  Steps before 0 give zero rows."""
+        return self._read(self.cursor.data_ptr(), -int(n_steps), n_steps, out)
 
     def skip(self, n_steps: int) -> None:
         """Advance the read position without reading (steps whose rows nobody needs)."""

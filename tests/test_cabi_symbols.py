@@ -76,7 +76,7 @@ def test_short_or_stale_descriptor_is_rejected_before_any_field_is_read(lib):
 
 
 def test_rate_exchange_layout(lib):
-    assert lib.reslic_rate_exchange_bytes(8, 256) == 256 * 8 * (4 * 8 + 8)
+    assert lib.reslic_rate_exchange_bytes(8, 256) == 256 * 8 * 64
     assert lib.reslic_rate_exchange_bytes(0, 4) == 0 and lib.reslic_rate_exchange_bytes(2, 0) == 0
     assert lib.reslic_workspace_bytes(24) == (4 * 24 + 4) * 8
 

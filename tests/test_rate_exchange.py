@@ -75,7 +75,8 @@ def test_exchange_descriptor_is_validated_without_a_gpu():
         setattr(x, field, bad)
         assert lib.reslic_gc_fwd_f32(C.byref(d), None) == -1, field
         setattr(x, field, keep)
-    assert lib.reslic_rate_exchange_read_f64(64, 2, 8, 0, 9, 64, 64, None) == -1      # more steps than ring slots
+    assert lib.reslic_rate_exchange_read_f64(64, 2, 8, None, 0, 9, 64, 64, None) == -1      # more steps than ring slots
+    assert lib.reslic_rate_exchange_read_f64(64, 2, 8, None, -1, 1, 64, 64, None) == -1     # negative step without a cursor
 
 
 # ----------------------------------------------------------------------------- GPU, one device
@@ -118,8 +119,18 @@ def test_world1_publish_and_read_over_ring_wraparound_and_graph_replays():
     torch.cuda.synchronize()
     ex.check()
     assert rows[:, 0].tolist() == [want] * 3 and int(ex.cursor.item()) == 13
-    # a graph of several batches on CONCURRENT branches: explicit step numbers, one advance behind the join — the slot
-    # of a batch must not depend on which branch finishes first (bench.py's launch pattern)
+    # whole-y (one launch) collects and publishes as well
+    path.forward(inp["y"], inp["mu"], inp["sigma"], inp["z"], exchange=ex, fuse_slices=True)
+    assert ex.read(1)[0, 0].item() == pytest.approx(want, rel=1e-6)
+    ex.check()
+
+
+@pytest.mark.gpu
+def test_concurrent_batches_of_one_graph_keep_their_slots():
+    """A graph of several batches on CONCURRENT branches (bench.py's launch pattern): explicit step numbers, one advance
+    behind the join — the slot of a batch must not depend on which branch finishes first."""
+    dev = torch.device("cuda:0")
+    ex = rdist.PeerRateExchange(dev, ring=16)
     paths = [_path(dev) for _ in range(3)]
     inps = [_inputs(dev, range(1 + k, 4 + 2 * k)) for k in range(3)]          # 3, 4, 5 images: three different rates
     for p_, i_ in zip(paths, inps):
@@ -141,19 +152,23 @@ def test_world1_publish_and_read_over_ring_wraparound_and_graph_replays():
         for s_ in side:
             cur.wait_stream(s_)
         ex.advance(6)
+    behind = torch.full((6, 4), -1.0, dtype=torch.float64, device=dev)
+    g3 = torch.cuda.CUDAGraph()          # a graph that opens with a read of what was published last (capturable form)
+    with torch.cuda.graph(g3):
+        ex.read_behind(6, out=behind)
+    g3.replay()
+    torch.cuda.synchronize()
+    assert behind.abs().sum().item() == 0.0                                   # nothing published yet: zero rows, no wait
     for _ in range(2):
         g2.replay()
         rows = ex.read(6)
+        g3.replay()
         torch.cuda.synchronize()
         ex.check()
         assert rows[:, 0].tolist() == [wants[j % 3] for j in range(6)]
         assert rows[:, 3].tolist() == [float(inps[j % 3]["y"].shape[0]) for j in range(6)]
-    assert int(ex.cursor.item()) == 25
-    ex.set_static(pixels=5 * 128 * 128, images=5, extra=2.5)
-    # whole-y (one launch) collects and publishes as well
-    path.forward(inp["y"], inp["mu"], inp["sigma"], inp["z"], exchange=ex, fuse_slices=True)
-    assert ex.read(1)[0, 0].item() == pytest.approx(want, rel=1e-6)
-    ex.check()
+        assert torch.equal(behind, rows)
+    assert int(ex.cursor.item()) == 12
 
 
 @pytest.mark.gpu
