@@ -53,10 +53,10 @@ def parse(argv=None):
     ap.add_argument("--config", type=int, default=DEFAULT_CONFIG, choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nbuf", type=int, default=3, help="rotating buffer sets (L2-cold inputs)")
-    ap.add_argument("--chains", type=int, default=3,
+    ap.add_argument("--nbuf", type=int, default=4, help="rotating buffer sets (L2-cold inputs)")
+    ap.add_argument("--chains", type=int, default=4,
                     help="independent batches in flight at once (graph branches; buffer set s always runs on chain s %% chains)")
-    ap.add_argument("--steps-per-graph", type=int, default=12, help="consecutive steps captured in one CUDA graph")
+    ap.add_argument("--steps-per-graph", type=int, default=24, help="consecutive steps captured in one CUDA graph")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--legs", default="auto", help="extra configs measured beside the main one: 'auto' (N=1: 2,4,5; N>1: 5), 'none', or a list '2,5'")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
