@@ -63,6 +63,7 @@ class RateReducer:
         self.device = device
         self.slots = int(slots)
         self.packed = torch.zeros(self.slots, len(self.FIELDS), dtype=torch.float64, device=device)
+        self.reduced: Optional[torch.Tensor] = None
 
     def pack(self, bits_per_image: torch.Tensor, sq_err: Optional[torch.Tensor], pixels: float, slot: int = 0
              ) -> torch.Tensor:
@@ -86,12 +87,17 @@ class RateReducer:
         return self.packed
 
     def all_reduce(self, async_op: bool = False):
+        """SUM over ranks of the packed matrix into ``self.reduced`` (the local matrix stays untouched: its static
+        fields — pixels, images — are filled once and must not be summed again by the next step's collective)."""
+        if self.reduced is None:
+            self.reduced = torch.empty_like(self.packed)
+        self.reduced.copy_(self.packed)
         if dist.is_initialized() and dist.get_world_size() > 1:
-            return dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, async_op=async_op)
+            return dist.all_reduce(self.reduced, op=dist.ReduceOp.SUM, async_op=async_op)
         return None
 
     def result(self, slot: int = 0) -> dict:
-        v = self.packed[slot].tolist()
+        v = (self.packed if self.reduced is None else self.reduced)[slot].tolist()
         pixels = max(v[2], 1.0)
         return {"bits": v[0], "sq_err": v[1], "pixels": v[2], "images": v[3],
                 "bpp": v[0] / pixels, "mse": v[1] / pixels}

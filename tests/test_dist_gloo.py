@@ -47,6 +47,7 @@ def _worker(rank, world, port, B, out_dir):
     red = rdist.RateReducer(torch.device("cpu"))
     red.pack(bits, torch.tensor(float(len(mine)) * 0.5, dtype=torch.float64), 64 * 64 * len(mine))
     red.all_reduce()
+    red.all_reduce()          # a second step: the static fields (pixels, images) must not be summed over the ranks again
     res = red.result()
     torch.save({"res": res, "bits": bits, "images": list(mine)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
