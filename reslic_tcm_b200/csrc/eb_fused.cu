@@ -15,6 +15,7 @@
 // CTA, both cumulative logits as packed f32x2 lanes; eb_fwd_kernel (per-tile staging, library tanhf)
 // is the RESLIC_MATH_MIRROR form.  Noise mode is FP32/MUFU-issue bound (24 tanh + 2 sigmoid per
 // element), not HBM bound; z is 3.75 % of y's elements.  DESIGN.md section 3.2.
+#include <cstdlib>
 #include "common.cuh"
 #include "eb_math.cuh"
 #include "reslic_internal.h"
@@ -29,6 +30,7 @@ struct EbParams {
   double* bits; unsigned long long* workspace; int bits_accumulate; int64_t B;
   int64_t ne;       // elements per image = C*hw
   int hw, C, tile, bpi, noise_mode, splits;
+  int ipc;          // eb_lut8_kernel: consecutive images per CTA (its 8 tables are staged once for all of them)
   float lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
   const float* next_y; int64_t next_y_bs, next_y_n;   // optional L2 prefetch hint (table mode)
@@ -183,49 +185,61 @@ __global__ void __launch_bounds__(kThreads) eb_lut8_kernel(const EbParams p) {
   griddep_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int octets = (p.C + kEbWarps - 1) / kEbWarps;
-  const int image = blockIdx.x / octets;
-  const int c = (blockIdx.x - image * octets) * kEbWarps + warp;
+  const int group = blockIdx.x / octets;                    // CTA = (group of p.ipc consecutive images, 8 channels)
+  const int octet = blockIdx.x - group * octets;
+  const int c = octet * kEbWarps + warp;
+  const int image0 = group * p.ipc;
+  const int image1 = min(static_cast<int>(p.B), image0 + p.ipc);
   const bool need_lik = p.lik || p.bits;
-  if (p.next_y != nullptr && threadIdx.x == 0) {
-    // this CTA's share of the image's next_y bytes, one bulk L2 prefetch (this launch moves 12 bytes per z element:
-    // HBM is idle, and the slice launch that follows is short enough to feel a third of its reads arriving early)
-    const unsigned int total = static_cast<unsigned int>(p.next_y_n) * 4u;
-    const unsigned int share = ((total + octets - 1) / octets + 15u) & ~15u;
-    const unsigned int off = static_cast<unsigned int>(blockIdx.x - image * octets) * share;
-    if (off < total) {
-      const unsigned int bytes = min(share, total - off);
-      const char* addr = reinterpret_cast<const char*>(p.next_y + static_cast<int64_t>(image) * p.next_y_bs) + off;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
-    }
-  }
-  float acc = 0.0f;
+  float med = 0.0f;
   if (c < p.C) {
-    const int64_t base_c = static_cast<int64_t>(c) * p.hw;
-    const float* __restrict__ z = p.z + image * p.z_bs + base_c;
-    const int chunks = (p.hw + 32 * kEbChunk - 1) / (32 * kEbChunk);
-    float zv[kEbChunk];
-    auto load_chunk = [&](int cc) {
-      const int rem = p.hw - cc * (32 * kEbChunk);
-#pragma unroll
-      for (int j = 0; j < kEbChunk; ++j) zv[j] = (lane + 32 * j < rem) ? ld_stream1(z + cc * (32 * kEbChunk) + lane + 32 * j) : 0.0f;
-    };
-    load_chunk(0);
-    const float med = p.medians[c];
-    if (need_lik) {
+    med = p.medians[c];
+    if (need_lik) {         // the channel's table: once per CTA, whatever the number of images it walks
       for (int t = lane; t < kLutN; t += 32) {
         s_lut[warp][t] = p.lut[static_cast<int64_t>(c) * (2 * kLutN) + t];
         s_lg[warp][t] = p.lut[static_cast<int64_t>(c) * (2 * kLutN) + kLutN + t];
       }
       __syncwarp();
     }
-    bool staged = false;
-    for (int ch = 0; ch < chunks; ++ch) {
+  }
+  bool staged = false;
+  // (image, chunk) pairs are walked as one flat sequence, the next pair's values loaded before the current pair is
+  // processed: with hw = 96 an image is ONE chunk per warp, and without the look-ahead a CTA would pay a full DRAM
+  // round trip per image
+  const int chunks = (p.hw + 32 * kEbChunk - 1) / (32 * kEbChunk);
+  const int iters = (image1 - image0) * chunks;
+  const int64_t base_c = static_cast<int64_t>(c) * p.hw;
+  float zv[kEbChunk];
+  auto load_iter = [&](int it) {
+    const int im = image0 + it / chunks, cc = it - (it / chunks) * chunks;
+    const float* __restrict__ z = p.z + im * p.z_bs + base_c;
+    const int rem = p.hw - cc * (32 * kEbChunk);
+#pragma unroll
+    for (int j = 0; j < kEbChunk; ++j) zv[j] = (lane + 32 * j < rem) ? ld_stream1(z + cc * (32 * kEbChunk) + lane + 32 * j) : 0.0f;
+  };
+  if (c < p.C && iters > 0) load_iter(0);
+  float acc = 0.0f;
+  for (int it = 0; it < iters; ++it) {
+    const int image = image0 + it / chunks, ch = it - (it / chunks) * chunks;
+    if (ch == 0 && p.next_y != nullptr && threadIdx.x == 0) {
+      // this CTA's share of the image's next_y bytes, one bulk L2 prefetch (this launch moves 12 bytes per z element:
+      // HBM is idle, and the slice launch that follows is short enough to feel a third of its reads arriving early)
+      const unsigned int total = static_cast<unsigned int>(p.next_y_n) * 4u;
+      const unsigned int share = ((total + octets - 1) / octets + 15u) & ~15u;
+      const unsigned int off = static_cast<unsigned int>(octet) * share;
+      if (off < total) {
+        const unsigned int bytes = min(share, total - off);
+        const char* addr = reinterpret_cast<const char*>(p.next_y + static_cast<int64_t>(image) * p.next_y_bs) + off;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+      }
+    }
+    if (c < p.C) {
       const int64_t off = base_c + ch * (32 * kEbChunk);
       const int rem = p.hw - ch * (32 * kEbChunk);
       float cur[kEbChunk];
 #pragma unroll
       for (int j = 0; j < kEbChunk; ++j) cur[j] = zv[j];
-      if (ch + 1 < chunks) load_chunk(ch + 1);
+      if (it + 1 < iters) load_iter(it + 1);
 #pragma unroll
       for (int j = 0; j < kEbChunk; ++j) {
         const int i = lane + 32 * j;
@@ -257,18 +271,20 @@ __global__ void __launch_bounds__(kThreads) eb_lut8_kernel(const EbParams p) {
         }
       }
     }
-  }
-  if (p.bits) {
-    const float v = warp_sum_f32(acc);
-    if (lane == 0) s_red[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      float total = 0.0f;
-      if (lane == 0) {
+    if (ch + 1 == chunks && p.bits) {                 // the image is complete: one commit per (CTA, image)
+      const float v = warp_sum_f32(acc);
+      acc = 0.0f;
+      __syncthreads();                                // the previous image's reader is done with s_red
+      if (lane == 0) s_red[warp] = v;
+      __syncthreads();
+      if (warp == 0) {
+        float total = 0.0f;
+        if (lane == 0) {
 #pragma unroll
-        for (int w = 0; w < kEbWarps; ++w) total += s_red[w];     // fixed order: reproducible
+          for (int w = 0; w < kEbWarps; ++w) total += s_red[w];     // fixed order: reproducible
+        }
+        rate_commit(total, image, static_cast<unsigned int>(octets), p.B, p.workspace, p.bits, p.bits_accumulate);
       }
-      rate_commit(total, image, static_cast<unsigned int>(octets), p.B, p.workspace, p.bits, p.bits_accumulate);
     }
   }
 }
@@ -517,8 +533,18 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     const int64_t octets = (d->C + kEbWarps - 1) / kEbWarps;
     if (octets * d->B > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");
     if (octets > 60000) return set_error(RESLIC_ERR_ARG, "eb_fwd: too many channels for the rate arrival count");
+    // a CTA walks `ipc` consecutive images with its eight tables staged once: about 1.3 CTAs per SM (a launch of one CTA
+    // per (image, octet) spends more on launching CTAs and copying tables than on z: 64 x 192 x 12 x 8 as 1536 CTAs took
+    // 11.2 us under ncu for 14 MB of traffic; measured in the config-3 step, images per CTA 1 / 3 / 8: 120.7 / 117.2 /
+    // 115.7 us)
+    int64_t ipc = (octets * d->B + 13LL * sm_count() / 10 - 1) / (13LL * sm_count() / 10);
+    if (ipc < 1) ipc = 1;
+    if (const char* e = std::getenv("RESLIC_EB_IPC")) { const long v = std::atol(e); if (v >= 1) ipc = v; }
+    if (ipc > d->B) ipc = d->B;
+    p.ipc = static_cast<int>(ipc);
+    const int64_t groups_of_images = (d->B + ipc - 1) / ipc;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(octets * d->B));
+    cfg.gridDim = dim3(static_cast<unsigned>(octets * groups_of_images));
     cfg.blockDim = dim3(kThreads);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
