@@ -53,10 +53,11 @@ def parse(argv=None):
     ap.add_argument("--config", type=int, default=DEFAULT_CONFIG, choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nbuf", type=int, default=4, help="rotating buffer sets (L2-cold inputs)")
-    ap.add_argument("--chains", type=int, default=4,
-                    help="independent batches in flight at once (graph branches; buffer set s always runs on chain s %% chains)")
-    ap.add_argument("--steps-per-graph", type=int, default=24, help="consecutive steps captured in one CUDA graph")
+    ap.add_argument("--nbuf", type=int, default=0, help="rotating buffer sets (L2-cold inputs); 0 = as many as chains")
+    ap.add_argument("--chains", type=int, default=0,
+                    help="independent batches in flight at once (graph branches; buffer set s always runs on chain s %% chains); "
+                         "0 = by launch size: 4, or 6 when a rank's slice launch is at most two waves of tiles (an 8-GPU shard)")
+    ap.add_argument("--steps-per-graph", type=int, default=48, help="consecutive steps captured in one CUDA graph")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--legs", default="auto", help="extra configs measured beside the main one: 'auto' (N=1: 2,4,5; N>1: 5), 'none', or a list '2,5'")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
@@ -421,6 +422,14 @@ class Workload:
         return r0.elapsed_time(r1) * 1e3 / (reps * per_graph), n_launch
 
 
+def pick_chains(c: synthetic.Config, images: int) -> int:
+    """Independent batches in flight: 4; 6 when one slice launch of this rank is at most two waves of tiles (740 CTA slots
+    of 1024 elements on B200) — launches that short are latency-bound, and two more batches in flight fill the gaps
+    (measured, 8 images of config 3: 16.1 -> 15.4 us per step; the full 64-image batch loses 1.4 % with 6, so it keeps 4)."""
+    slice_elems = images * c.y_elems_per_image // synthetic.NUM_SLICES
+    return 6 if slice_elems <= 2 * 740 * 1024 else 4
+
+
 def load_peak():
     peaks = {}
     try:
@@ -621,13 +630,16 @@ class PeerExchange:
 def measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
                    sampler=None, exchange_factory=None, steps=None, pin_host=False, light=False):
     """value / ms_per_step / roofline (+ whole-y) of one config for this rank's `images`."""
-    w = Workload(c, images, dev, args.nbuf, params, pin_host=pin_host)
+    chains = args.chains or pick_chains(c, len(images))
+    nbuf = args.nbuf or chains
+    w = Workload(c, images, dev, nbuf, params, pin_host=pin_host)
     steps = steps or args.steps
     ex = exchange_factory(w) if exchange_factory is not None else None
-    tm = Timer(w, args.steps_per_graph, args.chains, world, ex)
+    tm = Timer(w, args.steps_per_graph, chains, world, ex)
     ms_step = tm.timed(steps, args.warmup, barrier, sampler)
     out = {"workload": c.name, "cfg": c.cfg, "images_per_gpu": w.B, "value": global_elems / (ms_step * 1e-3) / 1e6, "unit": UNIT,
-           "ms_per_step": ms_step, "steps": steps, "launches_per_step": 1 + synthetic.NUM_SLICES}
+           "ms_per_step": ms_step, "steps": steps, "launches_per_step": 1 + synthetic.NUM_SLICES,
+           "batches_in_flight": min(chains, nbuf), "buffer_sets": nbuf}
     if ex is not None:
         # the exchanged global row against the checked fallback: an NCCL all-reduce of the same step's local row
         import torch.distributed as dist
@@ -642,12 +654,12 @@ def measure_config(c, images, dev, args, params, world, global_elems, peak, peak
                                  "match": bool(abs(got["bits"] - want[0]) <= 1e-9 * abs(want[0]) and got["pixels"] == want[2] and got["images"] == want[3])}
         out["exchange_name"] = ex.name
         ex.close()
-    out["roofline"] = roof_pair(w, False, args.chains, peak, peak_src, traffic_db, SLICE_WHAT)
+    out["roofline"] = roof_pair(w, False, chains, peak, peak_src, traffic_db, SLICE_WHAT)
     if not args.no_whole_y:
-        tw = Timer(w, args.steps_per_graph, args.chains, world, None, fuse_slices=True)
+        tw = Timer(w, args.steps_per_graph, chains, world, None, fuse_slices=True)
         wms = tw.timed(min(steps, 100) if light else steps, min(args.warmup, 6), barrier)
         out["whole_y"] = {"value": global_elems / (wms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wms, "launches_per_step": 2,
-                          "roofline": roof_pair(w, True, args.chains, peak, peak_src, traffic_db, WHOLE_WHAT)}
+                          "roofline": roof_pair(w, True, chains, peak, peak_src, traffic_db, WHOLE_WHAT)}
     return w, out
 
 
@@ -759,8 +771,8 @@ def run_ours(args):
         cfg.update({
             "images_per_gpu": main["images_per_gpu"], "launches_per_step": main["launches_per_step"],
             "step": f"1 EB + 5 GC launches per step (each GC launch waits for its predecessor), {args.steps_per_graph} steps per CUDA graph, "
-                    f"{min(args.chains, args.nbuf)} independent batches in flight (graph branches over different buffer sets)",
-            "l2": f"{args.nbuf} rotating buffer sets of {(bytes_per_y_elem(c) * main['images_per_gpu'] * c.y_elems_per_image + 12 * main['images_per_gpu'] * c.z_elems_per_image) / 1e6:.0f} MB each "
+                    f"{main['batches_in_flight']} independent batches in flight (graph branches over different buffer sets)",
+            "l2": f"{main['buffer_sets']} rotating buffer sets of {(bytes_per_y_elem(c) * main['images_per_gpu'] * c.y_elems_per_image + 12 * main['images_per_gpu'] * c.z_elems_per_image) / 1e6:.0f} MB each "
                   f"per GPU; inputs + outputs of one step exceed the 126 MB L2 only while a rank holds >= 13 images of this config — "
                   f"smaller shards are L2-assisted, which is what a real 8-GPU run sees too",
             "bpp_mean_rank0": float(bits0.mean()) / c.num_pixels_per_image,
