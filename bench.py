@@ -422,12 +422,22 @@ class Workload:
         return r0.elapsed_time(r1) * 1e3 / (reps * per_graph), n_launch
 
 
-def pick_chains(c: synthetic.Config, images: int) -> int:
-    """Independent batches in flight: 4; 6 when one slice launch of this rank is at most two waves of tiles (740 CTA slots
-    of 1024 elements on B200) — launches that short are latency-bound, and two more batches in flight fill the gaps
-    (measured, 8 images of config 3: 16.1 -> 15.4 us per step; the full 64-image batch loses 1.4 % with 6, so it keeps 4)."""
+def balanced_group(steps: int, max_group: int) -> int:
+    """Steps per CUDA graph: the timed region is cut into equal graphs of at most `max_group` steps (200 -> 5 x 40,
+    20 -> 1 x 20), so that no short tail graph runs with most of its branches empty."""
+    n_graphs = max(1, -(-steps // max(1, max_group)))
+    return max(1, -(-steps // n_graphs))
+
+
+def pick_chains(c: synthetic.Config, images: int, group: int) -> int:
+    """Independent batches in flight.  Launches of at most two waves of tiles (740 CTA slots of 1024 elements on B200: an
+    8-GPU shard of a slice) are latency-bound and gain from more batches in flight (measured, 8 images of config 3:
+    4 -> 6 batches 16.1 -> 15.4 us per step); the full 64-image batch loses 1.4 % with 6 and keeps 4.  Among the
+    candidates the one that deals the `group` steps of a graph evenly onto its branches wins (20 steps on 6 branches
+    leave two branches a step longer than the rest: 18.2 instead of 15.8 us per step)."""
     slice_elems = images * c.y_elems_per_image // synthetic.NUM_SLICES
-    return 6 if slice_elems <= 2 * 740 * 1024 else 4
+    cands = (6, 5, 4) if slice_elems <= 2 * 740 * 1024 else (4, 3)
+    return max(cands, key=lambda k: (group / (k * -(-group // k)), k))
 
 
 def load_peak():
@@ -512,10 +522,17 @@ class Timer:
     def timed(self, steps: int, warmup: int, barrier, sampler=None):
         import torch.distributed as dist
 
-        self.graph(self.group)
-        if steps % self.group:
-            self.graph(steps % self.group)
-        self.run(max(warmup, 3))
+        # warm-up: at least `warmup` steps, and every graph the timed region will replay at least once (the first launch of
+        # a CUDA graph uploads it: a graph first replayed inside the timed region costs that region hundreds of microseconds)
+        sizes = [n for n in dict.fromkeys([min(steps, self.group), steps % self.group if steps > self.group else 0]) if n]
+        done = 0
+        for n in sizes:
+            self.run(n)
+            done += n
+        if done < max(warmup, 3):
+            self.run(max(warmup, 3) - done)
+            done = max(warmup, 3)
+        self.warmup_steps = done
         barrier()
         if self.ex is not None:
             self.ex.verify()          # a broken exchange fails here, after the warm-up, not after minutes of timed-out reads
@@ -630,16 +647,17 @@ class PeerExchange:
 def measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
                    sampler=None, exchange_factory=None, steps=None, pin_host=False, light=False):
     """value / ms_per_step / roofline (+ whole-y) of one config for this rank's `images`."""
-    chains = args.chains or pick_chains(c, len(images))
+    steps = steps or args.steps
+    group = balanced_group(steps, args.steps_per_graph)
+    chains = args.chains or pick_chains(c, len(images), group)
     nbuf = args.nbuf or chains
     w = Workload(c, images, dev, nbuf, params, pin_host=pin_host)
-    steps = steps or args.steps
     ex = exchange_factory(w) if exchange_factory is not None else None
-    tm = Timer(w, args.steps_per_graph, chains, world, ex)
+    tm = Timer(w, group, chains, world, ex)
     ms_step = tm.timed(steps, args.warmup, barrier, sampler)
     out = {"workload": c.name, "cfg": c.cfg, "images_per_gpu": w.B, "value": global_elems / (ms_step * 1e-3) / 1e6, "unit": UNIT,
-           "ms_per_step": ms_step, "steps": steps, "launches_per_step": 1 + synthetic.NUM_SLICES,
-           "batches_in_flight": min(chains, nbuf), "buffer_sets": nbuf}
+           "ms_per_step": ms_step, "steps": steps, "warmup_steps": tm.warmup_steps, "launches_per_step": 1 + synthetic.NUM_SLICES,
+           "batches_in_flight": min(chains, nbuf), "buffer_sets": nbuf, "steps_per_graph": group}
     if ex is not None:
         # the exchanged global row against the checked fallback: an NCCL all-reduce of the same step's local row
         import torch.distributed as dist
@@ -656,7 +674,7 @@ def measure_config(c, images, dev, args, params, world, global_elems, peak, peak
         ex.close()
     out["roofline"] = roof_pair(w, False, chains, peak, peak_src, traffic_db, SLICE_WHAT)
     if not args.no_whole_y:
-        tw = Timer(w, args.steps_per_graph, chains, world, None, fuse_slices=True)
+        tw = Timer(w, group, chains, world, None, fuse_slices=True)
         wms = tw.timed(min(steps, 100) if light else steps, min(args.warmup, 6), barrier)
         out["whole_y"] = {"value": global_elems / (wms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wms, "launches_per_step": 2,
                           "roofline": roof_pair(w, True, chains, peak, peak_src, traffic_db, WHOLE_WHAT)}
@@ -770,7 +788,7 @@ def run_ours(args):
         cfg = workload_config(c, world, args.scaling)
         cfg.update({
             "images_per_gpu": main["images_per_gpu"], "launches_per_step": main["launches_per_step"],
-            "step": f"1 EB + 5 GC launches per step (each GC launch waits for its predecessor), {args.steps_per_graph} steps per CUDA graph, "
+            "step": f"1 EB + 5 GC launches per step (each GC launch waits for its predecessor), {main['steps_per_graph']} steps per CUDA graph, "
                     f"{main['batches_in_flight']} independent batches in flight (graph branches over different buffer sets)",
             "l2": f"{main['buffer_sets']} rotating buffer sets of {(bytes_per_y_elem(c) * main['images_per_gpu'] * c.y_elems_per_image + 12 * main['images_per_gpu'] * c.z_elems_per_image) / 1e6:.0f} MB each "
                   f"per GPU; inputs + outputs of one step exceed the 126 MB L2 only while a rank holds >= 13 images of this config — "
@@ -783,7 +801,7 @@ def run_ours(args):
             cfg["simulated_shard_of"] = sim
         line = {
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+            "warmup": main["warmup_steps"], "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": main["roofline"], "whole_y": main.get("whole_y"),
             "per_config": {str(c.cfg): {k: main[k] for k in ("workload", "value", "ms_per_step", "roofline", "whole_y") if k in main}, **legs},
