@@ -60,8 +60,10 @@ def parse(argv=None):
     ap.add_argument("--steps-per-graph", type=int, default=48, help="consecutive steps captured in one CUDA graph")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--legs", default="auto", help="extra configs measured beside the main one: 'auto' (N=1: 2,4,5; N>1: 5), 'none', or a list '2,5'")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
-                    help="rate exchange at N > 1: peer = fused NVLink stores from the collecting launch; nccl = packed all-reduce")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "fused", "branch", "nccl"],
+                    help="rate exchange at N > 1 over peer memory (auto = peer = fused: the step's collecting launch publishes itself; "
+                         "branch: a one-CTA publisher on a graph branch behind it — measured equal within 0.2 us per step) or nccl "
+                         "(packed all-reduce, the fallback)")
     ap.add_argument("--shard-of", type=int, default=0,
                     help="development aid: run rank 0's shard of a G-rank strong-scaling job on ONE GPU (no exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -343,11 +345,13 @@ class Workload:
         kw = dict(self.kw, offset=8 * i, **over)          # noise mode: every captured step draws its own Philox field
         return s["path"].forward(s["inp"]["y"], s["inp"]["mu"], s["inp"]["sigma"], s["inp"]["z"], **kw)
 
-    def capture(self, n_steps: int, chains: int = 1, first: int = 0, after_step=None, **over):
+    def capture(self, n_steps: int, chains: int = 1, first: int = 0, adapter=None, **over):
         """ONE graph of steps first .. first+n_steps-1.  Consecutive launches of a step are PDL edges; with
         chains > 1 the steps are dealt onto that many forked capture streams — buffer set s always on chain
         s % chains, so two steps over the same buffers stay ordered — i.e. `chains` independent batches are in
-        flight at once, each still a dependent chain.  `after_step(j, set)` is captured behind step j."""
+        flight at once, each still a dependent chain.  `adapter` (an exchange of bench.py) adds the multi-GPU rate
+        exchange: per-step keyword arguments, work captured behind a step, a prologue branch, streams to join and an
+        epilogue behind the join."""
         chains = max(1, min(chains, len(self.sets)))
         while len(self._side) < chains - 1:
             self._side.append(torch.cuda.Stream(device=self.dev))
@@ -357,30 +361,18 @@ class Workload:
             lanes = [cur] + self._side[:chains - 1]
             for s in lanes[1:]:
                 s.wait_stream(cur)
-            ex = over.get("exchange")
-            if ex is not None:              # open with a read of what the PREVIOUS graph published, on a branch of its own:
-                while len(self._side) < chains:     # it costs the steps nothing and keeps the ranks within a ring of each other
-                    self._side.append(torch.cuda.Stream(device=self.dev))
-                rd = self._side[chains - 1]
-                rd.wait_stream(cur)
-                with torch.cuda.stream(rd):
-                    ex.read_behind(n_steps, out=self._behind(ex, n_steps))
-                lanes_join = lanes[1:] + [rd]
-            else:
-                lanes_join = lanes[1:]
+            extra = adapter.prologue(self, cur, n_steps) if adapter is not None else []
             for j in range(first, first + n_steps):
                 si = j % len(self.sets)
                 with torch.cuda.stream(lanes[si % chains]):
-                    if ex is not None:      # the batch's number inside this graph: its exchange slot does not depend on
-                        self.step(j, **dict(over, exchange_step=j - first, exchange_advance=False))   # which chain finishes first
-                    else:
-                        self.step(j, **over)
-                    if after_step is not None:
-                        after_step(j - first, self.sets[si])
-            for s in lanes_join:
+                    kw = dict(over, **adapter.step_kwargs(j - first)) if adapter is not None else over
+                    self.step(j, **kw)
+                    if adapter is not None:
+                        adapter.after_step(j - first, self.sets[si], si % chains)
+            for s in lanes[1:] + list(extra) + (adapter.join_streams() if adapter is not None else []):
                 cur.wait_stream(s)
-            if ex is not None:
-                ex.advance(n_steps)         # behind the join: every replay publishes the next n_steps steps
+            if adapter is not None:
+                adapter.epilogue(n_steps)      # behind the join
         return g
 
     def _behind(self, ex, n):
@@ -498,13 +490,12 @@ class Timer:
 
     def __init__(self, w: Workload, group: int, chains: int, world: int, exchange=None, **over):
         self.w, self.group, self.chains, self.world, self.ex = w, max(1, group), chains, world, exchange
-        self.over = dict(over, **(exchange.step_kwargs() if exchange is not None else {}))
+        self.over = dict(over)
         self.graphs = {}
 
     def graph(self, n: int):
         if n not in self.graphs:
-            hook = self.ex.after_step if self.ex is not None else None
-            self.graphs[n] = self.w.capture(n, self.chains, after_step=hook, **self.over)
+            self.graphs[n] = self.w.capture(n, self.chains, adapter=self.ex, **self.over)
         return self.graphs[n]
 
     def run(self, n_steps: int):
@@ -576,11 +567,20 @@ class NcclExchange:
         self.red.set_static(0.0, w.B * w.c.num_pixels_per_image, w.B)
         self.work = None
 
-    def step_kwargs(self):
+    def prologue(self, w, cur, n):
+        return []
+
+    def step_kwargs(self, j):
         return {}
 
-    def after_step(self, j, s):
+    def after_step(self, j, s, chain):
         self.red.pack_bits(s["res"]["bits"], slot=j)
+
+    def join_streams(self):
+        return []
+
+    def epilogue(self, n):
+        pass
 
     def before_graph(self, n):
         if self.work is not None:         # stream-level wait: the previous collective has read the matrix
@@ -604,25 +604,55 @@ class NcclExchange:
 
 
 class PeerExchange:
-    """Rate exchange fused into the collecting launch (reslic_tcm_b200.dist.PeerRateExchange): the last slice launch
-    of every step stores the step's packed row into every rank's buffer over NVLink; no collective kernel exists.
-    Every graph opens, on a branch of its own, with one tiny read kernel over the rows the PREVIOUS graph published
-    (captured: Workload.capture) — off the steps' critical path, and what keeps a rank from running a ring ahead."""
+    """Rate exchange over peer memory (reslic_tcm_b200.dist.PeerRateExchange): every step stores its packed row into every
+    rank's buffer over NVLink; no collective kernel exists.  Two forms of the writer:
+      fused   — the step's collecting launch publishes (reslic_gc_desc.exchange): nothing but that launch runs;
+      branch  — the collecting launch stays the plain kernel and a one-CTA publisher (reslic_rate_exchange_publish_f64)
+                sits on a graph branch of its own behind it, so the chain's next step does not wait for the publish.
+    Every graph opens, on another branch, with one tiny read kernel over the rows the PREVIOUS graph published — off the
+    steps' critical path, and what keeps a rank from running a ring ahead."""
 
-    name = ("packed rate row stored to every rank over NVLink by the collecting launch itself (no collective kernel); "
-            "one read kernel per graph on a side branch, one graph behind")
-
-    def __init__(self, w: Workload, group: int):
+    def __init__(self, w: Workload, group: int, form: str):
         from reslic_tcm_b200 import dist as rdist
 
+        self.form = form
+        self.name = ("packed rate row stored to every rank over NVLink, no collective kernel; writer: " +
+                     ("the step's collecting launch itself (fused)" if form == "fused" else
+                      "a one-CTA publisher on a graph branch behind the collecting launch") +
+                     "; one read kernel per graph on a side branch, one graph behind")
         self.ex = rdist.PeerRateExchange(w.dev, ring=max(256, 8 * group))
         self.ex.set_static(w.B * w.c.num_pixels_per_image, w.B)
         self.published = 0
+        self.rd = torch.cuda.Stream(device=w.dev)
+        self.pub = {}
+        self.behind = torch.zeros(max(group, 64), 4, dtype=torch.float64, device=w.dev)
 
-    def step_kwargs(self):
-        return {"exchange": self.ex}
+    def prologue(self, w, cur, n):
+        self.rd.wait_stream(cur)
+        with torch.cuda.stream(self.rd):
+            self.ex.read_behind(n, out=self.behind[:n])
+        self._used = set()
+        return [self.rd]
 
-    after_step = None
+    def step_kwargs(self, j):
+        # the batch's number inside this graph: its exchange slot does not depend on which chain finishes first
+        return {"exchange": self.ex, "exchange_step": j, "exchange_advance": False} if self.form == "fused" else {}
+
+    def after_step(self, j, s, chain):
+        if self.form == "fused":
+            return
+        lane = torch.cuda.current_stream(self.ex.device)
+        pub = self.pub.setdefault(chain, torch.cuda.Stream(device=self.ex.device))
+        pub.wait_stream(lane)                     # behind this step's collecting launch only
+        with torch.cuda.stream(pub):
+            self.ex.publish(s["res"]["bits"], step=j)
+        self._used.add(chain)
+
+    def join_streams(self):
+        return [self.pub[c] for c in sorted(self._used)]
+
+    def epilogue(self, n):
+        self.ex.advance(n)                        # every replay publishes the next n steps
 
     def before_graph(self, n):
         pass
@@ -645,7 +675,7 @@ class PeerExchange:
 
 
 def measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
-                   sampler=None, exchange_factory=None, steps=None, pin_host=False, light=False):
+                   sampler=None, exchange_factory=None, steps=None, pin_host=False, light=False, sim_world=1):
     """value / ms_per_step / roofline (+ whole-y) of one config for this rank's `images`."""
     steps = steps or args.steps
     group = balanced_group(steps, args.steps_per_graph)
@@ -671,6 +701,17 @@ def measure_config(c, images, dev, args, params, world, global_elems, peak, peak
         out["exchange_check"] = {"exchange": got, "nccl_all_reduce": {"bits": want[0], "pixels": want[2], "images": want[3]},
                                  "match": bool(abs(got["bits"] - want[0]) <= 1e-9 * abs(want[0]) and got["pixels"] == want[2] and got["images"] == want[3])}
         out["exchange_name"] = ex.name
+    if ex is not None or sim_world > 1:
+        # where the step's time goes on this rank: the GC launches alone in the same launch pattern (kernel), the same step
+        # without the exchange (z launch, launch gaps, graph ramp on top of the kernel), and what the exchange adds
+        t_noex = Timer(w, group, chains, world, None).timed(steps, args.warmup, barrier) if ex is not None else ms_step
+        us_k, n_k = w.gc_only_us(False, chains)
+        out["step_budget"] = {
+            "us_per_step": ms_step * 1e3, "gc_kernels_us": us_k * n_k, "bottleneck_launch_gaps_ramp_us": t_noex * 1e3 - us_k * n_k,
+            "exchange_us": (ms_step - t_noex) * 1e3 if ex is not None else None,
+            "what": "per rank, max over ranks of each timed loop; gc_kernels = 5 x elapsed / launches of the GC launches "
+                                      "alone with the same batches in flight; exchange = step with the fused publish + read - the same step without"}
+    if ex is not None:
         ex.close()
     out["roofline"] = roof_pair(w, False, chains, peak, peak_src, traffic_db, SLICE_WHAT)
     if not args.no_whole_y:
@@ -727,7 +768,7 @@ def run_ours(args):
     sampler.start()
 
     exchange_name, exchange_factory = None, None
-    if world > 1 or args.exchange == "peer":          # (--exchange peer on one GPU: the whole exchange path with world = 1)
+    if world > 1 or args.exchange in ("peer", "fused", "branch"):   # (on one GPU: the whole exchange path with world = 1)
         def exchange_factory(w):
             return make_exchange(args, w, rank, world)
 
@@ -735,7 +776,7 @@ def run_ours(args):
     c = synthetic.CONFIGS[args.config]
     images, global_elems = shard(c)
     w, main = measure_config(c, images, dev, args, params, world, global_elems, peak, peak_src, traffic_db, barrier,
-                             sampler=sampler, exchange_factory=exchange_factory, pin_host=not args.no_e2e)
+                             sampler=sampler, exchange_factory=exchange_factory, pin_host=not args.no_e2e, sim_world=eff_world)
     exchange_name = main.pop("exchange_name", None)
 
     # ---- e2e leg: public API with host buffers
@@ -814,6 +855,8 @@ def run_ours(args):
             line["host_placement"] = placement
         if main.get("exchange_check") is not None:
             line["exchange_check"] = main["exchange_check"]
+        if main.get("step_budget") is not None:
+            line["step_budget"] = main["step_budget"]
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -828,14 +871,15 @@ def make_exchange(args, w, rank, world):
     fallback (--exchange nccl, or when the peer buffers cannot be mapped — then every rank must fall back together)."""
     import torch.distributed as dist
 
+    form = "branch" if args.exchange == "branch" else "fused"
     if world == 1:
-        return PeerExchange(w, args.steps_per_graph)
-    if args.exchange in ("auto", "peer"):
+        return PeerExchange(w, args.steps_per_graph, form)
+    if args.exchange != "nccl":
         ok, ex = 1, None
         try:
-            ex = PeerExchange(w, args.steps_per_graph)
+            ex = PeerExchange(w, args.steps_per_graph, form)
         except Exception as e:      # CUDA IPC not permitted in this container, no peer access, ...
-            if args.exchange == "peer":
+            if args.exchange != "auto":
                 raise
             print(f"[bench] peer exchange unavailable ({e!r}); falling back to NCCL", file=sys.stderr)
             ok = 0

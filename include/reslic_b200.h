@@ -149,6 +149,13 @@ int64_t reslic_rate_exchange_bytes(int32_t world, int32_t ring);
 int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t ring, const unsigned long long* cursor,
                                   int64_t first_step, int32_t n_steps, double* out, int32_t* status, void* stream);
 
+/* Stand-alone publisher: the same row a collecting launch publishes — {sum_b bits[b], extra, pixels, images} as step
+ * *cursor + ex->step — from a bits[B] vector that already exists (stream-ordered behind the launch that wrote it).  For
+ * callers that want the collecting launch itself untouched: in a CUDA graph this one-CTA kernel sits on a branch of its
+ * own behind the batch's last launch, off the next batch's critical path.  bits[b] are multiples of 2^-16 (the kernels'
+ * fixed-point commit), so the sum is exact and equals the fused form's bit for bit. */
+int reslic_rate_exchange_publish_f64(const reslic_rate_exchange* ex, const double* bits, int64_t B, void* stream);
+
 /* Peer-accessible device memory for the exchange buffers (CUDA IPC): `create` allocates `bytes` zero-filled bytes on
  * the current device and fills the 64-byte handle that another PROCESS on the same node passes to `open` (which
  * maps the buffer, enabling peer access) — torch.distributed moves the handles.  `close` unmaps, `destroy` frees. */

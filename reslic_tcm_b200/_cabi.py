@@ -225,6 +225,7 @@ EXPORTS = {
     "reslic_rate_exchange_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "reslic_rate_exchange_read_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "reslic_rate_exchange_publish_f64": (C.c_int, [C.POINTER(RateExchangeDesc), C.c_void_p, C.c_int64, C.c_void_p]),
     "reslic_peer_buffer_create": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "reslic_peer_buffer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "reslic_peer_buffer_close": (C.c_int, [C.c_void_p]),

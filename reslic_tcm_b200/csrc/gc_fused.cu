@@ -414,12 +414,14 @@ static cudaError_t launch_one(GcParams& p, cudaStream_t st) {
     // (measured: 61.5 -> 57.3 us on 24 x 491520; shorter launches lose more to the second prologue)
     grid = static_cast<int64_t>(resident_ctas(kernel, &occ)) * sm_count();
     if (total >= 16 * grid) grid *= 2;
-    else if (total > grid && total <= 2 * grid && gc_tuning().balance) {
-      // a little more than one wave of tiles (an 8-GPU shard of a slice: 768 tiles on 740 slots): the fewest CTAs that
-      // keep the longest range at two tiles, so that EVERY CTA has both of its tiles in flight together, instead of a full
-      // wave of one-tile CTAs plus a few stragglers that run a second tile alone — and the CTA slots left free host the
-      // next launch of an overlapping chain (measured, three chains in flight, 8 x 98304: 19.1 -> 16.0 us per 5 launches;
-      // mid-size launches lose: 24 x 98304 at 576 x 4 tiles 71 -> 80 us single chain, so the rule stops at two tiles)
+    else if (total > 3LL * sm_count() && total <= 2 * grid && gc_tuning().balance) {
+      // Between three tiles per SM and two waves of tiles (an 8-GPU shard of a slice: 768 tiles on 740 slots for 8 Kodak
+      // images, 512 for 32 training patches): two tiles per CTA.  EVERY CTA then has both of its tiles in flight together
+      // — instead of a full wave of one-tile CTAs plus, above one wave, a few stragglers that run a second tile alone —
+      // and the CTA slots left free host the next launch of an overlapping chain.  Measured with several batches in
+      // flight: 8 x 98304 19.8 -> 15.7 us per step, 32 x 16384 (noise) 18.5 -> 16.2; below three tiles per SM the halved
+      // CTA count costs more parallelism than it buys (3 x 98304: 10.5 -> 11.1), and mid-size launches lose
+      // (24 x 98304 as 576 x 4 tiles: 71 -> 80 us single chain), so the rule covers exactly this band.
       grid = (total + 1) / 2;
     }
   }

@@ -60,6 +60,31 @@ __global__ void rate_exchange_read_kernel(const char* base, int world, int ring,
   for (int j = 0; j < 4; ++j) out[static_cast<size_t>(s) * 4 + j] = acc[j];
 }
 
+// one CTA: sum of bits[0..B) (exact: multiples of 2^-16), then the row's 4 * world peer stores
+__global__ void __launch_bounds__(128) rate_exchange_publish_kernel(const double* bits, long long B, const RateEx ex) {
+  __shared__ double s_part[4];
+  griddep_wait();
+  griddep_launch_dependents();
+  double v = 0.0;
+  for (long long i = threadIdx.x; i < B; i += blockDim.x) v += bits[i];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double total = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+  const unsigned long long step = static_cast<unsigned long long>(ex.step_rel) +
+                                  (ex.cursor ? *reinterpret_cast<const volatile unsigned long long*>(ex.cursor) : 0ull);
+  const double extra = ex.extra ? *reinterpret_cast<const volatile double*>(ex.extra) : 0.0;
+  const size_t cell = (static_cast<size_t>(step % static_cast<unsigned long long>(ex.ring)) * ex.world + ex.rank) * 64;
+  for (int p = 0; p < ex.world; ++p) {
+    char* row = static_cast<char*>(ex.peer[p]) + cell;
+    st_cell(row, total, step + 1ull);
+    st_cell(row + 16, extra, step + 1ull);
+    st_cell(row + 32, ex.pixels, step + 1ull);
+    st_cell(row + 48, ex.images, step + 1ull);
+  }
+}
+
 }  // namespace reslic
 
 extern "C" {
@@ -81,6 +106,30 @@ int reslic_rate_exchange_read_f64(const void* own_base, int32_t world, int32_t r
       static_cast<const char*>(own_base), world, ring, cursor, first_step, n_steps, out, status);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "rate_exchange_read launch");
+  return RESLIC_OK;
+}
+
+int reslic_rate_exchange_publish_f64(const reslic_rate_exchange* x, const double* bits, int64_t B, void* stream) {
+  using namespace reslic;
+  if (!x || !bits || B < 1) return set_error(RESLIC_ERR_ARG, "rate_exchange_publish: null argument or B < 1");
+  if (x->struct_size != sizeof(reslic_rate_exchange))
+    return set_error(RESLIC_ERR_ARG, "rate_exchange_publish: struct_size != sizeof(reslic_rate_exchange) (ABI mismatch)");
+  if (x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->ring < 1 || !x->peer_base || x->step < 0)
+    return set_error(RESLIC_ERR_ARG, "rate_exchange_publish: bad world/rank/ring/step or null peer_base");
+  RateEx ex{};
+  ex.peer = x->peer_base; ex.cursor = x->cursor; ex.step_rel = x->step; ex.extra = x->extra; ex.pixels = x->pixels;
+  ex.images = x->images; ex.world = x->world; ex.rank = x->rank; ex.ring = x->ring;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(128);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gc_tuning().pdl ? 1 : 0;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, rate_exchange_publish_kernel, bits, static_cast<long long>(B), ex);
+  if (err != cudaSuccess) return set_cuda_error(err, "rate_exchange_publish launch");
   return RESLIC_OK;
 }
 

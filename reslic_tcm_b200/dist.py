@@ -208,6 +208,20 @@ class PeerRateExchange:
     def slot_of(self, step: int) -> int:
         return int(step) % self.ring
 
+    def publish(self, bits: torch.Tensor, step: int = 0) -> None:
+        """Stand-alone publisher (reslic_rate_exchange_publish_f64): the row of a batch whose per-image ``bits`` already
+        exist, as step ``cursor + step``, from a one-CTA kernel on the current stream — the same row, bit for bit, that
+        ``forward(..., exchange=self)`` publishes from inside the collecting launch.  In a CUDA graph put it on a branch
+        of its own behind the batch's last launch: the next batch then does not wait for it."""
+        if bits.dtype != torch.float64 or not bits.is_contiguous() or bits.device != self.device:
+            raise ValueError("publish(): bits must be a contiguous float64 tensor on the exchange's device")
+        lib = _cabi.load()
+        self.desc.step = int(step)
+        with torch.cuda.device(self.device):
+            code = lib.reslic_rate_exchange_publish_f64(C.byref(self.desc), bits.data_ptr(), bits.numel(),
+                                                        _cabi.current_stream_ptr(self.device))
+        _cabi.check(code, "reslic_rate_exchange_publish_f64")
+
     def advance(self, n: int = 1) -> None:
         """cursor += n on the current stream (capturable): call once behind the launches that published steps
         cursor .. cursor + n - 1."""

@@ -260,3 +260,25 @@ def test_two_processes_exchange_over_peer_memory_and_match_nccl(tmp_path):
     assert (outs[0]["rows"] == outs[0]["rows"][0]).all()
     assert first[0] == pytest.approx(outs[0]["nccl"]["bits"], rel=1e-12)
     assert first[2] == outs[0]["nccl"]["pixels"] == 6 * 128 * 128 and first[3] == 6.0
+
+
+@pytest.mark.gpu
+def test_standalone_publisher_equals_the_fused_publish():
+    """reslic_rate_exchange_publish_f64 (one CTA behind the collecting launch) publishes, bit for bit, the row the
+    collecting launch publishes itself."""
+    dev = torch.device("cuda:0")
+    path, inp = _path(dev), _inputs(dev, range(9))
+    fused, branch = rdist.PeerRateExchange(dev, ring=4), rdist.PeerRateExchange(dev, ring=4)
+    for ex in (fused, branch):
+        ex.set_static(pixels=9 * 128 * 128, images=9, extra=0.25)
+    for step in range(6):                         # round the ring
+        res = path.forward(inp["y"], inp["mu"], inp["sigma"], inp["z"], exchange=fused)
+        branch.publish(res["bits"], step=0)
+        branch.advance(1)
+        a, b = fused.read(1), branch.read(1)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b) and a[0, 0].item() == float(res["bits"].double().sum())
+    fused.check()
+    branch.check()
+    with pytest.raises(ValueError):
+        branch.publish(res["bits"].float())
