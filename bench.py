@@ -375,11 +375,6 @@ class Workload:
                 adapter.epilogue(n_steps)      # behind the join
         return g
 
-    def _behind(self, ex, n):
-        if getattr(self, "_behind_buf", None) is None or self._behind_buf.shape[0] < n:
-            self._behind_buf = torch.zeros(max(n, 64), 4, dtype=torch.float64, device=self.dev)
-        return self._behind_buf[:n]
-
     def drain_deferred(self):
         for s in self.sets:
             b = s["path"].buffers(s["inp"]["y"], s["inp"]["z"], self.c.with_indexes, self.c.training)

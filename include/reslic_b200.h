@@ -112,7 +112,7 @@ int reslic_rate_from_likelihood_f32(const float* lik, int64_t lik_bs, int64_t B,
  * src/train.py:168-169) before src/training/loss.py:24-27 reduces them.  Here the launch that COLLECTS a batch's
  * rate also publishes it: the warp that completes the batch stores one packed row
  *     { sum_b bits[b], extra[0] (e.g. the squared-error sum), pixels, images }      (4 doubles)
- * straight into every rank's exchange buffer over NVLink (peer stores) and then sets that row's flag — no
+ * straight into every rank's exchange buffer over NVLink (plain peer stores, each cell tagged with its step) — no
  * separate kernel, no NCCL call on the step.  reslic_rate_exchange_read_f64 later adds the `world` rows of a
  * step in rank order (bit-identical on every rank).
  *

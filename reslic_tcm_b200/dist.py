@@ -109,8 +109,9 @@ class PeerRateExchange:
     Every rank owns one small exchange buffer in peer-accessible device memory; the buffers are mapped into all
     ranks' address spaces once (CUDA IPC handles moved by ``torch.distributed``).  The Gaussian-conditional launch
     that COLLECTS a batch's rate (the last slice launch of ``TcmEntropyPath.forward(..., exchange=self)``) publishes
-    the packed row {sum of bits, extra, pixels, images} into slot ``step % ring`` of EVERY rank's buffer with plain
-    stores over NVLink and then sets the row's flag; nothing else runs on the step — compare ``RateReducer`` (one
+    the packed row {sum of bits, extra, pixels, images} into slot ``step % ring`` of EVERY rank's buffer as four
+    self-validating 16-byte cells {value, step + 1} with plain stores over NVLink (no fence, no flag word); nothing else
+    runs on the step — compare ``RateReducer`` (one
     NCCL all-reduce kernel per step or per graph, which lands in the middle of persistent-CTA launches) and the
     reference's ``nn.DataParallel`` gather of whole likelihood tensors (src/utils/helper.py:106-113,
     src/train.py:168-169).  ``read(n)`` adds the ``world`` rows of the next n steps in rank order on the device (a

@@ -72,3 +72,19 @@ def test_simulated_shard_line_on_gpu():
     lines = _run(["--steps", "24", "--warmup", "3", "--shard-of", "8", "--no-e2e", "--no-whole-y", "--no-cpu-baseline", "--legs", "none"])
     d = json.loads(lines[0])
     assert d["config"]["images_per_gpu"] == 8 and d["config"]["simulated_shard_of"] == 8 and d["value"] > 0
+
+
+def test_graph_and_branch_shaping_is_even_for_any_step_count():
+    """bench.balanced_group / pick_chains: the timed region is cut into equal graphs, and the batches in flight deal a
+    graph's steps evenly onto the branches (the driver runs --steps 20; the default is 200)."""
+    import bench
+
+    c3, c5 = bench.synthetic.CONFIGS[3], bench.synthetic.CONFIGS[5]
+    assert bench.balanced_group(200, 48) == 40 and bench.balanced_group(20, 48) == 20 and bench.balanced_group(192, 48) == 48
+    assert bench.balanced_group(1, 48) == 1 and bench.balanced_group(49, 48) == 25
+    for steps in (1, 7, 20, 24, 100, 192, 200):
+        g = bench.balanced_group(steps, 48)
+        assert 1 <= g <= 48 and -(-steps // g) == -(-steps // 48)          # as few graphs as the cap allows, none nearly empty
+    assert bench.pick_chains(c3, 64, 40) == 4 and bench.pick_chains(c3, 64, 20) == 4          # full batch: 4 in flight
+    assert bench.pick_chains(c3, 8, 20) == 5 and bench.pick_chains(c3, 8, 40) == 5 and bench.pick_chains(c3, 8, 48) == 6
+    assert bench.pick_chains(c5, 32, 20) == 5 and bench.pick_chains(c5, 256, 20) == 4
