@@ -50,7 +50,8 @@ enum {
 /* CompressAI EntropyModel.quantize modes. */
 enum {
   RESLIC_Q_DEQUANTIZE = 0, /* "dequantize": round(x - mu) + mu  (eval)            */
-  RESLIC_Q_NOISE = 1       /* "noise":      x + U(-1/2, 1/2)    (training)        */
+  RESLIC_Q_NOISE = 1,      /* "noise":      x + U(-1/2, 1/2)    (training)        */
+  RESLIC_Q_IDENTITY = 2    /* reslic_eb_bwd_f32 only: z IS the quantizer output (STanH bottleneck) */
 };
 
 /* Likelihood arithmetic of the Gaussian-conditional kernel (process-wide switch).
@@ -313,7 +314,9 @@ int reslic_eb_build_lut_f32(const reslic_eb_desc* d, float* lut, void* stream);
  * _logits_cumulative x2 + the sign trick + LowerBound (adaptive_entropy_bottleneck.py:525-543,
  * 658-666) in the reference's training step.  Parameter gradients are per-channel reductions over
  * all B*hw elements of the channel; they are OVERWRITTEN (raw-parameter space: softplus' / tanh'
- * already applied).  g_medians is non-zero only in DEQUANTIZE mode (z_hat = round(z-med)+med). */
+ * already applied).  g_medians is non-zero only in DEQUANTIZE mode (z_hat = round(z-med)+med).
+ * With the variable-bin fields at the end of the descriptor the same kernel is the backward of
+ * reslic_eb_stanh_fwd_f32's likelihood (the STanH quantizer itself is differentiated by reslic_stanh_gc_bwd_f32). */
 typedef struct reslic_eb_bwd_desc {
   uint64_t struct_size;                    /* = sizeof(reslic_eb_bwd_desc); checked by the library           */
   const float* z;      int64_t z_bs;
@@ -333,6 +336,16 @@ typedef struct reslic_eb_bwd_desc {
    * a fixed order (bit-reproducible); without it one CTA serves a whole channel.  Size:
    * reslic_eb_bwd_workspace_bytes(C). */
   void* workspace; int64_t workspace_bytes;
+  /* Variable bins (EntropyBottleneckStanh, adaptive_entropy_bottleneck.py:551-603,643-666), all optional: with
+   * half_lo / half_up the likelihood is |sigmoid(s f(x + up)) - sigmoid(s f(x - lo))| with per-element half-widths (as
+   * reslic_eb_stanh_fwd_f32 wrote them) instead of 1/2; with `cell` and `g_dist` the gradients w.r.t. the half-widths
+   * are summed per STanH level gap — g_dist[j-1] += dLoss/d lo, g_dist[j] += dLoss/d up for an element in cell j
+   * (cell < 0: outside every cell, no half-width gradient) — into g_dist[n_dist] (DEVICE doubles, zeroed by the
+   * caller; = dLoss / d distance_points).  Use with mode RESLIC_Q_IDENTITY and z = the quantizer's output. */
+  const float* half_lo;  int64_t half_lo_bs;
+  const float* half_up;  int64_t half_up_bs;
+  const int32_t* cell;   int64_t cell_bs;
+  double* g_dist;        int64_t n_dist;
 } reslic_eb_bwd_desc;
 
 int reslic_eb_bwd_f32(const reslic_eb_bwd_desc* d, void* stream);
@@ -436,6 +449,11 @@ typedef struct reslic_eb_stanh_desc {
   int32_t* sym; int64_t sym_bs;
   double* bits; int32_t bits_accumulate;
   void* workspace; int64_t workspace_bytes;
+  /* optional outputs for the backward (reslic_eb_bwd_f32 with variable bins): the half-widths of every element's
+   * level cell and the cell index j (0..K; -1 = outside every cell, both half-widths 0) */
+  float* half_lo;  int64_t half_lo_bs;
+  float* half_up;  int64_t half_up_bs;
+  int32_t* cell;   int64_t cell_bs;
 } reslic_eb_stanh_desc;
 
 int reslic_eb_stanh_fwd_f32(const reslic_eb_stanh_desc* d, void* stream);

@@ -21,7 +21,7 @@ PEER_HANDLE_BYTES = 64
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
 EB_LUT_STRIDE = 130
-Q_DEQUANTIZE, Q_NOISE = 0, 1
+Q_DEQUANTIZE, Q_NOISE, Q_IDENTITY = 0, 1, 2
 MATH_FAST, MATH_MIRROR = 0, 1
 
 c_f32p = C.c_void_p
@@ -134,6 +134,10 @@ class EbBwdDesc(C.Structure):
         ("g_medians", C.c_void_p),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("half_lo", C.c_void_p), ("half_lo_bs", C.c_int64),
+        ("half_up", C.c_void_p), ("half_up_bs", C.c_int64),
+        ("cell", C.c_void_p), ("cell_bs", C.c_int64),
+        ("g_dist", C.c_void_p), ("n_dist", C.c_int64),
     ]
 
 
@@ -202,6 +206,9 @@ class EbStanhDesc(C.Structure):
         ("sym", C.c_void_p), ("sym_bs", C.c_int64),
         ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("half_lo", C.c_void_p), ("half_lo_bs", C.c_int64),
+        ("half_up", C.c_void_p), ("half_up_bs", C.c_int64),
+        ("cell", C.c_void_p), ("cell_bs", C.c_int64),
     ]
 
 

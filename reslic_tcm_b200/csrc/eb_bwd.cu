@@ -24,6 +24,9 @@ struct EbBwdParams {
   int64_t B; int hw, C, noise_mode;
   float lik_bound;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  const float* half_lo; const float* half_up; const int32_t* cell; int64_t half_lo_bs, half_up_bs, cell_bs;   // variable bins
+  double* g_dist; int n_dist;    // optional: dLoss / d distance_points (summed per level gap)
+  int identity;                  // mode RESLIC_Q_IDENTITY: z is the quantizer's output
   int splits;                    // CTAs per channel
   unsigned int* counters;        // [C] arrival tickets (zero between launches)
   float* partials;               // [C][splits][kPartStride]
@@ -130,8 +133,8 @@ __device__ __forceinline__ float2 logits_pair_tape(const float* __restrict__ P, 
   return __ffma2_rn(make_float2(P[oM4 + 2], P[oM4 + 2]), h[2], a);
 }
 
-__device__ __forceinline__ float logits_backward_pair(const float* __restrict__ P, float2 x, float2 g, const float2 hin[4][3],
-                                                      const float2 th[4][3], float* gP) {
+__device__ __forceinline__ float2 logits_backward_pair(const float* __restrict__ P, float2 x, float2 g, const float2 hin[4][3],
+                                                       const float2 th[4][3], float* gP) {
   auto dot2 = [](float2 a, float2 b, float acc) { return fmaf(a.x, b.x, fmaf(a.y, b.y, acc)); };
   const float2 one = make_float2(1.0f, 1.0f);
   float2 gh[3];
@@ -163,7 +166,7 @@ __device__ __forceinline__ float logits_backward_pair(const float* __restrict__ 
       gh[k] = __ffma2_rn(make_float2(M[6 + k], M[6 + k]), gt[2], a);
     }
   }
-  float gx = 0.0f;
+  float2 gx = make_float2(0.0f, 0.0f);       // per lane: d loss / d (x - lo), d loss / d (x + up)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float2 tj = th[0][j];
@@ -172,7 +175,7 @@ __device__ __forceinline__ float logits_backward_pair(const float* __restrict__ 
     const float2 gt = __fmul2_rn(gh[j], __ffma2_rn(make_float2(P[oF0 + j], P[oF0 + j]), sech2, one));
     gP[oB0 + j] += gt.x + gt.y;
     gP[oM0 + j] = dot2(gt, x, gP[oM0 + j]);
-    gx = fmaf(P[oM0 + j], gt.x + gt.y, gx);
+    gx = __ffma2_rn(make_float2(P[oM0 + j], P[oM0 + j]), gt, gx);
   }
   return gx;
 }
@@ -202,6 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
   __shared__ float s_par[kEbStride + 1];
   __shared__ float s_red[kThreads / 32][kNP + 1];
   __shared__ bool s_last;
+  __shared__ double s_dist[1024];            // per-CTA sums of the half-width gradients (variable bins only)
+  if (p.g_dist)
+    for (int i = threadIdx.x; i < p.n_dist; i += kThreads) s_dist[i] = 0.0;
   const int c = blockIdx.x / p.splits;
   const int split = blockIdx.x - c * p.splits;
   if (threadIdx.x < kEbStride) s_par[threadIdx.x] = eb_staged_param(p, c, threadIdx.x);
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
   const int64_t base_c = static_cast<int64_t>(c) * p.hw;
   // The inputs of the NEXT element are loaded before the current one is evaluated: with one CTA of this kernel
   // per SM (8 warps) nothing else hides the ~0.8 us of a global load, and an element row is only ~0.8 us of math.
-  struct Ld { float zv, u, gl, gzh; int64_t b, e; };
+  struct Ld { float zv, u, gl, gzh, lo, up; int cell; int64_t b, e; };
   const int64_t step = static_cast<int64_t>(p.splits) * kThreads;
   auto fetch = [&](int64_t idx, Ld& r) {
     r.b = idx / p.hw;
@@ -224,6 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
     r.u = (p.noise_mode && p.noise) ? p.noise[r.b * p.noise_bs + r.e] : 0.0f;
     r.gl = p.g_lik ? p.g_lik[r.b * p.g_lik_bs + r.e] : 0.0f;
     r.gzh = p.g_zhat ? p.g_zhat[r.b * p.g_zhat_bs + r.e] : 0.0f;
+    r.lo = p.half_lo ? p.half_lo[r.b * p.half_lo_bs + r.e] : 0.5f;
+    r.up = p.half_up ? p.half_up[r.b * p.half_up_bs + r.e] : 0.5f;
+    r.cell = p.cell ? p.cell[r.b * p.cell_bs + r.e] : -1;
   };
   Ld nxt{};
   int64_t idx = static_cast<int64_t>(split) * kThreads + threadIdx.x;
@@ -234,7 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
     const int64_t b = cur.b, e = cur.e;
     const float zv = cur.zv;
     float x;
-    if (p.noise_mode) {
+    if (p.identity) {
+      x = zv;
+    } else if (p.noise_mode) {
       float u = cur.u;
       if (!p.noise) {
         const uint64_t eid = static_cast<uint64_t>(b) * static_cast<uint64_t>(static_cast<int64_t>(p.C) * p.hw) +
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
     if (p.g_lik) {
       const float gl = cur.gl;
       float2 hin[4][3], th[4][3];
-      const float2 xx = make_float2(x - 0.5f, x + 0.5f);
+      const float2 xx = make_float2(x - cur.lo, x + cur.up);
       float lower, upper;
       if (FAST) { const float2 lu = logits_pair_tape(s_par, xx, hin, th); lower = lu.x; upper = lu.y; }
       else { lower = logits_cumulative(s_par, xx.x); upper = logits_cumulative(s_par, xx.y); }
@@ -272,20 +283,31 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
       const float du = g * sd * sg * su * (1.0f - su);
       const float dl = -g * sd * sg * sl * (1.0f - sl);
       if (du != 0.0f || dl != 0.0f) {
-        if (FAST) gx = logits_backward_pair(s_par, xx, make_float2(dl, du), hin, th, gP);
+        float2 g2;
+        if (FAST) g2 = logits_backward_pair(s_par, xx, make_float2(dl, du), hin, th, gP);
         else {
-          gx = logits_backward(s_par, x + 0.5f, du, gP);
-          gx += logits_backward(s_par, x - 0.5f, dl, gP);
+          g2.y = logits_backward(s_par, xx.y, du, gP);
+          g2.x = logits_backward(s_par, xx.x, dl, gP);
+        }
+        gx = g2.x + g2.y;
+        if (p.g_dist && cur.cell >= 0) {       // x - lo and x + up: d/d lo = -lane 0, d/d up = +lane 1
+          if (cur.cell > 0 && cur.cell - 1 < p.n_dist) atomicAdd(&s_dist[cur.cell - 1], -static_cast<double>(g2.x));
+          if (cur.cell < p.n_dist) atomicAdd(&s_dist[cur.cell], static_cast<double>(g2.y));
         }
       }
     }
     const float gzh = cur.gzh;
-    if (p.noise_mode) {
+    if (p.noise_mode || p.identity) {
       if (p.g_z) p.g_z[b * p.g_z_bs + e] = gzh + gx;
     } else {
       if (p.g_z) p.g_z[b * p.g_z_bs + e] = 0.0f;                    // round() has zero gradient
       gmed += gzh + gx;                                              // z_hat = round(z - med) + med
     }
+  }
+  if (p.g_dist) {        // K-sized: a double atomic per touched level gap and CTA
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n_dist; i += kThreads)
+      if (s_dist[i] != 0.0) atomicAdd(&p.g_dist[i], s_dist[i]);
   }
   // deterministic CTA reduction of the 58 (+1) per-thread sums
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -344,8 +366,10 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   if (d->B < 0 || d->C < 0 || d->hw < 0) return set_error(RESLIC_ERR_ARG, "eb_bwd: negative size");
   if (d->C == 0) return RESLIC_OK;
   if (d->C > (1 << 20) || d->hw > (1LL << 30)) return set_error(RESLIC_ERR_ARG, "eb_bwd: size too large");
-  if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE)
+  if (d->mode != RESLIC_Q_DEQUANTIZE && d->mode != RESLIC_Q_NOISE && d->mode != RESLIC_Q_IDENTITY)
     return set_error(RESLIC_ERR_ARG, "eb_bwd: invalid quantization mode");
+  if (d->g_dist && (!d->cell || d->n_dist < 1 || d->n_dist > 1024))
+    return set_error(RESLIC_ERR_ARG, "eb_bwd: g_dist needs `cell` and 1 <= n_dist <= 1024");
   if ((d->B > 0 && d->hw > 0 && !d->z) || !d->medians) return set_error(RESLIC_ERR_ARG, "eb_bwd: z or medians is null");
   bool any_g = false, all_g = true;
   for (int i = 0; i < 5; ++i) {
@@ -365,7 +389,10 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   p.g_zhat = d->g_zhat; p.g_zhat_bs = d->g_zhat_bs; p.g_lik = d->g_lik; p.g_lik_bs = d->g_lik_bs;
   p.g_z = d->g_z; p.g_z_bs = d->g_z_bs;
   p.B = d->B; p.hw = static_cast<int>(d->hw); p.C = static_cast<int>(d->C);
-  p.noise_mode = d->mode == RESLIC_Q_NOISE; p.lik_bound = d->likelihood_bound;
+  p.noise_mode = d->mode == RESLIC_Q_NOISE; p.identity = d->mode == RESLIC_Q_IDENTITY; p.lik_bound = d->likelihood_bound;
+  p.half_lo = d->half_lo; p.half_up = d->half_up; p.cell = d->cell;
+  p.half_lo_bs = d->half_lo_bs; p.half_up_bs = d->half_up_bs; p.cell_bs = d->cell_bs;
+  p.g_dist = d->g_dist; p.n_dist = static_cast<int>(d->n_dist);
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
   // CTAs per channel: enough to fill the machine (one 256-thread CTA of this kernel per SM) about three times over

@@ -501,6 +501,7 @@ struct EbStanhParams {
   const float* z; int64_t z_bs;
   const float* matrix[5]; const float* bias[5]; const float* factor[4]; const float* medians;   // medians unused (zeros)
   float* zhat; float* lik; int32_t* sym; int64_t zhat_bs, lik_bs, sym_bs;
+  float* half_lo; float* half_up; int32_t* cell; int64_t half_lo_bs, half_up_bs, cell_bs;   // optional (for the backward)
   double* bits; unsigned long long* workspace; int bits_accumulate;
   StanhParams st;            // tables + beta/symmetric (tensor fields unused)
   int64_t B, ne; int hw, C, tile, bpi, training;
@@ -542,15 +543,20 @@ __global__ void __launch_bounds__(kThreads) eb_stanh_fwd_kernel(const EbStanhPar
       }
       if (p.zhat) st_stream1(p.zhat + image * p.zhat_bs + e, x);
       if (p.sym) st_stream1(p.sym + image * p.sym_bs + e, level + p.st.sym_offset);
-      if (need_lik) {
+      if (need_lik || p.cell || p.half_lo || p.half_up) {
         const float* P = s_par + (static_cast<int>(e / p.hw) - c_lo) * kEbStride;
         const int j = count_gt(x, T.avg, T.K, T.steps);
         const bool inside = (x > -1000.0f) && (x <= 1000.0f);
         const float low = (inside && j > 0) ? T.dist[j - 1] : 0.0f;
         const float up = (inside && j < T.K) ? T.dist[j] : 0.0f;
-        const float L = eb_combine(logits_cumulative(P, x - low), logits_cumulative(P, x + up), p.lik_bound);
-        if (p.lik) st_stream1(p.lik + image * p.lik_bs + e, L);
-        acc += log2f(L);
+        if (p.half_lo) p.half_lo[image * p.half_lo_bs + e] = low;
+        if (p.half_up) p.half_up[image * p.half_up_bs + e] = up;
+        if (p.cell) p.cell[image * p.cell_bs + e] = inside ? j : -1;
+        if (need_lik) {
+          const float L = eb_combine(logits_cumulative(P, x - low), logits_cumulative(P, x + up), p.lik_bound);
+          if (p.lik) st_stream1(p.lik + image * p.lik_bs + e, L);
+          acc += log2f(L);
+        }
       }
     }
   }
@@ -723,13 +729,16 @@ int eb_stanh_fwd_launch(const reslic_eb_stanh_desc* d, cudaStream_t st) {
   for (int i = 0; i < 5; ++i)
     if (!d->matrix[i] || !d->bias[i] || (i < 4 && !d->factor[i]))
       return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: a parameter pointer is null");
-  if (!d->zhat && !d->lik && !d->sym && !rate_requested(d->bits, d->bits_accumulate)) return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: no output requested");
+  if (!d->zhat && !d->lik && !d->sym && !d->cell && !d->half_lo && !d->half_up && !rate_requested(d->bits, d->bits_accumulate))
+    return set_error(RESLIC_ERR_ARG, "eb_stanh_fwd: no output requested");
   EbStanhParams p{};
   p.z = d->z; p.z_bs = d->z_bs;
   for (int i = 0; i < 5; ++i) { p.matrix[i] = d->matrix[i]; p.bias[i] = d->bias[i]; }
   for (int i = 0; i < 4; ++i) p.factor[i] = d->factor[i];
   p.medians = nullptr;
   p.zhat = d->zhat; p.lik = d->lik; p.sym = d->sym; p.zhat_bs = d->zhat_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs;
+  p.half_lo = d->half_lo; p.half_up = d->half_up; p.cell = d->cell;
+  p.half_lo_bs = d->half_lo_bs; p.half_up_bs = d->half_up_bs; p.cell_bs = d->cell_bs;
   fill_tables(p.st, &d->tables);
   p.B = d->B; p.ne = d->C * d->hw; p.hw = static_cast<int>(d->hw); p.C = static_cast<int>(d->C);
   p.training = d->training; p.lik_bound = d->likelihood_bound;

@@ -601,8 +601,15 @@ def eb_backward(
     need_params: bool = True,
     seed: int = 0,
     offset: int = 0,
+    half_lo: Optional[Tensor] = None,
+    half_up: Optional[Tensor] = None,
+    cell: Optional[Tensor] = None,
+    g_dist: Optional[Tensor] = None,
 ):
-    """Backward of eb_forward: (g_z, [g_matrix]*5, [g_bias]*5, [g_factor]*4, g_medians)."""
+    """Backward of eb_forward: (g_z, [g_matrix]*5, [g_bias]*5, [g_factor]*4, g_medians).
+    Variable bins (EntropyBottleneckStanh): ``z`` is the STanH quantizer's output, ``half_lo`` / ``half_up`` / ``cell`` what
+    the forward wrote, ``medians`` zeros; ``g_z`` is then the gradient w.r.t. the quantizer output and ``g_dist``
+    (float64 [K], zeroed by the caller) receives dLoss / d distance_points."""
     lib = _cabi.load()
     _require_cuda("z", z)
     B, Cc = z.shape[0], z.shape[1]
@@ -622,6 +629,21 @@ def eb_backward(
             setattr(d, name + "_bs", Cc * hw)
     d.B, d.C, d.hw = B, Cc, hw
     d.mode = _cabi.Q_NOISE if training else _cabi.Q_DEQUANTIZE
+    if half_lo is not None or half_up is not None or cell is not None:
+        d.mode = _cabi.Q_IDENTITY
+        for name, t, dt in (("half_lo", half_lo, torch.float32), ("half_up", half_up, torch.float32), ("cell", cell, torch.int32)):
+            if t is not None:
+                _require_cuda(name, t, dt)
+                if t.shape != z.shape:
+                    raise ValueError(f"{name} must be shaped like z")
+                tc = t.contiguous()
+                keep.append(tc)
+                setattr(d, name, tc.data_ptr())
+                setattr(d, name + "_bs", Cc * hw)
+        if g_dist is not None:
+            if g_dist.dtype != torch.float64 or not g_dist.is_contiguous() or g_dist.device != z.device:
+                raise ValueError("g_dist must be a contiguous float64 tensor on z's device")
+            d.g_dist, d.n_dist = g_dist.data_ptr(), g_dist.numel()
     d.likelihood_bound = float(likelihood_bound)
     gm, gb, gf = [], [], []
     for i in range(5):

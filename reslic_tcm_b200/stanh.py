@@ -443,6 +443,54 @@ def _stanh_quantize_launch(stanh, x: Tensor, means: Optional[Tensor], training: 
     return out
 
 
+class _EbStanhFn(torch.autograd.Function):
+    """Autograd node of EntropyBottleneckStanh.forward: the fused forward (which also leaves every element's bin
+    half-widths and level cell), and for the backward two kernels — reslic_eb_bwd_f32 with variable bins (gradient of the
+    bounded likelihood w.r.t. the quantizer output, the 58 parameters of every channel and the level gaps) and the STanH
+    quantizer's own backward (reslic_stanh_gc_bwd_f32 without a likelihood: d/dz, and d/dw, d/db of a trainable STanH,
+    to which the level-gap sums are added as the distance_points term)."""
+
+    @staticmethod
+    def forward(ctx, module, x, training, w, b, *params):
+        with torch.no_grad():
+            r = module._fused(x.detach(), training, ("zhat", "lik", "half_lo", "half_up", "cell"))
+        ctx.module, ctx.training = module, bool(training)
+        ctx.save_for_backward(x, r["zhat"], r["half_lo"], r["half_up"], r["cell"], w, b, *params)
+        ctx.set_materialize_grads(False)
+        return r["zhat"], r["lik"]
+
+    @staticmethod
+    def backward(ctx, g_zhat, g_lik):
+        x, zhat, lo, up, cell, w, b, *params = ctx.saved_tensors
+        mod = ctx.module
+        m, bi, f = params[:5], params[5:10], params[10:14]
+        want_par = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+        need_eb = any(ctx.needs_input_grad[5:])
+        K = int(mod.stanh.distance_points.numel())
+        g_dist = torch.zeros(K, dtype=torch.float64, device=x.device) if want_par else None
+        zero_med = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+        c = lambda t: None if t is None else t.contiguous()
+        g_q, gm, gb, gf, _ = ops.eb_backward(
+            zhat, m, bi, f, zero_med, training=True, g_zhat=c(g_zhat), g_lik=c(g_lik), need_z=True, need_params=need_eb,
+            likelihood_bound=mod._likelihood_bound if mod.use_likelihood_bound else 0.0,
+            half_lo=lo, half_up=up, cell=cell, g_dist=g_dist)
+        # through the quantizer z_hat = stanh(z): soft in training (derivative inside the saturation window), hard otherwise (zero)
+        g_x, _, _, g_par = _stanh_bwd(mod.stanh, x.detach(), None, None, ctx.training, False, 0.11, 0.0, mod.stanh.beta, g_q, None,
+                                      want_params=want_par)
+        g_w = g_b = None
+        if want_par:
+            Kt = (g_par.numel() - 2) // 5
+            g_par[-Kt:] += g_dist[:Kt]              # Hd: dLoss / d distance_points (the bins' half-widths)
+            g_w, g_b = _stanh_param_grads(mod.stanh, g_par, w, b)
+        grads = [None, g_x if ctx.needs_input_grad[1] else None, None,
+                 g_w if ctx.needs_input_grad[3] else None, g_b if ctx.needs_input_grad[4] else None]
+        if need_eb:
+            grads += [*gm, *gb, *gf]
+        else:
+            grads += [None] * 14
+        return tuple(grads)
+
+
 # ----------------------------------------------------------------------------- entropy model
 class _StanhGcFn(torch.autograd.Function):
     """Autograd node around the fused STanH forward / backward kernels.  ``w`` and ``b`` are the module's
@@ -819,10 +867,7 @@ class EntropyBottleneckStanh(EntropyModel):
             raise _cabi.ReslicError("the CUDA bottleneck supports filters=(3,3,3,3) only")
         m, b, f = self._params()
         if torch.is_grad_enabled() and any(t.requires_grad for t in (x, *m, *b, *f, self.stanh.w, self.stanh.b)):
-            raise _cabi.ReslicError(
-                "EntropyBottleneckStanh.forward is evaluation-only in this build: its likelihood has no backward kernel "
-                "yet, so it cannot sit inside a training step (src/models/stanh/wacnn_stanh.py:160, balle18_stanh.py:26 "
-                "call it there).  Call it under torch.no_grad(); quantize() is differentiable.")
+            raise _cabi.ReslicError("_fused / forward_fused record no autograd graph: call under torch.no_grad(), or use forward()")
         xc = x.contiguous()
         B, Cc = xc.shape[0], xc.shape[1]
         hw = 1
@@ -845,7 +890,8 @@ class EntropyBottleneckStanh(EntropyModel):
         d.tables, tk = self.stanh._tables(self.stanh.beta if beta is None else beta)
         keep.append(tk)
         res = {}
-        for name, dtype in (("zhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32)):
+        for name, dtype in (("zhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32),
+                            ("half_lo", torch.float32), ("half_up", torch.float32), ("cell", torch.int32)):
             if name in want:
                 t = torch.empty(xc.shape, dtype=dtype, device=x.device)
                 setattr(d, name, t.data_ptr())
@@ -881,6 +927,10 @@ class EntropyBottleneckStanh(EntropyModel):
 
     def forward(self, x: Tensor, training: bool = True):
         """:679-708 — note the reference default ``training=True``."""
+        m, b, f = self._params()
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, *m, *b, *f, self.stanh.w, self.stanh.b)):
+            # inside a training step (src/models/stanh/wacnn_stanh.py:160, balle18_stanh.py:26,124)
+            return _EbStanhFn.apply(self, x, bool(training), self.stanh.w, self.stanh.b, *m, *b, *f)
         r = self._fused(x, bool(training), ("zhat", "lik"))
         return r["zhat"], r["lik"]
 

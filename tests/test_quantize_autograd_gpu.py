@@ -90,16 +90,21 @@ def test_stanh_activation_and_compute_gap_path_under_grad():
     assert y.grad is not None and bool((y.grad >= 0).all())          # a sum of increasing tanh steps
 
 
-def test_entropy_bottleneck_stanh_forward_is_documented_eval_only():
+def test_entropy_bottleneck_stanh_forward_trains_and_the_fused_extension_refuses_grad():
+    """forward() records an autograd node (tests/test_eb_stanh_backward_gpu.py checks the gradients); the multi-output
+    forward_fused() extension has no backward and refuses to cut the graph silently."""
     cfg = dict(beta=4, num_sigmoids=0, extrema=6, trainable=True, symmetry=False)
     eb = stanh.EntropyBottleneckStanh(5, factorized_configuration=cfg).to(DEV)
     eb.stanh.update_state(torch.device(DEV))
     z = torch.randn(2, 5, 3, 3, device=DEV)
-    with pytest.raises(_cabi.ReslicError, match="evaluation-only"):
-        eb(z, training=True)
+    zh, lik = eb(z, training=True)                                  # the reference's call, grad enabled, trainable parameters
+    (zh.sum() + torch.log(lik).sum()).backward()
+    assert eb._matrix0.grad is not None and eb.stanh.w.grad is not None and bool(torch.isfinite(eb.stanh.w.grad).all())
+    with pytest.raises(_cabi.ReslicError, match="no autograd graph"):
+        eb.forward_fused(z, training=True)
     with torch.no_grad():
-        zh, lik = eb(z, training=True)
-    assert zh.shape == z.shape and bool((lik > 0).all())
-    zq = eb.quantize(z.requires_grad_(True), "training")            # the quantizer itself is differentiable
+        r = eb.forward_fused(z, training=True)
+    assert torch.equal(r["zhat"], zh.detach()) and torch.equal(r["lik"], lik.detach())
+    zq = eb.quantize(z.requires_grad_(True), "training")            # the quantizer alone is differentiable too
     zq.sum().backward()
     assert z.grad is not None and bool(torch.isfinite(z.grad).all())
