@@ -358,11 +358,10 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
 // softplus and tanh included — for every 256-element tile).  The group's elements of one image are one
 // contiguous run of cpc*hw floats; the next image's values are loaded before the current ones are
 // evaluated.  Both cumulative logits of an element run as the two lanes of packed f32x2 operations
-// (eb_math.cuh).  The eight warps' rates meet in shared memory and one thread commits per (CTA, image).
+// (eb_math.cuh).  Every warp commits its own rate per image (fixed point, so the order does not matter).
 constexpr int kEbRunMax = 4;      // elements per thread and image: runs of up to 1024 floats
 __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p, int cpc, int groups, int splits, float lik_floor) {
   __shared__ float s_par[kEbMaxCh * kEbStride];
-  __shared__ float s_red[2][kEbWarps];
   const int grp = blockIdx.x % groups;
   const int split = blockIdx.x / groups;
   const int c0 = grp * cpc;
@@ -370,7 +369,6 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
   const int run = nch * p.hw;                       // <= kEbRunMax * kThreads (host)
   const int64_t base = static_cast<int64_t>(c0) * p.hw;
   const bool need_lik = p.lik || p.bits;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float zv[kEbRunMax], nv[kEbRunMax];
   auto load_image = [&](int64_t b) {
     const float* __restrict__ z = p.z + b * p.z_bs + base;
@@ -419,9 +417,11 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
   // channel of this thread's j-th element: fixed for the whole launch
   int cl[kEbRunMax];
 #pragma unroll
-  for (int j = 0; j < kEbRunMax; ++j) cl[j] = min((threadIdx.x + j * kThreads) / p.hw, nch - 1);
-  int phase = 0;
-  for (; b < p.B; b += splits, phase ^= 1) {
+  for (int j = 0; j < kEbRunMax; ++j) cl[j] = (j * kThreads < run) ? min((threadIdx.x + j * kThreads) / p.hw, nch - 1) : 0;
+  const unsigned int expected = static_cast<unsigned int>(groups) * kEbWarps;   // warps committing to one image
+  unsigned long long pend_now = 0ull;
+  int pend_image = -1;
+  for (; b < p.B; b += splits) {
     float cz[kEbRunMax], cn[kEbRunMax];
 #pragma unroll
     for (int j = 0; j < kEbRunMax; ++j) { cz[j] = zv[j]; cn[j] = nv[j]; }
@@ -460,19 +460,17 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
       }
     }
     if (p.bits) {
-      const float v = warp_sum_f32(acc);
-      if (lane == 0) s_red[phase][warp] = v;
-      __syncthreads();                                 // s_red[phase] is rewritten two images later, behind the next barrier
-      if (warp == 0) {
-        float total = 0.0f;
-        if (lane == 0) {
-#pragma unroll
-          for (int w = 0; w < kEbWarps; ++w) total += s_red[phase][w];   // fixed order: reproducible
-        }
-        rate_commit(total, static_cast<int>(b), static_cast<unsigned int>(groups), p.B, p.workspace, p.bits, p.bits_accumulate);
+      // every warp commits its own sum (integer fixed point: order-free, reproducible) — no CTA barrier per image;
+      // the immediate forms look at the atomic's answer one image later, off the critical path
+      if (p.bits_accumulate == 2) rate_defer(acc, static_cast<int>(b), p.B, p.workspace);
+      else {
+        if (pend_image >= 0) rate_commit_finish(pend_now, pend_image, expected, p.B, p.workspace, p.bits, p.bits_accumulate == 1, p.bits_accumulate == 3);
+        pend_now = rate_commit_issue(acc, static_cast<int>(b), p.B, p.workspace);
+        pend_image = static_cast<int>(b);
       }
     }
   }
+  if (pend_image >= 0) rate_commit_finish(pend_now, pend_image, expected, p.B, p.workspace, p.bits, p.bits_accumulate == 1, p.bits_accumulate == 3);
 }
 
 int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
@@ -579,9 +577,17 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
     if (cpc > d->C) cpc = d->C;
     if (cpc < 1) cpc = 1;
     const int64_t groups = (d->C + cpc - 1) / cpc;
-    const bool fast_ok = math_mode() != RESLIC_MATH_MIRROR && cpc * d->hw <= kEbRunMax * kThreads && groups <= 60000;
+    const bool fast_ok = math_mode() != RESLIC_MATH_MIRROR && cpc * d->hw <= kEbRunMax * kThreads && groups * kEbWarps < 65536;   // 16-bit arrival count
     if (fast_ok) {
-      int64_t splits = (static_cast<int64_t>(sm_count()) * 4 + groups - 1) / groups;   // one resident wave
+      // one resident wave, never more: a CTA past the resident set starts when the first ones finish and
+      // runs its whole image list behind them (600 CTAs on 592 slots cost a second pass over the batch)
+      static const int resident = [] {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eb_fwd_fast_kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+        return n;
+      }();
+      static const long forced = [] { const char* e = std::getenv("RESLIC_EB_SPLITS"); return e ? std::atol(e) : 0L; }();
+      int64_t splits = forced >= 1 ? forced : static_cast<int64_t>(sm_count()) * resident / groups;
       if (splits > d->B) splits = d->B;
       if (splits < 1) splits = 1;
       const float lik_floor = d->likelihood_bound > 0.0f ? d->likelihood_bound : -__builtin_huge_valf();
