@@ -10,6 +10,7 @@
 // writes the channel's gradients once — no atomics, bit-reproducible.  FP32-issue bound (four MLP
 // evaluations + two MLP backwards per element); z is 3.75 % of y's elements.
 #include "common.cuh"
+#include <cstdlib>
 #include "eb_math.cuh"
 #include "reslic_internal.h"
 
@@ -34,6 +35,14 @@ struct EbBwdParams {
 
 constexpr int kPartStride = 64;
 constexpr int kEbBwdMaxSplits = 8;
+#ifndef RESLIC_EBB_THREADS
+#define RESLIC_EBB_THREADS 128
+#endif
+#ifndef RESLIC_EBB_MINB
+#define RESLIC_EBB_MINB 3
+#endif
+constexpr int kBT = RESLIC_EBB_THREADS;      // threads per CTA of eb_bwd_kernel
+constexpr int kBMinB = RESLIC_EBB_MINB;      // CTAs per SM the register allocation must allow
 constexpr int kNP = 58;   // transformed parameters per channel (median excluded)
 
 // Forward with tape, then backward: adds g_out * d logits / d P[j] to gP[j], returns d logits / d x * g_out.
@@ -201,13 +210,13 @@ __device__ __forceinline__ float eb_param_chain(const PP& p, int c, int j, float
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p) {
+__global__ void __launch_bounds__(kBT, kBMinB) eb_bwd_kernel(const EbBwdParams p) {
   __shared__ float s_par[kEbStride + 1];
-  __shared__ float s_red[kThreads / 32][kNP + 1];
+  __shared__ float s_red[kBT / 32][kNP + 1];
   __shared__ bool s_last;
   __shared__ double s_dist[1024];            // per-CTA sums of the half-width gradients (variable bins only)
   if (p.g_dist)
-    for (int i = threadIdx.x; i < p.n_dist; i += kThreads) s_dist[i] = 0.0;
+    for (int i = threadIdx.x; i < p.n_dist; i += kBT) s_dist[i] = 0.0;
   const int c = blockIdx.x / p.splits;
   const int split = blockIdx.x - c * p.splits;
   if (threadIdx.x < kEbStride) s_par[threadIdx.x] = eb_staged_param(p, c, threadIdx.x);
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
   // The inputs of the NEXT element are loaded before the current one is evaluated: with one CTA of this kernel
   // per SM (8 warps) nothing else hides the ~0.8 us of a global load, and an element row is only ~0.8 us of math.
   struct Ld { float zv, u, gl, gzh, lo, up; int cell; int64_t b, e; };
-  const int64_t step = static_cast<int64_t>(p.splits) * kThreads;
+  const int64_t step = static_cast<int64_t>(p.splits) * kBT;
   auto fetch = [&](int64_t idx, Ld& r) {
     r.b = idx / p.hw;
     r.e = base_c + (idx - r.b * p.hw);                                   // offset inside image b
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
     r.cell = p.cell ? p.cell[r.b * p.cell_bs + r.e] : -1;
   };
   Ld nxt{};
-  int64_t idx = static_cast<int64_t>(split) * kThreads + threadIdx.x;
+  int64_t idx = static_cast<int64_t>(split) * kBT + threadIdx.x;
   if (idx < total) fetch(idx, nxt);
   for (; idx < total; idx += step) {
     const Ld cur = nxt;
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
   }
   if (p.g_dist) {        // K-sized: a double atomic per touched level gap and CTA
     __syncthreads();
-    for (int i = threadIdx.x; i < p.n_dist; i += kThreads)
+    for (int i = threadIdx.x; i < p.n_dist; i += kBT)
       if (s_dist[i] != 0.0) atomicAdd(&p.g_dist[i], s_dist[i]);
   }
   // deterministic CTA reduction of the 58 (+1) per-thread sums
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) eb_bwd_kernel(const EbBwdParams p
   __syncthreads();
   float v = 0.0f;
   if (threadIdx.x <= kNP)
-    for (int w = 0; w < kThreads / 32; ++w) v += s_red[w][threadIdx.x];
+    for (int w = 0; w < kBT / 32; ++w) v += s_red[w][threadIdx.x];
   if (p.splits > 1) {
     // the channel's CTAs leave their sums in the workspace; the one that arrives last adds them in split order
     // (a fixed order whoever is last: bit-reproducible) and writes the gradients
@@ -395,13 +404,19 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   p.g_dist = d->g_dist; p.n_dist = static_cast<int>(d->n_dist);
   p.seed_lo = static_cast<uint32_t>(d->philox_seed); p.seed_hi = static_cast<uint32_t>(d->philox_seed >> 32);
   p.off_lo = static_cast<uint32_t>(d->philox_offset); p.off_hi = static_cast<uint32_t>(d->philox_offset >> 32);
-  // CTAs per channel: enough to fill the machine (one 256-thread CTA of this kernel per SM) about three times over
+  // CTAs per channel: as many as keep the whole grid inside ONE resident wave (a CTA is a channel's slice of the batch,
+  // so a partial second wave costs a full CTA time: 576 CTAs on 444 slots ran 50.7 us, 384 run 41.7 us on 192 channels)
   int64_t splits = 1;
   if (d->workspace) {
     if (d->workspace_bytes < eb_bwd_workspace_bytes(d->C) || (reinterpret_cast<uintptr_t>(d->workspace) & 15u))
       return set_error(RESLIC_ERR_WORKSPACE, "eb_bwd: workspace misaligned or smaller than reslic_eb_bwd_workspace_bytes(C)");
-    splits = (3 * static_cast<int64_t>(sm_count()) + d->C - 1) / d->C;
-    const int64_t per_thread = (d->B * d->hw + kThreads - 1) / kThreads;     // elements per thread of an unsplit channel
+    static const int resident[2] = {
+      [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eb_bwd_kernel<false>, kBT, 0) == cudaSuccess && n > 0) ? n : 1; }(),
+      [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eb_bwd_kernel<true>, kBT, 0) == cudaSuccess && n > 0) ? n : 1; }()};
+    splits = static_cast<int64_t>(sm_count()) * resident[math_mode() == RESLIC_MATH_MIRROR ? 0 : 1] / d->C;
+    static const long forced = [] { const char* e = std::getenv("RESLIC_EBB_SPLITS"); return e ? std::atol(e) : 0L; }();
+    if (forced >= 1) splits = forced;
+    const int64_t per_thread = (d->B * d->hw + kBT - 1) / kBT;     // elements per thread of an unsplit channel
     if (splits > per_thread) splits = per_thread;
     if (splits > kEbBwdMaxSplits) splits = kEbBwdMaxSplits;
     if (splits < 1) splits = 1;
@@ -411,8 +426,8 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   p.splits = static_cast<int>(splits);
   if (d->C * splits > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_bwd: grid too large");
   const int grid = static_cast<int>(d->C * splits);
-  if (math_mode() == RESLIC_MATH_MIRROR) eb_bwd_kernel<false><<<grid, kThreads, 0, st>>>(p);
-  else eb_bwd_kernel<true><<<grid, kThreads, 0, st>>>(p);
+  if (math_mode() == RESLIC_MATH_MIRROR) eb_bwd_kernel<false><<<grid, kBT, 0, st>>>(p);
+  else eb_bwd_kernel<true><<<grid, kBT, 0, st>>>(p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "eb_bwd launch");
   return RESLIC_OK;

@@ -705,13 +705,20 @@ int stanh_act_launch(const float* x, int64_t n, const reslic_stanh_tables* t, fl
   const bool soft = p.beta > 0.0f;
   const float sat_r = soft ? kSatT / p.beta : 0.0f, c2 = soft ? 2.0f * p.beta * 1.44269504088896340736f : 0.0f;
   const bool mirror = math_mode() == RESLIC_MATH_MIRROR;
-  auto launch = [&](auto kernel, size_t smem) {
-    kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
+  // grid-stride over float4s: never more CTAs than are resident at once (1184 CTAs on 740 slots ran as two waves)
+  static int resident[4] = {0, 0, 0, 0};             // per instantiation, filled on first use
+  auto launch = [&](auto kernel, size_t smem, int which) {
+    if (resident[which] == 0) {
+      int nb = 0;
+      resident[which] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, smem) == cudaSuccess && nb > 0) ? nb : 1;
+    }
+    const int64_t wave = static_cast<int64_t>(sm_count()) * resident[which];
+    kernel<<<static_cast<int>(grid < wave ? grid : wave), kThreads, smem, st>>>(p, out_soft, out_hard, partials, counter, vec, sat_r, c2);
   };
   if (p.K <= 256) {
-    if (mirror) launch(stanh_act_kernel<false, 256>, StanhSm<256>::kBytes); else launch(stanh_act_kernel<true, 256>, StanhSm<256>::kBytes);
+    if (mirror) launch(stanh_act_kernel<false, 256>, StanhSm<256>::kBytes, 0); else launch(stanh_act_kernel<true, 256>, StanhSm<256>::kBytes, 1);
   } else {
-    if (mirror) launch(stanh_act_kernel<false, 1024>, StanhSm<1024>::kBytes); else launch(stanh_act_kernel<true, 1024>, StanhSm<1024>::kBytes);
+    if (mirror) launch(stanh_act_kernel<false, 1024>, StanhSm<1024>::kBytes, 2); else launch(stanh_act_kernel<true, 1024>, StanhSm<1024>::kBytes, 3);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "stanh_act launch");
