@@ -317,7 +317,7 @@ class Workload:
     """One rank's share of one BASELINE config on the device: `nbuf` rotating buffer sets (each its own
     TcmEntropyPath = static outputs + rate workspace), graphs of consecutive steps, the kernel-only leg."""
 
-    def __init__(self, c: synthetic.Config, images: range, dev, nbuf: int, params, pin_host: bool = False):
+    def __init__(self, c: synthetic.Config, images: range, dev, nbuf: int, params, pin_host: bool = False, path_factory=None):
         from reslic_tcm_b200.pipeline import TcmEntropyPath
 
         self.c, self.dev, self.B = c, dev, len(images)
@@ -325,9 +325,13 @@ class Workload:
         self.kw = dict(training=c.training, with_indexes=c.with_indexes, num_pixels=c.num_pixels_per_image, seed=1234)
         self.sets = []
         for _ in range(max(1, nbuf)):
-            path = TcmEntropyPath().to(dev).eval()
-            synthetic.load_eb_parameters(path.entropy_bottleneck, params)
-            path.gaussian_conditional.scale_table = synthetic.scale_table(dev)
+            if path_factory is not None:          # another model's entropy pass over the same latents (stanh_step_leg)
+                path = path_factory().to(dev).eval()
+                synthetic.load_eb_parameters(path.entropy_bottleneck, params)
+            else:
+                path = TcmEntropyPath().to(dev).eval()
+                synthetic.load_eb_parameters(path.entropy_bottleneck, params)
+                path.gaussian_conditional.scale_table = synthetic.scale_table(dev)
             inp = {k: self.host[k].to(dev, non_blocking=True) for k in ("y", "mu", "sigma", "z")}
             torch.cuda.synchronize()
             res = path.forward(inp["y"], inp["mu"], inp["sigma"], inp["z"], **self.kw)   # warm-up: lazy init, LUT, allocator
@@ -786,6 +790,11 @@ def run_ours(args):
         training_kernels = training_kernels_leg(dev, peak)
     del w
     torch.cuda.empty_cache()
+    # ---- config 5 as the reference's STanH model runs it (annealed soft quantization), single-GPU runs
+    stanh_step = None
+    if world == 1 and not sim and not args.no_training_kernels:
+        stanh_step = stanh_step_leg(dev, params, peak)
+        torch.cuda.empty_cache()
 
     # ---- the other BASELINE configs: per-config roofline objects (N = 1) / config 5 sharded the same way (N > 1)
     if args.legs == "auto":
@@ -843,7 +852,7 @@ def run_ours(args):
             "per_config": {str(c.cfg): {k: main[k] for k in ("workload", "value", "ms_per_step", "roofline", "whole_y") if k in main}, **legs},
             "legs": {k: {"workload": v["workload"], "value": v["value"], "ms_per_step": v["ms_per_step"], "images_per_gpu": v["images_per_gpu"],
                          "scaling": args.scaling} for k, v in legs.items()},
-            "training_kernels": training_kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "training_kernels": training_kernels, "stanh_step": stanh_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": main["launches_per_step"] * args.steps, "clocks": clocks, "traffic_source": traffic_src,
         }
         if placement is not None:
@@ -954,6 +963,47 @@ def training_kernels_leg(dev, peak):
     timeit("eb_bwd_noise", lambda i: ops.eb_backward(zs[i % 3], mm, bb, ff, med, training=True, g_zhat=gs[i % 3], g_lik=gs[(i + 1) % 3],
                                                     seed=1, offset=i), n_z, 20)
     return {"shape": {"y_slice": [B, C, h, w], "z": [B, Cz, hz, hz]}, "kernels": out}
+
+
+def stanh_step_leg(dev, params, peak, beta: float = 10.0, nbuf: int = 4, group: int = 24, reps: int = 8):
+    """BASELINE config 5 ("noise + annealed soft quantization") as the reference's STanH model runs its entropy pass
+    (src/models/stanh/tcm_stanh.py:396-451; reslic_tcm_b200.pipeline.TcmStanhEntropyPath): noise-mode bottleneck on z,
+    five GaussianConditionalStanh launches (soft quantization at beta about the predicted mean, variable-bin
+    likelihood, ste value, rate) and one pass over the whole y for quantize("training") + compute_gap — 7 launches per
+    step, `nbuf` rotating buffer sets (each step's reads + writes = 28 B per y element > L2), steps dealt onto 4 graph
+    branches as in the main timed region; the same graph on ONE branch beside it.  `frac` = algorithmic bytes (y, mu,
+    sigma read; soft value, likelihood, ste value written; y read again by the gap pass) / time / the measured HBM
+    peak: these kernels are issue-bound, the fraction says how far from the copy roofline that leaves
+    the STanH step."""
+    from reslic_tcm_b200.pipeline import TcmStanhEntropyPath
+
+    c = synthetic.CONFIGS[5]
+    cfg = {"beta": beta, "num_sigmoids": 0, "extrema": 80, "symmetry": False, "trainable": False, "removing_mean": True}
+    w = Workload(c, range(c.batch), dev, nbuf, params, path_factory=lambda: TcmStanhEntropyPath(cfg, channels=64))
+    w.kw = dict(training=True, num_pixels=c.num_pixels_per_image, seed=1234)
+    elems = w.y_elems + w.z_elems
+    bytes_step = 28 * w.y_elems + 12 * w.z_elems
+    out = {"workload": c.name + "_stanh_soft", "beta": beta, "launches_per_step": 7, "bytes_per_y_elem": 28,
+           "images_per_gpu": w.B, "buffer_sets": nbuf}
+    for name, chains in (("in_flight", 4), ("single_chain", 1)):
+        g = w.capture(group, chains=chains)
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * group)
+        out[name] = {"us_per_step": round(us, 2), "melem_per_s": round(elems / us, 1), "achieved_gbs": round(bytes_step / us * 1e-3, 1),
+                     "frac": round(bytes_step / us * 1e-3 / peak, 3), "batches_in_flight": chains}
+        del g
+    res = w.sets[0]["res"]
+    out["bpp_mean"] = float((res["bits"].double() / c.num_pixels_per_image).mean())
+    out["gap"] = float(w.sets[0]["path"].gap(res, w.y_elems))
+    return out
 
 
 def run_e2e(args, c, w: Workload, dev, world, global_elems, packed_slots=False):

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define RESLIC_ABI_VERSION 16
+#define RESLIC_ABI_VERSION 17
 
 enum {
   RESLIC_OK = 0,
@@ -394,6 +394,8 @@ typedef struct reslic_stanh_gc_desc {
   int32_t* sym;  int64_t sym_bs;
   double* bits;  int32_t bits_accumulate;
   void* workspace; int64_t workspace_bytes;  /* as reslic_gc_desc                           */
+  float* ste;    int64_t ste_bs;           /* nullable: ste_round(y - mu) + mu, what TCM's slice loop carries on when the
+                                            * STanH is frozen (src/models/stanh/tcm_stanh.py:432-434) (ABI 17) */
 } reslic_stanh_gc_desc;
 
 int reslic_stanh_gc_fwd_f32(const reslic_stanh_gc_desc* d, void* stream);

@@ -16,7 +16,7 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 PEER_HANDLE_BYTES = 64
 RATE_DEFERRED = 2
 RATE_COLLECT = 3
@@ -167,6 +167,7 @@ class StanhGcDesc(C.Structure):
         ("sym", C.c_void_p), ("sym_bs", C.c_int64),
         ("bits", C.c_void_p), ("bits_accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("ste", C.c_void_p), ("ste_bs", C.c_int64),
     ]
 
 

@@ -37,8 +37,8 @@ constexpr float kSatT = 9.1f;             // |t| beyond which 2*sigmoid(2t)-1 ==
 struct StanhParams {
   const float* y; const float* mu; const float* sigma;
   int64_t y_bs, mu_bs, sigma_bs;
-  float* yhat; float* lik; int32_t* sym;
-  int64_t yhat_bs, lik_bs, sym_bs;
+  float* yhat; float* lik; int32_t* sym; float* ste;
+  int64_t yhat_bs, lik_bs, sym_bs, ste_bs;
   double* bits; unsigned long long* workspace; int bits_accumulate;
   const float* b; const float* w; const float* cum_w; const float* avg; const float* dist;
   int K, steps, symmetric, removing_mean, training, sym_offset;
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kThreads) stanh_gc_fwd_kernel(const StanhParam
         yhat = p.mu ? q + mu : q;
       }
       if (p.yhat) st_stream1(p.yhat + image * p.yhat_bs + e, yhat);
+      if (p.ste) st_stream1(p.ste + image * p.ste_bs + e, rintf(y - mu) + mu);     // ste_round(y - mu) + mu, tcm_stanh.py:434
       if (p.sym) st_stream1(p.sym + image * p.sym_bs + e, level + p.sym_offset);
       if (need_lik) {
         const float s = max_nan(ld_stream1(p.sigma + image * p.sigma_bs + e), p.scale_bound);
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 5) stanh_gc_vec_kernel(const StanhVe
     float* o_yhat = p.yhat ? at_seg(p.yhat, p.yhat_bs) : nullptr;
     float* o_lik = p.lik ? at_seg(p.lik, p.lik_bs) : nullptr;
     int32_t* o_sym = p.sym ? at_seg(p.sym, p.sym_bs) : nullptr;
+    float* o_ste = p.ste ? at_seg(p.ste, p.ste_bs) : nullptr;
     const int g = chunk0 * kThreads + threadIdx.x;
 
     auto load = [&](StanhIn& r, int k) {
@@ -355,6 +357,9 @@ __global__ void __launch_bounds__(kThreads, 5) stanh_gc_vec_kernel(const StanhVe
         }
       }
       if (o_yhat) st_stream4(at(o_yhat), make_float4(yh[0], yh[1], yh[2], yh[3]));
+      if (o_ste)     // ste_round(y - mu) + mu: the value the slice loop carries on when the STanH is frozen (tcm_stanh.py:433-434)
+        st_stream4(at(o_ste), make_float4(rintf(yy[0] - mm[0]) + mm[0], rintf(yy[1] - mm[1]) + mm[1], rintf(yy[2] - mm[2]) + mm[2],
+                                          rintf(yy[3] - mm[3]) + mm[3]));
       if (o_sym) st_stream4(at(o_sym), make_int4(lv[0] + p.sym_offset, lv[1] + p.sym_offset, lv[2] + p.sym_offset, lv[3] + p.sym_offset));
       if (need_lik) {
         const F2 s0 = max_nan2(make_float2(r.s.x, r.s.y), p.scale_bound), s1 = max_nan2(make_float2(r.s.z, r.s.w), p.scale_bound);
@@ -597,12 +602,13 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
   if (!d->y) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: y is null");
   const bool need_lik = d->lik || rate_requested(d->bits, d->bits_accumulate);
   if (need_lik && !d->sigma) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: sigma is null");
-  if (!d->yhat && !d->sym && !need_lik) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: no output requested");
+  if (!d->yhat && !d->sym && !d->ste && !need_lik) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: no output requested");
   if (need_lik && !(d->scale_bound > 0.0f)) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: scale_bound must be > 0");
   if (d->n >= (1LL << 31)) return set_error(RESLIC_ERR_ARG, "stanh_gc_fwd: more than 2^31 elements per image");
   StanhParams p{};
   p.y = d->y; p.mu = d->mu; p.sigma = d->sigma; p.y_bs = d->y_bs; p.mu_bs = d->mu_bs; p.sigma_bs = d->sigma_bs;
   p.yhat = d->yhat; p.lik = d->lik; p.sym = d->sym; p.yhat_bs = d->yhat_bs; p.lik_bs = d->lik_bs; p.sym_bs = d->sym_bs;
+  p.ste = d->ste; p.ste_bs = d->ste_bs;
   fill_tables(p, &d->tables);
   p.removing_mean = d->removing_mean; p.training = d->training;
   p.scale_bound = d->scale_bound; p.lik_bound = d->likelihood_bound;
@@ -620,7 +626,7 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
     if (ptr && ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (bs % 4) != 0)) vec = false;
   };
   chk(d->y, d->y_bs); chk(d->mu, d->mu_bs); if (need_lik) chk(d->sigma, d->sigma_bs);
-  chk(d->yhat, d->yhat_bs); chk(d->lik, d->lik_bs); chk(d->sym, d->sym_bs);
+  chk(d->yhat, d->yhat_bs); chk(d->lik, d->lik_bs); chk(d->sym, d->sym_bs); chk(d->ste, d->ste_bs);
   cudaError_t err = cudaSuccess;
   if (vec) {
     StanhVecParams q{};

@@ -159,6 +159,108 @@ class TcmEntropyPath(nn.Module):
         return graph, res
 
 
+class TcmStanhEntropyPath(nn.Module):
+    """The entropy pass of the reference's STanH model (src/models/stanh/tcm_stanh.py:331-336, 396-451): the plain
+    factorized bottleneck on z (inherited from TCM, :403) and, per channel slice of y, one
+    ``GaussianConditionalStanh`` call — annealed soft quantization about the predicted mean while ``training``
+    (beta > 0), hard levels otherwise, with the variable-bin Gaussian likelihood (:432) — whose launch also writes
+    ``ste_round(y - mu) + mu``, the value the slice loop carries on when the STanH is frozen (:433-434), and adds the
+    slice's rate to the workspace; then ONE pass over the whole y for ``quantize(y, "training")`` +
+    ``compute_gap`` (:448-449, 465-478: both squared-error sums in the same launch).
+
+    = 1 + 5 + 1 kernel launches per batch over static buffers (CUDA-graph capturable, ``capture()``).  ``levels``
+    mirrors the reference's one quantizer per lambda (``lv`` picks it)."""
+
+    def __init__(self, gaussian_configuration: dict, z_channels: int = synthetic.Z_CHANNELS,
+                 num_slices: int = synthetic.NUM_SLICES, levels: int = 1, channels: Optional[int] = None):
+        super().__init__()
+        from .stanh import GaussianConditionalStanh
+
+        self.num_slices = int(num_slices)
+        self.gaussian_configuration = dict(gaussian_configuration)
+        self.entropy_bottleneck = EntropyBottleneck(z_channels)                                   # tcm.py:416
+        self.gaussian_conditional = nn.ModuleList(                                                # tcm_stanh.py:331-336
+            GaussianConditionalStanh(None, channels=z_channels if channels is None else channels,
+                                     gaussian_configuration=self.gaussian_configuration) for _ in range(int(levels)))
+        self._bufs: Optional[Dict[str, Tensor]] = None
+        self._key = None
+
+    def buffers(self, y: Tensor, z: Tensor) -> Dict[str, Tensor]:
+        key = (tuple(y.shape), tuple(z.shape), y.device)
+        if self._key != key:
+            dev, B = y.device, y.shape[0]
+            lib = _cabi.load()
+            self._bufs = {
+                "y_hat": torch.empty_like(y),        # ste_round(y - mu) + mu
+                "y_q": torch.empty_like(y),          # the STanH output (soft while training, levels otherwise)
+                "y_lik": torch.empty_like(y),
+                "z_hat": torch.empty_like(z),
+                "z_lik": torch.empty_like(z),
+                "bits": torch.zeros(B, dtype=torch.float64, device=dev),
+                "workspace": torch.zeros(max(int(lib.reslic_workspace_bytes(B)), 16), dtype=torch.uint8, device=dev),
+                "gap_sums": torch.zeros(2, dtype=torch.float64, device=dev),
+                "gap_workspace": torch.zeros(int(lib.reslic_stanh_gap_workspace_bytes()), dtype=torch.uint8, device=dev),
+            }
+            self._key = key
+        return self._bufs
+
+    @torch.no_grad()
+    def forward(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, *, training: bool = True, lv: int = 0,
+                num_pixels: Optional[int] = None, seed: int = 0, offset: int = 0, noise_z: Optional[Tensor] = None,
+                with_gap: bool = True, skip_z: bool = False, defer_rate: bool = False, **_ignored) -> Dict[str, Tensor]:
+        """y/mu/sigma [B, C, h, w], z [B, Cz, h/4, w/4] on the GPU, fp32.  Returns views of static buffers:
+        ``y_hat`` (ste values), ``y_q`` (STanH outputs), likelihoods, ``bits`` [B] and ``gap_sums``
+        ([sum (y - soft)^2, sum (y - hard)^2]; gap = |difference| / y.numel(), tcm_stanh.py:465-478)."""
+        gc, eb = self.gaussian_conditional[lv], self.entropy_bottleneck
+        gc.stanh.update_state(y.device)              # tcm_stanh.py:399 (a no-op while w, b are unchanged)
+        b = self.buffers(y, z)
+        C = y.shape[1]
+        if C % self.num_slices:
+            raise ValueError(f"{C} channels do not split into {self.num_slices} slices")
+        cs = C // self.num_slices
+        if not skip_z:
+            m, bi, f = eb._params()
+            ops.eb_forward(z, m, bi, f, eb._medians_flat(), training=training, noise=noise_z,
+                           likelihood_bound=eb._likelihood_bound if eb.use_likelihood_bound else 0.0,
+                           want=("ste", "lik", "bits"),
+                           out={"ste": b["z_hat"], "lik": b["z_lik"], "bits_deferred": True, "workspace": b["workspace"]},
+                           seed=seed, offset=offset, lut=None if training else eb._eval_lut())
+        for k in range(self.num_slices):
+            sl = slice(cs * k, cs * (k + 1))
+            out = {"yhat": b["y_q"][:, sl], "lik": b["y_lik"][:, sl], "ste": b["y_hat"][:, sl], "workspace": b["workspace"]}
+            if k + 1 < self.num_slices or defer_rate:
+                out["bits_deferred"] = True
+            else:
+                out["bits"], out["bits_collect"] = b["bits"], True
+            gc.forward_fused(y[:, sl], sigma[:, sl], training=training, means=mu[:, sl],
+                             want=("yhat", "lik", "ste", "bits"), out=out)
+        if with_gap:
+            gc.stanh.gap_sums(y, out=b["gap_sums"], workspace=b["gap_workspace"])
+        res = {"y_hat": b["y_hat"], "y_q": b["y_q"], "z_hat": b["z_hat"], "bits": b["bits"],
+               "likelihoods": {"y": b["y_lik"], "z": b["z_lik"]}, "num_pixels": num_pixels}
+        if with_gap:
+            res["gap_sums"] = b["gap_sums"]
+        return res
+
+    def gap(self, res: Dict[str, Tensor], n: int) -> Tensor:
+        """|MSE(y, soft) - MSE(y, hard)| from a forward's ``gap_sums`` (compute_gap, tcm_stanh.py:465-478)."""
+        return torch.abs(res["gap_sums"][0] / n - res["gap_sums"][1] / n).to(torch.float32)
+
+    def capture(self, y: Tensor, mu: Tensor, sigma: Tensor, z: Tensor, **kw):
+        """As TcmEntropyPath.capture."""
+        self.buffers(y, z)
+        side = torch.cuda.Stream(device=y.device)
+        side.wait_stream(torch.cuda.current_stream(y.device))
+        with torch.cuda.stream(side):
+            self.forward(y, mu, sigma, z, **kw)
+        torch.cuda.current_stream(y.device).wait_stream(side)
+        torch.cuda.synchronize(y.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = self.forward(y, mu, sigma, z, **kw)
+        return graph, res
+
+
 class HostPipeline:
     """End-to-end pass for latents that live in HOST memory: pinned host y/mu/sigma/z in, host
     symbols/indexes/bits out.  The batch is cut into image chunks (contiguous in NCHW); chunk c's

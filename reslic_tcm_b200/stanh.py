@@ -79,14 +79,17 @@ class _StanHBase(nn.Module):
             return _StanhQuantizeFn.apply(self, x, None, float(beta) != -1.0, False, float(beta), self.w, self.b)
         return stanh_activation(self, x, beta)
 
-    def gap_sums(self, x: Tensor, beta=None) -> Tensor:
-        """[sum (x - stanh_beta(x))^2, sum (x - stanh_hard(x))^2] as a float64 GPU tensor."""
+    def gap_sums(self, x: Tensor, beta=None, out: Optional[Tensor] = None, workspace: Optional[Tensor] = None) -> Tensor:
+        """[sum (x - stanh_beta(x))^2, sum (x - stanh_hard(x))^2] as a float64 GPU tensor.  ``out`` (2 float64) and
+        ``workspace`` (>= reslic_stanh_gap_workspace_bytes() zeroed bytes) make the launch allocation-free for callers
+        with static buffers (pipeline.TcmStanhEntropyPath)."""
         if beta is None:
             beta = self.beta
-        return _stanh_act(self, x, beta, want_soft=False, want_hard=False, want_gap=True)[2]
+        return _stanh_act(self, x, beta, want_soft=False, want_hard=False, want_gap=True, gap_out=out, workspace=workspace)[2]
 
 
-def _stanh_act(mod: _StanHBase, x: Tensor, beta, want_soft: bool, want_hard: bool, want_gap: bool):
+def _stanh_act(mod: _StanHBase, x: Tensor, beta, want_soft: bool, want_hard: bool, want_gap: bool,
+               gap_out: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
     lib = _cabi.load()
     ops._require_cuda("x", x)
     xc = x.contiguous()
@@ -95,8 +98,13 @@ def _stanh_act(mod: _StanHBase, x: Tensor, beta, want_soft: bool, want_hard: boo
     hard = torch.empty_like(xc) if want_hard else None
     gap = ws = None
     if want_gap:
-        gap = torch.empty(2, dtype=torch.float64, device=x.device)
-        ws = _gap_workspace(x.device)
+        if gap_out is not None:
+            if gap_out.shape != (2,) or gap_out.dtype != torch.float64 or gap_out.device != x.device or not gap_out.is_contiguous():
+                raise ValueError("out must be a contiguous float64 tensor of 2 elements on the inputs' device")
+            gap = gap_out
+        else:
+            gap = torch.empty(2, dtype=torch.float64, device=x.device)
+        ws = workspace if workspace is not None else _gap_workspace(x.device)
     with torch.cuda.device(x.device):
         code = lib.reslic_stanh_act_f32(xc.data_ptr(), xc.numel(), C.byref(t), _cabi.ptr(soft), _cabi.ptr(hard),
                                         _cabi.ptr(gap), _cabi.ptr(ws), 0 if ws is None else ws.numel(),
@@ -575,7 +583,7 @@ class HypeEntropyModelSoS(EntropyModel):
         d.tables, tk = self.stanh._tables(self.stanh.beta if beta is None else beta)
         keep.append(tk)
         res = {}
-        for name, dtype in (("yhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32)):
+        for name, dtype in (("yhat", torch.float32), ("lik", torch.float32), ("sym", torch.int32), ("ste", torch.float32)):
             if name in want:
                 t = (out or {}).get(name)          # caller's buffer (static buffers of a captured graph), else a fresh one
                 if t is None:
