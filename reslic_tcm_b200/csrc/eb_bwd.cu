@@ -209,7 +209,10 @@ __device__ __forceinline__ float eb_param_chain(const PP& p, int c, int j, float
   return 1.0f;
 }
 
-template <bool FAST>
+// QUAD (fast math, in-kernel noise, hw % 4 == 0): one Philox call per four elements as in eb_fwd_fast_kernel — the four
+// lanes of a quad sit on the four elements of one counter, each evaluates the counter of a different one of its next
+// four loop iterations and a 4 x 4 transpose across the quad hands out the words (same field as the per-element form).
+template <bool FAST, bool QUAD = false>
 __global__ void __launch_bounds__(kBT, kBMinB) eb_bwd_kernel(const EbBwdParams p) {
   __shared__ float s_par[kEbStride + 1];
   __shared__ float s_red[kBT / 32][kNP + 1];
@@ -246,7 +249,27 @@ __global__ void __launch_bounds__(kBT, kBMinB) eb_bwd_kernel(const EbBwdParams p
   Ld nxt{};
   int64_t idx = static_cast<int64_t>(split) * kBT + threadIdx.x;
   if (idx < total) fetch(idx, nxt);
-  for (; idx < total; idx += step) {
+  float uq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  int64_t idx_w = idx - (threadIdx.x & 31);            // lane 0's index: the QUAD loop runs warp-uniformly (it shuffles)
+  for (int nq = 0; (QUAD ? idx_w : idx) < total; idx += step, idx_w += step, ++nq) {
+    if (QUAD && (nq & 3) == 0) {
+      const int k = threadIdx.x & 3;
+      int64_t ik = idx + k * step;
+      if (ik >= total) ik = idx < total ? idx : 0;      // past the end: any counter, the word is not used
+      const int64_t bk = ik / p.hw;
+      const uint64_t eid = static_cast<uint64_t>(bk) * static_cast<uint64_t>(static_cast<int64_t>(p.C) * p.hw) +
+                           static_cast<uint64_t>(base_c + (ik - bk * p.hw));
+      const uint64_t gid = eid >> 2;
+      const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+      float a[4] = {u32_to_centered_uniform(r.x), u32_to_centered_uniform(r.y), u32_to_centered_uniform(r.z), u32_to_centered_uniform(r.w)};
+      const bool odd = (k & 1) != 0, hi = (k & 2) != 0;
+      float r0 = __shfl_xor_sync(0xffffffffu, odd ? a[0] : a[1], 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? a[2] : a[3], 1);
+      if (odd) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
+      r0 = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[2], 2); r1 = __shfl_xor_sync(0xffffffffu, hi ? a[1] : a[3], 2);
+      if (hi) { a[0] = r0; a[1] = r1; } else { a[2] = r0; a[3] = r1; }
+      uq[0] = a[0]; uq[1] = a[1]; uq[2] = a[2]; uq[3] = a[3];
+    }
+    if (QUAD && idx >= total) continue;
     const Ld cur = nxt;
     if (idx + step < total) fetch(idx + step, nxt);
     const int64_t b = cur.b, e = cur.e;
@@ -256,7 +279,9 @@ __global__ void __launch_bounds__(kBT, kBMinB) eb_bwd_kernel(const EbBwdParams p
       x = zv;
     } else if (p.noise_mode) {
       float u = cur.u;
-      if (!p.noise) {
+      if (QUAD) {
+        u = uq[0]; uq[0] = uq[1]; uq[1] = uq[2]; uq[2] = uq[3];
+      } else if (!p.noise) {
         const uint64_t eid = static_cast<uint64_t>(b) * static_cast<uint64_t>(static_cast<int64_t>(p.C) * p.hw) +
                              static_cast<uint64_t>(e);
         const uint64_t gid = eid >> 2;
@@ -427,6 +452,7 @@ int eb_bwd_launch(const reslic_eb_bwd_desc* d, cudaStream_t st) {
   if (d->C * splits > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_bwd: grid too large");
   const int grid = static_cast<int>(d->C * splits);
   if (math_mode() == RESLIC_MATH_MIRROR) eb_bwd_kernel<false><<<grid, kBT, 0, st>>>(p);
+  else if (p.noise_mode && !p.noise && !p.identity && d->hw % 4 == 0) eb_bwd_kernel<true, true><<<grid, kBT, 0, st>>>(p);
   else eb_bwd_kernel<true><<<grid, kBT, 0, st>>>(p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error(err, "eb_bwd launch");

@@ -359,7 +359,13 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_kernel(const EbParams p) {
 // contiguous run of cpc*hw floats; the next image's values are loaded before the current ones are
 // evaluated.  Both cumulative logits of an element run as the two lanes of packed f32x2 operations
 // (eb_math.cuh).  Every warp commits its own rate per image (fixed point, so the order does not matter).
+//
+// QUAD (in-kernel noise, hw % 4 == 0, at most one element per thread and image): the four lanes of a quad hold the four
+// elements of ONE Philox counter (element group eid >> 2), so instead of four identical calls per image each lane
+// evaluates the counter of a different one of the CTA's next four images and a 4 x 4 transpose across the quad (four
+// shuffles) hands every lane its own word of each — one Philox call per four elements, same noise field.
 constexpr int kEbRunMax = 4;      // elements per thread and image: runs of up to 1024 floats
+template <bool QUAD>
 __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p, int cpc, int groups, int splits, float lik_floor) {
   __shared__ float s_par[kEbMaxCh * kEbStride];
   const int grp = blockIdx.x % groups;
@@ -421,11 +427,27 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
   const unsigned int expected = static_cast<unsigned int>(groups) * kEbWarps;   // warps committing to one image
   unsigned long long pend_now = 0ull;
   int pend_image = -1;
-  for (; b < p.B; b += splits) {
+  float uq[4] = {0.0f, 0.0f, 0.0f, 0.0f};             // QUAD: this element's noise in the next four images
+  for (int nq = 0; b < p.B; b += splits, ++nq) {
     float cz[kEbRunMax], cn[kEbRunMax];
 #pragma unroll
     for (int j = 0; j < kEbRunMax; ++j) { cz[j] = zv[j]; cn[j] = nv[j]; }
     if (b + splits < p.B) load_image(b + splits);
+    if (QUAD && (nq & 3) == 0) {
+      const int k = threadIdx.x & 3;
+      int64_t bk = b + static_cast<int64_t>(k) * splits;
+      if (bk >= p.B) bk = b;                            // past the CTA's last image: any counter, the word is not used
+      const uint64_t gid = (static_cast<uint64_t>(bk) * static_cast<uint64_t>(p.ne) + static_cast<uint64_t>(base + threadIdx.x)) >> 2;
+      const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), p.off_lo, p.off_hi, p.seed_lo, p.seed_hi);
+      float a[4] = {u32_to_centered_uniform(r.x), u32_to_centered_uniform(r.y), u32_to_centered_uniform(r.z), u32_to_centered_uniform(r.w)};
+      // rows = lanes (images), columns = words (elements): transpose in two exchange steps
+      const bool odd = (k & 1) != 0, hi = (k & 2) != 0;
+      float r0 = __shfl_xor_sync(0xffffffffu, odd ? a[0] : a[1], 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? a[2] : a[3], 1);
+      if (odd) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
+      r0 = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[2], 2); r1 = __shfl_xor_sync(0xffffffffu, hi ? a[1] : a[3], 2);
+      if (hi) { a[0] = r0; a[1] = r1; } else { a[2] = r0; a[3] = r1; }
+      uq[0] = a[0]; uq[1] = a[1]; uq[2] = a[2]; uq[3] = a[3];
+    }
     float acc = 0.0f;
 #pragma unroll
     for (int j = 0; j < kEbRunMax; ++j) {
@@ -438,7 +460,9 @@ __global__ void __launch_bounds__(kThreads) eb_fwd_fast_kernel(const EbParams p,
         float out = s;
         if (p.noise_mode) {
           float u = cn[j];
-          if (!p.noise) {
+          if (QUAD) {
+            u = uq[0]; uq[0] = uq[1]; uq[1] = uq[2]; uq[2] = uq[3];
+          } else if (!p.noise) {
             const uint64_t eid = static_cast<uint64_t>(b) * static_cast<uint64_t>(p.ne) + static_cast<uint64_t>(base + i);
             const uint64_t gid = eid >> 2;
             const Philox4 r = philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
@@ -583,7 +607,7 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
       // runs its whole image list behind them (600 CTAs on 592 slots cost a second pass over the batch)
       static const int resident = [] {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eb_fwd_fast_kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eb_fwd_fast_kernel<true>, kThreads, 0) != cudaSuccess || n < 1) n = 1;
         return n;
       }();
       static const long forced = [] { const char* e = std::getenv("RESLIC_EB_SPLITS"); return e ? std::atol(e) : 0L; }();
@@ -591,8 +615,12 @@ int eb_fwd_launch(const reslic_eb_desc* d, cudaStream_t st) {
       if (splits > d->B) splits = d->B;
       if (splits < 1) splits = 1;
       const float lik_floor = d->likelihood_bound > 0.0f ? d->likelihood_bound : -__builtin_huge_valf();
-      eb_fwd_fast_kernel<<<static_cast<int>(groups * splits), kThreads, 0, st>>>(p, static_cast<int>(cpc), static_cast<int>(groups),
-                                                                               static_cast<int>(splits), lik_floor);
+      // (the quad's word order needs element groups aligned to lanes: hw % 4 == 0 makes base and ne multiples of 4)
+      const bool quad = p.noise_mode && !p.noise && d->hw % 4 == 0 && cpc * d->hw <= kThreads;
+      if (quad) eb_fwd_fast_kernel<true><<<static_cast<int>(groups * splits), kThreads, 0, st>>>(p, static_cast<int>(cpc), static_cast<int>(groups),
+                                                                                         static_cast<int>(splits), lik_floor);
+      else eb_fwd_fast_kernel<false><<<static_cast<int>(groups * splits), kThreads, 0, st>>>(p, static_cast<int>(cpc), static_cast<int>(groups),
+                                                                                          static_cast<int>(splits), lik_floor);
     } else {
       const int64_t grid64 = bpi * d->B;
       if (grid64 > 0x7fffffffLL) return set_error(RESLIC_ERR_ARG, "eb_fwd: grid too large");

@@ -146,6 +146,33 @@ def test_eb_backward_split_channels_are_bit_reproducible_and_leave_the_workspace
     assert int(ws[: 4 * C].view(torch.int32).abs().sum()) == 0          # arrival counters back to zero
 
 
+@pytest.mark.parametrize("shape", [(300, 24, 4, 4), (37, 12, 2, 4), (9, 12, 3, 3)])
+def test_eb_backward_regenerates_the_forward_noise_field(shape):
+    """In-kernel Philox: the backward launch (quad form for hw % 4 == 0, per element otherwise) must see the very noise
+    the forward launch of the same (seed, offset) added — checked against a backward launch that is GIVEN that noise."""
+    from reslic_tcm_b200 import EntropyBottleneck, ops, synthetic
+
+    C = shape[1]
+    mod = EntropyBottleneck(C).to(DEV).train()
+    synthetic.load_eb_parameters(mod, synthetic.eb_parameters(C, trained_like=True, seed=8))
+    m, b, f = mod._params()
+    med = mod._medians_flat()
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    z = torch.randn(shape, device=DEV, generator=gen).mul_(4.0).round_().div_(4.0)      # quarter steps: z + u - z == u exactly
+    gz, gl = torch.randn(shape, device=DEV, generator=gen), torch.randn(shape, device=DEV, generator=gen)
+    fwd = ops.eb_forward(z, m, b, f, med, training=True, want=("zhat",), seed=31, offset=7)
+    u = fwd.zhat - z
+    assert float(u.abs().max()) <= 0.5
+    own = ops.eb_backward(z, m, b, f, med, training=True, g_zhat=gz, g_lik=gl, seed=31, offset=7)
+    given = ops.eb_backward(z, m, b, f, med, training=True, noise=u, g_zhat=gz, g_lik=gl)
+    flat = lambda r: [r[0]] + list(r[1]) + list(r[2]) + list(r[3])
+    for a, c in zip(flat(own), flat(given)):
+        scale = max(float(c.abs().max()), 1e-6)
+        assert float((a - c).abs().max()) <= 2e-5 * scale
+    other = ops.eb_backward(z, m, b, f, med, training=True, g_zhat=gz, g_lik=gl, seed=31, offset=8)
+    assert not torch.equal(other[0], own[0])
+
+
 @pytest.mark.parametrize("training,removing_mean,symmetry", [(True, True, False), (True, False, False),
                                                              (False, True, False), (True, True, True)])
 def test_stanh_backward_matches_autograd(training, removing_mean, symmetry):

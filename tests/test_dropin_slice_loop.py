@@ -99,7 +99,7 @@ def test_training_step_matches_cpu_reference_loop():
     loss_r.backward()
     loss_o, bpp_o = ours(y.to(DEV), noise_y.to(DEV), noise_z.to(DEV))
     loss_o.backward()
-    assert float(bpp_o) == pytest.approx(float(bpp_r), rel=2e-5)
+    assert float(bpp_o.detach()) == pytest.approx(float(bpp_r.detach()), rel=2e-5)
     assert float(loss_o) == pytest.approx(float(loss_r), rel=2e-5)
 
     def close(name, a, r):

@@ -99,6 +99,31 @@ def test_philox_noise_mode_consistency():
     assert_lik_close(r.lik, lik_ref, what="philox-mode z likelihood")
 
 
+def test_philox_field_is_the_same_in_every_kernel_form():
+    """One Philox call per four elements (the quad form of eb_fwd_fast_kernel: each lane of a quad evaluates the counter
+    of a different image and a 4 x 4 transpose redistributes the words) must draw exactly the field of the per-element
+    form — the mirror-math kernel and the backward kernel regenerate it element by element.  Shapes: CTAs with 6-7
+    images each (two word groups, the second one partial), and a spatial size that is no multiple of 4 (no quad form)."""
+    from reslic_tcm_b200 import _cabi
+
+    mod, _ = _pair(192, True)
+    for shape in ((300, 192, 4, 4), (150, 192, 2, 4), (9, 192, 3, 3)):
+        z = 2.0 * torch.randn(shape, generator=torch.Generator().manual_seed(4))
+        zd = z.to(DEV)
+        m, b, f = mod._params()
+        try:
+            fast = ops.eb_forward(zd, m, b, f, mod._medians_flat(), training=True, want=("zhat",), seed=77, offset=24)
+            _cabi.set_math_mode(_cabi.MATH_MIRROR)
+            mirror = ops.eb_forward(zd, m, b, f, mod._medians_flat(), training=True, want=("zhat",), seed=77, offset=24)
+        finally:
+            _cabi.set_math_mode(_cabi.MATH_FAST)
+        assert torch.equal(fast.zhat, mirror.zhat), shape
+        u = fast.zhat.cpu() - z
+        assert float(u.abs().max()) <= 0.5 + 1e-6 and abs(float(u.mean())) < 5e-3
+        other = ops.eb_forward(zd, m, b, f, mod._medians_flat(), training=True, want=("zhat",), seed=77, offset=25)
+        assert not torch.equal(other.zhat, fast.zhat)
+
+
 def test_full_size_config2_properties():
     c = synthetic.CONFIGS[2]
     batch = synthetic.make_batch(2, range(c.batch))
