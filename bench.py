@@ -130,6 +130,37 @@ def cpu_reference_throughput(c: synthetic.Config, n_images: int, repeats: int, b
     return elems / best / 1e6, times, cores, elems
 
 
+def gpu_reference_throughput(c: synthetic.Config, n_images: int, dev, reps: int = 5):
+    """The same unfused op chain (oracle/compressai_ref.py tcm_entropy_step: the reference's op order, stock PyTorch
+    eager kernels) run ON THE B200 — the "reference-on-GPU" line of SURVEY.md section 8(d), the fairer denominator for what
+    the fused kernels buy on the same silicon.  Inputs resident, CUDA events, best of `reps` after one warm-up."""
+    from oracle import compressai_ref as cr
+
+    batch = {k: v.to(dev) for k, v in synthetic.make_batch(c.cfg, range(n_images), with_noise=c.training).items()}
+    eb = ref_eb({k: v.to(dev) for k, v in synthetic.eb_parameters().items()})
+    table = synthetic.scale_table(dev)
+    elems = n_images * (c.y_elems_per_image + c.z_elems_per_image)
+
+    def once():
+        with torch.no_grad():
+            cr.tcm_entropy_step(batch["y"], batch["mu"], batch["sigma"], batch["z"], eb, table, training=c.training,
+                                with_indexes=c.with_indexes, num_pixels=n_images * c.num_pixels_per_image,
+                                noise_y=batch.get("noise_y"), noise_z=batch.get("noise_z"))
+
+    once()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return elems / (best * 1e-3) / 1e6, best, elems
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port;
     compressai itself is not installable here), all host threads, bounded sample per step."""
@@ -828,6 +859,15 @@ def run_ours(args):
                "sample": f"{n_img} of {c.batch} images of config {c.cfg} ({el} latent elements), best of {len(times)} passes "
                          f"after 1 warm-up, oracle/compressai_ref.py tcm_entropy_step, torch {torch.__version__} CPU",
                "cpu": cpu_model()}
+        try:
+            n_gpu = min(c.batch, 16)
+            gv, gms, gel = gpu_reference_throughput(c, n_gpu, dev)
+            cpu["on_gpu"] = {"value": gv, "unit": UNIT, "ms": gms,
+                             "what": f"the same unfused op chain (oracle port, reference op order) as stock PyTorch {torch.__version__} eager CUDA "
+                                     f"kernels on this B200, {n_gpu} of {c.batch} images ({gel} latent elements) resident, best of 5"}
+        except Exception as e:      # a baseline line, never the product: report and go on
+            cpu["on_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         cfg = workload_config(c, world, args.scaling)

@@ -51,11 +51,11 @@ def lower_bound(x: Tensor, bound: float) -> Tensor:
     """compressai.ops.LowerBound forward: ``torch.max(x, bound)`` with a 1-element
     *tensor* bound of x's dtype (so NaN propagates).  Backward rule:
     pass the gradient where ``x >= bound`` or ``grad < 0``."""
-    return torch.max(x, torch.tensor([bound], dtype=x.dtype))
+    return torch.max(x, torch.tensor([bound], dtype=x.dtype, device=x.device))
 
 
 def lower_bound_backward(x: Tensor, bound: float, grad: Tensor) -> Tensor:
-    b = torch.tensor([bound], dtype=x.dtype)
+    b = torch.tensor([bound], dtype=x.dtype, device=x.device)
     return ((x >= b) | (grad < 0)).to(grad.dtype) * grad
 
 
