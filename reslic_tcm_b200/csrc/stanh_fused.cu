@@ -227,15 +227,18 @@ __device__ __forceinline__ F2 stanh_mass2(F2 n1, F2 n2, F2 s) {
 }
 
 // soft quantizer value; beta > 0
-template <bool FAST, int KMAX>
-__device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r, float c2, const StanhSm<KMAX>& T) {
+// COUNT: also #{k : x > b_k} (the hard level's index) — every threshold below the window is below x, none above it is,
+// so the walk only has to count inside the window (compute_gap needs both values of every element)
+template <bool FAST, int KMAX, bool COUNT = false>
+__device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r, float c2, const StanhSm<KMAX>& T, int* below = nullptr) {
   const int lo = stanh_count_ge_b(x - sat_r, T);         // k <  lo: tanh == +1
   const float xr = x + sat_r;
   float acc = 0.0f;
-  int k = lo;
+  int k = lo, cnt = lo;
   for (;; ++k) {
     const float2 e = T.bw()[k];                            // (b_k, w_k / 2); NaN pad ends the loop
     if (!(e.x < xr)) break;
+    if (COUNT) cnt += (x > e.x) ? 1 : 0;
     if (FAST) {
       const float E = ex2_approx(c2 * (e.x - x));        // exp(-2 beta (x - b_k))
       acc = fmaf(e.y, (1.0f - E) * rcp_approx(1.0f + E), acc);
@@ -246,7 +249,20 @@ __device__ __forceinline__ float stanh_soft_sm(float x, float beta, float sat_r,
     }
   }                                                      // k >= hi (= k now): tanh == -1
   const float sat = 0.5f * ((T.cw()[lo] - T.cw0) - (T.cwK - T.cw()[k]));
+  if (COUNT) *below = cnt;
   return (x != x) ? x : sat + acc;
+}
+
+// hard level of x given c = #{k : x > b_k}
+template <int KMAX>
+__device__ __forceinline__ float stanh_hard_at(float x, int c, const StanhSm<KMAX>& T, bool symmetric) {
+  float v = T.cw()[c];
+  if (symmetric) {
+    int ce = c;
+    if (x == T.bw()[c].x) { do ++ce; while (x == T.bw()[ce].x); }   // sign(0) = 0: mean of the two adjacent levels at a tie
+    v = (x != x) ? 0.0f : 0.5f * (v + T.cw()[ce]);
+  }
+  return v;
 }
 
 // hard level of x; c_out = #{k : x > b_k}
@@ -432,6 +448,13 @@ __global__ void __launch_bounds__(kThreads) stanh_act_kernel(const StanhParams p
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int c;
+      if (want_soft && want_hard && p.beta > 0.0f) {        // compute_gap: the soft walk also yields the hard level's index
+        qs[j] = stanh_soft_sm<FAST, KMAX, true>(xs[j], p.beta, sat_r, c2, T, &c);
+        qh[j] = stanh_hard_at(xs[j], c, T, symmetric);
+        const float d0 = xs[j] - qs[j], d1 = xs[j] - qh[j];
+        ds = fmaf(d0, d0, ds); dh = fmaf(d1, d1, dh);
+        continue;
+      }
       if (want_soft) { qs[j] = soft_of(xs[j]); const float d = xs[j] - qs[j]; ds = fmaf(d, d, ds); }
       if (want_hard) { qh[j] = stanh_hard_sm(xs[j], T, symmetric, c); const float d = xs[j] - qh[j]; dh = fmaf(d, d, dh); }
     }
