@@ -21,7 +21,6 @@ launch.
 """
 from __future__ import annotations
 
-import warnings
 from typing import Any, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
