@@ -533,6 +533,7 @@ class Timer:
         left = n_steps
         while left > 0:
             n = min(left, self.group)
+            self.last_n = n
             if self.ex is not None:
                 self.ex.before_graph(n)
             self.graph(n).replay()
@@ -629,6 +630,9 @@ class NcclExchange:
         torch.cuda.synchronize()
         return self.red.result(0)
 
+    def result_set(self, w, last_n):
+        return 0                                   # result() is step 0 of the last graph = buffer set 0
+
     def close(self):
         pass
 
@@ -700,6 +704,11 @@ class PeerExchange:
         self.verify()
         return self.ex.result(row.tolist())
 
+    def result_set(self, w, last_n):
+        # result() is the LAST step of the last graph; in noise mode every step of a graph draws its own Philox field,
+        # so the local row to compare with must come from the buffer set that step wrote
+        return (last_n - 1) % len(w.sets)
+
     def close(self):
         self.ex.close()
 
@@ -723,8 +732,8 @@ def measure_config(c, images, dev, args, params, world, global_elems, peak, peak
         import torch.distributed as dist
 
         got = ex.result()
-        local = torch.tensor([float(w.sets[0]["res"]["bits"].double().sum()), 0.0, float(w.B * c.num_pixels_per_image), float(w.B)],
-                             dtype=torch.float64, device=dev)
+        local = torch.tensor([float(w.sets[ex.result_set(w, tm.last_n)]["res"]["bits"].double().sum()), 0.0,
+                              float(w.B * c.num_pixels_per_image), float(w.B)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(local)
         want = local.tolist()
@@ -823,8 +832,9 @@ def run_ours(args):
     torch.cuda.empty_cache()
     # ---- config 5 as the reference's STanH model runs it (annealed soft quantization), single-GPU runs
     stanh_step = None
-    if world == 1 and not sim and not args.no_training_kernels:
-        stanh_step = stanh_step_leg(dev, params, peak)
+    if not args.no_training_kernels and synthetic.CONFIGS[5].batch >= eff_world:
+        imgs5, gel5 = shard(synthetic.CONFIGS[5])
+        stanh_step = stanh_step_leg(args, dev, params, peak, imgs5, gel5, world, barrier)
         torch.cuda.empty_cache()
 
     # ---- the other BASELINE configs: per-config roofline objects (N = 1) / config 5 sharded the same way (N > 1)
@@ -1005,44 +1015,61 @@ def training_kernels_leg(dev, peak):
     return {"shape": {"y_slice": [B, C, h, w], "z": [B, Cz, hz, hz]}, "kernels": out}
 
 
-def stanh_step_leg(dev, params, peak, beta: float = 10.0, nbuf: int = 4, group: int = 24, reps: int = 8):
+def stanh_step_leg(args, dev, params, peak, images, global_elems, world, barrier, beta: float = 10.0):
     """BASELINE config 5 ("noise + annealed soft quantization") as the reference's STanH model runs its entropy pass
     (src/models/stanh/tcm_stanh.py:396-451; reslic_tcm_b200.pipeline.TcmStanhEntropyPath): noise-mode bottleneck on z,
     five GaussianConditionalStanh launches (soft quantization at beta about the predicted mean, variable-bin
     likelihood, ste value, rate) and one pass over the whole y for quantize("training") + compute_gap — 7 launches per
-    step, `nbuf` rotating buffer sets (each step's reads + writes = 28 B per y element > L2), steps dealt onto 4 graph
-    branches as in the main timed region; the same graph on ONE branch beside it.  `frac` = algorithmic bytes (y, mu,
-    sigma read; soft value, likelihood, ste value written; y read again by the gap pass) / time / the measured HBM
-    peak: these kernels are issue-bound, the fraction says how far from the copy roofline that leaves
-    the STanH step."""
+    step over this rank's `images` (the batch cut over the ranks as in the main leg), rotating buffer sets (each step's
+    reads + writes = 28 B per y element), steps dealt onto graph branches as in the main timed region, max over ranks.
+    N > 1: the collecting launch is a STanH kernel, so the rate row is published by the one-CTA publisher on a graph
+    branch behind it (PeerExchange "branch") and checked against an NCCL all-reduce.  N = 1: the same steps as ONE
+    dependent chain beside it.  `frac` = algorithmic bytes (y, mu, sigma read; soft value, likelihood, ste value
+    written; y read again by the gap pass) / time / the measured HBM peak: these kernels are issue-bound (DESIGN.md
+    section 3.3), the fraction says how far from the copy roofline that leaves the STanH step."""
     from reslic_tcm_b200.pipeline import TcmStanhEntropyPath
 
     c = synthetic.CONFIGS[5]
     cfg = {"beta": beta, "num_sigmoids": 0, "extrema": 80, "symmetry": False, "trainable": False, "removing_mean": True}
-    w = Workload(c, range(c.batch), dev, nbuf, params, path_factory=lambda: TcmStanhEntropyPath(cfg, channels=64))
+    steps = min(args.steps, 96)
+    group = balanced_group(steps, min(args.steps_per_graph, 24))
+    chains = args.chains or 4
+    nbuf = args.nbuf or chains
+    w = Workload(c, images, dev, nbuf, params, path_factory=lambda: TcmStanhEntropyPath(cfg, channels=64))
     w.kw = dict(training=True, num_pixels=c.num_pixels_per_image, seed=1234)
-    elems = w.y_elems + w.z_elems
     bytes_step = 28 * w.y_elems + 12 * w.z_elems
     out = {"workload": c.name + "_stanh_soft", "beta": beta, "launches_per_step": 7, "bytes_per_y_elem": 28,
-           "images_per_gpu": w.B, "buffer_sets": nbuf}
-    for name, chains in (("in_flight", 4), ("single_chain", 1)):
-        g = w.capture(group, chains=chains)
-        for _ in range(2):
-            g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / (reps * group)
-        out[name] = {"us_per_step": round(us, 2), "melem_per_s": round(elems / us, 1), "achieved_gbs": round(bytes_step / us * 1e-3, 1),
-                     "frac": round(bytes_step / us * 1e-3 / peak, 3), "batches_in_flight": chains}
-        del g
+           "images_per_gpu": w.B, "buffer_sets": nbuf, "steps": steps, "steps_per_graph": group, "scaling": args.scaling}
+    ex = None
+    if world > 1:
+        ex = NcclExchange(w, group) if args.exchange == "nccl" else PeerExchange(w, group, "branch")
+    tm = Timer(w, group, chains, world, ex)
+    ms = tm.timed(steps, min(args.warmup, 8), barrier)
+    us = ms * 1e3
+    out["in_flight"] = {"us_per_step": round(us, 2), "value": round(global_elems / us, 1), "unit": UNIT,
+                        "achieved_gbs_per_gpu": round(bytes_step / us * 1e-3, 1), "frac": round(bytes_step / us * 1e-3 / peak, 3),
+                        "batches_in_flight": min(chains, nbuf)}
+    if ex is not None:
+        import torch.distributed as dist
+
+        got = ex.result()
+        local = torch.tensor([float(w.sets[ex.result_set(w, tm.last_n)]["res"]["bits"].double().sum()),
+                              float(w.B * c.num_pixels_per_image), float(w.B)], dtype=torch.float64, device=dev)
+        dist.all_reduce(local)
+        want = local.tolist()
+        out["exchange_check"] = {"exchange": got, "nccl_all_reduce": {"bits": want[0], "pixels": want[1], "images": want[2]},
+                                 "match": bool(abs(got["bits"] - want[0]) <= 1e-9 * abs(want[0]) and got["pixels"] == want[1]
+                                               and got["images"] == want[2])}
+        out["exchange"] = ex.name
+        ex.close()
+    else:
+        us1 = Timer(w, group, 1, world, None).timed(steps, min(args.warmup, 8), barrier) * 1e3
+        out["single_chain"] = {"us_per_step": round(us1, 2), "value": round(global_elems / us1, 1), "unit": UNIT,
+                               "achieved_gbs_per_gpu": round(bytes_step / us1 * 1e-3, 1), "frac": round(bytes_step / us1 * 1e-3 / peak, 3),
+                               "batches_in_flight": 1}
     res = w.sets[0]["res"]
-    out["bpp_mean"] = float((res["bits"].double() / c.num_pixels_per_image).mean())
-    out["gap"] = float(w.sets[0]["path"].gap(res, w.y_elems))
+    out["bpp_mean_rank"] = float((res["bits"].double() / c.num_pixels_per_image).mean())
+    out["gap_rank"] = float(w.sets[0]["path"].gap(res, w.y_elems))
     return out
 
 
