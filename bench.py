@@ -1033,7 +1033,7 @@ def stanh_step_leg(args, dev, params, peak, images, global_elems, world, barrier
     cfg = {"beta": beta, "num_sigmoids": 0, "extrema": 80, "symmetry": False, "trainable": False, "removing_mean": True}
     steps = min(args.steps, 96)
     group = balanced_group(steps, min(args.steps_per_graph, 24))
-    chains = args.chains or 4
+    chains = args.chains or pick_chains(c, len(images), group)
     nbuf = args.nbuf or chains
     w = Workload(c, images, dev, nbuf, params, path_factory=lambda: TcmStanhEntropyPath(cfg, channels=64))
     w.kw = dict(training=True, num_pixels=c.num_pixels_per_image, seed=1234)

@@ -668,8 +668,20 @@ int stanh_gc_fwd_launch(const reslic_stanh_gc_desc* d, cudaStream_t st) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         *occ = nb;
       }
+      // This kernel is issue-bound: an SM's CTAs share its issue slots, so the launch ends when the SM with the most
+      // tiles is done.  With k CTAs on every SM that is k * ceil(tiles / (148 k)) tile times: take the k (>= 3 for
+      // latency hiding, <= resident) that minimises it, the larger k on a tie — 1,024 tiles run as 592 CTAs of <= 2
+      // tiles (8 per SM) instead of 740 of which 284 ran two (10 per SM); 4,096 as 592 x 7 (28) instead of 740 x 6 (30).
       int64_t grid = static_cast<int64_t>(*occ) * sm_count();
       if (grid > total) grid = total;
+      else {
+        int64_t best = -1;
+        for (int k = *occ; k >= 3; --k) {
+          const int64_t g = static_cast<int64_t>(k) * sm_count();
+          const int64_t cost = k * ((total + g - 1) / g);
+          if (best < 0 || cost < best) { best = cost; grid = g; }
+        }
+      }
       q.tpi = static_cast<unsigned int>(tpi);
       q.q_tiles = static_cast<unsigned int>(total / grid);
       q.r_tiles = static_cast<unsigned int>(total % grid);
