@@ -562,6 +562,11 @@ class Timer:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler is not None:
             sampler.active.set()
+        # The region is timed ON THE DEVICE: a ~100 us spin kernel goes first so that the start event and the first graph
+        # are already queued when the GPU reaches them — otherwise the host's cudaGraphLaunch of the first graph (tens of
+        # microseconds for ~140 nodes) sits between the event and the first kernel, which is host latency, not step time
+        # (it is 5 % of the driver's 20-step region on an 8-GPU shard).  The spin is before the start event: not timed.
+        torch.cuda._sleep(200_000)
         e0.record()
         self.run(steps)
         e1.record()
