@@ -554,27 +554,6 @@ class Timer:
         if done < max(warmup, 3):
             self.run(max(warmup, 3) - done)
             done = max(warmup, 3)
-        # ... and enough of them to bring the GPU out of its idle clocks: the driver's 20-step region lasts 0.3-2 ms, and a
-        # GPU that has just sat through a leg's host-side set-up needs tens of milliseconds of load before its SM clock is
-        # back up (the config-5 leg of an 8-GPU run measured 23.4 us per step right after set-up, 16.8 warmed up).  One
-        # replay is timed, then the same graph is replayed for ~40 ms — the same count on every rank (max over ranks).
-        n0 = sizes[0]
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        self.run(n0)
-        w1.record()
-        torch.cuda.synchronize()
-        ms_g = w0.elapsed_time(w1)
-        if self.world > 1:
-            t = torch.tensor([ms_g], dtype=torch.float64, device=self.w.dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_g = float(t.item())
-        extra = min(int(40.0 / max(ms_g, 1e-3)) + 1, 4000)
-        for k in range(extra):
-            self.run(n0)
-            if k % 64 == 63:
-                torch.cuda.synchronize()
-        done += (1 + extra) * n0
         self.warmup_steps = done
         barrier()
         if self.ex is not None:
@@ -583,11 +562,12 @@ class Timer:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler is not None:
             sampler.active.set()
-        # The region is timed ON THE DEVICE: a ~100 us spin kernel goes first so that the start event and the first graph
+        # The region is timed ON THE DEVICE: a ~1 ms spin kernel goes first so that the start event and the first graph
         # are already queued when the GPU reaches them — otherwise the host's cudaGraphLaunch of the first graph (tens of
-        # microseconds for ~140 nodes) sits between the event and the first kernel, which is host latency, not step time
-        # (it is 5 % of the driver's 20-step region on an 8-GPU shard).  The spin is before the start event: not timed.
-        torch.cuda._sleep(200_000)
+        # microseconds for ~140 nodes, more with eight ranks launching at once; the slowest rank sets the time) sits
+        # between the event and the first kernel, which is host latency, not step time (it is >= 5 % of the driver's
+        # 20-step region on an 8-GPU shard).  The spin is before the start event: not timed.
+        torch.cuda._sleep(2_000_000)
         e0.record()
         self.run(steps)
         e1.record()
