@@ -926,12 +926,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def make_exchange(args, w, rank, world):
-    """The rate exchange of an N > 1 run: peer stores fused into the collecting launch; the NCCL all-reduce is the
-    fallback (--exchange nccl, or when the peer buffers cannot be mapped — then every rank must fall back together)."""
+def make_exchange(args, w, rank, world, form=None):
+    """The rate exchange of an N > 1 run: peer stores fused into the collecting launch (`form` "branch": the one-CTA
+    publisher behind it, for passes whose collecting launch is not a Gaussian-conditional kernel); the NCCL all-reduce is
+    the fallback (--exchange nccl, or when the peer buffers cannot be mapped — then every rank must fall back together)."""
     import torch.distributed as dist
 
-    form = "branch" if args.exchange == "branch" else "fused"
+    form = form or ("branch" if args.exchange == "branch" else "fused")
     if world == 1:
         return PeerExchange(w, args.steps_per_graph, form)
     if args.exchange != "nccl":
@@ -1046,9 +1047,7 @@ def stanh_step_leg(args, dev, params, peak, images, global_elems, world, barrier
     bytes_step = 28 * w.y_elems + 12 * w.z_elems
     out = {"workload": c.name + "_stanh_soft", "beta": beta, "launches_per_step": 7, "bytes_per_y_elem": 28,
            "images_per_gpu": w.B, "buffer_sets": nbuf, "steps": steps, "steps_per_graph": group, "scaling": args.scaling}
-    ex = None
-    if world > 1:
-        ex = NcclExchange(w, group) if args.exchange == "nccl" else PeerExchange(w, group, "branch")
+    ex = make_exchange(args, w, 0, world, form="branch") if world > 1 else None
     tm = Timer(w, group, chains, world, ex)
     ms = tm.timed(steps, min(args.warmup, 8), barrier)
     us = ms * 1e3
