@@ -211,6 +211,12 @@ class TcmStanhEntropyPath(nn.Module):
         """y/mu/sigma [B, C, h, w], z [B, Cz, h/4, w/4] on the GPU, fp32.  Returns views of static buffers:
         ``y_hat`` (ste values), ``y_q`` (STanH outputs), likelihoods, ``bits`` [B] and ``gap_sums``
         ([sum (y - soft)^2, sum (y - hard)^2]; gap = |difference| / y.numel(), tcm_stanh.py:465-478)."""
+        if _ignored.get("exchange") is not None:
+            raise ValueError("TcmStanhEntropyPath: the collecting launch is a STanH kernel, which does not publish; call "
+                             "exchange.publish(res['bits']) behind the pass (bench.py: PeerExchange form 'branch')")
+        if _ignored.get("with_indexes") or _ignored.get("fuse_slices"):
+            raise ValueError("TcmStanhEntropyPath runs the training / evaluation forward per slice; symbols come from "
+                             "GaussianConditionalStanh.quantize(..., 'symbols')")
         gc, eb = self.gaussian_conditional[lv], self.entropy_bottleneck
         gc.stanh.update_state(y.device)              # tcm_stanh.py:399 (a no-op while w, b are unchanged)
         b = self.buffers(y, z)

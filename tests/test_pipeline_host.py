@@ -40,3 +40,12 @@ def test_stanh_pass_rejects_channel_counts_that_do_not_slice():
     assert st.num_slices == 5
     with pytest.raises(Exception):
         st(torch.zeros(1, 7, 4, 4), torch.zeros(1, 7, 4, 4), torch.ones(1, 7, 4, 4), torch.zeros(1, 8, 1, 1))
+
+
+def test_stanh_pass_rejects_options_it_would_otherwise_ignore():
+    st = TcmStanhEntropyPath(CFG, z_channels=8, channels=8)
+    y, z = torch.zeros(1, 20, 4, 4), torch.zeros(1, 8, 1, 1)
+    with pytest.raises(ValueError, match="publish"):
+        st(y, y, y + 1, z, exchange=object())
+    with pytest.raises(ValueError, match="symbols"):
+        st(y, y, y + 1, z, with_indexes=True)
