@@ -902,7 +902,8 @@ def run_ours(args):
             cfg["simulated_shard_of"] = sim
         line = {
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": main["warmup_steps"], "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+            "warmup": args.warmup, "warmup_steps_run": main["warmup_steps"],      # asked for / actually run (every graph of the timed region is replayed once first)
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": main["roofline"], "whole_y": main.get("whole_y"),
             "per_config": {str(c.cfg): {k: main[k] for k in ("workload", "value", "ms_per_step", "roofline", "whole_y") if k in main}, **legs},
