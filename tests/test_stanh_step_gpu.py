@@ -7,7 +7,8 @@ what src/models/stanh/tcm_stanh.py:396-451 runs between the dense transforms:
     y_gap = quantize(y, "training"); gap = compute_gap(y, y_gap)                 (:448-449, 465-478)
 
 Tolerances as tests/test_stanh_parity.py: ste values bit-exact, soft values 1e-5 scaled, likelihood evaluated by the
-oracle ON the kernel's own quantizer output 1e-5 relative (+3e-7 absolute), bits 1e-5 relative."""
+oracle ON the kernel's own quantizer output 1e-5 relative (+3e-7 absolute), bits 1e-5 relative, gap 2e-4 (a difference of
+two fp32 means in the reference)."""
 import pytest
 import torch
 
