@@ -488,6 +488,10 @@ int reslic_pmf_to_quantized_cdf(const float* pmf, int32_t n, int32_t precision, 
  * [n_cdfs] (= _cdf_length / _offset).  value = symbol - offset[idx]; values outside
  * [0, cdf_size-2) are escaped through 4-bit bypass groups. */
 void* reslic_rans_encoder_create(void);
+/* The encoder divides the state by a symbol's frequency through a table of 64-bit reciprocals (one multiply instead of
+ * a 64-bit divide per symbol).  This compares the table with the divide for every frequency 1..65535 at the edges of the
+ * admissible state range and at `samples_per_freq` pseudo-random states each; returns the number of mismatches (0). */
+int64_t reslic_rans_check_reciprocals(int64_t samples_per_freq, uint64_t seed);
 void reslic_rans_encoder_destroy(void* enc);
 int reslic_rans_encoder_push(void* enc, const int32_t* symbols, const int32_t* indexes, int64_t n,
                              const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,

@@ -256,6 +256,7 @@ EXPORTS = {
     "reslic_stanh_act_f32": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StanhTables), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "reslic_rans_encoder_create": (C.c_void_p, []),
+    "reslic_rans_check_reciprocals": (C.c_int64, [C.c_int64, C.c_uint64]),
     "reslic_rans_encoder_destroy": (None, [C.c_void_p]),
     "reslic_rans_encoder_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                            C.c_int32, C.c_void_p, C.c_void_p]),

@@ -151,3 +151,19 @@ def test_push_slots_gives_the_same_stream_as_push(tables):
     with pytest.raises(ValueError, match="ascending"):
         enc.encode_slots(slots[:10], torch.tensor([20], dtype=torch.int32), torch.tensor([3]))
     enc.flush()
+
+
+def test_reciprocal_table_equals_the_divide_for_every_frequency():
+    """The encoder replaces `state / freq` by a multiply with a tabulated 64-bit reciprocal; the library's self-check
+    compares the two for every frequency 1..65535 at the edges of the admissible state range and at random states."""
+    from reslic_tcm_b200 import _cabi
+
+    assert _cabi.load().reslic_rans_check_reciprocals(200, 7) == 0
+
+
+def test_probability_one_symbols_are_rejected_not_miscoded():
+    """A row whose only regular symbol has range 65536 does not fit the 16-bit range of a coder word."""
+    cdf = torch.tensor([[0, 65536, 65536]], dtype=torch.int32)
+    enc = rans.BufferedRansEncoder()
+    with pytest.raises(ValueError):
+        enc.encode_with_indexes([0], [0], cdf, [3], [0])
